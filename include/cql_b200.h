@@ -1,0 +1,166 @@
+/*
+ * cql_b200.h -- C ABI of the B200-native CQL recommender hot path.
+ *
+ * This is the drop-in boundary.  The reference has NO
+ * native interface for this path (it ships no native code at all, SURVEY.md
+ * section 2.2) -- the functions below replace *Python* call sites, cited per
+ * entry point as reference file:line where the call site is in the mounted
+ * checkout, or as the upstream d3rlpy / RePlay-CQL location ([EXT], not in
+ * the checkout) otherwise.  The Python host (replay_cql_b200/_lib.py) binds
+ * them with ctypes; INTEGRATION.md shows the stub a RePlay maintainer adds.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function
+ * returns 0 on success, non-zero on error (cql_last_error() has the text).
+ * "host" pointers are ordinary (ideally pinned) host memory, "dev" pointers
+ * are device memory on the handle's GPU.  One handle per GPU; a handle is not
+ * thread-safe.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ */
+#ifndef CQL_B200_H
+#define CQL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CQL_ABI_VERSION 1
+#define CQL_HIDDEN 256          /* d3rlpy default encoder: [256, 256] */
+#define CQL_OBS_DIM 2           /* (user_idx, item_idx) */
+#define CQL_ACT_DIM 1           /* relevance */
+#define CQL_MAX_CRITICS 4
+#define CQL_MAX_TOPK 1024
+
+/* precision of the 256x256 hidden-layer contraction */
+enum { CQL_PREC_FP32 = 0,      /* CUDA-core FP32 (exact-order reference path on the GPU) */
+       CQL_PREC_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-term split, FP32-grade */
+       CQL_PREC_BF16 = 2 };    /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate) */
+
+enum { CQL_SQUASH_EPS = 0, CQL_SQUASH_SOFTPLUS = 1 };
+enum { CQL_SCORE_Q = 0,        /* mean_i Q_i(x, tanh(mu(x)))  (d3rlpy predict_value(x, predict(x))) */
+       CQL_SCORE_POLICY = 1 }; /* tanh(mu(x))                  (d3rlpy predict(x)) */
+
+typedef struct cql_config {
+  int32_t struct_size;          /* = sizeof(cql_config), ABI check */
+  int32_t device;               /* CUDA ordinal */
+  int32_t batch_size;           /* B (per GPU) */
+  int32_t n_critics;            /* C, 1..CQL_MAX_CRITICS */
+  int32_t n_action_samples;     /* n, 1..10 */
+  int32_t precision;            /* CQL_PREC_* */
+  int32_t squash;               /* CQL_SQUASH_* */
+  int32_t rank, world_size;     /* data-parallel position (sampling streams only; no comms inside) */
+  float gamma, tau;
+  float actor_lr, critic_lr, temp_lr, alpha_lr;
+  float initial_temperature, initial_alpha;
+  float alpha_threshold, conservative_weight;
+  float beta1, beta2, adam_eps;
+  uint64_t seed;
+} cql_config;
+
+typedef struct cql_handle cql_handle;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* replaces: d3rlpy.algos.CQL(...).create_impl() [EXT d3rlpy/algos/cql.py]   */
+int  cql_create(const cql_config* cfg, cql_handle** out);
+void cql_destroy(cql_handle* h);
+const char* cql_last_error(const cql_handle* h);   /* h may be NULL: error of the last failed cql_create */
+int  cql_abi_version(void);
+
+/* ---- flat state -------------------------------------------------------- */
+/* Flat layout (floats), NET = 67136-float slot per network:
+ *   [actor | critic_0..C-1 | targ_actor | targ_critic_0..C-1 | scalars(64)]
+ *   net slot: W1[H][in] b1[H] W2[H][H] b2[H] W3[out][H] b3[out]  (PyTorch (out,in) row-major)
+ *   scalars : [0]=log_temp [1]=log_alpha
+ * replaces: torch state_dict save/load in the wrapper's _save_model/_load_model
+ *           (hook: replay/models/base_rec.py:280-284; caller replay/model_handler.py:38,90) */
+int64_t cql_state_floats(const cql_handle* h);
+int  cql_set_weights(cql_handle* h, const float* host_flat, int64_t n);
+int  cql_get_weights(cql_handle* h, float* host_flat, int64_t n);
+/* Adam moments (same flat layout, trainable part meaningful) + step counter: exact resume */
+int  cql_set_optimizer(cql_handle* h, const float* host_m, const float* host_v, int64_t n, int64_t step);
+int  cql_get_optimizer(cql_handle* h, float* host_m, float* host_v, int64_t n, int64_t* step);
+
+/* ---- replay table (K1) ------------------------------------------------- */
+/* Episode-ordered steps -> 32-byte transition rows resident in HBM.
+ * replaces: d3rlpy MDPDataset(...) + Episode._to_transitions [EXT d3rlpy/dataset.pyx]
+ * obs [n][2], act [n], rew [n], term [n]  (host).  next_obs = next row unless term. */
+int  cql_load_transitions(cql_handle* h, const float* obs, const float* act,
+                          const float* rew, const float* term, int64_t n);
+int64_t cql_num_transitions(const cql_handle* h);
+/* stand-alone gather for the K1 roofline sweep: out_dev [count][8] floats.
+ * idx_dev NULL => the handle's epoch permutation starting at position `pos`. */
+int  cql_sample_rows(cql_handle* h, const int64_t* idx_dev, int64_t pos, int64_t count,
+                     float* out_dev, void* stream);
+
+/* ---- update (K2-K4) ---------------------------------------------------- */
+/* n_steps fused updates with on-device sampling and Philox noise.
+ * metrics6 (host, may be NULL): temp_loss,temp,alpha_loss,alpha,critic_loss,actor_loss of the LAST step.
+ * replaces: d3rlpy CQL._update per step of CQL.fit [EXT d3rlpy/algos/cql.py, algos/torch/cql_impl.py] */
+int  cql_update(cql_handle* h, int64_t n_steps, float* metrics6, void* stream);
+
+/* One update on a caller-supplied minibatch (host buffers, B rows) -- the parity
+ * and end-to-end entry.  noise (host, may be NULL => Philox): packed
+ * [temp_eps B | alpha_eps_t B*n | alpha_eps_t1 B*n | alpha_u B*n |
+ *  critic_eps_t B*n | critic_eps_t1 B*n | critic_u B*n | actor_eps B].
+ * grads_out (host, may be NULL): trainable gradients in flat layout
+ * [actor | critics | scalars] = (1+C)*NET + 64 floats (averaged over the batch).
+ * replaces: CQLImpl.update_temp/update_alpha/update_critic/update_actor/update_*_target [EXT] */
+int  cql_update_batch(cql_handle* h, const float* obs, const float* act, const float* rew,
+                      const float* next_obs, const float* term, const float* noise,
+                      float* metrics6, float* grads_out, void* stream);
+
+/* Data-parallel split of one update.  The host all-reduces (mean) the exposed
+ * gradient buffer between phases; with world_size==1 the phases can be called
+ * back to back.  phase 0: sample + forward passes + temp/alpha grads
+ *                phase 1: temp/alpha Adam, critic backward  -> critic grads
+ *                phase 2: critic Adam + Polyak, actor passes -> actor grads
+ *                phase 3: actor Adam + Polyak, step counter                    */
+int  cql_step_phase(cql_handle* h, int phase, void* stream);
+enum { CQL_BUF_SCALAR_GRADS = 0,   /* 64 floats: [0]=d log_temp [1]=d log_alpha */
+       CQL_BUF_CRITIC_GRADS = 1,   /* C*NET floats */
+       CQL_BUF_ACTOR_GRADS = 2,    /* NET floats */
+       CQL_BUF_METRICS = 3,        /* 8 floats */
+       CQL_BUF_PARAMS = 4,
+       CQL_BUF_ALL_GRADS = 5 };    /* (1+C)*NET+64 floats: [actor | critics | scalars] */
+int  cql_device_buffer(cql_handle* h, int which, void** dev_ptr, int64_t* n_floats);
+
+/* ---- scoring (K5) ------------------------------------------------------ */
+/* For each user: relevance of every candidate item, minus the user's seen
+ * items (CSR, sorted item ids per user; seen_indptr may be NULL = no filter),
+ * top-k by (relevance desc, item asc).  Rows with fewer than k candidates are
+ * padded with item -1 / score -inf.
+ * replaces: CQL._predict per-user loop [EXT; pattern replay/models/neuromf.py:394-438]
+ *           + _filter_seen replay/models/base_rec.py:417-464
+ *           + get_top_k_recs replay/utils.py:112-127
+ * All pointers host; out_items [U][k] int32, out_scores [U][k] float. */
+int  cql_score_topk(cql_handle* h, const int32_t* users, int64_t n_users,
+                    const int32_t* items, int64_t n_items,
+                    const int64_t* seen_indptr, const int32_t* seen_items,
+                    int32_t k, int32_t mode,
+                    int32_t* out_items, float* out_scores, void* stream);
+/* same, every pointer already on the device (HBM-resident measurement) */
+int  cql_score_topk_dev(cql_handle* h, const int32_t* users, int64_t n_users,
+                        const int32_t* items, int64_t n_items,
+                        const int64_t* seen_indptr, const int32_t* seen_items,
+                        int32_t k, int32_t mode,
+                        int32_t* out_items, float* out_scores, void* stream);
+/* relevance of explicit (user,item) pairs (host pointers).
+ * replaces: the generic _predict_pairs fallback replay/models/base_rec.py:784-823 */
+int  cql_score_pairs(cql_handle* h, const int32_t* users, const int32_t* items, int64_t n,
+                     int32_t mode, float* out_scores, void* stream);
+
+/* Stand-alone HBM-bound top-k + seen filter over a materialised score matrix
+ * scores_dev [U][I] (the well-defined HBM denominator for scoring/top-k).
+ * users_dev gives each row's user id for the seen CSR (NULL => row index). */
+int  cql_topk_filter_dev(cql_handle* h, const float* scores_dev, int64_t n_users, int64_t n_items,
+                         const int32_t* users_dev, const int32_t* items_dev,
+                         const int64_t* seen_indptr, const int32_t* seen_items,
+                         int32_t k, int32_t* out_items, float* out_scores, void* stream);
+
+/* number of kernels this library has launched on the handle (bench "gpu_launches") */
+int64_t cql_launch_count(const cql_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CQL_B200_H */

@@ -1,0 +1,518 @@
+// capi.cu -- the extern "C" surface declared in include/cql_b200.h.
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include "engine.cuh"
+#include "update.cuh"
+#include "score.cuh"
+
+using namespace cql;
+
+struct cql_handle {
+  Handle h;
+  // CUDA graph of one sampled update (phases 0-3), captured lazily per stream
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  int64_t graph_launches = 0;
+  // grow-only device scratch for the host-pointer scoring entry points
+  void* sbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t sbuf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float* part_s = nullptr;
+  int* part_i = nullptr;
+  size_t part_elems = 0;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+void* scratch(cql_handle* ch, int slot, size_t bytes) {
+  if (bytes > ch->sbuf_bytes[slot]) {
+    if (ch->sbuf[slot]) CQL_CUDA(cudaFree(ch->sbuf[slot]));
+    ch->sbuf[slot] = nullptr;
+    ch->sbuf_bytes[slot] = 0;
+    const size_t cap = bytes + bytes / 4 + 256;
+    CQL_CUDA(cudaMalloc(&ch->sbuf[slot], cap));
+    ch->sbuf_bytes[slot] = cap;
+  }
+  return ch->sbuf[slot];
+}
+
+void set_kernel_attrs() {
+  CQL_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(mlp_bwd1_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD1_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(mlp_bwd1_kernel<3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD1_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(mlp_bwd1_kernel<2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD1_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, score_smem(CQL_MAX_TOPK)));
+  CQL_CUDA(cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+}
+
+void create_impl(const cql_config* cfg, cql_handle* ch) {
+  Handle& h = ch->h;
+  CQL_REQUIRE(cfg != nullptr, "cql_create: cfg is NULL");
+  CQL_REQUIRE(cfg->struct_size == (int32_t)sizeof(cql_config), "cql_create: cql_config size mismatch (ABI)");
+  CQL_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= (1 << 20), "cql_create: batch_size out of range");
+  CQL_REQUIRE(cfg->n_critics >= 1 && cfg->n_critics <= CQL_MAX_CRITICS, "cql_create: n_critics must be 1..4");
+  CQL_REQUIRE(cfg->n_action_samples >= 1 && cfg->n_action_samples <= 10, "cql_create: n_action_samples must be 1..10");
+  CQL_REQUIRE(cfg->precision == CQL_PREC_FP32, "cql_create: only CQL_PREC_FP32 is built in this version");
+  CQL_REQUIRE(cfg->squash == CQL_SQUASH_EPS || cfg->squash == CQL_SQUASH_SOFTPLUS, "cql_create: bad squash");
+  CQL_REQUIRE(cfg->world_size >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world_size, "cql_create: bad rank/world_size");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error{std::string("cql_create: no CUDA device available (") + cudaGetErrorString(e) +
+                "); this library has no CPU fallback"};
+  CQL_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "cql_create: device ordinal out of range");
+  CQL_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop{};
+  CQL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  CQL_REQUIRE(prop.major >= 10, "cql_create: built for sm_100a (B200); found an older GPU");
+  h.cfg = *cfg;
+  h.num_sms = prop.multiProcessorCount;
+  h.B = cfg->batch_size; h.n = cfg->n_action_samples; h.C = cfg->n_critics;
+  const int B = h.B, n = h.n, C = h.C, n3 = 3 * n;
+  h.rsA = n3; h.rsC = n3 + 1;
+  CQL_CUDA(cudaStreamCreateWithFlags(&h.own_stream, cudaStreamNonBlocking));
+  set_kernel_attrs();
+
+  const int64_t S = state_floats(C);
+  h.params = h.dalloc<float>(S);
+  h.adam_m = h.dalloc<float>(S);
+  h.adam_v = h.dalloc<float>(S);
+  h.grads = h.dalloc<float>(grad_floats(C));
+  h.step_dev = h.dalloc<long long>(1);
+  h.sample_pos = h.dalloc<long long>(1);
+  h.stepinfo = h.dalloc<StepInfo>(1);
+  h.metrics = h.dalloc<float>(8);
+  CQL_CUDA(cudaMallocHost(&h.metrics_host, 8 * sizeof(float)));
+  h.batch = h.dalloc<float>((size_t)B * 8);
+  CQL_CUDA(cudaMallocHost(&h.batch_host, (size_t)B * 8 * sizeof(float)));
+  h.noise_floats = 2 * (int64_t)B + 6 * (int64_t)B * n;
+  h.noise = h.dalloc<float>(h.noise_floats);
+  CQL_CUDA(cudaMallocHost(&h.noise_host, h.noise_floats * sizeof(float)));
+  const int tB = tiles_of(B), rowsC = B * (n3 + 1), tC = tiles_of(rowsC);
+  h.XA = h.dalloc<float4>(2 * (size_t)B);
+  h.outA = h.dalloc<float>(4 * (size_t)B);
+  h.h2A = h.dalloc<float>((size_t)tB * H * BM);
+  h.XAl = h.dalloc<float4>((size_t)B * n3);
+  h.offAl = h.dalloc<float>((size_t)B * n3);
+  h.QAl = h.dalloc<float>((size_t)C * B * n3);
+  h.XC = h.dalloc<float4>((size_t)rowsC);
+  h.offC = h.dalloc<float>((size_t)rowsC);
+  h.QC = h.dalloc<float>((size_t)C * rowsC);
+  h.h2C = h.dalloc<float>((size_t)C * tC * H * BM);
+  h.dQ = h.dalloc<float>((size_t)C * rowsC);
+  h.XT = h.dalloc<float4>(B);
+  h.QT = h.dalloc<float>((size_t)C * B);
+  h.XP = h.dalloc<float4>(B);
+  h.QP = h.dalloc<float>((size_t)C * B);
+  h.h2P = h.dalloc<float>((size_t)C * tB * H * BM);
+  h.dQP = h.dalloc<float>((size_t)C * B);
+  h.dXP = h.dalloc<float4>((size_t)C * B);
+  h.dOutA = h.dalloc<float>(2 * (size_t)B);
+  h.perb = h.dalloc<float>(4 * (size_t)B);
+  h.splitsC = std::max(1, std::min(tC, (2 * h.num_sms) / (4 * C)));
+  h.splitsA = std::max(1, std::min(tB, (2 * h.num_sms) / 4));
+  h.smallC = h.dalloc<float>((size_t)C * tC * SMALL_STRIDE);
+  h.smallA = h.dalloc<float>((size_t)tB * SMALL_STRIDE);
+  h.pw2C = h.dalloc<float>((size_t)C * h.splitsC * H * H);
+  h.pw2A = h.dalloc<float>((size_t)h.splitsA * H * H);
+  // scalars start at the configured initial values; networks are set by cql_set_weights
+  float sc[SCALAR_SLOT] = {0};
+  sc[0] = logf(cfg->initial_temperature);
+  sc[1] = logf(cfg->initial_alpha);
+  CQL_CUDA(cudaMemcpy(h.scalars(), sc, sizeof(sc), cudaMemcpyHostToDevice));
+}
+
+void destroy_graph(cql_handle* ch) {
+  if (ch->graph_exec) { cudaGraphExecDestroy(ch->graph_exec); ch->graph_exec = nullptr; }
+}
+
+template <typename F>
+int guarded(cql_handle* ch, F&& f) {
+  if (!ch) { g_create_error = "NULL handle"; return 1; }
+  try {
+    CQL_CUDA(cudaSetDevice(ch->h.cfg.device));
+    f();
+    return 0;
+  } catch (const Error& e) {
+    ch->h.err = e.msg;
+    return 1;
+  } catch (const std::exception& e) {
+    ch->h.err = e.what();
+    return 2;
+  }
+}
+
+void run_full_step(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
+  phase0(h, st, bs, ns);
+  phase1(h, st);
+  phase2(h, st);
+  phase3(h, st);
+}
+
+void score_topk_dev_impl(cql_handle* ch, const int32_t* users, int64_t U, const int32_t* items, int64_t I,
+                         const int64_t* seen_indptr, const int32_t* seen_items, int k, int mode, int32_t* out_items,
+                         float* out_scores, cudaStream_t st) {
+  Handle* h = &ch->h;
+  CQL_REQUIRE(k >= 1 && k <= CQL_MAX_TOPK, "cql_score_topk: k must be 1..1024");
+  CQL_REQUIRE(mode == CQL_SCORE_Q || mode == CQL_SCORE_POLICY, "cql_score_topk: bad mode");
+  CQL_REQUIRE(U >= 0 && I >= 0 && U < (1ll << 31), "cql_score_topk: bad sizes");
+  if (U == 0) return;
+  const int64_t tiles = (I + BM - 1) / BM;
+  if (tiles == 0) {  // no candidates: pad
+    CQL_CUDA(cudaMemsetAsync(out_items, 0xff, (size_t)U * k * sizeof(int32_t), st));
+    std::vector<float> ninf((size_t)U * k, -INFINITY);
+    CQL_CUDA(cudaMemcpyAsync(out_scores, ninf.data(), ninf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  // enough CTAs to fill the machine a few times over, at most one chunk per tile
+  int64_t want = (8ll * h->num_sms + U - 1) / U;
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, want));
+  int tpc = (int)((tiles + chunks - 1) / chunks);
+  chunks = (int)((tiles + tpc - 1) / tpc);
+  CQL_REQUIRE(chunks <= 65535 * 32, "cql_score_topk: too many chunks");
+  ScoreArgs a{};
+  a.params = h->params; a.users = users; a.items = items;
+  a.seen_indptr = seen_indptr; a.seen_items = seen_items;
+  a.n_users = U; a.n_items = I; a.C = h->C; a.k = k; a.mode = mode; a.chunks = chunks; a.tiles_per_chunk = tpc;
+  // users go on grid.y (max 65535): process in slabs
+  const int64_t slab = 65535;
+  for (int64_t u0 = 0; u0 < U; u0 += slab) {
+    const int64_t nu = std::min(slab, U - u0);
+    ScoreArgs s = a;
+    s.users = users + u0;
+    s.n_users = nu;
+    if (chunks == 1) {
+      s.part_s = out_scores + u0 * k;
+      s.part_i = out_items + u0 * k;
+    } else {
+      const size_t need = (size_t)nu * chunks * k;
+      if (need > ch->part_elems) {
+        if (ch->part_s) CQL_CUDA(cudaFree(ch->part_s));
+        if (ch->part_i) CQL_CUDA(cudaFree(ch->part_i));
+        ch->part_s = nullptr; ch->part_i = nullptr; ch->part_elems = 0;
+        CQL_CUDA(cudaMalloc(&ch->part_s, need * sizeof(float)));
+        CQL_CUDA(cudaMalloc(&ch->part_i, need * sizeof(int)));
+        ch->part_elems = need;
+      }
+      s.part_s = ch->part_s;
+      s.part_i = ch->part_i;
+    }
+    k_score_topk<<<dim3(chunks, (unsigned)nu), NT, score_smem(k), st>>>(s);
+    CQL_LAUNCH_CHECK(h);
+    if (chunks > 1) {
+      const int wpb = 4;
+      k_topk_merge<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, wpb * 2 * k * sizeof(float), st>>>(
+          ch->part_s, ch->part_i, nu, chunks, k, out_scores + u0 * k, out_items + u0 * k);
+      CQL_LAUNCH_CHECK(h);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cql_abi_version(void) { return CQL_ABI_VERSION; }
+
+int cql_create(const cql_config* cfg, cql_handle** out) {
+  if (!out) { g_create_error = "cql_create: out is NULL"; return 1; }
+  *out = nullptr;
+  cql_handle* ch = new cql_handle();
+  try {
+    create_impl(cfg, ch);
+  } catch (const Error& e) {
+    g_create_error = e.msg;
+    ch->h.free_all();
+    delete ch;
+    return 1;
+  }
+  *out = ch;
+  return 0;
+}
+
+void cql_destroy(cql_handle* ch) {
+  if (!ch) return;
+  cudaSetDevice(ch->h.cfg.device);
+  cudaDeviceSynchronize();
+  destroy_graph(ch);
+  for (int i = 0; i < 8; ++i) if (ch->sbuf[i]) cudaFree(ch->sbuf[i]);
+  if (ch->part_s) cudaFree(ch->part_s);
+  if (ch->part_i) cudaFree(ch->part_i);
+  ch->h.free_all();
+  delete ch;
+}
+
+const char* cql_last_error(const cql_handle* ch) { return ch ? ch->h.err.c_str() : g_create_error.c_str(); }
+
+int64_t cql_state_floats(const cql_handle* ch) { return ch ? state_floats(ch->h.C) : 0; }
+int64_t cql_num_transitions(const cql_handle* ch) { return ch ? ch->h.n_trans : 0; }
+int64_t cql_launch_count(const cql_handle* ch) { return ch ? ch->h.launches : 0; }
+
+int cql_set_weights(cql_handle* ch, const float* host_flat, int64_t n) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(host_flat && n == state_floats(ch->h.C), "cql_set_weights: n must equal cql_state_floats()");
+    CQL_CUDA(cudaDeviceSynchronize());
+    CQL_CUDA(cudaMemcpy(ch->h.params, host_flat, n * sizeof(float), cudaMemcpyHostToDevice));
+  });
+}
+
+int cql_get_weights(cql_handle* ch, float* host_flat, int64_t n) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(host_flat && n == state_floats(ch->h.C), "cql_get_weights: n must equal cql_state_floats()");
+    CQL_CUDA(cudaDeviceSynchronize());
+    CQL_CUDA(cudaMemcpy(host_flat, ch->h.params, n * sizeof(float), cudaMemcpyDeviceToHost));
+  });
+}
+
+int cql_set_optimizer(cql_handle* ch, const float* host_m, const float* host_v, int64_t n, int64_t step) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(host_m && host_v && n == state_floats(ch->h.C), "cql_set_optimizer: n must equal cql_state_floats()");
+    CQL_REQUIRE(step >= 0, "cql_set_optimizer: step must be >= 0");
+    CQL_CUDA(cudaDeviceSynchronize());
+    CQL_CUDA(cudaMemcpy(ch->h.adam_m, host_m, n * sizeof(float), cudaMemcpyHostToDevice));
+    CQL_CUDA(cudaMemcpy(ch->h.adam_v, host_v, n * sizeof(float), cudaMemcpyHostToDevice));
+    const long long s = step;
+    CQL_CUDA(cudaMemcpy(ch->h.step_dev, &s, sizeof(s), cudaMemcpyHostToDevice));
+  });
+}
+
+int cql_get_optimizer(cql_handle* ch, float* host_m, float* host_v, int64_t n, int64_t* step) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(host_m && host_v && step && n == state_floats(ch->h.C), "cql_get_optimizer: bad arguments");
+    CQL_CUDA(cudaDeviceSynchronize());
+    CQL_CUDA(cudaMemcpy(host_m, ch->h.adam_m, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CQL_CUDA(cudaMemcpy(host_v, ch->h.adam_v, n * sizeof(float), cudaMemcpyDeviceToHost));
+    long long s = 0;
+    CQL_CUDA(cudaMemcpy(&s, ch->h.step_dev, sizeof(s), cudaMemcpyDeviceToHost));
+    *step = s;
+  });
+}
+
+int cql_load_transitions(cql_handle* ch, const float* obs, const float* act, const float* rew, const float* term,
+                         int64_t n) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(obs && act && rew && term && n >= 1, "cql_load_transitions: bad arguments");
+    CQL_CUDA(cudaDeviceSynchronize());
+    if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
+    CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+    // stage the 20 B/step columns on the device, expand to 32 B rows there
+    float *d_obs, *d_act, *d_rew, *d_term;
+    CQL_CUDA(cudaMalloc(&d_obs, (size_t)n * 2 * sizeof(float)));
+    CQL_CUDA(cudaMalloc(&d_act, (size_t)n * 3 * sizeof(float)));
+    d_rew = d_act + n; d_term = d_rew + n;
+    cudaStream_t st = h.own_stream;
+    CQL_CUDA(cudaMemcpyAsync(d_obs, obs, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(d_act, act, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(d_rew, rew, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(d_term, term, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_build_transitions<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(d_obs), d_act, d_rew,
+                                                                    d_term, n, reinterpret_cast<float4*>(h.table));
+    CQL_LAUNCH_CHECK(&h);
+    CQL_CUDA(cudaStreamSynchronize(st));
+    CQL_CUDA(cudaFree(d_obs));
+    CQL_CUDA(cudaFree(d_act));
+    h.n_trans = n;
+    destroy_graph(ch);
+  });
+}
+
+int cql_sample_rows(cql_handle* ch, const int64_t* idx_dev, int64_t pos, int64_t count, float* out_dev, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(h.n_trans > 0, "cql_sample_rows: no transitions loaded");
+    CQL_REQUIRE(count >= 0 && out_dev, "cql_sample_rows: bad arguments");
+    if (count == 0) return;
+    cudaStream_t st = pick_stream(&h, stream);
+    k_sample<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(h.table), h.n_trans, idx_dev,
+                                                             nullptr, pos, count, std::max<int64_t>(1, h.B), 0, 1,
+                                                             h.cfg.seed, reinterpret_cast<float4*>(out_dev));
+    CQL_LAUNCH_CHECK(&h);
+  });
+}
+
+int cql_update(cql_handle* ch, int64_t n_steps, float* metrics6, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(n_steps >= 0, "cql_update: n_steps < 0");
+    CQL_REQUIRE(h.n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
+    cudaStream_t st = pick_stream(&h, stream);
+    if (!ch->graph_exec || ch->graph_stream != st) {
+      destroy_graph(ch);
+      cudaGraph_t g = nullptr;
+      const int64_t before = h.launches;
+      CQL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        run_full_step(&h, st, BatchSource::Sampled, NoiseSource::Philox);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CQL_CUDA(cudaStreamEndCapture(st, &g));
+      ch->graph_launches = h.launches - before;
+      h.launches = before;
+      CQL_CUDA(cudaGraphInstantiate(&ch->graph_exec, g, 0));
+      CQL_CUDA(cudaGraphDestroy(g));
+      ch->graph_stream = st;
+    }
+    for (int64_t i = 0; i < n_steps; ++i) CQL_CUDA(cudaGraphLaunch(ch->graph_exec, st));
+    h.launches += ch->graph_launches * n_steps;
+    if (metrics6) {
+      CQL_CUDA(cudaMemcpyAsync(h.metrics_host, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CQL_CUDA(cudaStreamSynchronize(st));
+      std::memcpy(metrics6, h.metrics_host, 6 * sizeof(float));
+    }
+  });
+}
+
+int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const float* rew, const float* next_obs,
+                     const float* term, const float* noise, float* metrics6, float* grads_out, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(obs && act && rew && next_obs && term, "cql_update_batch: NULL batch pointer");
+    cudaStream_t st = pick_stream(&h, stream);
+    const int B = h.B;
+    for (int b = 0; b < B; ++b) {
+      float* r = h.batch_host + (size_t)b * 8;
+      r[0] = obs[2 * b]; r[1] = obs[2 * b + 1]; r[2] = act[b]; r[3] = rew[b];
+      r[4] = next_obs[2 * b]; r[5] = next_obs[2 * b + 1]; r[6] = term[b]; r[7] = 0.f;
+    }
+    CQL_CUDA(cudaMemcpyAsync(h.batch, h.batch_host, (size_t)B * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (noise) {
+      std::memcpy(h.noise_host, noise, h.noise_floats * sizeof(float));
+      CQL_CUDA(cudaMemcpyAsync(h.noise, h.noise_host, h.noise_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+    if (metrics6) CQL_CUDA(cudaMemcpyAsync(h.metrics_host, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grads_out)
+      CQL_CUDA(cudaMemcpyAsync(grads_out, h.grads, grad_floats(h.C) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+    if (metrics6) std::memcpy(metrics6, h.metrics_host, 6 * sizeof(float));
+  });
+}
+
+int cql_step_phase(cql_handle* ch, int phase, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    cudaStream_t st = pick_stream(&h, stream);
+    switch (phase) {
+      case 0: phase0(&h, st, BatchSource::Sampled, NoiseSource::Philox); break;
+      case 1: phase1(&h, st); break;
+      case 2: phase2(&h, st); break;
+      case 3: phase3(&h, st); break;
+      default: throw Error{"cql_step_phase: phase must be 0..3"};
+    }
+  });
+}
+
+int cql_device_buffer(cql_handle* ch, int which, void** dev_ptr, int64_t* n_floats) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(dev_ptr && n_floats, "cql_device_buffer: NULL out pointer");
+    switch (which) {
+      case CQL_BUF_SCALAR_GRADS: *dev_ptr = h.g_scalars(); *n_floats = SCALAR_SLOT; break;
+      case CQL_BUF_CRITIC_GRADS: *dev_ptr = h.g_critics(); *n_floats = (int64_t)h.C * NET_STRIDE; break;
+      case CQL_BUF_ACTOR_GRADS: *dev_ptr = h.g_actor(); *n_floats = NET_STRIDE; break;
+      case CQL_BUF_METRICS: *dev_ptr = h.metrics; *n_floats = 8; break;
+      case CQL_BUF_PARAMS: *dev_ptr = h.params; *n_floats = state_floats(h.C); break;
+      case CQL_BUF_ALL_GRADS: *dev_ptr = h.grads; *n_floats = grad_floats(h.C); break;
+      default: throw Error{"cql_device_buffer: unknown buffer id"};
+    }
+  });
+}
+
+int cql_score_topk_dev(cql_handle* ch, const int32_t* users, int64_t n_users, const int32_t* items, int64_t n_items,
+                       const int64_t* seen_indptr, const int32_t* seen_items, int32_t k, int32_t mode,
+                       int32_t* out_items, float* out_scores, void* stream) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE((n_users == 0 || users) && (n_items == 0 || items) && out_items && out_scores,
+                "cql_score_topk_dev: NULL pointer");
+    score_topk_dev_impl(ch, users, n_users, items, n_items, seen_indptr, seen_items, k, mode, out_items, out_scores,
+                        pick_stream(&ch->h, stream));
+  });
+}
+
+int cql_score_topk(cql_handle* ch, const int32_t* users, int64_t n_users, const int32_t* items, int64_t n_items,
+                   const int64_t* seen_indptr, const int32_t* seen_items, int32_t k, int32_t mode, int32_t* out_items,
+                   float* out_scores, void* stream) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE((n_users == 0 || users) && (n_items == 0 || items) && (n_users == 0 || (out_items && out_scores)),
+                "cql_score_topk: NULL pointer");
+    CQL_REQUIRE(k >= 1 && k <= CQL_MAX_TOPK, "cql_score_topk: k must be 1..1024");
+    if (n_users == 0) return;
+    cudaStream_t st = pick_stream(&ch->h, stream);
+    int32_t* d_users = (int32_t*)scratch(ch, 0, (size_t)n_users * 4);
+    int32_t* d_items = (int32_t*)scratch(ch, 1, (size_t)std::max<int64_t>(1, n_items) * 4);
+    int32_t* d_oi = (int32_t*)scratch(ch, 2, (size_t)n_users * k * 4);
+    float* d_os = (float*)scratch(ch, 3, (size_t)n_users * k * 4);
+    CQL_CUDA(cudaMemcpyAsync(d_users, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, st));
+    if (n_items) CQL_CUDA(cudaMemcpyAsync(d_items, items, (size_t)n_items * 4, cudaMemcpyHostToDevice, st));
+    int64_t* d_ptr = nullptr;
+    int32_t* d_seen = nullptr;
+    if (seen_indptr) {
+      int32_t mx = 0;
+      for (int64_t i = 0; i < n_users; ++i) {
+        CQL_REQUIRE(users[i] >= 0, "cql_score_topk: negative user id");
+        mx = std::max(mx, users[i]);
+      }
+      const int64_t np = (int64_t)mx + 2;
+      const int64_t ns = seen_indptr[np - 1];
+      d_ptr = (int64_t*)scratch(ch, 4, (size_t)np * 8);
+      d_seen = (int32_t*)scratch(ch, 5, (size_t)std::max<int64_t>(1, ns) * 4);
+      CQL_CUDA(cudaMemcpyAsync(d_ptr, seen_indptr, (size_t)np * 8, cudaMemcpyHostToDevice, st));
+      if (ns) {
+        CQL_REQUIRE(seen_items, "cql_score_topk: seen_items is NULL");
+        CQL_CUDA(cudaMemcpyAsync(d_seen, seen_items, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+      }
+    }
+    score_topk_dev_impl(ch, d_users, n_users, d_items, n_items, d_ptr, d_seen, k, mode, d_oi, d_os, st);
+    CQL_CUDA(cudaMemcpyAsync(out_items, d_oi, (size_t)n_users * k * 4, cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaMemcpyAsync(out_scores, d_os, (size_t)n_users * k * 4, cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int cql_score_pairs(cql_handle* ch, const int32_t* users, const int32_t* items, int64_t n, int32_t mode,
+                    float* out_scores, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(n >= 0 && (n == 0 || (users && items && out_scores)), "cql_score_pairs: bad arguments");
+    CQL_REQUIRE(mode == CQL_SCORE_Q || mode == CQL_SCORE_POLICY, "cql_score_pairs: bad mode");
+    if (n == 0) return;
+    cudaStream_t st = pick_stream(&h, stream);
+    int32_t* d_u = (int32_t*)scratch(ch, 0, (size_t)n * 4);
+    int32_t* d_i = (int32_t*)scratch(ch, 1, (size_t)n * 4);
+    float* d_o = (float*)scratch(ch, 3, (size_t)n * 4);
+    CQL_CUDA(cudaMemcpyAsync(d_u, users, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(d_i, items, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_score_pairs<<<(unsigned)((n + BM - 1) / BM), NT, FWD_SMEM, st>>>(h.params, d_u, d_i, n, h.C, mode, d_o);
+    CQL_LAUNCH_CHECK(&h);
+    CQL_CUDA(cudaMemcpyAsync(out_scores, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int cql_topk_filter_dev(cql_handle* ch, const float* scores_dev, int64_t n_users, int64_t n_items,
+                        const int32_t* users_dev, const int32_t* items_dev, const int64_t* seen_indptr,
+                        const int32_t* seen_items, int32_t k, int32_t* out_items, float* out_scores, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(scores_dev && out_items && out_scores && n_users >= 0 && n_items >= 1, "cql_topk_filter_dev: bad arguments");
+    CQL_REQUIRE(k >= 1 && k <= 128, "cql_topk_filter_dev: k must be 1..128");
+    if (n_users == 0) return;
+    cudaStream_t st = pick_stream(&h, stream);
+    const int threads = 256;
+    k_topk_filter<<<(unsigned)n_users, threads, (threads / 32) * 2 * k * sizeof(float), st>>>(
+        scores_dev, n_items, users_dev, items_dev, seen_indptr, seen_items, k, out_scores, out_items);
+    CQL_LAUNCH_CHECK(&h);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// engine.cuh -- the per-GPU handle: configuration, HBM-resident state, scratch.
+#pragma once
+#include <vector>
+#include <string>
+#include "common.cuh"
+#include "mlp_simt.cuh"
+
+namespace cql {
+
+constexpr int N_NOISE_PARTS = 8;
+
+struct StepInfo {          // written by k_step_begin, read by the Adam kernels
+  double bc1, bc2_sqrt;    // 1 - beta1^t, sqrt(1 - beta2^t)
+  long long step;          // t (1-based) of the update in flight
+};
+
+struct Handle {
+  cql_config cfg{};
+  std::string err;
+  cudaStream_t own_stream = nullptr;
+  int num_sms = 148;
+  int64_t launches = 0;
+
+  // ---- learner state (flat layout, see common.cuh) ----
+  float* params = nullptr;   // state_floats(C)
+  float* adam_m = nullptr;   // same layout (trainable part used)
+  float* adam_v = nullptr;
+  float* grads = nullptr;    // grad_floats(C): [actor | critics | scalars]
+  long long* step_dev = nullptr;   // completed updates
+  StepInfo* stepinfo = nullptr;
+  float* metrics = nullptr;  // 8 floats: temp_loss,temp,alpha_loss,alpha,critic_loss,actor_loss,td_loss,-
+  float* metrics_host = nullptr;   // pinned
+
+  // ---- replay table ----
+  float* table = nullptr;    // [n_trans][8]: obs.x obs.y act rew nobs.x nobs.y term pad
+  int64_t n_trans = 0;
+  int64_t sample_pos_host = 0;  // position in the epoch stream for the stand-alone sampler
+  long long* sample_pos = nullptr;   // device: next position in the permutation stream
+
+  // ---- per-step scratch (B = batch, n = action samples, C = critics) ----
+  int B = 0, n = 0, C = 0;
+  int rsA = 0, rsC = 0;      // rows per batch element: alpha job (3n), critic job (3n+1)
+  float* batch = nullptr;    // [B][8] sampled transition rows (same row format as table)
+  float* batch_host = nullptr;   // pinned staging for cql_update_batch
+  float* noise = nullptr;    // packed, see header
+  float* noise_host = nullptr;
+  int64_t noise_floats = 0;
+  float4* XA = nullptr;      // [2B] actor inputs: s rows then s' rows
+  float* outA = nullptr;     // [2B][2] mu, raw logstd
+  float* h2A = nullptr;      // [tiles(B)][256][64] actor H2 of the s rows
+  float4* XAl = nullptr;     // [B*rsA] alpha-step critic rows
+  float* offAl = nullptr;    // [B*rsA] log-prob offsets
+  float* QAl = nullptr;      // [C][B*rsA]
+  float4* XC = nullptr;      // [B*rsC] critic-step rows (3n samples + data row)
+  float* offC = nullptr;     // [B*rsC]
+  float* QC = nullptr;       // [C][B*rsC]
+  float* h2C = nullptr;      // [C][tiles][256][64]
+  float* dQ = nullptr;       // [C][B*rsC]
+  float4* XT = nullptr;      // [B] target rows (s', tanh(mu(s')))
+  float* QT = nullptr;       // [C][B]
+  float4* XP = nullptr;      // [B] actor-step rows (s, a_pi)
+  float* QP = nullptr;       // [C][B]
+  float* h2P = nullptr;      // [C][tiles(B)][256][64]
+  float* dQP = nullptr;      // [C][B]
+  float4* dXP = nullptr;     // [C][B]
+  float* dOutA = nullptr;    // [B][2]
+  float* perb = nullptr;     // [B][4]: temp term, logp_pi, a_pi raw, -
+  float* smallC = nullptr;   // [C][tilesC][SMALL_STRIDE]
+  float* smallA = nullptr;   // [tilesB][SMALL_STRIDE]
+  float* pw2C = nullptr;     // [C][splitsC][H*H]
+  float* pw2A = nullptr;     // [splitsA][H*H]
+  int splitsC = 1, splitsA = 1;
+
+  std::vector<void*> allocs;
+
+  template <typename T>
+  T* dalloc(size_t count) {
+    void* p = nullptr;
+    CQL_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    CQL_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    allocs.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+  void free_all() {
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    if (table) { cudaFree(table); table = nullptr; }
+    if (metrics_host) { cudaFreeHost(metrics_host); metrics_host = nullptr; }
+    if (batch_host) { cudaFreeHost(batch_host); batch_host = nullptr; }
+    if (noise_host) { cudaFreeHost(noise_host); noise_host = nullptr; }
+    if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
+  }
+
+  float* net_params(int slot) const { return params + (size_t)slot * NET_STRIDE; }
+  float* scalars() const { return params + scalars_off(C); }
+  // grads buffer parts
+  float* g_actor() const { return grads; }
+  float* g_critics() const { return grads + NET_STRIDE; }
+  float* g_scalars() const { return grads + (size_t)(1 + C) * NET_STRIDE; }
+};
+
+inline cudaStream_t pick_stream(Handle* h, void* stream) {
+  return stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+}
+
+#define CQL_LAUNCH_CHECK(h)                 \
+  do {                                      \
+    (h)->launches++;                        \
+    CQL_CUDA(cudaGetLastError());           \
+  } while (0)
+
+}  // namespace cql

@@ -1,0 +1,287 @@
+// score.cuh -- K5: batched user x item relevance, seen filter, per-user top-k.
+//
+// Scores are never materialised: a CTA owns (user, item chunk), pushes 64-item
+// tiles through actor (greedy action) and the C critics, and a warp folds the
+// tile into a running top-k held in shared memory.  The seen filter is *lazy*:
+// only candidates that already beat the current k-th score are looked up in the
+// user's sorted seen list (CSR), so the filter costs nothing on the hot loop.
+// Order: relevance desc, then item id asc (the reference leaves ties arbitrary,
+// replay/utils.py:125).
+#pragma once
+#include "engine.cuh"
+
+namespace cql {
+
+__device__ __forceinline__ bool better(float s, int i, float s2, int i2) {
+  return s > s2 || (s == s2 && (unsigned)i < (unsigned)i2);  // item -1 (empty slot) sorts last
+}
+
+__device__ __forceinline__ bool is_seen(const int32_t* __restrict__ seen, int64_t lo, int64_t hi, int item) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int v = __ldg(seen + mid);
+    if (v == item) return true;
+    if (v < item) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// Whole-warp insertion of (s,i) into the descending list top[0..k).  Caller guarantees
+// the candidate beats top[k-1].
+__device__ __forceinline__ void warp_topk_insert(float* topS, int* topI, int k, float s, int i) {
+  const int lane = threadIdx.x & 31;
+  int cnt = 0;
+  for (int e = lane; e < k; e += 32) cnt += better(topS[e], topI[e], s, i) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int pos = cnt;
+  for (int base = ((k - 1) / 32) * 32; base + 31 > pos; base -= 32) {   // chunks from the top down
+    const int e = base + lane;
+    float ps = 0.f; int pi = 0;
+    const bool mv = e > pos && e < k;
+    if (mv) { ps = topS[e - 1]; pi = topI[e - 1]; }
+    __syncwarp();
+    if (mv) { topS[e] = ps; topI[e] = pi; }
+    __syncwarp();
+    if (base == 0) break;
+  }
+  if (lane == 0) { topS[pos] = s; topI[pos] = i; }
+  __syncwarp();
+}
+
+// Fold up to 64 candidates (cs/ci in smem; invalid = item < 0) into the list.  Executed by warp 0.
+__device__ __forceinline__ void warp_fold_tile(float* topS, int* topI, int k, const float* cs, const int* ci, int cnt,
+                                               const int32_t* __restrict__ seen, int64_t lo, int64_t hi) {
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < cnt; base += 32) {
+    const int r = base + lane;
+    const float s = r < cnt ? cs[r] : -INFINITY;
+    const int i = r < cnt ? ci[r] : -1;
+    bool cand = i >= 0 && better(s, i, topS[k - 1], topI[k - 1]);
+    if (cand && seen != nullptr && is_seen(seen, lo, hi, i)) cand = false;
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float s2 = __shfl_sync(0xffffffffu, s, src);
+      const int i2 = __shfl_sync(0xffffffffu, i, src);
+      if (better(s2, i2, topS[k - 1], topI[k - 1])) warp_topk_insert(topS, topI, k, s2, i2);
+    }
+  }
+}
+
+struct ScoreArgs {
+  const float* params;        // flat state
+  const int32_t* users;       // [U]
+  const int32_t* items;       // [I]
+  const int64_t* seen_indptr; // [max_user+2] CSR over user id, or nullptr
+  const int32_t* seen_items;
+  int64_t n_users, n_items;
+  int C, k, mode, chunks, tiles_per_chunk;
+  float* part_s;              // [U][chunks][k]
+  int* part_i;
+};
+
+constexpr int SCORE_SMEM_BASE = FWD_SMEM;
+inline int score_smem(int k) { return SCORE_SMEM_BASE + k * 8 + BM * 8; }
+
+// relevance of the 64 rows in Xs (x = user, y = item); result in sc[r] (smem) after return
+__device__ __forceinline__ void score_tile(const float* __restrict__ params, int C, int mode, float4* Xs, float* As,
+                                           float* Bs, float* outs, float* sc) {
+  const int tid = threadIdx.x;
+  fwd_tile<2, 2>(params + (size_t)slot_actor() * NET_STRIDE, Xs, As, Bs, outs, nullptr);
+  float a = 0.f;
+  if (tid < BM) {
+    a = tanhf(outs[tid * 2]);
+    Xs[tid].z = a;
+  }
+  __syncthreads();
+  if (mode == CQL_SCORE_POLICY) {
+    if (tid < BM) sc[tid] = a;
+    __syncthreads();
+    return;
+  }
+  float q = 0.f;
+  for (int c = 0; c < C; ++c) {
+    fwd_tile<3, 1>(params + (size_t)slot_critic(c) * NET_STRIDE, Xs, As, Bs, outs, nullptr);
+    if (tid < BM) q += outs[tid];
+    __syncthreads();
+  }
+  if (tid < BM) sc[tid] = q / (float)C;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 2) k_score_topk(const ScoreArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = As + H * BM;
+  float4* Xs = reinterpret_cast<float4*>(Bs + 2 * BK * H);
+  float* topS = reinterpret_cast<float*>(Xs + BM);
+  int* topI = reinterpret_cast<int*>(topS + a.k);
+  float* cs = reinterpret_cast<float*>(topI + a.k);
+  int* ci = reinterpret_cast<int*>(cs + BM);
+  __shared__ float outs[BM * 2];
+  const int tid = threadIdx.x;
+  const int64_t urow = blockIdx.y;
+  const int user = a.users[urow];
+  for (int e = tid; e < a.k; e += NT) { topS[e] = -INFINITY; topI[e] = -1; }
+  int64_t lo = 0, hi = 0;
+  if (a.seen_indptr) { lo = a.seen_indptr[user]; hi = a.seen_indptr[user + 1]; }
+  const int64_t tile0 = (int64_t)blockIdx.x * a.tiles_per_chunk;
+  for (int t = 0; t < a.tiles_per_chunk; ++t) {
+    const int64_t i0 = (tile0 + t) * BM;
+    if (i0 >= a.n_items) break;
+    const int cnt = (int)min((int64_t)BM, a.n_items - i0);
+    if (tid < BM) {
+      const int item = tid < cnt ? a.items[i0 + tid] : -1;
+      Xs[tid] = make_float4((float)user, (float)max(item, 0), 0.f, 0.f);
+      ci[tid] = item;
+    }
+    __syncthreads();
+    score_tile(a.params, a.C, a.mode, Xs, As, Bs, outs, cs);
+    if (tid < 32) warp_fold_tile(topS, topI, a.k, cs, ci, cnt, a.seen_indptr ? a.seen_items : nullptr, lo, hi);
+    __syncthreads();
+  }
+  float* ps = a.part_s + ((size_t)urow * a.chunks + blockIdx.x) * a.k;
+  int* pi = a.part_i + ((size_t)urow * a.chunks + blockIdx.x) * a.k;
+  for (int e = tid; e < a.k; e += NT) { ps[e] = topS[e]; pi[e] = topI[e]; }
+}
+
+// merge the per-chunk lists of one user (one warp per user; lists are sorted, already seen-filtered)
+__global__ void k_topk_merge(const float* __restrict__ part_s, const int* __restrict__ part_i, int64_t n_users,
+                             int chunks, int k, float* __restrict__ out_s, int* __restrict__ out_i) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t u = (int64_t)blockIdx.x * wpb + warp;
+  float* topS = smem + (size_t)warp * 2 * k;
+  int* topI = reinterpret_cast<int*>(topS + k);
+  if (u >= n_users) return;
+  for (int e = lane; e < k; e += 32) { topS[e] = -INFINITY; topI[e] = -1; }
+  __syncwarp();
+  for (int c = 0; c < chunks; ++c) {
+    const float* ps = part_s + ((size_t)u * chunks + c) * k;
+    const int* pi = part_i + ((size_t)u * chunks + c) * k;
+    for (int e = 0; e < k; ++e) {
+      const float s = ps[e];
+      const int i = pi[e];
+      if (i < 0 || !better(s, i, topS[k - 1], topI[k - 1])) break;  // sorted: nothing further can enter
+      warp_topk_insert(topS, topI, k, s, i);
+    }
+  }
+  for (int e = lane; e < k; e += 32) { out_s[u * k + e] = topS[e]; out_i[u * k + e] = topI[e]; }
+}
+
+// explicit (user,item) pairs -> relevance
+__global__ void __launch_bounds__(NT, 2) k_score_pairs(const float* __restrict__ params, const int32_t* __restrict__ users,
+                                                       const int32_t* __restrict__ items, int64_t n, int C, int mode,
+                                                       float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = As + H * BM;
+  float4* Xs = reinterpret_cast<float4*>(Bs + 2 * BK * H);
+  __shared__ float outs[BM * 2];
+  __shared__ float sc[BM];
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * BM;
+  if (tid < BM) {
+    const int64_t r = r0 + tid;
+    Xs[tid] = r < n ? make_float4((float)users[r], (float)items[r], 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  score_tile(params, C, mode, Xs, As, Bs, outs, sc);
+  if (tid < BM && r0 + tid < n) out[r0 + tid] = sc[tid];
+}
+
+// ---- stand-alone HBM-bound top-k + lazy seen filter over materialised scores [U][I] ----
+// One CTA per user row; each warp streams a strided share of the row with 16-byte loads and
+// keeps its own list; warp 0 merges the lists.  k <= 32 per-warp lists live in smem.
+__global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ scores, int64_t n_items,
+                                                     const int32_t* __restrict__ users, const int32_t* __restrict__ items,
+                                                     const int64_t* __restrict__ seen_indptr,
+                                                     const int32_t* __restrict__ seen_items, int k,
+                                                     float* __restrict__ out_s, int* __restrict__ out_i) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float* topS = smem + (size_t)warp * 2 * k;
+  int* topI = reinterpret_cast<int*>(topS + k);
+  const int64_t urow = blockIdx.x;
+  const int user = users ? users[urow] : (int)urow;
+  int64_t lo = 0, hi = 0;
+  if (seen_indptr) { lo = seen_indptr[user]; hi = seen_indptr[user + 1]; }
+  for (int e = lane; e < k; e += 32) { topS[e] = -INFINITY; topI[e] = -1; }
+  __syncwarp();
+  const float* row = scores + (size_t)urow * n_items;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int64_t nvec = vec_ok ? n_items / 4 : 0;
+  // vector body: 2 x float4 in flight per lane
+  for (int64_t v0 = (int64_t)warp * 64; v0 < nvec; v0 += (int64_t)nw * 64) {
+    float4 x[2];
+    int64_t vi[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      vi[q] = v0 + q * 32 + lane;
+      x[q] = vi[q] < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi[q])
+                          : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float vals[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t col = vi[q] * 4 + c;
+        const float s = vals[c];
+        int item = -1;
+        bool cand = vi[q] < nvec && s >= topS[k - 1];
+        if (cand) {
+          item = items ? items[col] : (int)col;
+          cand = better(s, item, topS[k - 1], topI[k - 1]);
+          if (cand && seen_indptr && is_seen(seen_items, lo, hi, item)) cand = false;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float s2 = __shfl_sync(0xffffffffu, s, src);
+          const int i2 = __shfl_sync(0xffffffffu, item, src);
+          if (better(s2, i2, topS[k - 1], topI[k - 1])) warp_topk_insert(topS, topI, k, s2, i2);
+        }
+      }
+    }
+  }
+  // scalar tail (and the whole row when it is not 16-byte aligned)
+  for (int64_t c0 = nvec * 4 + (int64_t)warp * 32; c0 < n_items; c0 += (int64_t)nw * 32) {
+    const int64_t col = c0 + lane;
+    const float s = col < n_items ? row[col] : -INFINITY;
+    int item = -1;
+    bool cand = col < n_items && s >= topS[k - 1];
+    if (cand) {
+      item = items ? items[col] : (int)col;
+      cand = better(s, item, topS[k - 1], topI[k - 1]);
+      if (cand && seen_indptr && is_seen(seen_items, lo, hi, item)) cand = false;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float s2 = __shfl_sync(0xffffffffu, s, src);
+      const int i2 = __shfl_sync(0xffffffffu, item, src);
+      if (better(s2, i2, topS[k - 1], topI[k - 1])) warp_topk_insert(topS, topI, k, s2, i2);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < nw; ++w) {
+      const float* ps = smem + (size_t)w * 2 * k;
+      const int* pi = reinterpret_cast<const int*>(ps + k);
+      for (int e = 0; e < k; ++e) {
+        const float s = ps[e];
+        const int i = pi[e];
+        if (i < 0 || !better(s, i, topS[k - 1], topI[k - 1])) break;
+        warp_topk_insert(topS, topI, k, s, i);
+      }
+    }
+    for (int e = lane; e < k; e += 32) { out_s[urow * k + e] = topS[e]; out_i[urow * k + e] = topI[e]; }
+  }
+}
+
+}  // namespace cql

@@ -1,0 +1,547 @@
+// update.cuh -- one CQL update: replay sampling, noise, loss glue, Adam/Polyak, phase driver.
+//
+// Order of one update: temp -> alpha -> critic -> actor -> Polyak.
+// The actor does not change until the very end, so its forward on s and s' is
+// computed ONCE and shared by the temp step, both conservative-loss evaluations,
+// the TD target and the actor step (a result-preserving saving).
+#pragma once
+#include "engine.cuh"
+
+namespace cql {
+
+// ---------------------------------------------------------------- K1: replay sampling
+// Bijective pseudo-random permutation of [0, n): 4-round Feistel over 2*hb bits + cycle walking.
+__host__ __device__ inline uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ inline uint64_t feistel_perm(uint64_t x, uint64_t n, uint64_t key) {
+  int bits = 2;
+  while (bits < 62 && (1ull << bits) < n) bits += 2;   // even number of bits >= log2(n)
+  const int hb = bits / 2;
+  const uint64_t mask = (1ull << hb) - 1;
+  do {
+    uint64_t l = x >> hb, r = x & mask;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t f = mix32((uint32_t)r * 0x9E3779B1u + (uint32_t)(key >> (i * 13)) + 0x85ebca6bu * (i + 1) +
+                               (uint32_t)(r >> 16) * 0xc2b2ae35u);
+      const uint64_t nl = r, nr = (l ^ f) & mask;
+      l = nl; r = nr;
+    }
+    x = (l << hb) | r;
+  } while (x >= n);
+  return x;
+}
+
+// position p of the sampling stream -> transition index.  An epoch covers n_eff = n - n % chunk
+// positions (d3rlpy drops the last partial minibatch); each epoch uses a fresh permutation.
+__host__ __device__ inline int64_t stream_index(int64_t p, int64_t n, int64_t chunk, uint64_t seed) {
+  int64_t n_eff = n - n % chunk;
+  if (n_eff <= 0) n_eff = n;
+  const int64_t epoch = p / n_eff, q = p % n_eff;
+  return (int64_t)feistel_perm((uint64_t)q, (uint64_t)n, seed * 0x9E3779B97F4A7C15ull + (uint64_t)epoch * 0xD1B54A32D192ED03ull + 1);
+}
+
+// One thread per row: two 16-byte loads of a 32-byte transition row (one DRAM sector).
+__global__ void k_sample(const float4* __restrict__ table, int64_t n_trans, const int64_t* __restrict__ idx,
+                         const long long* __restrict__ step_dev, int64_t pos0, int64_t count, int64_t chunk,
+                         int rank, int world, uint64_t seed, float4* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  int64_t t;
+  if (idx) {
+    t = idx[j];
+  } else {
+    // training: position = (completed_steps * world + rank) * B + j ; stand-alone sweep: pos0 + j
+    const int64_t p = step_dev ? ((int64_t)(*step_dev) * world + rank) * count + j : pos0 + j;
+    t = stream_index(p, n_trans, chunk, seed);
+  }
+  const float4 a = __ldg(table + 2 * t), b = __ldg(table + 2 * t + 1);
+  out[2 * j] = a;
+  out[2 * j + 1] = b;
+}
+
+// episode-ordered steps -> transition rows
+__global__ void k_build_transitions(const float2* __restrict__ obs, const float* __restrict__ act,
+                                    const float* __restrict__ rew, const float* __restrict__ term, int64_t n,
+                                    float4* __restrict__ table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 o = obs[i];
+  const float tm = term[i];
+  float2 nx = make_float2(0.f, 0.f);
+  if (tm == 0.f && i + 1 < n) nx = obs[i + 1];
+  table[2 * i] = make_float4(o.x, o.y, act[i], rew[i]);
+  table[2 * i + 1] = make_float4(nx.x, nx.y, tm, 0.f);
+}
+
+// ---------------------------------------------------------------- noise (Philox)
+__global__ void k_noise(float* __restrict__ noise, int64_t total, int B, int n, uint64_t seed,
+                        const long long* __restrict__ step_dev, int rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  uint32_t r[4];
+  Philox::gen(seed ^ 0x5851F42D4C957F2Dull, ((uint64_t)(*step_dev) << 8) | (uint64_t)(rank & 0xff), (uint64_t)i, r);
+  const int64_t Bn = (int64_t)B * n;
+  const int64_t a = i - B;  // position inside the six B*n blocks
+  const bool uniform = a >= 0 && a < 6 * Bn && ((a / Bn) % 3 == 2);
+  const float u1 = u01(r[0]), u2 = u01(r[1]);
+  noise[i] = uniform ? fmaf(2.f, u1, -1.f) : sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+// ---------------------------------------------------------------- step bookkeeping
+__global__ void k_step_begin(const long long* step_dev, StepInfo* info, float beta1, float beta2) {
+  const long long t = *step_dev + 1;
+  info->step = t;
+  info->bc1 = 1.0 - pow((double)beta1, (double)t);
+  info->bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)t));
+}
+__global__ void k_step_end(long long* step_dev) { *step_dev += 1; }
+
+// ---------------------------------------------------------------- squashed Gaussian
+struct Sample { float a, logp, raw, t, std_; };
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ Sample policy_sample(float mu, float ls, float eps, int squash) {
+  Sample s;
+  s.std_ = expf(ls);
+  s.raw = fmaf(s.std_, eps, mu);
+  s.a = tanhf(s.raw);
+  s.t = (s.raw - mu) / s.std_;
+  const float normal_logp = -0.5f * s.t * s.t - ls - 0.91893853320467274f;
+  const float logdet = squash == CQL_SQUASH_EPS ? logf(1.f - s.a * s.a + 1e-6f)
+                                                : 2.f * (0.69314718055994531f - s.raw - softplus_t(-2.f * s.raw));
+  s.logp = normal_logp - logdet;
+  return s;
+}
+__device__ __forceinline__ float clamp_ls(float x) { return fminf(fmaxf(x, -20.f), 2.f); }
+
+__global__ void k_actor_rows(const float4* __restrict__ batch, int B, float4* __restrict__ XA) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * B) return;
+  if (i < B) {
+    const float4 a = batch[2 * i];
+    XA[i] = make_float4(a.x, a.y, 0.f, 0.f);
+  } else {
+    const float4 b = batch[2 * (i - B) + 1];
+    XA[i] = make_float4(b.x, b.y, 0.f, 0.f);
+  }
+}
+
+// Builds every critic input row of the update from the shared actor outputs.
+// thread (b, l): rows j = l, l+64, ... of batch element b; j in [0, 6n+4).
+__global__ void k_prep(const float4* __restrict__ batch, const float* __restrict__ outA,
+                       const float* __restrict__ noise, int B, int n, int squash,
+                       float4* __restrict__ XAl, float* __restrict__ offAl,
+                       float4* __restrict__ XC, float* __restrict__ offC,
+                       float4* __restrict__ XT, float4* __restrict__ XP, float4* __restrict__ perb) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = g >> 6, l = g & 63;
+  if (b >= B) return;
+  const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
+  const float mu_s = outA[2 * b], ls_s = clamp_ls(outA[2 * b + 1]);
+  const float mu_n = outA[2 * (B + b)], ls_n = clamp_ls(outA[2 * (B + b) + 1]);
+  const int64_t Bn = (int64_t)B * n;
+  const int n3 = 3 * n;
+  for (int j = l; j < 2 * n3 + 4; j += 64) {
+    if (j < 2 * n3) {
+      const int job = j / n3, jj = j % n3, kind = jj / n, i = jj % n;
+      const float* nz = noise + B + (int64_t)job * 3 * Bn + (int64_t)kind * Bn + (int64_t)b * n + i;
+      float a, off;
+      if (kind == 2) {
+        a = *nz;
+        off = -0.69314718055994531f * CQL_ACT_DIM;  // log(0.5^act_dim)
+      } else {
+        const Sample s = policy_sample(kind == 0 ? mu_s : mu_n, kind == 0 ? ls_s : ls_n, *nz, squash);
+        a = s.a;
+        off = s.logp;
+      }
+      const float4 x = make_float4(r0.x, r0.y, a, 0.f);  // value observation is ALWAYS s
+      if (job == 0) { XAl[(int64_t)b * n3 + jj] = x; offAl[(int64_t)b * n3 + jj] = off; }
+      else { XC[(int64_t)b * (n3 + 1) + jj] = x; offC[(int64_t)b * (n3 + 1) + jj] = off; }
+    } else if (j == 2 * n3) {       // data row (s, a)
+      XC[(int64_t)b * (n3 + 1) + n3] = make_float4(r0.x, r0.y, r0.z, 0.f);
+      offC[(int64_t)b * (n3 + 1) + n3] = 0.f;
+    } else if (j == 2 * n3 + 1) {   // TD target row (s', best_action(s'))
+      XT[b] = make_float4(r1.x, r1.y, tanhf(mu_n), 0.f);
+    } else if (j == 2 * n3 + 2) {   // actor-step row (s, a_pi)
+      const Sample s = policy_sample(mu_s, ls_s, noise[B + 6 * Bn + b], squash);
+      XP[b] = make_float4(r0.x, r0.y, s.a, 0.f);
+      perb[b].y = s.logp;
+    } else {                        // temperature step: logp - action_size
+      const Sample s = policy_sample(mu_s, ls_s, noise[b], squash);
+      perb[b].x = s.logp - (float)CQL_ACT_DIM;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- block reductions (fixed order)
+template <int NTHREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0) {
+    t = lane < NTHREADS / 32 ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  return t;
+}
+
+__device__ __forceinline__ float lse_rows(const float* __restrict__ q, const float* __restrict__ off, int cnt,
+                                          float& m_out, float& s_out) {
+  float m = -INFINITY;
+  for (int j = 0; j < cnt; ++j) m = fmaxf(m, q[j] - off[j]);
+  float s = 0.f;
+  for (int j = 0; j < cnt; ++j) s += expf(q[j] - off[j] - m);
+  m_out = m; s_out = s;
+  return m + logf(s);
+}
+
+struct LossConsts {
+  int B, n, C;
+  float gamma, cw, thr, temp_lr, alpha_lr, beta1, beta2, eps;
+};
+
+// temp + alpha gradients (one CTA, fixed-order sums).  g_scalars[0]=d log_temp, [1]=d log_alpha.
+__global__ void __launch_bounds__(1024) k_scalar_grads(const float4* __restrict__ perb, const float* __restrict__ QAl,
+                                                       const float* __restrict__ offAl, const float* __restrict__ QC,
+                                                       const float* __restrict__ scalars, LossConsts k,
+                                                       float* __restrict__ g_scalars, float* __restrict__ metrics) {
+  __shared__ float red[32];
+  const int n3 = 3 * k.n, rsC = n3 + 1;
+  float st = 0.f;
+  for (int b = threadIdx.x; b < k.B; b += 1024) st += perb[b].x;
+  st = block_sum<1024>(st, red);
+  float sl = 0.f, sd = 0.f;
+  for (int p = threadIdx.x; p < k.C * k.B; p += 1024) {
+    const int c = p / k.B, b = p % k.B;
+    float m, s;
+    sl += lse_rows(QAl + ((int64_t)c * k.B + b) * n3, offAl + (int64_t)b * n3, n3, m, s);
+    sd += QC[((int64_t)c * k.B + b) * rsC + n3];
+  }
+  sl = block_sum<1024>(sl, red);
+  sd = block_sum<1024>(sd, red);
+  if (threadIdx.x == 0) {
+    const float lt = scalars[0], la = scalars[1];
+    const float temp_loss = -expf(lt) * (st / (float)k.B);
+    const float inv = 1.f / ((float)k.C * (float)k.B);
+    const float raw = sl * inv - sd * inv;
+    const float e = expf(la), clipped = fminf(fmaxf(e, 0.f), 1e6f);
+    const float alpha_loss = -clipped * (k.cw * raw - k.thr);
+    g_scalars[0] = temp_loss;                 // d/d log_temp of -exp(lt)*mean = the loss itself
+    g_scalars[1] = e <= 1e6f ? alpha_loss : 0.f;
+    metrics[0] = temp_loss;
+    metrics[2] = alpha_loss;
+  }
+}
+
+__device__ __forceinline__ float adam_scalar(float p, float g, float& m, float& v, float lr, const LossConsts& k,
+                                             const StepInfo& si) {
+  m = m + (g - m) * (1.f - k.beta1);
+  v = v * k.beta2 + (1.f - k.beta2) * g * g;
+  const float denom = sqrtf(v) / (float)si.bc2_sqrt + k.eps;
+  return p - (float)((double)lr / si.bc1) * (m / denom);
+}
+
+// scalar Adam (temp, alpha) then d critic_loss / d Q for every critic-job row (one CTA).
+__global__ void __launch_bounds__(1024) k_critic_dq(const float4* __restrict__ batch, const float* __restrict__ QC,
+                                                    const float* __restrict__ offC, const float* __restrict__ QT,
+                                                    float* __restrict__ scalars, float* __restrict__ sc_m,
+                                                    float* __restrict__ sc_v, const float* __restrict__ g_scalars,
+                                                    const StepInfo* __restrict__ si, LossConsts k,
+                                                    float* __restrict__ dQ, float* __restrict__ metrics) {
+  __shared__ float red[32];
+  __shared__ float alpha_sh;
+  if (threadIdx.x == 0) {
+    float lt = scalars[0], la = scalars[1];
+    if (k.temp_lr > 0.f) { float m = sc_m[0], v = sc_v[0]; lt = adam_scalar(lt, g_scalars[0], m, v, k.temp_lr, k, *si); sc_m[0] = m; sc_v[0] = v; scalars[0] = lt; }
+    if (k.alpha_lr > 0.f) { float m = sc_m[1], v = sc_v[1]; la = adam_scalar(la, g_scalars[1], m, v, k.alpha_lr, k, *si); sc_m[1] = m; sc_v[1] = v; scalars[1] = la; }
+    metrics[1] = expf(lt);
+    metrics[3] = expf(la);
+    alpha_sh = fminf(fmaxf(expf(la), 0.f), 1e6f);
+  }
+  __syncthreads();
+  const float alpha = alpha_sh;
+  const int n3 = 3 * k.n, rsC = n3 + 1;
+  const float coef = alpha * k.cw / ((float)k.C * (float)k.B);
+  float s_td = 0.f, s_lse = 0.f, s_d = 0.f;
+  for (int p = threadIdx.x; p < k.C * k.B; p += 1024) {
+    const int c = p / k.B, b = p % k.B;
+    float qt = QT[b];
+    for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, QT[(int64_t)c2 * k.B + b]);
+    const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
+    const float y = r0.w + k.gamma * qt * (1.f - r1.z);
+    const float* q = QC + ((int64_t)c * k.B + b) * rsC;
+    const float* off = offC + (int64_t)b * rsC;
+    float* dq = dQ + ((int64_t)c * k.B + b) * rsC;
+    float m, s;
+    s_lse += lse_rows(q, off, n3, m, s);
+    const float inv_s = 1.f / s;
+    for (int j = 0; j < n3; ++j) dq[j] = coef * (expf(q[j] - off[j] - m) * inv_s);
+    const float qd = q[n3], e = qd - y;
+    dq[n3] = 2.f * e / (float)k.B - coef;
+    s_td += e * e;
+    s_d += qd;
+  }
+  s_td = block_sum<1024>(s_td, red);
+  s_lse = block_sum<1024>(s_lse, red);
+  s_d = block_sum<1024>(s_d, red);
+  if (threadIdx.x == 0) {
+    const float td = s_td / (float)k.B;
+    const float inv = 1.f / ((float)k.C * (float)k.B);
+    const float cons = alpha * (k.cw * (s_lse * inv - s_d * inv) - k.thr);
+    metrics[4] = td + cons;
+    metrics[6] = td;
+  }
+}
+
+// actor loss + d/dQ through the min over critics (one CTA)
+__global__ void __launch_bounds__(1024) k_actor_dq(const float* __restrict__ QP, const float4* __restrict__ perb,
+                                                   const float* __restrict__ scalars, int B, int C,
+                                                   float* __restrict__ dQP, float* __restrict__ metrics) {
+  __shared__ float red[32];
+  const float T = expf(scalars[0]);
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 1024) {
+    int arg = 0;
+    float qm = QP[b];
+    for (int c = 1; c < C; ++c) {
+      const float q = QP[(int64_t)c * B + b];
+      if (q < qm) { qm = q; arg = c; }
+    }
+    for (int c = 0; c < C; ++c) dQP[(int64_t)c * B + b] = c == arg ? -1.f / (float)B : 0.f;
+    s += T * perb[b].y - qm;
+  }
+  s = block_sum<1024>(s, red);
+  if (threadIdx.x == 0) metrics[5] = s / (float)B;
+}
+
+// d actor_loss / d (mu, raw logstd): mirrors autograd through rsample, tanh, log-prob, clamp.
+__global__ void k_actor_dout(const float* __restrict__ outA, const float* __restrict__ noise_actor,
+                             const float4* __restrict__ dXP, const float* __restrict__ scalars, int B, int C,
+                             int squash, float* __restrict__ dOutA) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float da = 0.f;
+  for (int c = 0; c < C; ++c) da += dXP[(int64_t)c * B + b].z;
+  const float mu = outA[2 * b], ls_raw = outA[2 * b + 1], ls = clamp_ls(ls_raw);
+  const float eps = noise_actor[b];
+  const Sample s = policy_sample(mu, ls, eps, squash);
+  const float w = expf(scalars[0]) / (float)B;   // d loss / d logp
+  const float one_m_a2 = 1.f - s.a * s.a;
+  float g_raw = w * (-s.t / s.std_);
+  if (squash == CQL_SQUASH_EPS) {
+    const float g_a = da + w * (2.f * s.a / (one_m_a2 + 1e-6f));
+    g_raw += g_a * one_m_a2;
+  } else {
+    const float sig = 1.f / (1.f + expf(2.f * s.raw));  // sigmoid(-2 raw)
+    g_raw += w * (2.f - 4.f * sig) + da * one_m_a2;
+  }
+  const float g_mu = g_raw + w * (s.t / s.std_);
+  const float g_std = g_raw * eps + w * (s.t * s.t / s.std_);
+  const float g_ls = g_std * s.std_ - w;
+  dOutA[2 * b] = g_mu;
+  dOutA[2 * b + 1] = (ls_raw >= -20.f && ls_raw <= 2.f) ? g_ls : 0.f;
+}
+
+// ---------------------------------------------------------------- gradient reduction, Adam, Polyak
+// grads[net][idx] = sum of the per-tile "small" partials / per-split dW2 partials, in fixed order.
+__global__ void k_reduce_grads(const float* __restrict__ small, const float* __restrict__ pw2, int in_dim, int out_dim,
+                               int tiles, int splits, float* __restrict__ grads) {
+  const int net = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NET_STRIDE) return;
+  const int w2_lo = off_W2(in_dim), w2_hi = w2_lo + H * H, total = net_floats(in_dim, out_dim);
+  float s = 0.f;
+  if (idx >= w2_lo && idx < w2_hi) {
+    const float* p = pw2 + (size_t)net * splits * H * H + (idx - w2_lo);
+    for (int i = 0; i < splits; ++i) s += p[(size_t)i * H * H];
+  } else if (idx < total) {
+    const int sidx = idx < w2_lo ? idx : idx - H * H;
+    const float* p = small + (size_t)net * tiles * SMALL_STRIDE + sidx;
+    for (int i = 0; i < tiles; ++i) s += p[(size_t)i * SMALL_STRIDE];
+  }
+  grads[(size_t)net * NET_STRIDE + idx] = s;
+}
+
+// torch.optim.Adam (defaults) fused with the Polyak update of the target copy.
+__global__ void k_adam_polyak(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                              const float* __restrict__ g, float* __restrict__ targ, int64_t count, float lr,
+                              float beta1, float beta2, float eps, float tau, const StepInfo* __restrict__ si) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float step_size = (float)((double)lr / si->bc1);
+  const float bc2s = (float)si->bc2_sqrt;
+  const float gi = g[i];
+  const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+  const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float pn = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+  p[i] = pn;
+  if (targ) targ[i] = targ[i] * (1.f - tau) + tau * pn;
+}
+
+// ---------------------------------------------------------------- launch helpers
+template <int IN, int OUT>
+inline void launch_fwd(Handle* h, FwdJobs& jobs, cudaStream_t st) {
+  int t = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    jobs.j[i].tile_begin = t;
+    t += tiles_of(jobs.j[i].rows) * jobs.j[i].n_nets;
+  }
+  jobs.total_tiles = t;
+  if (t == 0) return;
+  static bool attr = false;
+  if (!attr) {
+    CQL_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<IN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr = true;
+  }
+  mlp_fwd_kernel<IN, OUT><<<t, NT, FWD_SMEM, st>>>(jobs);
+  CQL_LAUNCH_CHECK(h);
+}
+
+template <int IN, int OUT, bool WGRADS, bool DX>
+inline void launch_bwd1(Handle* h, const BwdJob& jb, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CQL_CUDA(cudaFuncSetAttribute(mlp_bwd1_kernel<IN, OUT, WGRADS, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD1_SMEM));
+    attr = true;
+  }
+  mlp_bwd1_kernel<IN, OUT, WGRADS, DX><<<tiles_of(jb.rows) * jb.n_nets, NT, BWD1_SMEM, st>>>(jb);
+  CQL_LAUNCH_CHECK(h);
+}
+
+template <int IN, int OUT>
+inline void launch_bwd2(Handle* h, const BwdJob& jb, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<IN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
+    attr = true;
+  }
+  mlp_bwd2_kernel<IN, OUT><<<dim3(4, jb.splits, jb.n_nets), NT, BWD2_SMEM, st>>>(jb);
+  CQL_LAUNCH_CHECK(h);
+}
+
+inline LossConsts loss_consts(const Handle* h) {
+  const cql_config& c = h->cfg;
+  return LossConsts{h->B, h->n, h->C, c.gamma, c.conservative_weight, c.alpha_threshold,
+                    c.temp_lr, c.alpha_lr, c.beta1, c.beta2, c.adam_eps};
+}
+
+enum class BatchSource { Sampled, Provided };
+enum class NoiseSource { Philox, Provided };
+
+// phase 0: (sample, noise,) shared actor forward, all critic forwards, scalar gradients
+inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
+  const int B = h->B, C = h->C, n3 = 3 * h->n;
+  const cql_config& c = h->cfg;
+  k_step_begin<<<1, 1, 0, st>>>(h->step_dev, h->stepinfo, c.beta1, c.beta2);
+  CQL_LAUNCH_CHECK(h);
+  if (bs == BatchSource::Sampled) {
+    CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
+    k_sample<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4*>(h->table), h->n_trans, nullptr,
+                                              h->step_dev, 0, B, (int64_t)B * c.world_size, c.rank, c.world_size,
+                                              c.seed, reinterpret_cast<float4*>(h->batch));
+    CQL_LAUNCH_CHECK(h);
+  }
+  if (ns == NoiseSource::Philox) {
+    k_noise<<<(int)((h->noise_floats + 255) / 256), 256, 0, st>>>(h->noise, h->noise_floats, B, h->n, c.seed,
+                                                                  h->step_dev, c.rank);
+    CQL_LAUNCH_CHECK(h);
+  }
+  const float4* batch4 = reinterpret_cast<const float4*>(h->batch);
+  k_actor_rows<<<(2 * B + 255) / 256, 256, 0, st>>>(batch4, B, h->XA);
+  CQL_LAUNCH_CHECK(h);
+  {
+    FwdJobs jobs{};
+    jobs.n = 2;
+    jobs.j[0] = FwdJob{h->XA, h->net_params(slot_actor()), h->outA, h->h2A, B, 1, 0};
+    jobs.j[1] = FwdJob{h->XA + B, h->net_params(slot_actor()), h->outA + 2 * (size_t)B, nullptr, B, 1, 0};
+    launch_fwd<2, 2>(h, jobs, st);
+  }
+  k_prep<<<(B * 64 + 255) / 256, 256, 0, st>>>(batch4, h->outA, h->noise, B, h->n, c.squash, h->XAl, h->offAl, h->XC,
+                                               h->offC, h->XT, h->XP, reinterpret_cast<float4*>(h->perb));
+  CQL_LAUNCH_CHECK(h);
+  {
+    FwdJobs jobs{};
+    jobs.n = 3;
+    jobs.j[0] = FwdJob{h->XAl, h->net_params(slot_critic(0)), h->QAl, nullptr, B * n3, C, 0};
+    jobs.j[1] = FwdJob{h->XC, h->net_params(slot_critic(0)), h->QC, h->h2C, B * (n3 + 1), C, 0};
+    jobs.j[2] = FwdJob{h->XT, h->net_params(slot_targ_critic(C, 0)), h->QT, nullptr, B, C, 0};
+    launch_fwd<3, 1>(h, jobs, st);
+  }
+  k_scalar_grads<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->perb), h->QAl, h->offAl, h->QC, h->scalars(),
+                                     loss_consts(h), h->g_scalars(), h->metrics);
+  CQL_LAUNCH_CHECK(h);
+}
+
+// phase 1: temp/alpha Adam, critic backward -> critic gradients
+inline void phase1(Handle* h, cudaStream_t st) {
+  const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
+  const int64_t so = scalars_off(C);
+  k_critic_dq<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->batch), h->QC, h->offC, h->QT, h->scalars(),
+                                  h->adam_m + so, h->adam_v + so, h->g_scalars(), h->stepinfo, loss_consts(h), h->dQ,
+                                  h->metrics);
+  CQL_LAUNCH_CHECK(h);
+  BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
+  launch_bwd1<3, 1, true, false>(h, jb, st);
+  launch_bwd2<3, 1>(h, jb, st);
+  k_reduce_grads<<<dim3((NET_STRIDE + 255) / 256, C), 256, 0, st>>>(h->smallC, h->pw2C, 3, 1, tiles_of(rows),
+                                                                   h->splitsC, h->g_critics());
+  CQL_LAUNCH_CHECK(h);
+}
+
+// phase 2: critic Adam + Polyak, actor loss through the updated critics -> actor gradients
+inline void phase2(Handle* h, cudaStream_t st) {
+  const int B = h->B, C = h->C;
+  const cql_config& c = h->cfg;
+  const int64_t cnt = (int64_t)C * NET_STRIDE;
+  k_adam_polyak<<<(int)((cnt + 255) / 256), 256, 0, st>>>(
+      h->net_params(slot_critic(0)), h->adam_m + (size_t)NET_STRIDE, h->adam_v + (size_t)NET_STRIDE, h->g_critics(),
+      h->net_params(slot_targ_critic(C, 0)), cnt, c.critic_lr, c.beta1, c.beta2, c.adam_eps, c.tau, h->stepinfo);
+  CQL_LAUNCH_CHECK(h);
+  {
+    FwdJobs jobs{};
+    jobs.n = 1;
+    jobs.j[0] = FwdJob{h->XP, h->net_params(slot_critic(0)), h->QP, h->h2P, B, C, 0};
+    launch_fwd<3, 1>(h, jobs, st);
+  }
+  k_actor_dq<<<1, 1024, 0, st>>>(h->QP, reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
+                                 h->metrics);
+  CQL_LAUNCH_CHECK(h);
+  {
+    BwdJob jb{h->XP, h->dQP, h->h2P, h->net_params(slot_critic(0)), nullptr, h->dXP, nullptr, B, C, 1};
+    launch_bwd1<3, 1, false, true>(h, jb, st);
+  }
+  k_actor_dout<<<(B + 127) / 128, 128, 0, st>>>(h->outA, h->noise + B + 6 * (int64_t)B * h->n, h->dXP, h->scalars(), B,
+                                                C, c.squash, h->dOutA);
+  CQL_LAUNCH_CHECK(h);
+  BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
+  launch_bwd1<2, 2, true, false>(h, ja, st);
+  launch_bwd2<2, 2>(h, ja, st);
+  k_reduce_grads<<<dim3((NET_STRIDE + 255) / 256, 1), 256, 0, st>>>(h->smallA, h->pw2A, 2, 2, tiles_of(B), h->splitsA,
+                                                                   h->g_actor());
+  CQL_LAUNCH_CHECK(h);
+}
+
+// phase 3: actor Adam + Polyak of the target policy, step counter
+inline void phase3(Handle* h, cudaStream_t st) {
+  const cql_config& c = h->cfg;
+  k_adam_polyak<<<(NET_STRIDE + 255) / 256, 256, 0, st>>>(h->net_params(slot_actor()), h->adam_m, h->adam_v,
+                                                         h->g_actor(), h->net_params(slot_targ_actor(h->C)),
+                                                         (int64_t)NET_STRIDE, c.actor_lr, c.beta1, c.beta2, c.adam_eps,
+                                                         c.tau, h->stepinfo);
+  CQL_LAUNCH_CHECK(h);
+  k_step_end<<<1, 1, 0, st>>>(h->step_dev);
+  CQL_LAUNCH_CHECK(h);
+}
+
+}  // namespace cql

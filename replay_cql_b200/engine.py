@@ -1,0 +1,258 @@
+"""Host driver of the CUDA library: one ``CqlEngine`` per GPU.
+
+Mirrors the *role* of d3rlpy's ``CQLImpl`` for the RePlay wrapper ([EXT]
+``d3rlpy/algos/torch/cql_impl.py``): owns the learner state, runs updates,
+answers ``predict`` / ``predict_value`` -- but every number is produced by the
+sm_100a kernels behind ``include/cql_b200.h``.  PyTorch appears only as
+plumbing (``torch.distributed`` for the data-parallel gradient all-reduce and a
+zero-copy view of the library's gradient buffer).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, asdict
+from typing import Callable, Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, layout
+
+METRIC_NAMES = ("temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss")
+NOISE_KEYS = ("temp_eps", "alpha_eps_t", "alpha_eps_t1", "alpha_u",
+              "critic_eps_t", "critic_eps_t1", "critic_u", "actor_eps")
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "bf16": _lib.PREC_BF16}
+SQUASH = {"eps": _lib.SQUASH_EPS, "softplus": _lib.SQUASH_SOFTPLUS}
+SCORE_MODES = {"q": _lib.SCORE_Q, "policy": _lib.SCORE_POLICY}
+
+
+@dataclass
+class CqlHyperParams:
+    """d3rlpy CQL defaults; ``batch_size`` 1024 per BASELINE.json."""
+
+    batch_size: int = 1024
+    n_critics: int = 2
+    n_action_samples: int = 10
+    gamma: float = 0.99
+    tau: float = 0.005
+    actor_lr: float = 1e-4
+    critic_lr: float = 3e-4
+    temp_lr: float = 1e-4
+    alpha_lr: float = 1e-4
+    initial_temperature: float = 1.0
+    initial_alpha: float = 1.0
+    alpha_threshold: float = 10.0
+    conservative_weight: float = 5.0
+    beta1: float = 0.9
+    beta2: float = 0.999
+    adam_eps: float = 1e-8
+    precision: str = "fp32"
+    squash: str = "eps"
+    seed: int = 12345
+
+
+def _ptr(arr: Optional[np.ndarray]):
+    return None if arr is None else arr.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and out.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {out.shape}")
+    return out
+
+
+class _DevView:
+    """Zero-copy ``__cuda_array_interface__`` view of a library-owned float buffer."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {
+            "shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+class CqlEngine:
+    """Learner + scorer on one GPU."""
+
+    def __init__(self, hp: CqlHyperParams | None = None, device: int = 0, rank: int = 0, world_size: int = 1):
+        self.hp = hp or CqlHyperParams()
+        if self.hp.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        if self.hp.squash not in SQUASH:
+            raise ValueError(f"squash must be one of {sorted(SQUASH)}")
+        self._lib = _lib.load()
+        cfg = _lib.CqlConfig()
+        cfg.struct_size = C.sizeof(cfg)
+        cfg.device = device
+        cfg.batch_size = self.hp.batch_size
+        cfg.n_critics = self.hp.n_critics
+        cfg.n_action_samples = self.hp.n_action_samples
+        cfg.precision = PRECISIONS[self.hp.precision]
+        cfg.squash = SQUASH[self.hp.squash]
+        cfg.rank, cfg.world_size = rank, world_size
+        for name in ("gamma", "tau", "actor_lr", "critic_lr", "temp_lr", "alpha_lr", "initial_temperature",
+                     "initial_alpha", "alpha_threshold", "conservative_weight", "beta1", "beta2", "adam_eps"):
+            setattr(cfg, name, float(getattr(self.hp, name)))
+        cfg.seed = int(self.hp.seed) & (2**64 - 1)
+        self._h = C.c_void_p()
+        rc = self._lib.cql_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.cql_last_error(None)
+            self._h = None
+            raise _lib.CqlLibraryError(f"cql_create failed: {msg.decode() if msg else rc}")
+        self.device, self.rank, self.world_size = device, rank, world_size
+        self.n_state = int(self._lib.cql_state_floats(self._h))
+        assert self.n_state == layout.state_floats(self.hp.n_critics)
+        self.set_state(layout.init_state(self.hp.n_critics, self.hp.seed, self.hp.initial_temperature,
+                                         self.hp.initial_alpha))
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.cql_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> None:
+        _lib.check(self._h, rc, what)
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, flat: np.ndarray) -> None:
+        flat = _f32(flat, (self.n_state,))
+        self._check(self._lib.cql_set_weights(self._h, _ptr(flat), flat.size), "cql_set_weights")
+
+    def get_state(self) -> np.ndarray:
+        flat = np.empty(self.n_state, dtype=np.float32)
+        self._check(self._lib.cql_get_weights(self._h, _ptr(flat), flat.size), "cql_get_weights")
+        return flat
+
+    def set_optimizer(self, m: np.ndarray, v: np.ndarray, step: int) -> None:
+        m, v = _f32(m, (self.n_state,)), _f32(v, (self.n_state,))
+        self._check(self._lib.cql_set_optimizer(self._h, _ptr(m), _ptr(v), m.size, int(step)), "cql_set_optimizer")
+
+    def get_optimizer(self):
+        m = np.empty(self.n_state, dtype=np.float32)
+        v = np.empty(self.n_state, dtype=np.float32)
+        step = C.c_int64(0)
+        self._check(self._lib.cql_get_optimizer(self._h, _ptr(m), _ptr(v), m.size, C.byref(step)), "cql_get_optimizer")
+        return m, v, int(step.value)
+
+    # ------------------------------------------------------------------ replay table
+    def load_transitions(self, obs, act, rew, term) -> None:
+        """Episode-ordered steps (MDP builder output) -> HBM-resident transition rows."""
+        obs = _f32(obs)
+        n = obs.shape[0]
+        obs = _f32(obs, (n, 2))
+        act, rew, term = (_f32(np.reshape(a, -1), (n,)) for a in (act, rew, term))
+        self._check(self._lib.cql_load_transitions(self._h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(term), n),
+                    "cql_load_transitions")
+
+    @property
+    def n_transitions(self) -> int:
+        return int(self._lib.cql_num_transitions(self._h))
+
+    # ------------------------------------------------------------------ updates
+    def update(self, n_steps: int = 1, want_metrics: bool = True, stream: int | None = None) -> Optional[Dict[str, float]]:
+        """``n_steps`` updates with on-device sampling + Philox noise (CUDA-graph replay)."""
+        m = np.zeros(6, dtype=np.float32) if want_metrics else None
+        self._check(self._lib.cql_update(self._h, int(n_steps), _ptr(m), stream), "cql_update")
+        return dict(zip(METRIC_NAMES, map(float, m))) if want_metrics else None
+
+    def pack_noise(self, noise: Dict[str, np.ndarray]) -> np.ndarray:
+        B, n = self.hp.batch_size, self.hp.n_action_samples
+        parts = []
+        for key in NOISE_KEYS:
+            want = (B, 1) if key in ("temp_eps", "actor_eps") else (B, n)
+            parts.append(_f32(noise[key], want).reshape(-1))
+        return np.concatenate(parts)
+
+    def update_batch(self, batch: Dict[str, np.ndarray], noise: Optional[Dict[str, np.ndarray]] = None,
+                     want_grads: bool = False, stream: int | None = None):
+        """One update on a host minibatch (parity / end-to-end entry).  -> (metrics, grads|None)"""
+        B = self.hp.batch_size
+        obs, nobs = _f32(batch["obs"], (B, 2)), _f32(batch["next_obs"], (B, 2))
+        act, rew, term = (_f32(np.reshape(batch[k], -1), (B,)) for k in ("act", "rew", "term"))
+        nz = self.pack_noise(noise) if noise is not None else None
+        m = np.zeros(6, dtype=np.float32)
+        g = np.zeros(layout.grad_floats(self.hp.n_critics), dtype=np.float32) if want_grads else None
+        self._check(self._lib.cql_update_batch(self._h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(nobs), _ptr(term),
+                                               _ptr(nz), _ptr(m), _ptr(g), stream), "cql_update_batch")
+        metrics = dict(zip(METRIC_NAMES, map(float, m)))
+        return metrics, (layout.unpack_grads(g, self.hp.n_critics) if want_grads else None)
+
+    def device_buffer(self, which: int):
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._check(self._lib.cql_device_buffer(self._h, which, C.byref(ptr), C.byref(n)), "cql_device_buffer")
+        return int(ptr.value), int(n.value)
+
+    def grad_tensor(self, which: int = _lib.BUF_ALL_GRADS):
+        """torch view (no copy) of a gradient buffer, for ``torch.distributed.all_reduce``."""
+        import torch
+        ptr, n = self.device_buffer(which)
+        return torch.as_tensor(_DevView(ptr, n), device=f"cuda:{self.device}")
+
+    def step_phase(self, phase: int, stream: int | None = None) -> None:
+        self._check(self._lib.cql_step_phase(self._h, phase, stream), "cql_step_phase")
+
+    def update_data_parallel(self, allreduce_mean: Callable[[int], None], stream: int | None = None) -> None:
+        """One data-parallel update: the host averages the three gradient groups between phases.
+
+        ``allreduce_mean(buffer_id)`` must average that device buffer over ranks on ``stream``
+        (see ``parallel.GradAllReducer``).  Weights stay bit-identical across ranks because every
+        rank applies the same Adam step to the same reduced gradient.
+        """
+        self.step_phase(0, stream)
+        allreduce_mean(_lib.BUF_SCALAR_GRADS)
+        self.step_phase(1, stream)
+        allreduce_mean(_lib.BUF_CRITIC_GRADS)
+        self.step_phase(2, stream)
+        allreduce_mean(_lib.BUF_ACTOR_GRADS)
+        self.step_phase(3, stream)
+
+    def read_metrics(self) -> Dict[str, float]:
+        import torch
+        ptr, n = self.device_buffer(_lib.BUF_METRICS)
+        t = torch.as_tensor(_DevView(ptr, n), device=f"cuda:{self.device}").cpu().numpy()
+        return dict(zip(METRIC_NAMES, map(float, t[:6])))
+
+    # ------------------------------------------------------------------ scoring
+    def score_topk(self, users, items, k: int, seen_indptr=None, seen_items=None, mode: str = "q"):
+        """Top-``k`` unseen items per user.  -> (items [U,k] int32 (-1 pad), scores [U,k] float32 (-inf pad))"""
+        if mode not in SCORE_MODES:
+            raise ValueError(f"mode must be one of {sorted(SCORE_MODES)}")
+        if not 1 <= int(k) <= _lib.MAX_TOPK:
+            raise ValueError(f"k must be in 1..{_lib.MAX_TOPK}")
+        users = np.ascontiguousarray(users, dtype=np.int32).reshape(-1)
+        items = np.ascontiguousarray(items, dtype=np.int32).reshape(-1)
+        U = users.size
+        out_i = np.full((U, k), -1, dtype=np.int32)
+        out_s = np.full((U, k), -np.inf, dtype=np.float32)
+        if U == 0:
+            return out_i, out_s
+        if seen_indptr is not None:
+            seen_indptr = np.ascontiguousarray(seen_indptr, dtype=np.int64)
+            seen_items = np.ascontiguousarray(seen_items if seen_items is not None else [], dtype=np.int32)
+            if seen_indptr.size < int(users.max()) + 2:
+                raise ValueError("seen_indptr must cover every requested user id (+1)")
+        self._check(self._lib.cql_score_topk(self._h, _ptr(users), U, _ptr(items), items.size, _ptr(seen_indptr),
+                                             _ptr(seen_items) if seen_indptr is not None else None, int(k),
+                                             SCORE_MODES[mode], _ptr(out_i), _ptr(out_s), None), "cql_score_topk")
+        return out_i, out_s
+
+    def score_pairs(self, users, items, mode: str = "q") -> np.ndarray:
+        users = np.ascontiguousarray(users, dtype=np.int32).reshape(-1)
+        items = np.ascontiguousarray(items, dtype=np.int32).reshape(-1)
+        if users.size != items.size:
+            raise ValueError("users and items must have the same length")
+        out = np.empty(users.size, dtype=np.float32)
+        self._check(self._lib.cql_score_pairs(self._h, _ptr(users), _ptr(items), users.size, SCORE_MODES[mode],
+                                              _ptr(out), None), "cql_score_pairs")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cql_launch_count(self._h))

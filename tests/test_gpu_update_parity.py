@@ -1,0 +1,56 @@
+"""GPU parity of one CQL update (K2-K4) against the CPU oracle, through the C-ABI.
+
+Tolerance (BASELINE.json north_star): 1e-4 relative in FP32 for the six losses
+and the updated tensors; here "relative" is max|gpu-ref| / max|ref| per tensor.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cql_oracle as O
+from replay_cql_b200 import layout
+from tests import helpers as Hp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _compare_grads(g_gpu, g_ref, tol=TOL):
+    worst = 0.0
+    for k in layout.NET_KEYS:
+        worst = max(worst, Hp.rel_err(g_gpu["actor"][k], g_ref["actor"][k].numpy()))
+        for c in range(len(g_ref["critics"])):
+            worst = max(worst, Hp.rel_err(g_gpu["critics"][c][k], g_ref["critics"][c][k].numpy()))
+    return worst
+
+
+@pytest.mark.parametrize("scale,squash", [(1.0, "eps"), (1e-3, "eps"), (1e-3, "softplus")])
+@pytest.mark.parametrize("B", [256])
+def test_update_steps_match_oracle(engine_factory, B, scale, squash):
+    cfg = O.OracleConfig(squash=squash)
+    st = O.init_state(cfg, seed=7)
+    eng = engine_factory(batch_size=B, squash=squash)
+    eng.set_state(Hp.oracle_state_to_flat(st))
+    for step in range(3):
+        batch = Hp.make_batch(B, seed=100 + step, scale=scale)
+        noise = O.make_noise(B, cfg.n_action_samples, seed=200 + step)
+        m_ref, g_ref = O.update(cfg, st, batch, noise, want_grads=True)
+        m_gpu, g_gpu = eng.update_batch(Hp.batch_to_numpy(batch), Hp.noise_to_numpy(noise), want_grads=True)
+        for name in ("temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss"):
+            ref = m_ref[name]
+            assert abs(m_gpu[name] - ref) <= TOL * max(1.0, abs(ref)), (step, name, m_gpu[name], ref)
+        assert abs(g_gpu["log_temp"] - float(g_ref["log_temp"])) <= TOL * max(1.0, abs(float(g_ref["log_temp"])))
+        assert abs(g_gpu["log_alpha"] - float(g_ref["log_alpha"])) <= TOL * max(1.0, abs(float(g_ref["log_alpha"])))
+        assert _compare_grads(g_gpu, g_ref) <= TOL, step
+    flat_ref = Hp.oracle_state_to_flat(st)
+    flat_gpu = eng.get_state()
+    ref, gpu = layout.unpack_state(flat_ref, cfg.n_critics), layout.unpack_state(flat_gpu, cfg.n_critics)
+    for grp in ("actor", "targ_actor"):
+        for k in layout.NET_KEYS:
+            assert Hp.rel_err(gpu[grp][k], ref[grp][k]) <= TOL, (grp, k)
+    for grp in ("critics", "targ_critics"):
+        for c in range(cfg.n_critics):
+            for k in layout.NET_KEYS:
+                assert Hp.rel_err(gpu[grp][c][k], ref[grp][c][k]) <= TOL, (grp, c, k)
+    assert abs(gpu["log_temp"] - ref["log_temp"]) <= 1e-6
+    assert abs(gpu["log_alpha"] - ref["log_alpha"]) <= 1e-6
