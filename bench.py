@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- CQL updates/s (batch 1024) and users scored top-10/s on the ML-20M-shaped synthetic log.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun ... bench.py --gpus N ...        (N > 1: one rank per GPU, NCCL)
+
+One JSON line on stdout (rank 0).  A *step* is one CQL update (temp -> alpha -> critic ->
+actor -> Polyak) on one batch of 1024 transitions per GPU.  ``value`` = batch-1024 updates
+per second over all ranks with the replay table resident in HBM and sampling on the GPU;
+``e2e`` = the same update through the host-buffer C-ABI call (`cql_update_batch`: pinned
+minibatch H2D + metrics D2H every step).  ``scoring`` carries the second half of the
+BASELINE.json metric (users scored to top-10 per second, seen filter on).
+``--impl reference`` times the CPU oracle (eager PyTorch restatement of d3rlpy's update --
+d3rlpy/pyspark cannot be installed here) on the host cores for the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 1024
+K_TOP = 10
+WORKLOAD = "ml20m-train"          # BASELINE.json configs[2]: 138 493 users x 26 744 items, 20 000 263 rows
+SCORE_USERS = 2048                # users scored per timed scoring pass (bounded sample of configs[3])
+FLOP_PER_ROW = 2 * (3 * 256 + 256 * 256 + 256)   # f_c = 133 120
+FLOP_PER_UPDATE_PER_B = 269 * FLOP_PER_ROW       # 269 forward-equivalent rows per batch element
+FLOP_PER_PAIR = 3 * FLOP_PER_ROW                 # 2 critics + actor = 399 360
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(log_rows: int | None = None):
+    from replay_cql_b200.mdp import build_mdp
+    from replay_cql_b200.synthetic import make_log, SHAPES
+    log = make_log("ml20m", seed=12345, n_rows=log_rows)
+    mdp = build_mdp(log, top_k=K_TOP, action_randomization_scale=1e-3, seed=12345)
+    return log, mdp, SHAPES["ml20m"]
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_update_rate(steps: int, warmup: int, threads: int | None = None):
+    """Oracle updates/s at B=1024 on the host cores (bounded sample: `steps` updates)."""
+    import torch
+    from oracle import cql_oracle as O
+    from tests import helpers as Hp
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig()
+    st = O.init_state(cfg, seed=7)
+    batches = [Hp.make_batch(BATCH, seed=s, n_users=138_493, n_items=26_744) for s in range(4)]
+    noises = [O.make_noise(BATCH, cfg.n_action_samples, seed=50 + s) for s in range(4)]
+    for s in range(warmup):
+        O.update(cfg, st, batches[s % 4], noises[s % 4])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        O.update(cfg, st, batches[s % 4], noises[s % 4])
+    dt = time.perf_counter() - t0
+    return steps / dt, dt, threads
+
+
+def cpu_scoring_rate(n_users: int, n_items: int = 26_744, threads: int | None = None):
+    """Per-user loop in the style of replay/models/neuromf.py:394-438 (users/s, k=10, filter seen)."""
+    import torch
+    from oracle import cql_oracle as O
+    from oracle import recs_oracle
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    st = O.init_state(O.OracleConfig(), seed=7)
+    rng = np.random.default_rng(0)
+    users = rng.choice(138_493, size=n_users, replace=False).astype(np.int32)
+    items = np.arange(n_items, dtype=np.int32)
+    seen = {int(u): set(rng.choice(n_items, size=144, replace=False).tolist()) for u in users}
+    t0 = time.perf_counter()
+    recs_oracle.brute_force_topk(lambda obs: O.relevance(st, torch.from_numpy(obs), "q").numpy(), users, items, seen, K_TOP)
+    dt = time.perf_counter() - t0
+    return n_users / dt, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    rate, dt, threads = cpu_update_rate(steps, max(1, min(args.warmup, 5)))
+    srate, sdt, _ = cpu_scoring_rate(8)
+    line = {
+        "impl": "reference", "metric": "CQL updates/sec (batch 1024)", "value": rate, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": BATCH, "hidden": 256, "n_critics": 2, "n_action_samples": 10,
+                   "note": "CPU oracle = eager PyTorch restatement of d3rlpy CQL._update (d3rlpy and Spark are not "
+                           "installable here); batches pre-built in host memory"},
+        "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} updates at batch 1024 after warm-up, torch threads={threads}"},
+        "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scoring": {"metric": "users scored top-10/sec", "value": srate, "unit": "users/s",
+                    "sample": f"8 users x 26744 items, per-user loop, filter_seen, {sdt:.1f} s"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from replay_cql_b200 import _lib
+    from replay_cql_b200.engine import CqlEngine, CqlHyperParams
+    from replay_cql_b200.mdp import seen_csr, to_transitions
+    from replay_cql_b200.parallel import GradAllReducer, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    pk, pk_kind = peaks()
+
+    log, mdp, shape = build_workload(args.rows)
+    eng = CqlEngine(CqlHyperParams(batch_size=BATCH, seed=12345), device=local_rank, rank=rank, world_size=world)
+    eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+    stream = torch.cuda.Stream(device=dev)
+    sh = stream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    reducer = GradAllReducer(eng) if world > 1 else None
+
+    def do_steps(k):
+        with torch.cuda.stream(stream):
+            if world == 1:
+                eng.update(k, want_metrics=False, stream=sh)
+            else:
+                for _ in range(k):
+                    eng.update_data_parallel(reducer, stream=sh)
+
+    # ---- HBM-resident updates/s ----
+    do_steps(max(3, args.warmup))
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    do_steps(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launch_count - l0
+    clk = clocks.stop()
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- per-kernel durations (events inside one real update), rank 0 reporting ----
+    timings = [eng.timed_update(stream=sh) for _ in range(5)][1:]
+    tk = {k: float(np.mean([t[k] for t in timings])) for k in timings[0]}
+    n3 = 30
+    fwd_rows = 2 * (BATCH * n3 + BATCH * (n3 + 1) + BATCH)        # alpha + critic + target rows, 2 nets
+    fwd_flop = fwd_rows * FLOP_PER_ROW
+    achieved = fwd_flop / (tk["critic_fwd"] / 1e3) / 1e12
+    peak_tf = pk.get("bf16_tflops_sustained", 1400.0)
+
+    # ---- e2e: host minibatch in, metrics out, every step ----
+    tr = to_transitions(mdp)
+    rng = np.random.default_rng(rank)
+    n_e2e = max(10, min(args.steps, 200))
+    pool = []
+    for _ in range(8):
+        idx = rng.integers(0, len(mdp), BATCH)
+        pool.append({k: np.ascontiguousarray(v[idx]) for k, v in tr.items()})
+    for i in range(3):
+        eng.update_batch(pool[i % 8])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        eng.update_batch(pool[i % 8])
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n_e2e / e2e_s
+
+    # ---- scoring: users sharded over ranks, all items, seen filter, k=10 ----
+    n_score = SCORE_USERS * world
+    users_all = np.sort(np.random.default_rng(1).choice(shape["n_users"], size=n_score, replace=False)).astype(np.int32)
+    lo, hi = shard_range(n_score, rank, world)
+    users = users_all[lo:hi]
+    items = np.arange(shape["n_items"], dtype=np.int32)
+    sub = log[log["user_idx"].isin(users)]
+    indptr, seen = seen_csr(sub, shape["n_users"])
+    with torch.cuda.stream(stream):
+        d_users = torch.from_numpy(users).to(dev)
+        d_items = torch.from_numpy(items).to(dev)
+        d_ptr = torch.from_numpy(indptr).to(dev)
+        d_seen = torch.from_numpy(seen).to(dev)
+        oi = torch.empty((users.size, K_TOP), dtype=torch.int32, device=dev)
+        osc = torch.empty((users.size, K_TOP), dtype=torch.float32, device=dev)
+        eng.score_topk_device(d_users[:64], d_items, K_TOP, d_ptr, d_seen, out_items=oi[:64], out_scores=osc[:64], stream=sh)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l1 = eng.launch_count
+    s0.record(stream)
+    with torch.cuda.stream(stream):
+        eng.score_topk_device(d_users, d_items, K_TOP, d_ptr, d_seen, out_items=oi, out_scores=osc, stream=sh)
+    s1.record(stream)
+    barrier()
+    score_ms = max_over_ranks(s0.elapsed_time(s1))
+    score_launches = eng.launch_count - l1
+    users_per_s = n_score / (score_ms / 1e3)
+    t0 = time.perf_counter()
+    eng.score_topk(users, items, K_TOP, indptr, seen)
+    score_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    pairs = float(users.size) * shape["n_items"]
+    score_tf = pairs * FLOP_PER_PAIR / (score_ms / 1e3) / 1e12
+
+    # ---- K1 stand-alone gather sweep (HBM random gather, 36 B/row algorithmic) ----
+    cnt = 1 << 20
+    out = torch.empty((cnt, 8), dtype=torch.float32, device=dev)
+    with torch.cuda.stream(stream):
+        eng.sample_rows(cnt, pos=0, out=out, stream=sh)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for r in range(10):
+            eng.sample_rows(cnt, pos=(r + 1) * cnt, out=out, stream=sh)
+        g1.record(stream)
+    torch.cuda.synchronize(dev)
+    gather_gbs = 10 * cnt * 64 / (g0.elapsed_time(g1) / 1e3) / 1e9    # 32 B read + 32 B written per row
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            rate, dt, threads = cpu_update_rate(40, 3)
+            cpu = {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
+                   "sample": f"40 oracle updates at batch 1024 ({dt:.1f} s), torch threads={threads}"}
+        line = {
+            "metric": "CQL updates/sec (batch 1024)", "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "users": shape["n_users"], "items": shape["n_items"],
+                       "rows": len(mdp), "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                       "parallelism": f"dp{world}", "hidden": 256, "n_critics": 2, "n_action_samples": 10,
+                       "precision": "fp32",
+                       "l2": "inputs larger than L2: 640 MB replay table, fresh random gather every step; "
+                             "weights/activations are the step-to-step state of the algorithm"},
+            "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": BATCH * 32,
+                    "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batch (host minibatch in, metrics out)"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_source": f"bf16_tflops_sustained ({pk_kind})", "traffic": None,
+                         "flop_per_launch": fwd_flop, "ms_per_launch": tk["critic_fwd"],
+                         "update_tflops": value / world * BATCH * FLOP_PER_UPDATE_PER_B / 1e12},
+            "kernel_ms": tk,
+            "cpu_baseline": cpu,
+            "scoring": {"metric": "users scored top-10/sec", "value": users_per_s, "unit": "users/s",
+                        "users": int(n_score), "items": shape["n_items"], "k": K_TOP, "filter_seen": True,
+                        "ms": score_ms, "tflops": score_tf * world, "frac_of_peak": score_tf / peak_tf,
+                        "gpu_launches": int(score_launches),
+                        "e2e": {"value": n_score / score_e2e_s, "unit": "users/s",
+                                "h2d_bytes": int(users.nbytes + items.nbytes + indptr.nbytes + seen.nbytes),
+                                "d2h_bytes": int(users.size * K_TOP * 8), "api": "cql_score_topk (host ids + CSR in, top-k out)"}},
+            "sampler": {"metric": "replay gather", "value": gather_gbs, "unit": "GB/s", "rows": cnt,
+                        "frac_of_hbm": gather_gbs / pk.get("hbm_gbs", 6650.0)},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--rows", type=int, default=None, help="override the log size (debugging)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,11 @@
  * returns 0 on success, non-zero on error (cql_last_error() has the text).
  * "host" pointers are ordinary (ideally pinned) host memory, "dev" pointers
  * are device memory on the handle's GPU.  One handle per GPU; a handle is not
- * thread-safe.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ * thread-safe.  `stream` is a cudaStream_t passed as void*.  NULL selects the
+ * handle's own non-blocking stream; functions that take caller-owned DEVICE
+ * pointers then synchronise that stream before returning (the caller must have
+ * finished producing the inputs), so a NULL-stream call is always safe to follow
+ * with work on any other stream.
  */
 #ifndef CQL_B200_H
 #define CQL_B200_H
@@ -156,6 +160,13 @@ int  cql_topk_filter_dev(cql_handle* h, const float* scores_dev, int64_t n_users
                          const int32_t* users_dev, const int32_t* items_dev,
                          const int64_t* seen_indptr, const int32_t* seen_items,
                          int32_t k, int32_t* out_items, float* out_scores, void* stream);
+
+/* Measurement aid: runs ONE sampled update with CUDA events around the heavy launches and
+ * returns their durations in milliseconds (synchronises).  out_ms[0] = critic forward (alpha +
+ * critic + target rows), [1] = critic backward-1, [2] = critic backward-2 (dW2), [3] = whole
+ * update, [4] = actor-step critic forward, [5] = actor backward (1+2), [6] = shared actor
+ * forward, [7] = everything else.  The update is a real one (weights advance). */
+int  cql_timed_update(cql_handle* h, float* out_ms8, void* stream);
 
 /* number of kernels this library has launched on the handle (bench "gpu_launches") */
 int64_t cql_launch_count(const cql_handle* h);

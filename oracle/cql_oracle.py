@@ -211,15 +211,18 @@ def make_noise(B: int, n: int, seed: int, dtype=torch.float32) -> Dict[str, torc
 
 
 def update(cfg: OracleConfig, st: Dict, batch: Dict[str, torch.Tensor],
-           noise: Dict[str, torch.Tensor], want_grads: bool = False):
+           noise: Dict[str, torch.Tensor], want_grads: bool = False, grad_hook=None):
     """One ``CQL._update(batch)``: temp -> alpha -> critic -> actor -> Polyak.
 
     ``batch``: obs [B,2], act [B,1], rew [B,1], next_obs [B,2], term [B,1].
     Mutates ``st`` in place.  Returns (metrics dict, grads dict or None).
+    ``grad_hook(list_of_grad_tensors) -> list`` (optional) is applied to each of the four
+    gradient groups before its Adam step -- the data-parallel tests average over ranks there.
     ``metrics`` keys follow d3rlpy: temp_loss, temp, alpha_loss, alpha,
     critic_loss, actor_loss (temp/alpha are the post-update values).
     """
     assert not cfg.soft_q_backup
+    hook = grad_hook if grad_hook is not None else (lambda gs: gs)
     s, a, r, s1, done = (batch[k] for k in ("obs", "act", "rew", "next_obs", "term"))
     st["step"] += 1
     step = st["step"]
@@ -234,7 +237,7 @@ def update(cfg: OracleConfig, st: Dict, batch: Dict[str, torch.Tensor],
             targ_temp = logp - cfg.act_dim
         lt = st["log_temp"].detach().clone().requires_grad_(True)
         loss = -(lt.exp() * targ_temp).mean()
-        (g,) = torch.autograd.grad(loss, lt)
+        (g,) = hook(list(torch.autograd.grad(loss, lt)))
         grads["log_temp"] = g.clone()
         adam_step(st["log_temp"], g, st["adam"]["log_temp"], cfg.temp_lr, step, cfg)
         metrics["temp_loss"] = float(loss.detach())
@@ -245,7 +248,7 @@ def update(cfg: OracleConfig, st: Dict, batch: Dict[str, torch.Tensor],
         la = st["log_alpha"].detach().clone().requires_grad_(True)
         loss = -conservative(cfg, critics, actor, la, s, a, s1,
                              noise["alpha_eps_t"], noise["alpha_eps_t1"], noise["alpha_u"])
-        (g,) = torch.autograd.grad(loss, la)
+        (g,) = hook(list(torch.autograd.grad(loss, la)))
         grads["log_alpha"] = g.clone()
         adam_step(st["log_alpha"], g, st["adam"]["log_alpha"], cfg.alpha_lr, step, cfg)
         metrics["alpha_loss"] = float(loss.detach())
@@ -265,7 +268,7 @@ def update(cfg: OracleConfig, st: Dict, batch: Dict[str, torch.Tensor],
                         noise["critic_eps_t"], noise["critic_eps_t1"], noise["critic_u"])
     loss = td + cons
     flat = [c[k] for c in leaf for k in NET_KEYS]
-    gs = torch.autograd.grad(loss, flat)
+    gs = hook(list(torch.autograd.grad(loss, flat)))
     grads["critics"] = []
     it = iter(gs)
     for ci, c in enumerate(critics):
@@ -285,7 +288,7 @@ def update(cfg: OracleConfig, st: Dict, batch: Dict[str, torch.Tensor],
     entropy = st["log_temp"].exp() * logp
     q_min = q_ensemble(critics, s, a_pi).min(dim=0).values.unsqueeze(1)
     loss = (entropy - q_min).mean()
-    gs = torch.autograd.grad(loss, [aleaf[k] for k in NET_KEYS])
+    gs = hook(list(torch.autograd.grad(loss, [aleaf[k] for k in NET_KEYS])))
     grads["actor"] = {}
     for k, g in zip(NET_KEYS, gs):
         grads["actor"][k] = g.clone()

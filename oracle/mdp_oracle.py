@@ -29,21 +29,21 @@ def build_mdp(log: pd.DataFrame, top_k: int = 10, action_noise: np.ndarray | Non
     n = len(df)
     if action_noise is None:
         action_noise = np.zeros(n, dtype=np.float64)
-    df["_row"] = np.arange(n)
-    df["_action"] = df["relevance"].astype(np.float32).astype(np.float64) + action_noise
+    df["row_"] = np.arange(n)
+    df["action_"] = df["relevance"].astype(np.float32).astype(np.float64) + action_noise
     obs, act, rew, term, nxt = [], [], [], [], []
     for user, grp in df.groupby("user_idx", sort=True):
-        g = grp.sort_values(["timestamp", "_row"], kind="stable")
+        g = grp.sort_values(["timestamp", "row_"], kind="stable")
         rows = list(g.itertuples(index=False))
         # reward ranking: relevance desc, timestamp desc, then input order
         rank_order = sorted(range(len(rows)),
                             key=lambda j: (-rows[j].relevance, -pd.Timestamp(rows[j].timestamp).value
                                            if not isinstance(rows[j].timestamp, (int, float, np.integer, np.floating))
-                                           else -rows[j].timestamp, rows[j]._row))
+                                           else -rows[j].timestamp, rows[j].row_))
         rewarded = set(rank_order[:top_k])
         for j, row in enumerate(rows):
             obs.append((float(user), float(row.item_idx)))
-            act.append(row._action)
+            act.append(row.action_)
             rew.append(1.0 if j in rewarded else 0.0)
             last = j == len(rows) - 1
             term.append(1.0 if last else 0.0)

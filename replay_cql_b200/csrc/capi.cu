@@ -334,6 +334,7 @@ int cql_sample_rows(cql_handle* ch, const int64_t* idx_dev, int64_t pos, int64_t
                                                              nullptr, pos, count, std::max<int64_t>(1, h.B), 0, 1,
                                                              h.cfg.seed, reinterpret_cast<float4*>(out_dev));
     CQL_LAUNCH_CHECK(&h);
+    if (!stream) CQL_CUDA(cudaStreamSynchronize(st));   // NULL stream = the handle's own stream: return when done
   });
 }
 
@@ -369,6 +370,30 @@ int cql_update(cql_handle* ch, int64_t n_steps, float* metrics6, void* stream) {
       CQL_CUDA(cudaStreamSynchronize(st));
       std::memcpy(metrics6, h.metrics_host, 6 * sizeof(float));
     }
+  });
+}
+
+int cql_timed_update(cql_handle* ch, float* out_ms8, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(out_ms8 != nullptr, "cql_timed_update: out is NULL");
+    CQL_REQUIRE(h.n_trans > 0, "cql_timed_update: no transitions loaded");
+    cudaStream_t st = pick_stream(&h, stream);
+    for (int i = 0; i < 13; ++i)
+      if (!h.ev[i]) CQL_CUDA(cudaEventCreate(&h.ev[i]));
+    h.timing = true;
+    try {
+      run_full_step(&h, st, BatchSource::Sampled, NoiseSource::Philox);
+    } catch (...) {
+      h.timing = false;
+      throw;
+    }
+    h.timing = false;
+    CQL_CUDA(cudaStreamSynchronize(st));
+    auto ms = [&](int a, int b) { float t = 0.f; CQL_CUDA(cudaEventElapsedTime(&t, h.ev[a], h.ev[b])); return t; };
+    out_ms8[0] = ms(3, 4); out_ms8[1] = ms(5, 6); out_ms8[2] = ms(6, 7); out_ms8[3] = ms(0, 12);
+    out_ms8[4] = ms(8, 9); out_ms8[5] = ms(10, 11); out_ms8[6] = ms(1, 2);
+    out_ms8[7] = out_ms8[3] - (out_ms8[0] + out_ms8[1] + out_ms8[2] + out_ms8[4] + out_ms8[5] + out_ms8[6]);
   });
 }
 
@@ -436,6 +461,7 @@ int cql_score_topk_dev(cql_handle* ch, const int32_t* users, int64_t n_users, co
                 "cql_score_topk_dev: NULL pointer");
     score_topk_dev_impl(ch, users, n_users, items, n_items, seen_indptr, seen_items, k, mode, out_items, out_scores,
                         pick_stream(&ch->h, stream));
+    if (!stream) CQL_CUDA(cudaStreamSynchronize(pick_stream(&ch->h, stream)));
   });
 }
 
@@ -512,6 +538,7 @@ int cql_topk_filter_dev(cql_handle* ch, const float* scores_dev, int64_t n_users
     k_topk_filter<<<(unsigned)n_users, threads, (threads / 32) * 2 * k * sizeof(float), st>>>(
         scores_dev, n_items, users_dev, items_dev, seen_indptr, seen_items, k, out_scores, out_items);
     CQL_LAUNCH_CHECK(&h);
+    if (!stream) CQL_CUDA(cudaStreamSynchronize(st));
   });
 }
 

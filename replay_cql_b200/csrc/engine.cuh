@@ -71,6 +71,10 @@ struct Handle {
   float* pw2A = nullptr;     // [splitsA][H*H]
   int splitsC = 1, splitsA = 1;
 
+  // optional event marks for cql_timed_update
+  bool timing = false;
+  cudaEvent_t ev[16] = {};
+
   std::vector<void*> allocs;
 
   template <typename T>
@@ -89,6 +93,7 @@ struct Handle {
     if (batch_host) { cudaFreeHost(batch_host); batch_host = nullptr; }
     if (noise_host) { cudaFreeHost(noise_host); noise_host = nullptr; }
     if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
+    for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   }
 
   float* net_params(int slot) const { return params + (size_t)slot * NET_STRIDE; }
@@ -98,6 +103,10 @@ struct Handle {
   float* g_critics() const { return grads + NET_STRIDE; }
   float* g_scalars() const { return grads + (size_t)(1 + C) * NET_STRIDE; }
 };
+
+inline void mark(Handle* h, cudaStream_t st, int i) {
+  if (h->timing) CQL_CUDA(cudaEventRecord(h->ev[i], st));
+}
 
 inline cudaStream_t pick_stream(Handle* h, void* stream) {
   return stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;

@@ -102,16 +102,23 @@ __global__ void k_step_end(long long* step_dev) { *step_dev += 1; }
 // ---------------------------------------------------------------- squashed Gaussian
 struct Sample { float a, logp, raw, t, std_; };
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+// Mirrors the oracle op by op (separately rounded mul/add, no FMA contraction): the
+// log(1 - a^2 + 1e-6) term is ill-conditioned near |a| -> 1, so even the rounding of a*a matters.
 __device__ __forceinline__ Sample policy_sample(float mu, float ls, float eps, int squash) {
   Sample s;
   s.std_ = expf(ls);
-  s.raw = fmaf(s.std_, eps, mu);
+  s.raw = __fadd_rn(mu, __fmul_rn(s.std_, eps));
   s.a = tanhf(s.raw);
-  s.t = (s.raw - mu) / s.std_;
-  const float normal_logp = -0.5f * s.t * s.t - ls - 0.91893853320467274f;
-  const float logdet = squash == CQL_SQUASH_EPS ? logf(1.f - s.a * s.a + 1e-6f)
-                                                : 2.f * (0.69314718055994531f - s.raw - softplus_t(-2.f * s.raw));
-  s.logp = normal_logp - logdet;
+  s.t = __fdiv_rn(__fsub_rn(s.raw, mu), s.std_);
+  const float normal_logp =
+      __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, __fmul_rn(s.t, s.t)), ls), 0.91893853320467274f);
+  float logdet;
+  if (squash == CQL_SQUASH_EPS) {
+    logdet = logf(__fadd_rn(__fsub_rn(1.f, __fmul_rn(s.a, s.a)), 1e-6f));
+  } else {
+    logdet = __fmul_rn(2.f, __fsub_rn(__fsub_rn(0.69314718055994531f, s.raw), softplus_t(__fmul_rn(-2.f, s.raw))));
+  }
+  s.logp = __fsub_rn(normal_logp, logdet);
   return s;
 }
 __device__ __forceinline__ float clamp_ls(float x) { return fminf(fmaxf(x, -20.f), 2.f); }
@@ -335,10 +342,10 @@ __global__ void k_actor_dout(const float* __restrict__ outA, const float* __rest
   const float eps = noise_actor[b];
   const Sample s = policy_sample(mu, ls, eps, squash);
   const float w = expf(scalars[0]) / (float)B;   // d loss / d logp
-  const float one_m_a2 = 1.f - s.a * s.a;
+  const float one_m_a2 = __fsub_rn(1.f, __fmul_rn(s.a, s.a));
   float g_raw = w * (-s.t / s.std_);
   if (squash == CQL_SQUASH_EPS) {
-    const float g_a = da + w * (2.f * s.a / (one_m_a2 + 1e-6f));
+    const float g_a = da + w * (2.f * s.a / __fadd_rn(one_m_a2, 1e-6f));
     g_raw += g_a * one_m_a2;
   } else {
     const float sig = 1.f / (1.f + expf(2.f * s.raw));  // sigmoid(-2 raw)
@@ -443,6 +450,7 @@ enum class NoiseSource { Philox, Provided };
 inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
   const int B = h->B, C = h->C, n3 = 3 * h->n;
   const cql_config& c = h->cfg;
+  mark(h, st, 0);
   k_step_begin<<<1, 1, 0, st>>>(h->step_dev, h->stepinfo, c.beta1, c.beta2);
   CQL_LAUNCH_CHECK(h);
   if (bs == BatchSource::Sampled) {
@@ -465,7 +473,9 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     jobs.n = 2;
     jobs.j[0] = FwdJob{h->XA, h->net_params(slot_actor()), h->outA, h->h2A, B, 1, 0};
     jobs.j[1] = FwdJob{h->XA + B, h->net_params(slot_actor()), h->outA + 2 * (size_t)B, nullptr, B, 1, 0};
+    mark(h, st, 1);
     launch_fwd<2, 2>(h, jobs, st);
+    mark(h, st, 2);
   }
   k_prep<<<(B * 64 + 255) / 256, 256, 0, st>>>(batch4, h->outA, h->noise, B, h->n, c.squash, h->XAl, h->offAl, h->XC,
                                                h->offC, h->XT, h->XP, reinterpret_cast<float4*>(h->perb));
@@ -476,7 +486,9 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     jobs.j[0] = FwdJob{h->XAl, h->net_params(slot_critic(0)), h->QAl, nullptr, B * n3, C, 0};
     jobs.j[1] = FwdJob{h->XC, h->net_params(slot_critic(0)), h->QC, h->h2C, B * (n3 + 1), C, 0};
     jobs.j[2] = FwdJob{h->XT, h->net_params(slot_targ_critic(C, 0)), h->QT, nullptr, B, C, 0};
+    mark(h, st, 3);
     launch_fwd<3, 1>(h, jobs, st);
+    mark(h, st, 4);
   }
   k_scalar_grads<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->perb), h->QAl, h->offAl, h->QC, h->scalars(),
                                      loss_consts(h), h->g_scalars(), h->metrics);
@@ -492,8 +504,11 @@ inline void phase1(Handle* h, cudaStream_t st) {
                                   h->metrics);
   CQL_LAUNCH_CHECK(h);
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
+  mark(h, st, 5);
   launch_bwd1<3, 1, true, false>(h, jb, st);
+  mark(h, st, 6);
   launch_bwd2<3, 1>(h, jb, st);
+  mark(h, st, 7);
   k_reduce_grads<<<dim3((NET_STRIDE + 255) / 256, C), 256, 0, st>>>(h->smallC, h->pw2C, 3, 1, tiles_of(rows),
                                                                    h->splitsC, h->g_critics());
   CQL_LAUNCH_CHECK(h);
@@ -512,7 +527,9 @@ inline void phase2(Handle* h, cudaStream_t st) {
     FwdJobs jobs{};
     jobs.n = 1;
     jobs.j[0] = FwdJob{h->XP, h->net_params(slot_critic(0)), h->QP, h->h2P, B, C, 0};
+    mark(h, st, 8);
     launch_fwd<3, 1>(h, jobs, st);
+    mark(h, st, 9);
   }
   k_actor_dq<<<1, 1024, 0, st>>>(h->QP, reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
                                  h->metrics);
@@ -525,8 +542,10 @@ inline void phase2(Handle* h, cudaStream_t st) {
                                                 C, c.squash, h->dOutA);
   CQL_LAUNCH_CHECK(h);
   BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
+  mark(h, st, 10);
   launch_bwd1<2, 2, true, false>(h, ja, st);
   launch_bwd2<2, 2>(h, ja, st);
+  mark(h, st, 11);
   k_reduce_grads<<<dim3((NET_STRIDE + 255) / 256, 1), 256, 0, st>>>(h->smallA, h->pw2A, 2, 2, tiles_of(B), h->splitsA,
                                                                    h->g_actor());
   CQL_LAUNCH_CHECK(h);
@@ -542,6 +561,7 @@ inline void phase3(Handle* h, cudaStream_t st) {
   CQL_LAUNCH_CHECK(h);
   k_step_end<<<1, 1, 0, st>>>(h->step_dev);
   CQL_LAUNCH_CHECK(h);
+  mark(h, st, 12);
 }
 
 }  // namespace cql

@@ -120,6 +120,19 @@ class CqlEngine:
     def _check(self, rc: int, what: str) -> None:
         _lib.check(self._h, rc, what)
 
+    def _torch_stream(self, stream):
+        """Stream for calls that consume caller-owned cuda tensors: torch's current stream when it is a
+        real (non-default) stream; otherwise drain torch's default stream and use the handle's own
+        stream (NULL), which the library synchronises before returning."""
+        if stream is not None:
+            return C.c_void_p(stream)
+        import torch
+        cur = torch.cuda.current_stream(torch.device("cuda", self.device))
+        if cur.cuda_stream != 0:
+            return C.c_void_p(cur.cuda_stream)
+        cur.synchronize()
+        return None
+
     # ------------------------------------------------------------------ state
     def set_state(self, flat: np.ndarray) -> None:
         flat = _f32(flat, (self.n_state,))
@@ -155,12 +168,39 @@ class CqlEngine:
     def n_transitions(self) -> int:
         return int(self._lib.cql_num_transitions(self._h))
 
+    def sample_rows(self, count: int, idx=None, pos: int = 0, out=None, stream: int | None = None):
+        """Stand-alone replay gather (K1).  ``idx``: explicit int64 indices (numpy or cuda tensor) or
+        None for the epoch permutation stream starting at ``pos``.  -> cuda tensor [count, 8]
+        rows ``(obs.x, obs.y, act, rew, next_obs.x, next_obs.y, term, 0)``."""
+        import torch
+        dev = f"cuda:{self.device}"
+        if out is None:
+            out = torch.empty((count, 8), dtype=torch.float32, device=dev)
+        idx_ptr = None
+        if idx is not None:
+            if not isinstance(idx, torch.Tensor):
+                idx = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int64), device=dev)
+            if idx.dtype != torch.int64 or idx.numel() != count:
+                raise ValueError("idx must be int64 with `count` elements")
+            idx_ptr = C.c_void_p(idx.data_ptr())
+        stream = self._torch_stream(stream)
+        self._check(self._lib.cql_sample_rows(self._h, idx_ptr, int(pos), int(count), C.c_void_p(out.data_ptr()),
+                                              stream), "cql_sample_rows")
+        return out
+
     # ------------------------------------------------------------------ updates
     def update(self, n_steps: int = 1, want_metrics: bool = True, stream: int | None = None) -> Optional[Dict[str, float]]:
         """``n_steps`` updates with on-device sampling + Philox noise (CUDA-graph replay)."""
         m = np.zeros(6, dtype=np.float32) if want_metrics else None
         self._check(self._lib.cql_update(self._h, int(n_steps), _ptr(m), stream), "cql_update")
         return dict(zip(METRIC_NAMES, map(float, m))) if want_metrics else None
+
+    def timed_update(self, stream: int | None = None) -> Dict[str, float]:
+        """One real sampled update with CUDA events around the heavy kernels (milliseconds)."""
+        out = np.zeros(8, dtype=np.float32)
+        self._check(self._lib.cql_timed_update(self._h, _ptr(out), stream), "cql_timed_update")
+        keys = ("critic_fwd", "critic_bwd1", "critic_bwd2", "update", "actor_step_fwd", "actor_bwd", "actor_fwd", "other")
+        return dict(zip(keys, map(float, out)))
 
     def pack_noise(self, noise: Dict[str, np.ndarray]) -> np.ndarray:
         B, n = self.hp.batch_size, self.hp.n_action_samples
@@ -252,6 +292,36 @@ class CqlEngine:
         self._check(self._lib.cql_score_pairs(self._h, _ptr(users), _ptr(items), users.size, SCORE_MODES[mode],
                                               _ptr(out), None), "cql_score_pairs")
         return out
+
+    def score_topk_device(self, users_t, items_t, k: int, seen_indptr_t=None, seen_items_t=None, mode: str = "q",
+                          out_items=None, out_scores=None, stream: int | None = None):
+        """HBM-resident variant: every argument is a cuda tensor (int32 ids, int64 indptr)."""
+        import torch
+        U = users_t.numel()
+        if out_items is None:
+            out_items = torch.empty((U, k), dtype=torch.int32, device=users_t.device)
+        if out_scores is None:
+            out_scores = torch.empty((U, k), dtype=torch.float32, device=users_t.device)
+        stream = self._torch_stream(stream)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        self._check(self._lib.cql_score_topk_dev(self._h, p(users_t), U, p(items_t), items_t.numel(),
+                                                 p(seen_indptr_t), p(seen_items_t), int(k), SCORE_MODES[mode],
+                                                 p(out_items), p(out_scores), stream), "cql_score_topk_dev")
+        return out_items, out_scores
+
+    def topk_filter_device(self, scores_t, k: int, users_t=None, items_t=None, seen_indptr_t=None,
+                           seen_items_t=None, stream: int | None = None):
+        """Stand-alone top-k + lazy seen filter over a materialised cuda score matrix [U, I]."""
+        import torch
+        U, I = scores_t.shape
+        out_items = torch.empty((U, k), dtype=torch.int32, device=scores_t.device)
+        out_scores = torch.empty((U, k), dtype=torch.float32, device=scores_t.device)
+        stream = self._torch_stream(stream)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        self._check(self._lib.cql_topk_filter_dev(self._h, p(scores_t), U, I, p(users_t), p(items_t),
+                                                  p(seen_indptr_t), p(seen_items_t), int(k), p(out_items),
+                                                  p(out_scores), stream), "cql_topk_filter_dev")
+        return out_items, out_scores
 
     @property
     def launch_count(self) -> int:

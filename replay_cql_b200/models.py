@@ -1,0 +1,246 @@
+"""``CQL`` -- the drop-in recommender (the class a RePlay user imports as ``replay.models.CQL``).
+
+Keeps the wrapper's public contract: ``fit(log)``,
+``predict(log, k, users, items, filter_seen_items)``, ``predict_pairs``, ``fit_predict``,
+``_init_args`` / ``_save_model`` / ``_load_model`` for ``save``/``load``.  Inside, d3rlpy's
+``CQL.fit`` loop and the per-user scoring loop are replaced by ``engine.CqlEngine``.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Any, Dict, Optional
+
+import numpy as np
+import pandas as pd
+
+from .engine import CqlEngine, CqlHyperParams
+from .mdp import build_mdp, seen_csr
+from .parallel import GradAllReducer, dist_info, gather_rows, shard_range
+from .recommender import Recommender, _rec_frame
+
+
+class CQL(Recommender):
+    """Conservative Q-Learning recommender (Kumar et al. 2020) on RePlay's plug-in API.
+
+    Observation = ``(user_idx, item_idx)``, action = ``relevance`` (one episode per user);
+    relevance of a pair at predict time is ``mean_i Q_i(x, pi_greedy(x))`` (``score="q"``,
+    d3rlpy ``predict_value(x, predict(x))``) or the greedy action itself (``score="policy"``).
+    """
+
+    _observation_shape = (2,)
+    _action_size = 1
+    can_predict_cold_users = False
+    can_predict_cold_items = False
+
+    _search_space = {
+        "actor_learning_rate": {"type": "loguniform", "args": [1e-5, 1e-3]},
+        "critic_learning_rate": {"type": "loguniform", "args": [3e-5, 3e-4]},
+        "temp_learning_rate": {"type": "loguniform", "args": [1e-5, 1e-3]},
+        "alpha_learning_rate": {"type": "loguniform", "args": [1e-5, 1e-3]},
+        "gamma": {"type": "loguniform", "args": [0.9, 0.999]},
+        "n_critics": {"type": "int", "args": [2, 4]},
+    }
+
+    # pylint: disable=too-many-arguments
+    def __init__(
+        self,
+        top_k: int = 10,
+        action_randomization_scale: float = 1e-3,
+        n_epochs: int = 1,
+        batch_size: int = 1024,
+        actor_learning_rate: float = 1e-4,
+        critic_learning_rate: float = 3e-4,
+        temp_learning_rate: float = 1e-4,
+        alpha_learning_rate: float = 1e-4,
+        gamma: float = 0.99,
+        tau: float = 0.005,
+        n_critics: int = 2,
+        initial_temperature: float = 1.0,
+        initial_alpha: float = 1.0,
+        alpha_threshold: float = 10.0,
+        conservative_weight: float = 5.0,
+        n_action_samples: int = 10,
+        soft_q_backup: bool = False,
+        use_gpu: bool = True,
+        precision: str = "fp32",
+        score: str = "q",
+        squash: str = "eps",
+        seed: int = 12345,
+        n_steps_per_epoch: Optional[int] = None,
+    ):
+        if soft_q_backup:
+            raise ValueError("soft_q_backup=True is not supported (d3rlpy default False is restated)")
+        if not use_gpu:
+            raise ValueError("replay_cql_b200.CQL runs on a B200 only (use_gpu must be True); there is no CPU path")
+        if score not in ("q", "policy"):
+            raise ValueError("score must be 'q' or 'policy'")
+        if top_k < 0 or n_epochs < 0 or batch_size < 1:
+            raise ValueError("top_k, n_epochs must be >= 0 and batch_size >= 1")
+        self.top_k = top_k
+        self.action_randomization_scale = action_randomization_scale
+        self.n_epochs = n_epochs
+        self.batch_size = batch_size
+        self.actor_learning_rate = actor_learning_rate
+        self.critic_learning_rate = critic_learning_rate
+        self.temp_learning_rate = temp_learning_rate
+        self.alpha_learning_rate = alpha_learning_rate
+        self.gamma = gamma
+        self.tau = tau
+        self.n_critics = n_critics
+        self.initial_temperature = initial_temperature
+        self.initial_alpha = initial_alpha
+        self.alpha_threshold = alpha_threshold
+        self.conservative_weight = conservative_weight
+        self.n_action_samples = n_action_samples
+        self.soft_q_backup = soft_q_backup
+        self.use_gpu = use_gpu
+        self.precision = precision
+        self.score = score
+        self.squash = squash
+        self.seed = seed
+        self.n_steps_per_epoch = n_steps_per_epoch
+        self.engine: Optional[CqlEngine] = None
+        self.last_metrics: Optional[Dict[str, float]] = None
+
+    @property
+    def _init_args(self) -> dict:
+        return {
+            "top_k": self.top_k,
+            "action_randomization_scale": self.action_randomization_scale,
+            "n_epochs": self.n_epochs,
+            "batch_size": self.batch_size,
+            "actor_learning_rate": self.actor_learning_rate,
+            "critic_learning_rate": self.critic_learning_rate,
+            "temp_learning_rate": self.temp_learning_rate,
+            "alpha_learning_rate": self.alpha_learning_rate,
+            "gamma": self.gamma,
+            "tau": self.tau,
+            "n_critics": self.n_critics,
+            "initial_temperature": self.initial_temperature,
+            "initial_alpha": self.initial_alpha,
+            "alpha_threshold": self.alpha_threshold,
+            "conservative_weight": self.conservative_weight,
+            "n_action_samples": self.n_action_samples,
+            "soft_q_backup": self.soft_q_backup,
+            "use_gpu": self.use_gpu,
+            "precision": self.precision,
+            "score": self.score,
+            "squash": self.squash,
+            "seed": self.seed,
+            "n_steps_per_epoch": self.n_steps_per_epoch,
+        }
+
+    # ------------------------------------------------------------------ engine
+    def _hyper_params(self) -> CqlHyperParams:
+        return CqlHyperParams(
+            batch_size=self.batch_size, n_critics=self.n_critics, n_action_samples=self.n_action_samples,
+            gamma=self.gamma, tau=self.tau, actor_lr=self.actor_learning_rate, critic_lr=self.critic_learning_rate,
+            temp_lr=self.temp_learning_rate, alpha_lr=self.alpha_learning_rate,
+            initial_temperature=self.initial_temperature, initial_alpha=self.initial_alpha,
+            alpha_threshold=self.alpha_threshold, conservative_weight=self.conservative_weight,
+            precision=self.precision, squash=self.squash, seed=self.seed,
+        )
+
+    def _make_engine(self) -> CqlEngine:
+        rank, world, local_rank = dist_info()
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = CqlEngine(self._hyper_params(), device=local_rank, rank=rank, world_size=world)
+        return self.engine
+
+    def _clear_cache(self) -> None:
+        pass
+
+    # ------------------------------------------------------------------ fit
+    def _fit(self, log: pd.DataFrame, user_features=None, item_features=None) -> None:
+        """MDP build -> HBM replay table -> ``n_epochs`` x (N // (B*world)) fused updates."""
+        mdp = build_mdp(log, top_k=self.top_k, action_randomization_scale=self.action_randomization_scale,
+                        seed=self.seed)
+        eng = self._make_engine()
+        eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+        rank, world, _ = dist_info()
+        per_epoch = self.n_steps_per_epoch
+        if per_epoch is None:
+            per_epoch = len(mdp) // (self.batch_size * world)   # d3rlpy drops the last partial minibatch
+        total = int(self.n_epochs) * int(per_epoch)
+        if total == 0:
+            self.logger.warning("CQL.fit: 0 update steps (log has %d rows, batch_size*world = %d)",
+                                len(mdp), self.batch_size * world)
+            return
+        if world == 1:
+            done = 0
+            while done < total:
+                chunk = min(per_epoch, total - done)
+                self.last_metrics = eng.update(chunk)
+                done += chunk
+                self.logger.debug("CQL epoch %d/%d %s", done // max(per_epoch, 1), self.n_epochs, self.last_metrics)
+        else:
+            reducer = GradAllReducer(eng)
+            import torch
+            with torch.cuda.device(eng.device):
+                side = torch.cuda.Stream()          # a real stream: kernels and NCCL are ordered on it
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(total):
+                        eng.update_data_parallel(reducer, stream=side.cuda_stream)
+                side.synchronize()
+            self.last_metrics = eng.read_metrics()
+
+    # ------------------------------------------------------------------ predict
+    def _predict(self, log: Optional[pd.DataFrame], k: int, users: pd.DataFrame, items: pd.DataFrame,
+                 user_features=None, item_features=None, filter_seen_items: bool = True) -> pd.DataFrame:
+        """Fused user x item scoring + seen filter + top-k on the GPU; users sharded over ranks."""
+        if self.engine is None:
+            raise AttributeError("CQL model is not fitted or loaded")
+        u = np.sort(users["user_idx"].to_numpy().astype(np.int32))
+        it = np.sort(items["item_idx"].to_numpy().astype(np.int32))
+        if u.size == 0 or it.size == 0:
+            return _rec_frame([], [], [])
+        rank, world, _ = dist_info()
+        lo, hi = shard_range(u.size, rank, world)
+        u_local = u[lo:hi]
+        indptr = seen = None
+        if filter_seen_items and log is not None and len(log):
+            sub = log[log["user_idx"].isin(u_local)] if u_local.size else log.iloc[:0]
+            indptr, seen = seen_csr(sub, int(u.max()) + 1)
+        kk = min(int(k), int(it.size))
+        top_i, top_s = self.engine.score_topk(u_local, it, kk, indptr, seen, mode=self.score)
+        rows_u = np.repeat(u_local, kk).reshape(-1, 1)
+        packed = np.concatenate([rows_u.astype(np.float64), top_i.reshape(-1, 1).astype(np.float64),
+                                 top_s.reshape(-1, 1).astype(np.float64)], axis=1)
+        if world > 1:
+            packed = gather_rows(packed)
+        keep = packed[:, 1] >= 0
+        return _rec_frame(packed[keep, 0], packed[keep, 1], packed[keep, 2])
+
+    def _predict_pairs(self, pairs: pd.DataFrame, log: Optional[pd.DataFrame] = None) -> pd.DataFrame:
+        """Native pair scoring instead of the generic fallback (``base_rec.py:784-823``)."""
+        if self.engine is None:
+            raise AttributeError("CQL model is not fitted or loaded")
+        u = pairs["user_idx"].to_numpy().astype(np.int32)
+        it = pairs["item_idx"].to_numpy().astype(np.int32)
+        rel = self.engine.score_pairs(u, it, mode=self.score) if u.size else np.zeros(0, dtype=np.float32)
+        return _rec_frame(u, it, rel)
+
+    # ------------------------------------------------------------------ persistence (model_handler.py:38, :90)
+    def _save_model(self, path: str) -> None:
+        os.makedirs(path, exist_ok=True)
+        if self.engine is None:
+            with open(os.path.join(path, "meta.json"), "w") as f:
+                json.dump({"fitted": False}, f)
+            return
+        m, v, step = self.engine.get_optimizer()
+        np.savez(os.path.join(path, "state.npz"), state=self.engine.get_state(), adam_m=m, adam_v=v)
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump({"fitted": True, "step": step, "format": 1}, f)
+
+    def _load_model(self, path: str) -> None:
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if not meta.get("fitted"):
+            return
+        data = np.load(os.path.join(path, "state.npz"))
+        eng = self._make_engine()
+        eng.set_state(data["state"])
+        eng.set_optimizer(data["adam_m"], data["adam_v"], int(meta["step"]))

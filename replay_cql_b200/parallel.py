@@ -1,0 +1,80 @@
+"""Data-parallel plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch).
+
+Training shards *samples*: every rank draws its own minibatch from its own
+Philox/permutation stream, and the three gradient groups of an update are
+averaged over ranks.  Prediction shards *users*: no
+collective until the final gather of the U x k result.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def dist_info() -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from torch.distributed if initialised, else the torchrun env, else (0,1,0)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+    except Exception:  # pragma: no cover
+        pass
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) share of ``n`` units for ``rank``; sizes differ by at most one."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_mean_(tensor, group=None) -> None:
+    """In-place mean over ranks (works for NCCL on device tensors and gloo on CPU tensors)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    tensor.div_(world)
+
+
+class GradAllReducer:
+    """Averages the engine's gradient buffers in place, zero-copy, on torch's current stream."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self._views = {}
+
+    def __call__(self, buffer_id: int) -> None:
+        view = self._views.get(buffer_id)
+        if view is None:
+            view = self._views[buffer_id] = self.engine.grad_tensor(buffer_id)
+        allreduce_mean_(view, self.group)
+
+
+def gather_rows(local: np.ndarray, group=None) -> np.ndarray:
+    """Concatenate per-rank arrays (ragged in dim 0) on every rank, in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = np.zeros((mx,) + local.shape[1:], dtype=local.dtype)
+    pad[: local.shape[0]] = local
+    t = torch.from_numpy(pad).to(dev)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return np.concatenate([o.cpu().numpy()[:s] for o, s in zip(outs, sizes)], axis=0)

@@ -1,0 +1,240 @@
+"""pandas/pyarrow mirror of RePlay's ``Recommender`` template methods.
+
+The reference base class (``replay/models/base_rec.py``) is written against
+PySpark, which cannot run in this image (no JVM).  This module restates the
+template -- same method names, argument meaning, error behaviour and result
+schema -- on pandas, so a model written against it (``models.CQL``) is a
+drop-in for the hot path, and so the reference's conformance tests can be
+re-targeted here (``tests/test_recommender_conformance.py``).  Reference lines
+are cited per method.  Frames may be pandas, pyarrow Tables or (if pyspark is
+importable) Spark DataFrames; results come back in the flavour of the input.
+"""
+from __future__ import annotations
+
+import logging
+from abc import ABC, abstractmethod
+from typing import Any, Dict, Iterable, Optional, Union
+
+import numpy as np
+import pandas as pd
+
+from .frames import get_ids, like_input, to_pandas
+
+REC_COLUMNS = ["user_idx", "item_idx", "relevance"]  # replay/constants.py:25-31 (REC_SCHEMA)
+
+
+def _rec_frame(users, items, relevance) -> pd.DataFrame:
+    return pd.DataFrame({
+        "user_idx": np.asarray(users, dtype=np.int32),
+        "item_idx": np.asarray(items, dtype=np.int32),
+        "relevance": np.asarray(relevance, dtype=np.float64),
+    })
+
+
+def get_top_k(df: pd.DataFrame, partition_by: str, order_by: list, ascending: list, k: int) -> pd.DataFrame:
+    """``replay/utils.py:59-109``: ``row_number() over (partition ... order by ...) <= k``."""
+    if len(df) == 0:
+        return df
+    ordered = df.sort_values([partition_by] + order_by, ascending=[True] + ascending, kind="stable")
+    rank = ordered.groupby(partition_by, sort=False).cumcount()
+    return ordered[rank < k]
+
+
+def get_top_k_recs(recs: pd.DataFrame, k: int) -> pd.DataFrame:
+    """``replay/utils.py:112-127``.  Spark leaves ties arbitrary; here ties go to the lower item_idx."""
+    return get_top_k(recs, "user_idx", ["relevance", "item_idx"], [False, True], k)
+
+
+class Recommender(ABC):
+    """Base class for models that fit on an interaction log (``base_rec.py:59-78, 1202-1335``)."""
+
+    can_predict_cold_users: bool = False
+    can_predict_cold_items: bool = False
+    _search_space: Optional[Dict[str, Dict[str, Any]]] = None
+    _logger: Optional[logging.Logger] = None
+    study = None
+
+    # ------------------------------------------------------------ hooks (base_rec.py:143-149, 276-284, 376, 607)
+    @property
+    @abstractmethod
+    def _init_args(self) -> dict:
+        """Constructor kwargs, JSON-serialisable (``model_handler.py:40-43``)."""
+
+    @property
+    def _dataframes(self) -> dict:
+        return {}
+
+    def _save_model(self, path: str) -> None:
+        pass
+
+    def _load_model(self, path: str) -> None:
+        pass
+
+    @abstractmethod
+    def _fit(self, log: pd.DataFrame, user_features=None, item_features=None) -> None:
+        ...
+
+    @abstractmethod
+    def _predict(self, log: Optional[pd.DataFrame], k: int, users: pd.DataFrame, items: pd.DataFrame,
+                 user_features=None, item_features=None, filter_seen_items: bool = True) -> pd.DataFrame:
+        ...
+
+    def _clear_cache(self) -> None:
+        pass
+
+    # ------------------------------------------------------------ small public surface
+    @property
+    def logger(self) -> logging.Logger:
+        if self._logger is None:
+            self._logger = logging.getLogger("replay")
+        return self._logger
+
+    def set_params(self, **params: Any) -> None:
+        """``base_rec.py:315-324``."""
+        for param, value in params.items():
+            setattr(self, param, value)
+        self._clear_cache()
+
+    def __str__(self) -> str:
+        return type(self).__name__
+
+    def _get_fit_counts(self, entity: str) -> int:
+        if not hasattr(self, f"_num_{entity}s"):
+            setattr(self, f"_num_{entity}s", len(getattr(self, f"fit_{entity}s")))
+        return getattr(self, f"_num_{entity}s")
+
+    @property
+    def users_count(self) -> int:
+        return self._get_fit_counts("user")
+
+    @property
+    def items_count(self) -> int:
+        return self._get_fit_counts("item")
+
+    def _get_fit_dims(self, entity: str) -> int:
+        """max idx + 1, recomputed lazily after ``load`` (``base_rec.py:671-695``)."""
+        if not hasattr(self, f"_{entity}_dim_size"):
+            frame = getattr(self, f"fit_{entity}s")  # AttributeError before fit, like the reference
+            setattr(self, f"_{entity}_dim_size", int(frame[f"{entity}_idx"].max()) + 1)
+        return getattr(self, f"_{entity}_dim_size")
+
+    @property
+    def _user_dim(self) -> int:
+        return self._get_fit_dims("user")
+
+    @property
+    def _item_dim(self) -> int:
+        return self._get_fit_dims("item")
+
+    # ------------------------------------------------------------ fit (base_rec.py:329-373, 1205-1217)
+    def fit(self, log: Any) -> None:
+        self._fit_wrap(log, None, None)
+
+    def _fit_wrap(self, log: Any, user_features=None, item_features=None) -> None:
+        self.logger.debug("Starting fit %s", type(self).__name__)
+        pdf = to_pandas(log)
+        self.fit_users = pd.DataFrame({"user_idx": np.sort(pd.unique(pdf["user_idx"]))})
+        self.fit_items = pd.DataFrame({"item_idx": np.sort(pd.unique(pdf["item_idx"]))})
+        self._num_users = len(self.fit_users)
+        self._num_items = len(self.fit_items)
+        self._user_dim_size = int(self.fit_users["user_idx"].max()) + 1
+        self._item_dim_size = int(self.fit_items["item_idx"].max()) + 1
+        self._fit(pdf, user_features, item_features)
+
+    # ------------------------------------------------------------ cold filtering (base_rec.py:560-603)
+    def _filter_cold(self, df: Optional[pd.DataFrame], entity: str):
+        if getattr(self, f"can_predict_cold_{entity}s") or df is None:
+            return 0, df
+        col = f"{entity}_idx"
+        known = getattr(self, f"fit_{entity}s")[col]
+        mask = df[col].isin(known)
+        num_cold = int(df.loc[~mask, col].nunique())
+        if num_cold == 0:
+            return 0, df
+        return num_cold, df[mask]
+
+    def _filter_cold_for_predict(self, main_df, log_df, entity: str):
+        num_new, main_df = self._filter_cold(main_df, entity)
+        if num_new > 0:
+            self.logger.info("%s model can't predict cold %ss, they will be ignored", self, entity)
+        _, log_df = self._filter_cold(log_df, entity)
+        return main_df, log_df
+
+    # ------------------------------------------------------------ seen filter (base_rec.py:417-464)
+    def _filter_seen(self, recs: pd.DataFrame, log: pd.DataFrame, k: int, users: pd.DataFrame) -> pd.DataFrame:
+        """Drop items present in ``log`` from each user's recs, after the reference's crop to k + seen."""
+        users_log = log.merge(users[["user_idx"]].drop_duplicates(), on="user_idx")
+        num_seen = users_log.groupby("user_idx")["item_idx"].count().rename("seen_count").reset_index()
+        max_seen = int(num_seen["seen_count"].max()) if len(num_seen) else 0
+        if len(recs) == 0:
+            return recs
+        ordered = recs.sort_values(["user_idx", "relevance", "item_idx"], ascending=[True, False, True], kind="stable")
+        ordered = ordered.assign(temp_rank=ordered.groupby("user_idx", sort=False).cumcount() + 1)
+        ordered = ordered[ordered["temp_rank"] <= max_seen + k]
+        ordered = ordered.merge(num_seen, on="user_idx", how="left")
+        ordered["seen_count"] = ordered["seen_count"].fillna(0)
+        ordered = ordered[ordered["temp_rank"] <= ordered["seen_count"] + k].drop(columns=["temp_rank", "seen_count"])
+        seen_key = users_log["user_idx"].to_numpy().astype(np.int64) * (2 ** 32) + users_log["item_idx"].to_numpy().astype(np.int64)
+        rec_key = ordered["user_idx"].to_numpy().astype(np.int64) * (2 ** 32) + ordered["item_idx"].to_numpy().astype(np.int64)
+        return ordered[~np.isin(rec_key, seen_key)]
+
+    # ------------------------------------------------------------ predict (base_rec.py:467-539, 1220-1257)
+    def predict(self, log: Any, k: int, users: Optional[Union[Any, Iterable]] = None,
+                items: Optional[Union[Any, Iterable]] = None, filter_seen_items: bool = True,
+                recs_file_path: Optional[str] = None):
+        return self._predict_wrap(log, k, users, items, None, None, filter_seen_items, recs_file_path)
+
+    def _predict_wrap(self, log, k: int, users=None, items=None, user_features=None, item_features=None,
+                      filter_seen_items: bool = True, recs_file_path: Optional[str] = None):
+        self.logger.debug("Starting predict %s", type(self).__name__)
+        template = log
+        log_pdf = to_pandas(log)
+        user_data = users if users is not None else (log_pdf if log_pdf is not None else self.fit_users)
+        users_df = get_ids(user_data, "user_idx")
+        users_df, log_pdf = self._filter_cold_for_predict(users_df, log_pdf, "user")
+        item_data = items if items is not None else self.fit_items
+        items_df = get_ids(item_data, "item_idx")
+        items_df, log_pdf = self._filter_cold_for_predict(items_df, log_pdf, "item")
+        if len(items_df) < k:
+            self.logger.debug("k = %d > number of items = %d", k, len(items_df))
+        recs = self._predict(log_pdf, k, users_df, items_df, user_features, item_features, filter_seen_items)
+        if filter_seen_items and log_pdf is not None:
+            recs = self._filter_seen(recs=recs, log=log_pdf, users=users_df, k=k)
+        recs = get_top_k_recs(recs, k)[REC_COLUMNS].reset_index(drop=True)
+        if recs_file_path is not None:
+            recs.to_parquet(recs_file_path, index=False)
+            return None
+        return like_input(recs, template)
+
+    def fit_predict(self, log: Any, k: int, users=None, items=None, filter_seen_items: bool = True,
+                    recs_file_path: Optional[str] = None):
+        """``base_rec.py:1287-1323``."""
+        self._fit_wrap(log, None, None)
+        return self._predict_wrap(log, k, users, items, None, None, filter_seen_items, recs_file_path)
+
+    # ------------------------------------------------------------ predict_pairs (base_rec.py:725-823, 1259-1285)
+    def predict_pairs(self, pairs: Any, log: Any = None, recs_file_path: Optional[str] = None,
+                      k: Optional[int] = None):
+        template = pairs
+        pairs_pdf, log_pdf = to_pandas(pairs), to_pandas(log)
+        if sorted(pairs_pdf.columns) != ["item_idx", "user_idx"]:
+            raise ValueError("pairs must be a dataframe with columns strictly [user_idx, item_idx]")
+        pairs_pdf, log_pdf = self._filter_cold_for_predict(pairs_pdf, log_pdf, "user")
+        pairs_pdf, log_pdf = self._filter_cold_for_predict(pairs_pdf, log_pdf, "item")
+        pred = self._predict_pairs(pairs_pdf, log_pdf)
+        if k:
+            pred = get_top_k(pred, "user_idx", ["relevance", "item_idx"], [False, True], k)
+        pred = pred[REC_COLUMNS].reset_index(drop=True)
+        if recs_file_path is not None:
+            pred.to_parquet(recs_file_path, index=False)
+            return None
+        return like_input(pred, template)
+
+    def _predict_pairs(self, pairs: pd.DataFrame, log: Optional[pd.DataFrame] = None) -> pd.DataFrame:
+        """Generic fallback (``base_rec.py:784-823``): full predict joined with ``pairs``."""
+        self.logger.warning("native predict_pairs is not implemented for this model. "
+                            "Falling back to usual predict method and filtering the results.")
+        users = pd.DataFrame({"user_idx": pd.unique(pairs["user_idx"])})
+        items = pd.DataFrame({"item_idx": pd.unique(pairs["item_idx"])})
+        pred = self._predict(log, len(items), users, items, None, None, False)
+        return pred.merge(pairs[["user_idx", "item_idx"]], on=["user_idx", "item_idx"], how="inner")

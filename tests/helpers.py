@@ -69,3 +69,29 @@ def rel_err(a, b) -> float:
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / den) if den > 0 else float(np.max(np.abs(a - b)))
+
+
+def flat_to_oracle_state(flat: np.ndarray, cfg, dtype=torch.float32):
+    """Flat product-layout state -> fresh oracle state dict (zero Adam moments, step 0)."""
+    un = layout.unpack_state(np.asarray(flat, dtype=np.float32), cfg.n_critics)
+    t = lambda net: {k: torch.from_numpy(v.copy()).to(dtype) for k, v in net.items()}
+    st = O.init_state(cfg, seed=0, dtype=dtype)
+    st["actor"], st["targ_actor"] = t(un["actor"]), t(un["targ_actor"])
+    st["critics"] = [t(c) for c in un["critics"]]
+    st["targ_critics"] = [t(c) for c in un["targ_critics"]]
+    st["log_temp"] = torch.tensor(un["log_temp"], dtype=dtype)
+    st["log_alpha"] = torch.tensor(un["log_alpha"], dtype=dtype)
+    return st
+
+
+def digest(flat: np.ndarray, n_probe: int = 512, seed: int = 99) -> np.ndarray:
+    """Compact fingerprint of a flat buffer: per-network-slot L2 norm and sum + probed entries."""
+    flat = np.asarray(flat, dtype=np.float64)
+    n_slots = flat.size // layout.NET_STRIDE
+    parts = []
+    for s in range(n_slots):
+        sl = flat[s * layout.NET_STRIDE:(s + 1) * layout.NET_STRIDE]
+        parts += [np.sqrt((sl * sl).sum()), sl.sum()]
+    parts += list(flat[n_slots * layout.NET_STRIDE:n_slots * layout.NET_STRIDE + 2])
+    idx = np.random.default_rng(seed).integers(0, n_slots * layout.NET_STRIDE, size=n_probe)
+    return np.concatenate([np.asarray(parts), flat[idx]])

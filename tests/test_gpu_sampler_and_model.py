@@ -1,0 +1,112 @@
+"""GPU: replay table + sampler (K1) properties, and the CQL model end to end through the
+Recommender API (fit / predict / predict_pairs / save / load), re-targeting the reference's
+conformance tests (tests/models/test_all_models.py, test_save_load_models.py:48-70)."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from replay_cql_b200.mdp import build_mdp, to_transitions
+from replay_cql_b200.models import CQL
+from replay_cql_b200.model_handler import load, save
+from replay_cql_b200.synthetic import make_log
+
+pytestmark = pytest.mark.gpu
+
+
+def test_replay_table_and_sampler(engine_factory):
+    log = make_log("tiny")
+    mdp = build_mdp(log, top_k=10, seed=1)
+    tr = to_transitions(mdp)
+    N = len(mdp)
+    eng = engine_factory(batch_size=64)
+    eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+    assert eng.n_transitions == N
+    # explicit indices: bit-exact rows (table build on the GPU == host expansion)
+    idx = np.random.default_rng(0).integers(0, N, 777)
+    rows = eng.sample_rows(777, idx=idx).cpu().numpy()
+    want = np.concatenate([tr["obs"], tr["act"], tr["rew"], tr["next_obs"], tr["term"], np.zeros((N, 1), np.float32)], 1)[idx]
+    assert np.array_equal(rows, want)
+    # one epoch of the permutation stream visits n_eff distinct rows exactly once
+    n_eff = N - N % 64
+    ep0 = eng.sample_rows(n_eff, pos=0).cpu().numpy()
+    full = np.concatenate([tr["obs"], tr["act"], tr["rew"], tr["next_obs"], tr["term"], np.zeros((N, 1), np.float32)], 1)
+    # act carries per-row Gaussian noise -> rows are unique; map back to indices
+    lookup = {full[i].tobytes(): i for i in range(N)}
+    seen_idx = np.array([lookup[r.tobytes()] for r in ep0])
+    assert len(set(seen_idx.tolist())) == n_eff
+    ep1 = eng.sample_rows(n_eff, pos=n_eff).cpu().numpy()
+    idx1 = np.array([lookup[r.tobytes()] for r in ep1])
+    assert len(set(idx1.tolist())) == n_eff and not np.array_equal(idx1, seen_idx)   # fresh permutation
+    assert abs(np.corrcoef(seen_idx[:-1], seen_idx[1:])[0, 1]) < 0.1               # shuffled, not a scan
+
+
+def test_sampled_updates_run_and_are_deterministic(engine_factory):
+    log = make_log("tiny")
+    mdp = build_mdp(log, seed=1)
+    outs = []
+    for _ in range(2):
+        eng = engine_factory(batch_size=64, seed=5)
+        eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+        m = eng.update(20)
+        assert all(np.isfinite(v) for v in m.values())
+        outs.append(eng.get_state())
+    assert np.array_equal(outs[0], outs[1])          # same seed -> bit-identical weights
+    m_, v_, step = eng.get_optimizer()
+    assert step == 20
+
+
+@pytest.fixture(scope="module")
+def fitted():
+    log = make_log("tiny")
+    model = CQL(top_k=3, n_epochs=2, batch_size=64, seed=3)
+    model.fit(log)
+    yield model, log
+    model.engine.close()
+
+
+def test_fit_predict_contract(fitted):
+    model, log = fitted
+    assert model._user_dim == 64 and model._item_dim == int(log["item_idx"].max()) + 1
+    recs = model.predict(log, k=5)
+    assert list(recs.columns) == ["user_idx", "item_idx", "relevance"]
+    assert recs.groupby("user_idx").size().max() <= 5 and recs["user_idx"].nunique() == 64
+    seen = set(zip(log["user_idx"], log["item_idx"]))
+    assert not any((u, i) in seen for u, i in zip(recs["user_idx"], recs["item_idx"]))
+    # subset of users / items, no filtering
+    r2 = model.predict(log, k=3, users=[1, 2, 999], items=[0, 1, 2, 3], filter_seen_items=False)
+    assert set(r2["user_idx"]) == {1, 2} and set(r2["item_idx"]) <= {0, 1, 2, 3}
+    assert r2.groupby("user_idx").size().tolist() == [3, 3]
+
+
+def test_predict_and_predict_pairs_agree(fitted):   # tests/models/test_all_models.py:63-96
+    model, log = fitted
+    recs = model.predict(log, k=4, filter_seen_items=False)
+    pairs = model.predict_pairs(recs[["user_idx", "item_idx"]], log)
+    merged = recs.merge(pairs, on=["user_idx", "item_idx"], suffixes=("_a", "_b"))
+    assert len(merged) == len(recs)
+    scale = max(1.0, merged["relevance_a"].abs().max())
+    assert (merged["relevance_a"] - merged["relevance_b"]).abs().max() <= 1e-5 * scale
+    assert model.predict_pairs(recs[["user_idx", "item_idx"]], log, k=2).groupby("user_idx").size().max() <= 2
+
+
+def test_save_load_roundtrip(fitted, tmp_path):     # tests/models/test_save_load_models.py:48-70
+    model, log = fitted
+    base = model.predict(log, k=5)
+    path = str(tmp_path / "cql_model")
+    save(model, path)
+    loaded = load(path)
+    assert str(loaded) == "CQL" and loaded._init_args == model._init_args
+    again = loaded.predict(log, k=5)
+    pd.testing.assert_frame_equal(base, again)
+    loaded.engine.close()
+
+
+def test_score_policy_mode(fitted):
+    model, log = fitted
+    model.score = "policy"
+    try:
+        recs = model.predict(log, k=2)
+        assert recs["relevance"].abs().max() <= 1.0     # tanh(mu)
+    finally:
+        model.score = "q"

@@ -1,0 +1,120 @@
+"""GPU parity of K5 (user x item relevance + lazy seen filter + top-k) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): Q-scores within 1e-5 (relative to max|Q|);
+top-k lists identical up to exact ties.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cql_oracle as O
+from oracle import recs_oracle
+from replay_cql_b200 import layout
+from tests import helpers as Hp
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+TOL = 1e-5
+
+
+def _lists_match(ti, ts, ri, rs):
+    """identical lists except where the reference scores tie (to TOL)"""
+    scale = max(1.0, float(np.max(np.abs(rs[np.isfinite(rs)]))) if np.isfinite(rs).any() else 1.0)
+    fin = np.isfinite(rs)
+    assert np.array_equal(np.isfinite(ts), fin)
+    assert np.max(np.abs(ts[fin] - rs[fin])) <= TOL * scale
+    bad = ti != ri
+    for r, c in zip(*np.nonzero(bad)):
+        # a swap is only legal between (near-)equal scores
+        assert abs(rs[r, c] - ts[r, c]) <= TOL * scale
+        assert ti[r, c] in ri[r] or np.any(np.abs(rs[r] - ts[r, c]) <= TOL * scale)
+
+
+@pytest.mark.parametrize("name", ["score_small.npz", "score_k1.npz"])
+def test_golden_scores(engine_factory, name):
+    z = np.load(GOLD / name)
+    eng = engine_factory(batch_size=64)
+    eng.set_state(layout.init_state(2, int(z["init_seed"])))
+    ti, ts = eng.score_topk(z["users"], z["items"], int(z["k"]), z["seen_indptr"], z["seen_items"], mode="q")
+    _lists_match(ti, ts, z["top_items"], z["top_scores"])
+    pi, ps = eng.score_topk(z["users"], z["items"], int(z["k"]), z["seen_indptr"], z["seen_items"], mode="policy")
+    _lists_match(pi, ps, z["pol_items"], z["pol_scores"])
+
+
+def _oracle_state(seed):
+    cfg = O.OracleConfig()
+    flat = layout.init_state(cfg.n_critics, seed)
+    return flat, Hp.flat_to_oracle_state(flat, cfg)
+
+
+@pytest.mark.parametrize("U,I,k", [(5, 1000, 10), (700, 130, 7), (3, 63, 100), (2, 64, 64)])
+def test_random_against_brute_force(engine_factory, U, I, k):
+    flat, st = _oracle_state(11)
+    eng = engine_factory(batch_size=64)
+    eng.set_state(flat)
+    rng = np.random.default_rng(U * 1000 + I)
+    users = np.sort(rng.choice(6040, size=U, replace=False)).astype(np.int32)
+    items = np.sort(rng.choice(3706, size=I, replace=False)).astype(np.int32)
+    seen = {int(u): set(rng.choice(items, size=int(rng.integers(0, min(50, I))), replace=False).tolist()) for u in users}
+    seen[int(users[0])] = set(items.tolist())          # a user who has seen everything
+    indptr = np.zeros(int(users.max()) + 2, dtype=np.int64)
+    flat_seen = []
+    for u in range(int(users.max()) + 1):
+        flat_seen.extend(sorted(seen.get(u, ())))
+        indptr[u + 1] = len(flat_seen)
+    ri, rs = recs_oracle.brute_force_topk(lambda obs: O.relevance(st, torch.from_numpy(obs), "q").numpy(),
+                                          users, items, seen, k)
+    ti, ts = eng.score_topk(users, items, k, indptr, np.asarray(flat_seen, dtype=np.int32))
+    _lists_match(ti, ts, ri, rs)
+    assert np.all(ti[0] == -1) and np.all(np.isneginf(ts[0]))
+    # without the filter
+    ri2, rs2 = recs_oracle.brute_force_topk(lambda obs: O.relevance(st, torch.from_numpy(obs), "q").numpy(),
+                                            users[:2], items, {}, k)
+    ti2, ts2 = eng.score_topk(users[:2], items, k)
+    _lists_match(ti2, ts2, ri2, rs2)
+
+
+def test_score_pairs_and_edge_cases(engine_factory):
+    flat, st = _oracle_state(12)
+    eng = engine_factory(batch_size=64)
+    eng.set_state(flat)
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, 6040, 1000).astype(np.int32)
+    i = rng.integers(0, 3706, 1000).astype(np.int32)
+    obs = torch.from_numpy(np.stack([u, i], 1).astype(np.float32))
+    for mode in ("q", "policy"):
+        ref = O.relevance(st, obs, mode).numpy()
+        got = eng.score_pairs(u, i, mode)
+        assert np.max(np.abs(got - ref)) <= TOL * max(1.0, np.max(np.abs(ref)))
+    assert eng.score_pairs([], []).shape == (0,)
+    ti, ts = eng.score_topk([], [1, 2, 3], 3)
+    assert ti.shape == (0, 3)
+    ti, ts = eng.score_topk([4, 5], [], 3)                      # no candidates -> all padding
+    assert np.all(ti == -1) and np.all(np.isneginf(ts))
+    with pytest.raises(ValueError):
+        eng.score_topk([1], [1], 0)
+    with pytest.raises(ValueError):
+        eng.score_topk([1], [1], 5000)
+
+
+def test_standalone_topk_filter(engine_factory):
+    eng = engine_factory(batch_size=64)
+    rng = np.random.default_rng(3)
+    U, I, k = 37, 5003, 10
+    scores = rng.standard_normal((U, I)).astype(np.float32)
+    scores[:, ::7] = scores[:, 1::7]                            # plenty of exact ties
+    seen = {u: set(rng.choice(I, size=60, replace=False).tolist()) for u in range(U)}
+    indptr = np.zeros(U + 1, dtype=np.int64)
+    flat = []
+    for u in range(U):
+        flat.extend(sorted(seen[u]))
+        indptr[u + 1] = len(flat)
+    ri, rs = recs_oracle.brute_force_topk(lambda obs: scores[int(obs[0, 0])], np.arange(U), np.arange(I), seen, k)
+    dev = "cuda:0"
+    ti, ts = eng.topk_filter_device(torch.from_numpy(scores).to(dev), k,
+                                    seen_indptr_t=torch.from_numpy(indptr).to(dev),
+                                    seen_items_t=torch.tensor(flat, dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(ti.cpu().numpy(), ri) and np.array_equal(ts.cpu().numpy(), rs)   # bit-exact selection

@@ -1,0 +1,155 @@
+"""CPU: the pandas mirror of RePlay's Recommender template behaves like the reference's
+(re-targeted from /root/reference/tests/models/test_base_rec.py and test_all_models.py),
+and its post-processing equals the line-by-line oracle restatement (oracle/recs_oracle.py)."""
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import recs_oracle
+from replay_cql_b200.recommender import Recommender, get_top_k_recs
+
+LOG = pd.DataFrame([  # reference fixture `log`, tests/utils.py:59-76
+    [0, 0, datetime(2019, 8, 22), 4.0], [0, 2, datetime(2019, 8, 23), 3.0], [0, 1, datetime(2019, 8, 27), 2.0],
+    [1, 3, datetime(2019, 8, 24), 3.0], [1, 0, datetime(2019, 8, 25), 4.0], [2, 1, datetime(2019, 8, 26), 5.0],
+    [2, 0, datetime(2019, 8, 26), 5.0], [2, 2, datetime(2019, 8, 26), 3.0], [3, 1, datetime(2019, 8, 26), 5.0],
+    [3, 0, datetime(2019, 8, 26), 5.0], [3, 0, datetime(2019, 8, 26), 1.0]],
+    columns=["user_idx", "item_idx", "timestamp", "relevance"])
+
+
+class DerivedRec(Recommender):
+    """Minimal subclass, as in tests/models/test_base_rec.py:12-35."""
+
+    @property
+    def _init_args(self):
+        return {}
+
+    def _fit(self, log, user_features=None, item_features=None):
+        pass
+
+    def _predict(self, log, k, users, items, user_features=None, item_features=None, filter_seen_items=True):
+        pass
+
+
+class PopLike(Recommender):
+    """Returns ALL user x item pairs with popularity as relevance (Appendix-B style _predict)."""
+
+    @property
+    def _init_args(self):
+        return {}
+
+    def _fit(self, log, user_features=None, item_features=None):
+        self.pop = log.groupby("item_idx")["user_idx"].nunique() / log["user_idx"].nunique()
+
+    def _predict(self, log, k, users, items, user_features=None, item_features=None, filter_seen_items=True):
+        u = users["user_idx"].to_numpy()
+        i = items["item_idx"].to_numpy()
+        return pd.DataFrame({"user_idx": np.repeat(u, len(i)), "item_idx": np.tile(i, len(u)),
+                             "relevance": np.tile(self.pop.reindex(i).fillna(0.0).to_numpy(), len(u))})
+
+
+@pytest.mark.parametrize("array", [None, [1, 2, 2, 3]])
+def test_extract_if_needed(array):   # test_base_rec.py:43-48
+    from replay_cql_b200.frames import get_ids
+    log = pd.DataFrame({"test": [1, 2, 3]})
+    assert sorted(get_ids(array if array is not None else log, "test")["test"]) == [1, 2, 3]
+    with pytest.raises(ValueError):
+        get_ids(5, "test")
+
+
+def test_users_items_count_and_str():   # test_base_rec.py:51-66
+    model = DerivedRec()
+    with pytest.raises(AttributeError):
+        model._user_dim
+    with pytest.raises(AttributeError):
+        model._item_dim
+    model.fit(LOG)
+    assert model._user_dim == 4 and model._item_dim == 4
+    assert model.users_count == 4 and model.items_count == 4
+    assert str(model) == "DerivedRec"
+
+
+def test_filter_seen():   # test_all_models.py:265-278
+    model = PopLike()
+    model.fit(LOG[LOG["user_idx"] != 0])
+    assert len(model.predict(log=LOG, users=[3], k=5)) == 2          # user 3 saw items 0,1 -> 2 left
+    assert len(model.predict(log=LOG, users=[0], k=5)) == 0          # cold user is dropped
+    model.can_predict_cold_users = True
+    assert len(model.predict(log=LOG, users=[0], k=5)) == 1          # saw 0,1,2 -> item 3 left
+    assert len(model.predict(log=LOG, users=[0], k=5, filter_seen_items=False)) == 4
+
+
+def test_predict_pairs_k_and_columns():   # test_all_models.py:128-144
+    model = PopLike()
+    model.fit(LOG)
+    pairs = LOG[["user_idx", "item_idx"]]
+    assert model.predict_pairs(pairs, log=LOG, k=2).groupby("user_idx").size().max() <= 2
+    assert model.predict_pairs(pairs, log=LOG).groupby("user_idx").size().max() > 2
+    with pytest.raises(ValueError):
+        model.predict_pairs(LOG[["user_idx", "item_idx", "relevance"]])
+
+
+def test_recs_file_path(tmp_path):   # test_all_models.py:406-447
+    model = PopLike()
+    model.fit(LOG)
+    direct = model.predict(LOG, k=2)
+    path = str(tmp_path / "recs.parquet")
+    assert model.predict(LOG, k=2, recs_file_path=path) is None
+    pd.testing.assert_frame_equal(direct, pd.read_parquet(path))
+    assert list(direct.columns) == ["user_idx", "item_idx", "relevance"]
+
+
+def test_pyarrow_in_pyarrow_out():
+    import pyarrow as pa
+    model = PopLike()
+    table = pa.Table.from_pandas(LOG)
+    model.fit(table)
+    out = model.predict(table, k=1)
+    assert isinstance(out, pa.Table) and out.column_names == ["user_idx", "item_idx", "relevance"]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_wrapper_equals_oracle_restatement(seed):
+    rng = np.random.default_rng(seed)
+    U, I, k = 9, 30, 4
+    log = pd.DataFrame({"user_idx": rng.integers(0, U - 1, 80), "item_idx": rng.integers(0, I, 80),
+                        "timestamp": np.arange(80), "relevance": 1.0})
+
+    class Rand(PopLike):
+        def _predict(self, log, k, users, items, user_features=None, item_features=None, filter_seen_items=True):
+            df = super()._predict(log, k, users, items)
+            table = np.random.default_rng(seed).standard_normal((U, I))   # relevance = f(user, item)
+            df["relevance"] = table[df["user_idx"].to_numpy(), df["item_idx"].to_numpy()]
+            return df
+
+    model = Rand()
+    model.fit(log)
+    users = pd.DataFrame({"user_idx": np.sort(log["user_idx"].unique())})
+    items = pd.DataFrame({"item_idx": np.sort(log["item_idx"].unique())})
+    allp = model._predict(log, k, users, items)
+    ref = recs_oracle.predict_wrap(allp, log, k, users)
+    got = model.predict(log, k).sort_values(["user_idx", "relevance", "item_idx"], ascending=[True, False, True]).reset_index(drop=True)
+    pd.testing.assert_frame_equal(ref.reset_index(drop=True), got, check_dtype=False)
+
+
+def test_top_k_doctest_case():   # utils.py:69-92
+    log = pd.DataFrame({"user_idx": [1, 1, 1, 2], "item_idx": [2, 3, 4, 1], "relevance": [1.0, 1.0, 0.5, 1.0]})
+    out = get_top_k_recs(log, 1)
+    assert sorted(out["user_idx"]) == [1, 2] and out[out.user_idx == 2]["item_idx"].iloc[0] == 1
+
+
+def test_cql_init_args_roundtrip_json():
+    import json
+    from inspect import getfullargspec
+    from replay_cql_b200.models import CQL
+    m = CQL(top_k=3, n_epochs=2, batch_size=64, n_critics=3)
+    args = json.loads(json.dumps(m._init_args))
+    names = getfullargspec(CQL.__init__).args[1:]
+    assert sorted(args) == sorted(names)            # model_handler.py:70-80 can rebuild the model
+    m2 = CQL(**args)
+    assert m2._init_args == m._init_args and str(m2) == "CQL"
+    with pytest.raises(ValueError):
+        CQL(use_gpu=False)
+    with pytest.raises(ValueError):
+        CQL(soft_q_backup=True)
