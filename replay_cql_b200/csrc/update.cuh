@@ -108,7 +108,7 @@ __device__ __forceinline__ Sample policy_sample(float mu, float ls, float eps, i
   Sample s;
   s.std_ = expf(ls);
   s.raw = __fadd_rn(mu, __fmul_rn(s.std_, eps));
-  s.a = tanhf(s.raw);
+  s.a = (float)tanh((double)s.raw);   // correctly rounded: log(1-a^2+1e-6) amplifies tanh's last ulp ~1e6x
   s.t = __fdiv_rn(__fsub_rn(s.raw, mu), s.std_);
   const float normal_logp =
       __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, __fmul_rn(s.t, s.t)), ls), 0.91893853320467274f);
@@ -170,7 +170,7 @@ __global__ void k_prep(const float4* __restrict__ batch, const float* __restrict
       XC[(int64_t)b * (n3 + 1) + n3] = make_float4(r0.x, r0.y, r0.z, 0.f);
       offC[(int64_t)b * (n3 + 1) + n3] = 0.f;
     } else if (j == 2 * n3 + 1) {   // TD target row (s', best_action(s'))
-      XT[b] = make_float4(r1.x, r1.y, tanhf(mu_n), 0.f);
+      XT[b] = make_float4(r1.x, r1.y, (float)tanh((double)mu_n), 0.f);
     } else if (j == 2 * n3 + 2) {   // actor-step row (s, a_pi)
       const Sample s = policy_sample(mu_s, ls_s, noise[B + 6 * Bn + b], squash);
       XP[b] = make_float4(r0.x, r0.y, s.a, 0.f);
