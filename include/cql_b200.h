@@ -168,6 +168,11 @@ int  cql_topk_filter_dev(cql_handle* h, const float* scores_dev, int64_t n_users
  * forward, [7] = everything else.  The update is a real one (weights advance). */
 int  cql_timed_update(cql_handle* h, float* out_ms8, void* stream);
 
+/* Self-test of the tensor-core building blocks (tcgen05.mma + TMEM + operand layout):
+ * D[128][n] = A[128][k] * B[n][k]^T with `precision` = CQL_PREC_BF16 or CQL_PREC_TF32X3 (host pointers). */
+int  cql_selftest_umma(cql_handle* h, int precision, const float* A_host, const float* B_host,
+                       int n, int k, float* D_host);
+
 /* number of kernels this library has launched on the handle (bench "gpu_launches") */
 int64_t cql_launch_count(const cql_handle* h);
 

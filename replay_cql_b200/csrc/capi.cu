@@ -5,6 +5,7 @@
 #include "engine.cuh"
 #include "update.cuh"
 #include "score.cuh"
+#include "tc_selftest.cuh"
 
 using namespace cql;
 
@@ -370,6 +371,38 @@ int cql_update(cql_handle* ch, int64_t n_steps, float* metrics6, void* stream) {
       CQL_CUDA(cudaStreamSynchronize(st));
       std::memcpy(metrics6, h.metrics_host, 6 * sizeof(float));
     }
+  });
+}
+
+int cql_selftest_umma(cql_handle* ch, int precision, const float* A_host, const float* B_host, int n, int k,
+                      float* D_host) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(precision == CQL_PREC_TF32X3 || precision == CQL_PREC_BF16, "cql_selftest_umma: precision must be tf32x3 or bf16");
+    const bool tf32 = precision == CQL_PREC_TF32X3;
+    CQL_REQUIRE(A_host && B_host && D_host, "cql_selftest_umma: NULL pointer");
+    CQL_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "cql_selftest_umma: n must be a multiple of 16 in 16..256");
+    CQL_REQUIRE(k >= 32 && k % 32 == 0, "cql_selftest_umma: k must be a multiple of 32");
+    const size_t smem = tc::selftest_smem(tf32, n, k);
+    CQL_REQUIRE(smem <= 227 * 1024, "cql_selftest_umma: operands do not fit in shared memory");
+    float *dA, *dB, *dD;
+    CQL_CUDA(cudaMalloc(&dA, (size_t)128 * k * 4));
+    CQL_CUDA(cudaMalloc(&dB, (size_t)n * k * 4));
+    CQL_CUDA(cudaMalloc(&dD, (size_t)128 * n * 4));
+    cudaStream_t st = h.own_stream;
+    CQL_CUDA(cudaMemcpyAsync(dA, A_host, (size_t)128 * k * 4, cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(dB, B_host, (size_t)n * k * 4, cudaMemcpyHostToDevice, st));
+    if (tf32) {
+      CQL_CUDA(cudaFuncSetAttribute(tc::umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc::umma_selftest_kernel<true><<<1, 128, smem, st>>>(dA, dB, dD, n, k);
+    } else {
+      CQL_CUDA(cudaFuncSetAttribute(tc::umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc::umma_selftest_kernel<false><<<1, 128, smem, st>>>(dA, dB, dD, n, k);
+    }
+    CQL_LAUNCH_CHECK(&h);
+    CQL_CUDA(cudaMemcpyAsync(D_host, dD, (size_t)128 * n * 4, cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+    CQL_CUDA(cudaFree(dA)); CQL_CUDA(cudaFree(dB)); CQL_CUDA(cudaFree(dD));
   });
 }
 

@@ -202,6 +202,17 @@ class CqlEngine:
         keys = ("critic_fwd", "critic_bwd1", "critic_bwd2", "update", "actor_step_fwd", "actor_bwd", "actor_fwd", "other")
         return dict(zip(keys, map(float, out)))
 
+    def selftest_umma(self, A: np.ndarray, B: np.ndarray, precision: str) -> np.ndarray:
+        """D = A @ B.T on the tensor cores (A [128,k], B [n,k]); building-block self-test."""
+        A, B = _f32(A), _f32(B)
+        n, k = B.shape
+        if A.shape != (128, k):
+            raise ValueError("A must be [128, k]")
+        D = np.empty((128, n), dtype=np.float32)
+        self._check(self._lib.cql_selftest_umma(self._h, PRECISIONS[precision], _ptr(A), _ptr(B), n, k, _ptr(D)),
+                    "cql_selftest_umma")
+        return D
+
     def pack_noise(self, noise: Dict[str, np.ndarray]) -> np.ndarray:
         B, n = self.hp.batch_size, self.hp.n_action_samples
         parts = []
