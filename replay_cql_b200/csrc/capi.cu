@@ -49,6 +49,10 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
   CQL_CUDA(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, score_smem(CQL_MAX_TOPK)));
   CQL_CUDA(cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false>::BYTES));
 }
 
 void create_impl(const cql_config* cfg, cql_handle* ch) {
@@ -58,7 +62,8 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   CQL_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= (1 << 20), "cql_create: batch_size out of range");
   CQL_REQUIRE(cfg->n_critics >= 1 && cfg->n_critics <= CQL_MAX_CRITICS, "cql_create: n_critics must be 1..4");
   CQL_REQUIRE(cfg->n_action_samples >= 1 && cfg->n_action_samples <= 10, "cql_create: n_action_samples must be 1..10");
-  CQL_REQUIRE(cfg->precision == CQL_PREC_FP32, "cql_create: only CQL_PREC_FP32 is built in this version");
+  CQL_REQUIRE(cfg->precision == CQL_PREC_FP32 || cfg->precision == CQL_PREC_TF32X3 || cfg->precision == CQL_PREC_BF16,
+              "cql_create: bad precision");
   CQL_REQUIRE(cfg->squash == CQL_SQUASH_EPS || cfg->squash == CQL_SQUASH_SOFTPLUS, "cql_create: bad squash");
   CQL_REQUIRE(cfg->world_size >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world_size, "cql_create: bad rank/world_size");
   int ndev = 0;
@@ -121,6 +126,13 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   h.smallA = h.dalloc<float>((size_t)tB * SMALL_STRIDE);
   h.pw2C = h.dalloc<float>((size_t)C * h.splitsC * H * H);
   h.pw2A = h.dalloc<float>((size_t)h.splitsA * H * H);
+  if (cfg->precision != CQL_PREC_FP32) {
+    h.packed_net_bytes = cfg->precision == CQL_PREC_TF32X3 ? tc::Cfg<true>::PACKED_NET_BYTES : tc::Cfg<false>::PACKED_NET_BYTES;
+    h.packed_fwd = h.dalloc<uint8_t>((size_t)(2 + 2 * C) * h.packed_net_bytes);
+    const int slices = cfg->precision == CQL_PREC_TF32X3 ? tc::Cfg<true>::SLICES : tc::Cfg<false>::SLICES;
+    h.part_floats = (size_t)C * slices * ((size_t)B * (2 * n3 + 2)) * 2 + 4096;
+    h.part = h.dalloc<float>(h.part_floats);
+  }
   // scalars start at the configured initial values; networks are set by cql_set_weights
   float sc[SCALAR_SLOT] = {0};
   sc[0] = logf(cfg->initial_temperature);
@@ -260,6 +272,8 @@ int cql_set_weights(cql_handle* ch, const float* host_flat, int64_t n) {
     CQL_REQUIRE(host_flat && n == state_floats(ch->h.C), "cql_set_weights: n must equal cql_state_floats()");
     CQL_CUDA(cudaDeviceSynchronize());
     CQL_CUDA(cudaMemcpy(ch->h.params, host_flat, n * sizeof(float), cudaMemcpyHostToDevice));
+    pack_all_weights(&ch->h, ch->h.own_stream);
+    CQL_CUDA(cudaStreamSynchronize(ch->h.own_stream));
   });
 }
 

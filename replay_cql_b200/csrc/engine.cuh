@@ -71,6 +71,12 @@ struct Handle {
   float* pw2A = nullptr;     // [splitsA][H*H]
   int splitsC = 1, splitsA = 1;
 
+  // ---- tensor-core path (precision != FP32): packed W2 per slot, layer-3 partial sums ----
+  uint8_t* packed_fwd = nullptr;   // [(2+2C) slots][PACKED_NET_BYTES]  B[n][k] = W2[n][k]
+  size_t packed_net_bytes = 0;
+  float* part = nullptr;           // scratch for [n_nets][SLICES][rows][OUT] partials
+  size_t part_floats = 0;
+
   // optional event marks for cql_timed_update
   bool timing = false;
   cudaEvent_t ev[16] = {};

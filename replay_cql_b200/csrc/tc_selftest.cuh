@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) D[(size_t)(warp * 32 + lane) * N + c0 + i] = v[i];
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < N) D[(size_t)(warp * 32 + lane) * N + c0 + i] = v[i];
   }
   tc_fence_before();
   __syncthreads();

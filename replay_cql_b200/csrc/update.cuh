@@ -6,6 +6,7 @@
 // the TD target and the actor step (a result-preserving saving).
 #pragma once
 #include "engine.cuh"
+#include "mlp_tc.cuh"
 
 namespace cql {
 
@@ -415,6 +416,67 @@ inline void launch_fwd(Handle* h, FwdJobs& jobs, cudaStream_t st) {
   CQL_LAUNCH_CHECK(h);
 }
 
+// ---- tensor-core forward: same job list, W2 from the packed copy, partial sums folded afterwards
+template <bool TF32, int IN, int OUT>
+inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
+  using C = tc::Cfg<TF32>;
+  tc::TcFwdJobs tj{};
+  tj.n = jobs.n;
+  size_t part_off = 0;
+  int items = 0;
+  float* part_of[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < jobs.n; ++i) {
+    const FwdJob& j = jobs.j[i];
+    const int slot = (int)((j.params - h->params) / NET_STRIDE);
+    tj.item_begin[i] = items;
+    items += j.n_nets * C::SLICES * ((j.rows + tc::TM - 1) / tc::TM);
+    part_of[i] = h->part + part_off;
+    part_off += (size_t)j.n_nets * C::SLICES * j.rows * OUT;
+    tj.j[i] = tc::TcFwdJob{j.X, j.params, h->packed_fwd + (size_t)slot * h->packed_net_bytes, part_of[i], j.h2, j.rows,
+                           j.n_nets};
+  }
+  tj.item_begin[jobs.n] = items;
+  CQL_REQUIRE(part_off <= h->part_floats, "internal: partial-sum scratch too small");
+  if (items == 0) return;
+  const int grid = items < h->num_sms ? items : h->num_sms;
+  tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::TC_THREADS, tc::FwdSmem<TF32>::BYTES, st>>>(tj);
+  CQL_LAUNCH_CHECK(h);
+  for (int i = 0; i < jobs.n; ++i) {
+    const FwdJob& j = jobs.j[i];
+    const int n = j.n_nets * j.rows * OUT;
+    tc::k_sum_partials<IN, OUT><<<(n + 255) / 256, 256, 0, st>>>(part_of[i], j.params, j.rows, j.n_nets, C::SLICES, j.out);
+    CQL_LAUNCH_CHECK(h);
+  }
+}
+
+template <int IN, int OUT>
+inline void launch_fwd_any(Handle* h, FwdJobs& jobs, cudaStream_t st) {
+  if (h->cfg.precision == CQL_PREC_TF32X3) launch_fwd_tc<true, IN, OUT>(h, jobs, st);
+  else if (h->cfg.precision == CQL_PREC_BF16) launch_fwd_tc<false, IN, OUT>(h, jobs, st);
+  else launch_fwd<IN, OUT>(h, jobs, st);
+}
+
+// refresh the packed (tensor-core operand layout) copy of W2 for `n_slots` networks starting at `slot`
+inline void pack_weights(Handle* h, int slot, int n_slots, int in_dim, cudaStream_t st) {
+  if (h->cfg.precision == CQL_PREC_FP32) return;
+  const float* p = h->net_params(slot);
+  uint8_t* dst = h->packed_fwd + (size_t)slot * h->packed_net_bytes;
+  if (h->cfg.precision == CQL_PREC_TF32X3) {
+    const int chunks = H * (H / tc::Cfg<true>::EPC);
+    tc::k_pack_w2<true, false><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dst);
+  } else {
+    const int chunks = H * (H / tc::Cfg<false>::EPC);
+    tc::k_pack_w2<false, false><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dst);
+  }
+  CQL_LAUNCH_CHECK(h);
+}
+inline void pack_all_weights(Handle* h, cudaStream_t st) {
+  pack_weights(h, slot_actor(), 1, 2, st);
+  pack_weights(h, slot_critic(0), h->C, 3, st);
+  pack_weights(h, slot_targ_actor(h->C), 1, 2, st);
+  pack_weights(h, slot_targ_critic(h->C, 0), h->C, 3, st);
+}
+
 template <int IN, int OUT, bool WGRADS, bool DX>
 inline void launch_bwd1(Handle* h, const BwdJob& jb, cudaStream_t st) {
   static bool attr = false;
@@ -474,7 +536,7 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     jobs.j[0] = FwdJob{h->XA, h->net_params(slot_actor()), h->outA, h->h2A, B, 1, 0};
     jobs.j[1] = FwdJob{h->XA + B, h->net_params(slot_actor()), h->outA + 2 * (size_t)B, nullptr, B, 1, 0};
     mark(h, st, 1);
-    launch_fwd<2, 2>(h, jobs, st);
+    launch_fwd_any<2, 2>(h, jobs, st);
     mark(h, st, 2);
   }
   k_prep<<<(B * 64 + 255) / 256, 256, 0, st>>>(batch4, h->outA, h->noise, B, h->n, c.squash, h->XAl, h->offAl, h->XC,
@@ -487,7 +549,7 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     jobs.j[1] = FwdJob{h->XC, h->net_params(slot_critic(0)), h->QC, h->h2C, B * (n3 + 1), C, 0};
     jobs.j[2] = FwdJob{h->XT, h->net_params(slot_targ_critic(C, 0)), h->QT, nullptr, B, C, 0};
     mark(h, st, 3);
-    launch_fwd<3, 1>(h, jobs, st);
+    launch_fwd_any<3, 1>(h, jobs, st);
     mark(h, st, 4);
   }
   k_scalar_grads<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->perb), h->QAl, h->offAl, h->QC, h->scalars(),
@@ -523,12 +585,14 @@ inline void phase2(Handle* h, cudaStream_t st) {
       h->net_params(slot_critic(0)), h->adam_m + (size_t)NET_STRIDE, h->adam_v + (size_t)NET_STRIDE, h->g_critics(),
       h->net_params(slot_targ_critic(C, 0)), cnt, c.critic_lr, c.beta1, c.beta2, c.adam_eps, c.tau, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
+  pack_weights(h, slot_critic(0), C, 3, st);
+  pack_weights(h, slot_targ_critic(C, 0), C, 3, st);
   {
     FwdJobs jobs{};
     jobs.n = 1;
     jobs.j[0] = FwdJob{h->XP, h->net_params(slot_critic(0)), h->QP, h->h2P, B, C, 0};
     mark(h, st, 8);
-    launch_fwd<3, 1>(h, jobs, st);
+    launch_fwd_any<3, 1>(h, jobs, st);
     mark(h, st, 9);
   }
   k_actor_dq<<<1, 1024, 0, st>>>(h->QP, reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
@@ -559,6 +623,7 @@ inline void phase3(Handle* h, cudaStream_t st) {
                                                          (int64_t)NET_STRIDE, c.actor_lr, c.beta1, c.beta2, c.adam_eps,
                                                          c.tau, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
+  pack_weights(h, slot_actor(), 1, 2, st);
   k_step_end<<<1, 1, 0, st>>>(h->step_dev);
   CQL_LAUNCH_CHECK(h);
   mark(h, st, 12);
