@@ -65,6 +65,8 @@ struct Handle {
   float4* dXP = nullptr;     // [C][B]
   float* dOutA = nullptr;    // [B][2]
   float* perb = nullptr;     // [B][4]: temp term, logp_pi, a_pi raw, -
+  float* pairv = nullptr;    // [C][B] PairVals {lse_alpha, lse_critic, q_data, td_err}
+  float* loss_sums = nullptr;  // [8] reduced sums / conservative coefficient
   float* smallC = nullptr;   // [C][tilesC][SMALL_STRIDE]
   float* smallA = nullptr;   // [tilesB][SMALL_STRIDE]
   float* pw2C = nullptr;     // [C][splitsC][H*H]

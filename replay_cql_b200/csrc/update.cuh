@@ -217,36 +217,81 @@ struct LossConsts {
   float gamma, cw, thr, temp_lr, alpha_lr, beta1, beta2, eps;
 };
 
-// temp + alpha gradients (one CTA, fixed-order sums).  g_scalars[0]=d log_temp, [1]=d log_alpha.
-__global__ void __launch_bounds__(1024) k_scalar_grads(const float4* __restrict__ perb, const float* __restrict__ QAl,
-                                                       const float* __restrict__ offAl, const float* __restrict__ QC,
-                                                       const float* __restrict__ scalars, LossConsts k,
-                                                       float* __restrict__ g_scalars, float* __restrict__ metrics) {
-  __shared__ float red[32];
+// ---- loss glue, split so that nothing heavy runs in a single CTA -------------------------------
+// (1) k_lse: one warp per (critic, batch element): logsumexp of the alpha-step rows and of the
+//     critic-step rows, unscaled softmax weights (into dQ), TD target / error.   -> pairv[c][b]
+// (2) k_scalar_reduce: one CTA sums the C*B pair values in a fixed order -> temp/alpha gradients
+//     [data-parallel: the host all-reduces the two scalar gradients here]
+// (3) k_scalar_adam: one thread: Adam on log_temp/log_alpha, conservative coefficient, loss metrics
+// (4) k_dq: every critic-job row: dQ = coef * softmax (samples) or 2(q-y)/B - coef (data row)
+struct PairVals { float lse_a, lse_c, qd, err; };
+
+__device__ __forceinline__ float warp_lse(const float* __restrict__ q, const float* __restrict__ off, int cnt, int lane,
+                                          float& m_out, float& v_out) {
+  const float v = lane < cnt ? q[lane] - off[lane] : -INFINITY;
+  const float m = warp_max(v);
+  const float e = lane < cnt ? expf(v - m) : 0.f;
+  const float s = warp_sum(e);
+  m_out = m;
+  v_out = e / s;         // softmax weight of this lane's row
+  return m + logf(s);
+}
+
+__global__ void __launch_bounds__(256) k_lse(const float4* __restrict__ batch, const float* __restrict__ QAl,
+                                             const float* __restrict__ offAl, const float* __restrict__ QC,
+                                             const float* __restrict__ offC, const float* __restrict__ QT, LossConsts k,
+                                             float* __restrict__ dQ, PairVals* __restrict__ pairv) {
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= k.C * k.B) return;
+  const int c = p / k.B, b = p % k.B;
   const int n3 = 3 * k.n, rsC = n3 + 1;
+  float m, w;
+  PairVals pv;
+  pv.lse_a = warp_lse(QAl + ((int64_t)c * k.B + b) * n3, offAl + (int64_t)b * n3, n3, lane, m, w);
+  const float* q = QC + ((int64_t)c * k.B + b) * rsC;
+  pv.lse_c = warp_lse(q, offC + (int64_t)b * rsC, n3, lane, m, w);
+  if (lane < n3) dQ[((int64_t)c * k.B + b) * rsC + lane] = w;
+  if (lane == 0) {
+    float qt = QT[b];
+    for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, QT[(int64_t)c2 * k.B + b]);
+    const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
+    const float y = r0.w + k.gamma * qt * (1.f - r1.z);
+    pv.qd = q[n3];
+    pv.err = pv.qd - y;
+    pairv[p] = pv;
+  }
+}
+
+// sums[0]=sum td err^2  [1]=sum lse_c  [2]=sum qd
+__global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict__ perb, const PairVals* __restrict__ pairv,
+                                                        const float* __restrict__ scalars, LossConsts k,
+                                                        float* __restrict__ g_scalars, float* __restrict__ sums,
+                                                        float* __restrict__ metrics) {
+  __shared__ float red[32];
   float st = 0.f;
   for (int b = threadIdx.x; b < k.B; b += 1024) st += perb[b].x;
   st = block_sum<1024>(st, red);
-  float sl = 0.f, sd = 0.f;
+  float sa = 0.f, sc = 0.f, sd = 0.f, se = 0.f;
   for (int p = threadIdx.x; p < k.C * k.B; p += 1024) {
-    const int c = p / k.B, b = p % k.B;
-    float m, s;
-    sl += lse_rows(QAl + ((int64_t)c * k.B + b) * n3, offAl + (int64_t)b * n3, n3, m, s);
-    sd += QC[((int64_t)c * k.B + b) * rsC + n3];
+    const PairVals pv = pairv[p];
+    sa += pv.lse_a; sc += pv.lse_c; sd += pv.qd; se += pv.err * pv.err;
   }
-  sl = block_sum<1024>(sl, red);
+  sa = block_sum<1024>(sa, red);
+  sc = block_sum<1024>(sc, red);
   sd = block_sum<1024>(sd, red);
+  se = block_sum<1024>(se, red);
   if (threadIdx.x == 0) {
     const float lt = scalars[0], la = scalars[1];
     const float temp_loss = -expf(lt) * (st / (float)k.B);
     const float inv = 1.f / ((float)k.C * (float)k.B);
-    const float raw = sl * inv - sd * inv;
+    const float raw = sa * inv - sd * inv;
     const float e = expf(la), clipped = fminf(fmaxf(e, 0.f), 1e6f);
     const float alpha_loss = -clipped * (k.cw * raw - k.thr);
     g_scalars[0] = temp_loss;                 // d/d log_temp of -exp(lt)*mean = the loss itself
     g_scalars[1] = e <= 1e6f ? alpha_loss : 0.f;
     metrics[0] = temp_loss;
     metrics[2] = alpha_loss;
+    sums[0] = se; sums[1] = sc; sums[2] = sd;
   }
 }
 
@@ -258,56 +303,34 @@ __device__ __forceinline__ float adam_scalar(float p, float g, float& m, float& 
   return p - (float)((double)lr / si.bc1) * (m / denom);
 }
 
-// scalar Adam (temp, alpha) then d critic_loss / d Q for every critic-job row (one CTA).
-__global__ void __launch_bounds__(1024) k_critic_dq(const float4* __restrict__ batch, const float* __restrict__ QC,
-                                                    const float* __restrict__ offC, const float* __restrict__ QT,
-                                                    float* __restrict__ scalars, float* __restrict__ sc_m,
-                                                    float* __restrict__ sc_v, const float* __restrict__ g_scalars,
-                                                    const StepInfo* __restrict__ si, LossConsts k,
-                                                    float* __restrict__ dQ, float* __restrict__ metrics) {
-  __shared__ float red[32];
-  __shared__ float alpha_sh;
-  if (threadIdx.x == 0) {
-    float lt = scalars[0], la = scalars[1];
-    if (k.temp_lr > 0.f) { float m = sc_m[0], v = sc_v[0]; lt = adam_scalar(lt, g_scalars[0], m, v, k.temp_lr, k, *si); sc_m[0] = m; sc_v[0] = v; scalars[0] = lt; }
-    if (k.alpha_lr > 0.f) { float m = sc_m[1], v = sc_v[1]; la = adam_scalar(la, g_scalars[1], m, v, k.alpha_lr, k, *si); sc_m[1] = m; sc_v[1] = v; scalars[1] = la; }
-    metrics[1] = expf(lt);
-    metrics[3] = expf(la);
-    alpha_sh = fminf(fmaxf(expf(la), 0.f), 1e6f);
-  }
-  __syncthreads();
-  const float alpha = alpha_sh;
-  const int n3 = 3 * k.n, rsC = n3 + 1;
-  const float coef = alpha * k.cw / ((float)k.C * (float)k.B);
-  float s_td = 0.f, s_lse = 0.f, s_d = 0.f;
-  for (int p = threadIdx.x; p < k.C * k.B; p += 1024) {
-    const int c = p / k.B, b = p % k.B;
-    float qt = QT[b];
-    for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, QT[(int64_t)c2 * k.B + b]);
-    const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
-    const float y = r0.w + k.gamma * qt * (1.f - r1.z);
-    const float* q = QC + ((int64_t)c * k.B + b) * rsC;
-    const float* off = offC + (int64_t)b * rsC;
-    float* dq = dQ + ((int64_t)c * k.B + b) * rsC;
-    float m, s;
-    s_lse += lse_rows(q, off, n3, m, s);
-    const float inv_s = 1.f / s;
-    for (int j = 0; j < n3; ++j) dq[j] = coef * (expf(q[j] - off[j] - m) * inv_s);
-    const float qd = q[n3], e = qd - y;
-    dq[n3] = 2.f * e / (float)k.B - coef;
-    s_td += e * e;
-    s_d += qd;
-  }
-  s_td = block_sum<1024>(s_td, red);
-  s_lse = block_sum<1024>(s_lse, red);
-  s_d = block_sum<1024>(s_d, red);
-  if (threadIdx.x == 0) {
-    const float td = s_td / (float)k.B;
-    const float inv = 1.f / ((float)k.C * (float)k.B);
-    const float cons = alpha * (k.cw * (s_lse * inv - s_d * inv) - k.thr);
-    metrics[4] = td + cons;
-    metrics[6] = td;
-  }
+// sums[3] <- conservative coefficient alpha*cw/(C*B) for k_dq
+__global__ void k_scalar_adam(float* __restrict__ scalars, float* __restrict__ sc_m, float* __restrict__ sc_v,
+                              const float* __restrict__ g_scalars, const StepInfo* __restrict__ si, LossConsts k,
+                              float* __restrict__ sums, float* __restrict__ metrics) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float lt = scalars[0], la = scalars[1];
+  if (k.temp_lr > 0.f) { float m = sc_m[0], v = sc_v[0]; lt = adam_scalar(lt, g_scalars[0], m, v, k.temp_lr, k, *si); sc_m[0] = m; sc_v[0] = v; scalars[0] = lt; }
+  if (k.alpha_lr > 0.f) { float m = sc_m[1], v = sc_v[1]; la = adam_scalar(la, g_scalars[1], m, v, k.alpha_lr, k, *si); sc_m[1] = m; sc_v[1] = v; scalars[1] = la; }
+  metrics[1] = expf(lt);
+  metrics[3] = expf(la);
+  const float alpha = fminf(fmaxf(expf(la), 0.f), 1e6f);
+  const float inv = 1.f / ((float)k.C * (float)k.B);
+  const float td = sums[0] / (float)k.B;
+  const float cons = alpha * (k.cw * (sums[1] * inv - sums[2] * inv) - k.thr);
+  metrics[4] = td + cons;
+  metrics[6] = td;
+  sums[3] = alpha * k.cw * inv;
+}
+
+__global__ void k_dq(const PairVals* __restrict__ pairv, const float* __restrict__ sums, LossConsts k,
+                     float* __restrict__ dQ) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rsC = 3 * k.n + 1;
+  if (i >= (int64_t)k.C * k.B * rsC) return;
+  const int j = (int)(i % rsC);
+  const float coef = sums[3];
+  if (j < rsC - 1) dQ[i] = coef * dQ[i];
+  else dQ[i] = 2.f * pairv[i / rsC].err / (float)k.B - coef;
 }
 
 // actor loss + d/dQ through the min over critics (one CTA)
@@ -552,8 +575,11 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     launch_fwd_any<3, 1>(h, jobs, st);
     mark(h, st, 4);
   }
-  k_scalar_grads<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->perb), h->QAl, h->offAl, h->QC, h->scalars(),
-                                     loss_consts(h), h->g_scalars(), h->metrics);
+  k_lse<<<(C * B * 32 + 255) / 256, 256, 0, st>>>(batch4, h->QAl, h->offAl, h->QC, h->offC, h->QT, loss_consts(h), h->dQ,
+                                                 reinterpret_cast<PairVals*>(h->pairv));
+  CQL_LAUNCH_CHECK(h);
+  k_scalar_reduce<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
+                                      h->scalars(), loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics);
   CQL_LAUNCH_CHECK(h);
 }
 
@@ -561,9 +587,11 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
 inline void phase1(Handle* h, cudaStream_t st) {
   const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
   const int64_t so = scalars_off(C);
-  k_critic_dq<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->batch), h->QC, h->offC, h->QT, h->scalars(),
-                                  h->adam_m + so, h->adam_v + so, h->g_scalars(), h->stepinfo, loss_consts(h), h->dQ,
-                                  h->metrics);
+  k_scalar_adam<<<1, 32, 0, st>>>(h->scalars(), h->adam_m + so, h->adam_v + so, h->g_scalars(), h->stepinfo,
+                                 loss_consts(h), h->loss_sums, h->metrics);
+  CQL_LAUNCH_CHECK(h);
+  k_dq<<<(int)(((int64_t)C * rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<const PairVals*>(h->pairv), h->loss_sums,
+                                                              loss_consts(h), h->dQ);
   CQL_LAUNCH_CHECK(h);
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);
