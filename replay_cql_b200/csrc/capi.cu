@@ -53,6 +53,17 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false>::BYTES));
+  const int f1 = (int)tc::FwdSmem<true>::BYTES, f0 = (int)tc::FwdSmem<false>::BYTES;
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<false, 3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f0));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<false, 3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f0));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<false, 2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f0));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2Cfg<true>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2Cfg<true>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2Cfg<false>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2Cfg<false>::BYTES));
 }
 
 void create_impl(const cql_config* cfg, cql_handle* ch) {
@@ -134,6 +145,14 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
     const int slices = cfg->precision == CQL_PREC_TF32X3 ? tc::Cfg<true>::SLICES : tc::Cfg<false>::SLICES;
     h.part_floats = (size_t)C * slices * ((size_t)B * (2 * n3 + 2)) * 2 + 4096;
     h.part = h.dalloc<float>(h.part_floats);
+    h.tc_slices = slices;
+    h.packed_bwd = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes);
+    h.slots1 = 4 * h.num_sms;
+    h.splits_tc = h.num_sms;
+    h.small1 = h.dalloc<float>((size_t)C * h.slots1 * SMALL_STRIDE);
+    h.small2 = h.dalloc<float>((size_t)C * h.splits_tc * SMALL_STRIDE);
+    h.pw2_tc = h.dalloc<float>((size_t)(h.num_sms + C) * H * H);
+    h.dX_part = h.dalloc<float4>((size_t)C * slices * B);
   }
   // scalars start at the configured initial values; networks are set by cql_set_weights
   float sc[SCALAR_SLOT] = {0};

@@ -78,6 +78,12 @@ struct Handle {
   size_t packed_net_bytes = 0;
   float* part = nullptr;           // scratch for [n_nets][SLICES][rows][OUT] partials
   size_t part_floats = 0;
+  uint8_t* packed_bwd = nullptr;   // [(1+C) slots: actor, critics][PACKED_NET_BYTES]  B[n][k] = W2[k][n]
+  float* small1 = nullptr;         // [C][slots1][SMALL_STRIDE] bwd1 partials (W1 | b1), slots1 = 4 * num_sms
+  float* small2 = nullptr;         // [C][splits_tc][SMALL_STRIDE] bwd2 partials (b2 | W3 | b3)
+  float* pw2_tc = nullptr;         // [C][splits_tc][H*H]
+  float4* dX_part = nullptr;       // [C*SLICES][B]
+  int slots1 = 0, splits_tc = 0, tc_slices = 1;
 
   // optional event marks for cql_timed_update
   bool timing = false;

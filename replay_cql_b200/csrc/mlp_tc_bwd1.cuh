@@ -1,0 +1,307 @@
+// mlp_tc_bwd1.cuh -- tensor-core input gradient of the hidden layer:  dH1 = dZ2 W2, then
+// dZ1 = dH1 * relu'(Z1), dW1, db1 and (optionally) dx.  Same warp-specialised pipeline as the forward
+// (mlp_tc.cuh): W2^T resident in shared memory, the A operand (dZ2) generated per K-chunk by the
+// producer warps from (dOut, W3, H2 > 0), two TMEM accumulators.  In the epilogue a thread owns one row:
+// dx is a thread-local dot product; dW1/db1 need a sum over rows, done with a 31-shuffle butterfly
+// reduce-scatter per 32-column chunk and then kept in registers across all tiles of the CTA.
+#pragma once
+#include "mlp_tc.cuh"
+
+namespace cql {
+namespace tc {
+
+struct Bwd1Job {
+  const float4* X;        // [rows]
+  const float* dOut;      // [n_nets][rows][OUT]
+  const float* h2;        // [n_nets][tiles64][256][64]
+  const float* params;    // first net slot (fp32)
+  const uint8_t* packedT; // packed W2^T of the first net (B[n=k][kk=j] = W2[j][k])
+  float* small1;          // [n_nets][slots][SMALL_STRIDE]: only W1 | b1 entries written; slots = 4*gridDim.x, zeroed by caller
+  float4* dX_part;        // [n_nets][SLICES][rows] or nullptr
+  int rows, n_nets, slots;
+};
+
+// after the call lane l holds sum over the warp's 32 lanes of v[l]
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <bool TF32, int IN, int OUT, bool WGRADS, bool DX>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb) {
+  using C = Cfg<TF32>;
+  using S = FwdSmem<TF32>;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint8_t* Bs = sm + S::OFF_B;
+  uint8_t* As = sm + S::OFF_A;
+  float2* w3s = reinterpret_cast<float2*>(sm + S::OFF_W1);    // [256] (W3[0][j], W3[1][j])
+  float4* ebs = reinterpret_cast<float4*>(sm + S::OFF_EB);    // [NS]  (W1[k][0..2], b1[k]) of the slice's columns
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bload = tempty + 2;
+  uint64_t* drain = bload + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + S::OFF_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = (jb.rows + TM - 1) / TM;
+  const int tiles64 = (jb.rows + 63) / 64;
+  const int total = jb.n_nets * C::SLICES * tiles;             // item = (net, slice, tile), pair-major
+  const int item_lo = (int)((long long)total * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 12) {
+    tmem_alloc(slot, C::TMEM_COLS);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], N_PROD_WARPS); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+      mbar_init(bload, 1);
+      mbar_init(drain, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (warp == 12) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TM, C::NS);
+      const uint32_t a_lbo = TM * 16, b_lbo = C::NS * 16;
+      const uint32_t b_base = smem_u32(Bs);
+      int cur_pair = -1;
+      uint32_t it = 0, nb = 0, nd = 0, tcount = 0;
+      for (int item = item_lo; item < item_hi; ++item) {
+        const int pair = item / tiles;
+        if (pair != cur_pair) {
+          if (cur_pair >= 0) { umma_commit(drain); mbar_wait(drain, nd & 1); ++nd; }
+          const uint8_t* src = jb.packedT + (size_t)(pair / C::SLICES) * C::PACKED_NET_BYTES + (size_t)(pair % C::SLICES) * C::B_BYTES;
+          mbar_arrive_expect_tx(bload, C::B_BYTES);
+          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+          mbar_wait(bload, nb & 1);
+          ++nb;
+          cur_pair = pair;
+        }
+        const uint32_t acc = tcount & 1;
+        mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + acc * C::NS;
+        for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+          const uint32_t s = it % C::STAGES;
+          mbar_wait(&full[s], (it / C::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(As + s * C::A_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < C::KC / C::UK; ++j) {
+            const uint32_t g = c * (C::KC / C::UK) + j;
+            const uint64_t a_hi = smem_desc(a_base + 2 * j * a_lbo, a_lbo, 128);
+            const uint64_t b_hi = smem_desc(b_base + 2 * g * b_lbo, b_lbo, 128);
+            const uint32_t first = (c == 0 && j == 0) ? 0u : 1u;
+            if constexpr (TF32) {
+              const uint64_t a_lo = smem_desc(a_base + C::A_TERM_BYTES + 2 * j * a_lbo, a_lbo, 128);
+              const uint64_t b_lo = smem_desc(b_base + C::B_TERM_BYTES + 2 * g * b_lbo, b_lbo, 128);
+              umma<TF32>(d_tmem, a_lo, b_hi, idesc, first);
+              umma<TF32>(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma<TF32>(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma<TF32>(d_tmem, a_hi, b_hi, idesc, first);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[acc]);
+        ++tcount;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- producers: dZ2 tile -> operand ring ----------------
+    const int pw = warp - 4, ptid = tid - 128;
+    int cur_net = -1;
+    uint32_t it = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES;
+      if (net_i != cur_net) {
+        cur_net = net_i;
+        asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS));
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        w3s[ptid] = make_float2(net[off_W3(IN) + ptid], OUT == 2 ? net[off_W3(IN) + H + ptid] : 0.f);
+        asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS));
+      }
+      float d0[4], d1[4];
+      const float* h2r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = tile * TM + lane + 32 * i;
+        const bool ok = r < jb.rows;
+        d0[i] = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT) : 0.f;
+        d1[i] = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1) : 0.f;
+        const int rc = ok ? r : 0;     // clamp: the value is multiplied by dOut = 0 anyway
+        h2r[i] = jb.h2 + ((size_t)net_i * tiles64 + (rc >> 6)) * H * 64 + (rc & 63);
+      }
+      for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        const uint32_t s = it % C::STAGES;
+        mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+        uint8_t* stage = As + s * C::A_STAGE_BYTES;
+        const int j0 = c * C::KC + pw * C::EPC;
+        float z[4][C::EPC];
+#pragma unroll
+        for (int e = 0; e < C::EPC; ++e) {
+          const float2 w = w3s[j0 + e];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float hv = __ldg(h2r[i] + (size_t)(j0 + e) * 64);
+            float g = d0[i] * w.x;
+            if (OUT == 2) g = fmaf(d1[i], w.y, g);
+            z[i][e] = hv > 0.f ? g : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = chunk_off(TM, lane + 32 * i, pw);
+          if constexpr (TF32) {
+            float4 hi, lo;
+            split_tf32(z[i][0], hi.x, lo.x); split_tf32(z[i][1], hi.y, lo.y);
+            split_tf32(z[i][2], hi.z, lo.z); split_tf32(z[i][3], hi.w, lo.w);
+            *reinterpret_cast<float4*>(stage + off) = hi;
+            *reinterpret_cast<float4*>(stage + C::A_TERM_BYTES + off) = lo;
+          } else {
+            __nv_bfloat162 q[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q[e] = __floats2bfloat162_rn(z[i][2 * e], z[i][2 * e + 1]);
+            *reinterpret_cast<uint4*>(stage + off) = *reinterpret_cast<uint4*>(q);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: dZ1, dx, dW1/db1 ----------------
+    constexpr int NCH = C::NS / 32;
+    float a_b[NCH], a_w0[NCH], a_w1[NCH], a_w2[NCH];      // lane l <-> column chunk*32 + l of the current slice
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) { a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f; }
+    auto flush = [&](int pair) {
+      if (!WGRADS || pair < 0) return;
+      const int net_i = pair / C::SLICES, slice = pair % C::SLICES;
+      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 4 + warp) * SMALL_STRIDE;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int k = slice * C::NS + q * 32 + lane;
+        o[k * IN + 0] = a_w0[q];
+        o[k * IN + 1] = a_w1[q];
+        if (IN == 3) o[k * IN + 2] = a_w2[q];
+        o[H * IN + k] = a_b[q];
+        a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f;
+      }
+    };
+    int cur_pair = -1;
+    uint32_t tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES, slice = pair % C::SLICES;
+      if (pair != cur_pair) {
+        flush(cur_pair);
+        cur_pair = pair;
+        asm volatile("bar.sync 2, 128;");
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        for (int cidx = tid; cidx < C::NS; cidx += 128) {
+          const int k = slice * C::NS + cidx;
+          ebs[cidx] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
+                                  IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+        }
+        asm volatile("bar.sync 2, 128;");
+      }
+      const uint32_t acc = tcount & 1;
+      const int row = tile * TM + warp * 32 + lane;
+      const float4 x = row < jb.rows ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * C::NS + q * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 w = ebs[q * 32 + i];
+          float z = fmaf(x.y, w.y, x.x * w.x);
+          if (IN == 3) z = fmaf(x.z, w.z, z);
+          z += w.w;
+          const float d = z > 0.f ? v[i] : 0.f;
+          v[i] = d;
+          if (DX) {
+            dx0 = fmaf(d, w.x, dx0);
+            dx1 = fmaf(d, w.y, dx1);
+            if (IN == 3) dx2 = fmaf(d, w.z, dx2);
+          }
+        }
+        if (WGRADS) {
+          float t[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x.x;
+          a_w0[q] += warp_reduce_scatter32(t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x.y;
+          a_w1[q] += warp_reduce_scatter32(t);
+          if (IN == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = v[i] * x.z;
+            a_w2[q] += warp_reduce_scatter32(t);
+          }
+          a_b[q] += warp_reduce_scatter32(v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (DX && row < jb.rows)
+        jb.dX_part[((size_t)net_i * C::SLICES + slice) * jb.rows + row] = make_float4(dx0, dx1, dx2, 0.f);
+      ++tcount;
+    }
+    flush(cur_pair);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// grads[net][idx] from the tensor-core partials: W2 <- pw2 (bwd2 splits); b2|W3|b3 <- small2 (bwd2 splits);
+// W1|b1 <- small1 (bwd1 warp slots).  Fixed summation order.
+__global__ void k_reduce_grads_tc(const float* __restrict__ small1, int slots1, const float* __restrict__ small2,
+                                  const float* __restrict__ pw2, int splits, int in_dim, int out_dim,
+                                  float* __restrict__ grads) {
+  const int net = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NET_STRIDE) return;
+  const int w2_lo = off_W2(in_dim), w2_hi = w2_lo + H * H, total = net_floats(in_dim, out_dim);
+  float s = 0.f;
+  if (idx >= w2_lo && idx < w2_hi) {
+    const float* p = pw2 + (size_t)net * splits * H * H + (idx - w2_lo);
+    for (int i = 0; i < splits; ++i) s += p[(size_t)i * H * H];
+  } else if (idx < w2_lo) {
+    const float* p = small1 + (size_t)net * slots1 * SMALL_STRIDE + idx;
+    for (int i = 0; i < slots1; ++i) s += p[(size_t)i * SMALL_STRIDE];
+  } else if (idx < total) {
+    const float* p = small2 + (size_t)net * splits * SMALL_STRIDE + (idx - H * H);
+    for (int i = 0; i < splits; ++i) s += p[(size_t)i * SMALL_STRIDE];
+  }
+  grads[(size_t)net * NET_STRIDE + idx] = s;
+}
+
+}  // namespace tc
+}  // namespace cql

@@ -7,6 +7,8 @@
 #pragma once
 #include "engine.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc_bwd1.cuh"
+#include "mlp_tc_bwd2.cuh"
 
 namespace cql {
 
@@ -356,12 +358,12 @@ __global__ void __launch_bounds__(1024) k_actor_dq(const float* __restrict__ QP,
 
 // d actor_loss / d (mu, raw logstd): mirrors autograd through rsample, tanh, log-prob, clamp.
 __global__ void k_actor_dout(const float* __restrict__ outA, const float* __restrict__ noise_actor,
-                             const float4* __restrict__ dXP, const float* __restrict__ scalars, int B, int C,
+                             const float4* __restrict__ dXP, const float* __restrict__ scalars, int B, int n_parts,
                              int squash, float* __restrict__ dOutA) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float da = 0.f;
-  for (int c = 0; c < C; ++c) da += dXP[(int64_t)c * B + b].z;
+  for (int c = 0; c < n_parts; ++c) da += dXP[(int64_t)c * B + b].z;   // parts = critics (x column slices)
   const float mu = outA[2 * b], ls_raw = outA[2 * b + 1], ls = clamp_ls(ls_raw);
   const float eps = noise_actor[b];
   const Sample s = policy_sample(mu, ls, eps, squash);
@@ -492,7 +494,47 @@ inline void pack_weights(Handle* h, int slot, int n_slots, int in_dim, cudaStrea
     tc::k_pack_w2<false, false><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dst);
   }
   CQL_LAUNCH_CHECK(h);
+  if (slot <= h->C) {   // trainable nets also need W2^T for the backward
+    uint8_t* dt = h->packed_bwd + (size_t)slot * h->packed_net_bytes;
+    if (h->cfg.precision == CQL_PREC_TF32X3) {
+      const int chunks = H * (H / tc::Cfg<true>::EPC);
+      tc::k_pack_w2<true, true><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dt);
+    } else {
+      const int chunks = H * (H / tc::Cfg<false>::EPC);
+      tc::k_pack_w2<false, true><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dt);
+    }
+    CQL_LAUNCH_CHECK(h);
+  }
 }
+
+// ---- tensor-core backward of one job: bwd1 (dH1, dW1, db1, dx) + bwd2 (dW2, db2, dW3, db3) + reduce
+template <bool TF32, int IN, int OUT, bool WGRADS, bool DX>
+inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStream_t st) {
+  using C = tc::Cfg<TF32>;
+  const int slot = (int)((jb.params - h->params) / NET_STRIDE);
+  const int tiles = (jb.rows + tc::TM - 1) / tc::TM;
+  const int items = jb.n_nets * C::SLICES * tiles;
+  const int grid1 = items < h->num_sms ? items : h->num_sms;
+  const int slots1 = 4 * grid1;
+  if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
+  tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes, h->small1,
+                 DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
+  tc::tc_bwd1_kernel<TF32, IN, OUT, WGRADS, DX><<<grid1, tc::TC_THREADS, tc::FwdSmem<TF32>::BYTES, st>>>(j1);
+  CQL_LAUNCH_CHECK(h);
+  if (!WGRADS) return;
+  const int n_stage = (jb.rows + tc::B2Cfg<TF32>::RS - 1) / tc::B2Cfg<TF32>::RS;
+  int splits = h->num_sms / jb.n_nets;
+  if (splits > n_stage) splits = n_stage;
+  if (splits > h->splits_tc) splits = h->splits_tc;
+  if (splits < 1) splits = 1;
+  tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
+  tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
+  CQL_LAUNCH_CHECK(h);
+  tc::k_reduce_grads_tc<<<dim3((NET_STRIDE + 255) / 256, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
+                                                                                  splits, IN, OUT, grads_out);
+  CQL_LAUNCH_CHECK(h);
+}
+
 inline void pack_all_weights(Handle* h, cudaStream_t st) {
   pack_weights(h, slot_actor(), 1, 2, st);
   pack_weights(h, slot_critic(0), h->C, 3, st);
@@ -595,6 +637,13 @@ inline void phase1(Handle* h, cudaStream_t st) {
   CQL_LAUNCH_CHECK(h);
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);
+  if (h->cfg.precision != CQL_PREC_FP32) {
+    if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st);
+    else launch_bwd_tc<false, 3, 1, true, false>(h, jb, h->g_critics(), st);
+    mark(h, st, 6);
+    mark(h, st, 7);
+    return;
+  }
   launch_bwd1<3, 1, true, false>(h, jb, st);
   mark(h, st, 6);
   launch_bwd2<3, 1>(h, jb, st);
@@ -628,13 +677,23 @@ inline void phase2(Handle* h, cudaStream_t st) {
   CQL_LAUNCH_CHECK(h);
   {
     BwdJob jb{h->XP, h->dQP, h->h2P, h->net_params(slot_critic(0)), nullptr, h->dXP, nullptr, B, C, 1};
-    launch_bwd1<3, 1, false, true>(h, jb, st);
+    if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 3, 1, false, true>(h, jb, nullptr, st);
+    else if (h->cfg.precision == CQL_PREC_BF16) launch_bwd_tc<false, 3, 1, false, true>(h, jb, nullptr, st);
+    else launch_bwd1<3, 1, false, true>(h, jb, st);
   }
-  k_actor_dout<<<(B + 127) / 128, 128, 0, st>>>(h->outA, h->noise + B + 6 * (int64_t)B * h->n, h->dXP, h->scalars(), B,
-                                                C, c.squash, h->dOutA);
+  const bool tcm = h->cfg.precision != CQL_PREC_FP32;
+  k_actor_dout<<<(B + 127) / 128, 128, 0, st>>>(h->outA, h->noise + B + 6 * (int64_t)B * h->n,
+                                                tcm ? h->dX_part : h->dXP, h->scalars(), B,
+                                                tcm ? C * h->tc_slices : C, c.squash, h->dOutA);
   CQL_LAUNCH_CHECK(h);
   BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
   mark(h, st, 10);
+  if (tcm) {
+    if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 2, 2, true, false>(h, ja, h->g_actor(), st);
+    else launch_bwd_tc<false, 2, 2, true, false>(h, ja, h->g_actor(), st);
+    mark(h, st, 11);
+    return;
+  }
   launch_bwd1<2, 2, true, false>(h, ja, st);
   launch_bwd2<2, 2>(h, ja, st);
   mark(h, st, 11);

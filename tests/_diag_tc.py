@@ -23,6 +23,7 @@ for scale in (1e-3, 1.0):
               'critic grad W2 %.2e' % Hp.rel_err(g['critics'][0]['W2'], g0['critics'][0]['W2']),
               'actor grad W2 %.2e' % Hp.rel_err(g['actor']['W2'], g0['actor']['W2']),
               'state %.2e' % Hp.rel_err(s, s0), flush=True)
+        print('     grads', {k: ('%.1e' % Hp.rel_err(g['actor'][k], g0['actor'][k]), '%.1e' % Hp.rel_err(g['critics'][0][k], g0['critics'][0][k]), '%.1e' % Hp.rel_err(g['critics'][1][k], g0['critics'][1][k])) for k in layout.NET_KEYS}, flush=True)
 N = 200000
 rng = np.random.default_rng(0)
 obs = np.stack([rng.integers(0, 6040, N), rng.integers(0, 3706, N)], 1).astype(np.float32)
