@@ -36,6 +36,11 @@ SCORE_USERS = 2048                # users scored per timed scoring pass (bounded
 FLOP_PER_ROW = 2 * (3 * 256 + 256 * 256 + 256)   # f_c = 133 120
 FLOP_PER_UPDATE_PER_B = 269 * FLOP_PER_ROW       # 269 forward-equivalent rows per batch element
 FLOP_PER_PAIR = 3 * FLOP_PER_ROW                 # 2 critics + actor = 399 360
+DTYPES = {"fp32": "f32", "tf32x3": "f32 (tf32x3: tensor-core 3-term split, fp32 accumulate, 1e-4 parity-gated)",
+          "bf16": "bf16 (fp32 accumulate; non-parity variant)"}
+KERNEL_NAMES = {"fp32": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
+                "tf32x3": "tc_fwd_kernel<tf32x3,3,1> (critic forward, tcgen05 kind::tf32 3-term split)",
+                "bf16": "tc_fwd_kernel<bf16,3,1> (critic forward, tcgen05 kind::f16)"}
 
 
 def peaks():
@@ -189,7 +194,8 @@ def run_ours(args):
     pk, pk_kind = peaks()
 
     log, mdp, shape = build_workload(args.rows)
-    eng = CqlEngine(CqlHyperParams(batch_size=BATCH, seed=12345), device=local_rank, rank=rank, world_size=world)
+    eng = CqlEngine(CqlHyperParams(batch_size=BATCH, seed=12345, precision=args.precision), device=local_rank,
+                    rank=rank, world_size=world)
     eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
     stream = torch.cuda.Stream(device=dev)
     sh = stream.cuda_stream
@@ -316,18 +322,18 @@ def run_ours(args):
         line = {
             "metric": "CQL updates/sec (batch 1024)", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "users": shape["n_users"], "items": shape["n_items"],
                        "rows": len(mdp), "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "parallelism": f"dp{world}", "hidden": 256, "n_critics": 2, "n_action_samples": 10,
-                       "precision": "fp32",
+                       "precision": args.precision,
                        "l2": "inputs larger than L2: 640 MB replay table, fresh random gather every step; "
                              "weights/activations are the step-to-step state of the algorithm"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": BATCH * 32,
                     "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batch (host minibatch in, metrics out)"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
+            "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[args.precision],
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": f"bf16_tflops_sustained ({pk_kind})", "traffic": None,
                          "flop_per_launch": fwd_flop, "ms_per_launch": tk["critic_fwd"],
@@ -357,6 +363,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=None, help="override the log size (debugging)")
+    ap.add_argument("--precision", choices=["fp32", "tf32x3", "bf16"], default="tf32x3",
+                    help="hidden-layer contraction: fp32 = CUDA-core FMA; tf32x3 = tcgen05 3-term split (FP32-grade, "
+                         "default); bf16 = tcgen05 bf16 operands (non-parity variant)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
