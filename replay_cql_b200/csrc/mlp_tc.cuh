@@ -28,8 +28,10 @@ struct Cfg {
   static constexpr int TERMS = TF32 ? 2 : 1;         // operand copies (hi, lo)
   static constexpr int NS = TF32 ? 64 : 256;         // output columns per CTA
   static constexpr int SLICES = H / NS;
-  static constexpr int KC = TF32 ? 32 : 64;          // K elements per ring stage
-  static constexpr int STAGES = TF32 ? 2 : 4;
+  static constexpr int KC = TF32 ? 16 : 64;          // K elements per ring stage
+  static constexpr int STAGES = 4;
+  static constexpr int PIECES = KC / EPC;            // 16-byte K pieces per row per stage (one producer warp each)
+  static constexpr int GROUPS = 8 / PIECES;          // producer-warp groups; group g fills stages with it % GROUPS == g
   static constexpr int NCHUNK = H / KC;              // stages per tile
   static constexpr uint32_t A_TERM_BYTES = TM * KC * ES;           // 16 KB
   static constexpr uint32_t A_STAGE_BYTES = TERMS * A_TERM_BYTES;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
   if (warp == 12) {
     tmem_alloc(slot, C::TMEM_COLS);
     if (lane == 0) {
-      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], N_PROD_WARPS); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::PIECES); mbar_init(&empty[s], 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
       mbar_init(bload, 1);
       mbar_init(drain, 1);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
             const uint64_t a_hi = smem_desc(a_base + 2 * j * a_lbo, a_lbo, 128);
             const uint64_t b_hi = smem_desc(b_base + 2 * g * b_lbo, b_lbo, 128);
             const uint32_t first = (c == 0 && j == 0) ? 0u : 1u;
-            if (TF32) {
+            if constexpr (TF32) {
               const uint64_t a_lo = smem_desc(a_base + C::A_TERM_BYTES + 2 * j * a_lbo, a_lbo, 128);
               const uint64_t b_lo = smem_desc(b_base + C::B_TERM_BYTES + 2 * g * b_lbo, b_lbo, 128);
               umma<TF32>(d_tmem, a_lo, b_hi, idesc, first);
@@ -237,13 +239,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
         x[i] = r < jb.rows ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        if ((int)(it % C::GROUPS) != pw / C::PIECES) continue;     // the other warp group fills this stage
         const uint32_t s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
         uint8_t* stage = As + s * C::A_STAGE_BYTES;
-        // this warp owns 16-byte K-pieces {pw, pw+8, ...} of the chunk, for all 128 rows (4 per lane)
-        constexpr int PIECES = C::KC / C::EPC;          // 8
-#pragma unroll
-        for (int p = pw; p < PIECES; p += N_PROD_WARPS) {
+        // this warp owns one 16-byte K-piece of the chunk, for all 128 rows (4 per lane)
+        const int p = pw % C::PIECES;
+        {
           float z[4][C::EPC];
 #pragma unroll
           for (int e = 0; e < C::EPC; ++e) {
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t off = chunk_off(TM, lane + 32 * i, p);
-            if (TF32) {
+            if constexpr (TF32) {
               float4 hi, lo;
               split_tf32(z[i][0], hi.x, lo.x); split_tf32(z[i][1], hi.y, lo.y);
               split_tf32(z[i][2], hi.z, lo.z); split_tf32(z[i][3], hi.w, lo.w);

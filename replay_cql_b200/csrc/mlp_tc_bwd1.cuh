@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
   if (warp == 12) {
     tmem_alloc(slot, C::TMEM_COLS);
     if (lane == 0) {
-      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], N_PROD_WARPS); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::PIECES); mbar_init(&empty[s], 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
       mbar_init(bload, 1);
       mbar_init(drain, 1);
@@ -152,10 +152,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
         h2r[i] = jb.h2 + ((size_t)net_i * tiles64 + (rc >> 6)) * H * 64 + (rc & 63);
       }
       for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        if ((int)(it % C::GROUPS) != pw / C::PIECES) continue;     // the other warp group fills this stage
         const uint32_t s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
         uint8_t* stage = As + s * C::A_STAGE_BYTES;
-        const int j0 = c * C::KC + pw * C::EPC;
+        const int p = pw % C::PIECES;
+        const int j0 = c * C::KC + p * C::EPC;
         float z[4][C::EPC];
 #pragma unroll
         for (int e = 0; e < C::EPC; ++e) {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t off = chunk_off(TM, lane + 32 * i, pw);
+          const uint32_t off = chunk_off(TM, lane + 32 * i, p);
           if constexpr (TF32) {
             float4 hi, lo;
             split_tf32(z[i][0], hi.x, lo.x); split_tf32(z[i][1], hi.y, lo.y);

@@ -124,8 +124,30 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_kernel(const Bwd2Job jb
 #pragma unroll
     for (int o = 0; o < OUT; ++o) { s_dw3[o] = 0.f; s_db3[o] = 0.f; }
     uint32_t it = 0;
+    constexpr int NV = C::RS / 4;                      // float4 loads of H2 per thread per stage
+    constexpr bool PREFETCH = NV <= 4;                 // keep next stage's H2 in registers (tf32: 16 regs)
+    float4 hnext[PREFETCH ? NV : 1];
+    auto h2_ptr = [&](int sg) {
+      const int row0 = sg * C::RS;
+      return jb.h2 + (((size_t)net_i * tiles64 + (row0 >> 6)) * H + t) * 64 + (row0 & 63);
+    };
+    if (PREFETCH && st_lo < st_hi) {
+      const float* hp = h2_ptr(st_lo);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) hnext[q] = __ldg(reinterpret_cast<const float4*>(hp) + q);
+    }
     for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
       const uint32_t s = it % C::STAGES;
+      float4 hcur[PREFETCH ? NV : 1];
+      if (PREFETCH) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) hcur[q] = hnext[q];
+        if (sg + 1 < st_hi) {
+          const float* hp = h2_ptr(sg + 1);
+#pragma unroll
+          for (int q = 0; q < NV; ++q) hnext[q] = __ldg(reinterpret_cast<const float4*>(hp) + q);
+        }
+      }
       mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
       const int row0 = sg * C::RS;
       float4* xst = xs + s * C::RS;
@@ -140,7 +162,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_kernel(const Bwd2Job jb
       asm volatile("bar.sync 1, 256;");
       uint8_t* Ast = sm + s * C::STAGE_BYTES;
       uint8_t* Bst = Ast + C::OP_BYTES;
-      const float* h2p = jb.h2 + (((size_t)net_i * tiles64 + (row0 >> 6)) * H + t) * 64 + (row0 & 63);
+      const float* h2p = h2_ptr(sg);
 #pragma unroll
       for (int kc = 0; kc < C::RS / C::EPC; ++kc) {
         float hv[C::EPC], dz[C::EPC], h1[C::EPC];
@@ -150,7 +172,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_kernel(const Bwd2Job jb
           hv[0] = p0.x; hv[1] = p0.y; hv[2] = p0.z; hv[3] = p0.w;
           hv[4] = p1.x; hv[5] = p1.y; hv[6] = p1.z; hv[7] = p1.w;
         } else {
-          const float4 p0 = __ldg(reinterpret_cast<const float4*>(h2p + kc * 4));
+          const float4 p0 = PREFETCH ? hcur[kc % NV] : __ldg(reinterpret_cast<const float4*>(h2p + kc * 4));
           hv[0] = p0.x; hv[1] = p0.y; hv[2] = p0.z; hv[3] = p0.w;
         }
 #pragma unroll

@@ -127,17 +127,18 @@ __host__ __device__ constexpr uint32_t chunk_off(uint32_t rows, uint32_t row, ui
   return kchunk * (rows * 16u) + (row >> 3) * 128u + (row & 7u) * 16u;
 }
 
-// tf32 split with round-to-nearest on both terms: hi = rna_tf32(x), lo = rna_tf32(x - hi) (x - hi is exact in
+// tf32 split with round-to-nearest on both terms: hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in
 // fp32).  |x - hi - lo| <= 2^-23 |x| and the error is sign-symmetric, whereas letting kind::tf32 truncate
 // raw fp32 bits would leave a one-sided 2^-21 bias that accumulates over the K = 256 products.
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// Rounding is done on the bit pattern (add half an ulp of the 10-bit mantissa, clear the low 13 bits:
+// round-half-away in sign-magnitude); `cvt.rna.tf32.f32` expands to ~6 instructions on sm_100a.
+// Inputs are finite activations / weights, so the exponent carry into Inf cannot occur.
+__device__ __forceinline__ float rn_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = rna_tf32(x);
-  lo = rna_tf32(x - hi);
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - hi);
 }
 
 }  // namespace tc
