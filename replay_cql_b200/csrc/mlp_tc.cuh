@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
   const uint32_t tmem = *slot;
 
   if (warp == 12) {
-    // =============================== MMA issuer (one lane) ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (whole warp, one elected lane issues) ===============================
+    {
       const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TM, C::NS);
       const uint32_t a_lbo = TM * 16, b_lbo = C::NS * 16;
       const uint32_t b_base = smem_u32(Bs);
@@ -168,14 +168,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
         const ItemInfo ii = decode_item<TF32>(jobs, item);
         if (ii.pair_id != cur_pair) {
           if (cur_pair >= 0) {              // old W2 slice must not be overwritten while MMAs still read it
-            umma_commit(drain);
+            if (elect_one()) umma_commit(drain);
+            __syncwarp();
             mbar_wait(drain, nd & 1);
             ++nd;
           }
           const TcFwdJob& jb = jobs.j[ii.job];
           const uint8_t* src = jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + (size_t)ii.slice * C::B_BYTES;
-          mbar_arrive_expect_tx(bload, C::B_BYTES);
-          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bload, C::B_BYTES);
+            for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+          }
+          __syncwarp();
           mbar_wait(bload, nb & 1);
           ++nb;
           cur_pair = ii.pair_id;
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
           mbar_wait(&full[s], (it / C::STAGES) & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As + s * C::A_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < C::KC / C::UK; ++j) {
             const uint32_t g = c * (C::KC / C::UK) + j;
@@ -206,8 +211,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
             }
           }
           umma_commit(&empty[s]);           // stage reusable once these MMAs have read it
+          if (c == C::NCHUNK - 1) umma_commit(&tfull[acc]);   // accumulator complete
+          }
+          __syncwarp();
         }
-        umma_commit(&tfull[acc]);           // accumulator complete
         ++tcount;
       }
     }

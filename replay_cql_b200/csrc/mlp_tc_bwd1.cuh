@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
   const uint32_t tmem = *slot;
 
   if (warp == 12) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TM, C::NS);
       const uint32_t a_lbo = TM * 16, b_lbo = C::NS * 16;
       const uint32_t b_base = smem_u32(Bs);
@@ -87,10 +87,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
       for (int item = item_lo; item < item_hi; ++item) {
         const int pair = item / tiles;
         if (pair != cur_pair) {
-          if (cur_pair >= 0) { umma_commit(drain); mbar_wait(drain, nd & 1); ++nd; }
+          if (cur_pair >= 0) { if (elect_one()) umma_commit(drain); __syncwarp(); mbar_wait(drain, nd & 1); ++nd; }
           const uint8_t* src = jb.packedT + (size_t)(pair / C::SLICES) * C::PACKED_NET_BYTES + (size_t)(pair % C::SLICES) * C::B_BYTES;
-          mbar_arrive_expect_tx(bload, C::B_BYTES);
-          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bload, C::B_BYTES);
+            for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+          }
+          __syncwarp();
           mbar_wait(bload, nb & 1);
           ++nb;
           cur_pair = pair;
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
           mbar_wait(&full[s], (it / C::STAGES) & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As + s * C::A_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < C::KC / C::UK; ++j) {
             const uint32_t g = c * (C::KC / C::UK) + j;
@@ -121,8 +125,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
             }
           }
           umma_commit(&empty[s]);
+          if (c == C::NCHUNK - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
         }
-        umma_commit(&tfull[acc]);
         ++tcount;
       }
     }

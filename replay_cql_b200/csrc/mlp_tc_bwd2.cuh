@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_kernel(const Bwd2Job jb
   const uint32_t tmem = *slot;
 
   if (warp == B2_PROD_WARPS) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, 128, 256);
       const uint32_t lbo = H * 16;
       uint32_t it = 0;
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_kernel(const Bwd2Job jb
         tc_fence_after();
         const uint32_t a_base = smem_u32(sm + s * C::STAGE_BYTES);
         const uint32_t b_base = a_base + C::OP_BYTES;
+        if (elect_one()) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -108,8 +109,10 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_kernel(const Bwd2Job jb
           }
         }
         umma_commit(&empty[s]);
+        if (sg == st_hi - 1) umma_commit(done);
+        }
+        __syncwarp();
       }
-      umma_commit(done);
     }
   } else {
     // ---------------- producers: thread t = hidden unit t (A row j = t, B row k = t) ----------------
