@@ -49,11 +49,11 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
   CQL_CUDA(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, score_smem(CQL_MAX_TOPK)));
   CQL_CUDA(cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true>::BYTES));
-  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true>::BYTES));
-  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false>::BYTES));
-  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false>::BYTES));
-  const int f1 = (int)tc::FwdSmem<true>::BYTES, f0 = (int)tc::FwdSmem<false>::BYTES;
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true, tc::FWD_NPW>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true, tc::FWD_NPW>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
+  const int f1 = (int)tc::FwdSmem<true, tc::BWD1_NPW>::BYTES, f0 = (int)tc::FwdSmem<false, tc::BWD1_NPW>::BYTES;
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));

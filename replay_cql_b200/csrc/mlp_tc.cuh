@@ -16,9 +16,6 @@ namespace cql {
 namespace tc {
 
 constexpr int TM = 128;                  // rows per tile (UMMA M)
-constexpr int TC_THREADS = 13 * 32;
-constexpr int N_PROD_WARPS = 8;
-constexpr int PROD_THREADS = N_PROD_WARPS * 32;
 
 template <bool TF32>
 struct Cfg {
@@ -28,18 +25,29 @@ struct Cfg {
   static constexpr int TERMS = TF32 ? 2 : 1;         // operand copies (hi, lo)
   static constexpr int NS = TF32 ? 64 : 256;         // output columns per CTA
   static constexpr int SLICES = H / NS;
-  static constexpr int KC = TF32 ? 16 : 64;          // K elements per ring stage
-  static constexpr int STAGES = 4;
-  static constexpr int PIECES = KC / EPC;            // 16-byte K pieces per row per stage (one producer warp each)
-  static constexpr int GROUPS = 8 / PIECES;          // producer-warp groups; group g fills stages with it % GROUPS == g
-  static constexpr int NCHUNK = H / KC;              // stages per tile
-  static constexpr uint32_t A_TERM_BYTES = TM * KC * ES;           // 16 KB
-  static constexpr uint32_t A_STAGE_BYTES = TERMS * A_TERM_BYTES;
   static constexpr uint32_t B_TERM_BYTES = NS * H * ES;
   static constexpr uint32_t B_BYTES = TERMS * B_TERM_BYTES;         // 128 KB
   static constexpr uint32_t TMEM_COLS = 2 * NS < 32 ? 32 : 2 * NS;
   static constexpr size_t PACKED_NET_BYTES = (size_t)SLICES * B_BYTES;
 };
+
+// pipeline shape: NPW producer warps (CUDA-core operand generation is issue-bound, so the forward runs 16)
+template <bool TF32, int NPW>
+struct Pipe : Cfg<TF32> {
+  using C = Cfg<TF32>;
+  static constexpr int KC = TF32 ? 16 : 64;                    // K elements per ring stage
+  static constexpr int STAGES = TF32 ? 5 : 4;
+  static constexpr int PIECES = KC / C::EPC;                   // 16-byte K pieces per row per stage (one warp each)
+  static constexpr int GROUPS = NPW / PIECES;                  // warp group g fills stages with it % GROUPS == g
+  static constexpr int NCHUNK = H / KC;                        // stages per tile
+  static constexpr uint32_t A_TERM_BYTES = TM * KC * C::ES;
+  static constexpr uint32_t A_STAGE_BYTES = C::TERMS * A_TERM_BYTES;
+  static constexpr int MMA_WARP = 4 + NPW;
+  static constexpr int THREADS = (5 + NPW) * 32;
+  static constexpr int PROD_THREADS = NPW * 32;
+};
+constexpr int FWD_NPW = 16;
+constexpr int BWD1_NPW = 8;
 
 // packed weights: per net, per slice: [term][kchunk16][n_local/8][8][16 B]  (chunk_off with rows = NS)
 // TRANSPOSE=false: B[n][k] = W2[n][k] (forward);  true: B[n][k] = W2[k][n] (backward dH1 = dZ2 * W2)
@@ -105,9 +113,9 @@ __device__ __forceinline__ ItemInfo decode_item(const TcFwdJobs& jobs, int item)
   return it;
 }
 
-template <bool TF32>
+template <bool TF32, int NPW>
 struct FwdSmem {
-  using C = Cfg<TF32>;
+  using C = Pipe<TF32, NPW>;
   static constexpr uint32_t OFF_B = 0;
   static constexpr uint32_t OFF_A = C::B_BYTES;
   static constexpr uint32_t OFF_W1 = OFF_A + C::STAGES * C::A_STAGE_BYTES;   // float4[256]: w0,w1,w2,b1
@@ -118,10 +126,26 @@ struct FwdSmem {
   static constexpr uint32_t BYTES = OFF_SLOT + 16;
 };
 
+// packed fp32x2 FMA (sm_100a): d = a * b + c on two lanes of a 64-bit register pair
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+// cheap split for the producers: hi rounded to nearest tf32, lo = exact remainder (the MMA truncates it to tf32:
+// <= 2^-23 |x|, negligible next to the accumulation error)
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+  hi = rn_tf32(x);
+  lo = x - hi;
+}
+
 template <bool TF32, int IN, int OUT>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs jobs) {
-  using C = Cfg<TF32>;
-  using S = FwdSmem<TF32>;
+__global__ void __launch_bounds__(Pipe<TF32, FWD_NPW>::THREADS, 1) tc_fwd_kernel(const TcFwdJobs jobs) {
+  using C = Pipe<TF32, FWD_NPW>;
+  using S = FwdSmem<TF32, FWD_NPW>;
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Bs = sm + S::OFF_B;
   uint8_t* As = sm + S::OFF_A;
@@ -141,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
   const int item_lo = (int)((long long)total * blockIdx.x / gridDim.x);
   const int item_hi = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp == 12) {
+  if (warp == C::MMA_WARP) {
     tmem_alloc(slot, C::TMEM_COLS);
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::PIECES); mbar_init(&empty[s], 1); }
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
   tc_fence_after();
   const uint32_t tmem = *slot;
 
-  if (warp == 12) {
+  if (warp == C::MMA_WARP) {
     // =============================== MMA issuer (whole warp, one elected lane issues) ===============================
     {
       const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TM, C::NS);
@@ -231,12 +255,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
         cur_pair = ii.pair_id;
         if (netkey != cur_netkey) {         // (re)load W1|b1 of this net
           cur_netkey = netkey;
-          asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS));
+          asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
           const float* net = jb.params + (size_t)ii.net * NET_STRIDE;
-          const int k = ptid;
-          w1s[k] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
-                               IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
-          asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS));
+          for (int k = ptid; k < H; k += C::PROD_THREADS)
+            w1s[k] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
+                                 IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+          asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
         }
       }
       float4 x[4];
@@ -257,11 +281,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
 #pragma unroll
           for (int e = 0; e < C::EPC; ++e) {
             const float4 w = w1s[c * C::KC + p * C::EPC + e];
+            const float2 bw = make_float2(w.w, w.w), wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y),
+                         wz = make_float2(w.z, w.z);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float v = fmaf(x[i].y, w.y, x[i].x * w.x);
-              if (IN == 3) v = fmaf(x[i].z, w.z, v);
-              z[i][e] = fmaxf(v + w.w, 0.f);
+            for (int i = 0; i < 4; i += 2) {     // two rows per packed FMA; chain starts from the bias
+              float2 v = ffma2(make_float2(x[i].x, x[i + 1].x), wx, bw);
+              v = ffma2(make_float2(x[i].y, x[i + 1].y), wy, v);
+              if (IN == 3) v = ffma2(make_float2(x[i].z, x[i + 1].z), wz, v);
+              z[i][e] = fmaxf(v.x, 0.f);
+              z[i + 1][e] = fmaxf(v.y, 0.f);
             }
           }
 #pragma unroll
@@ -269,8 +297,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
             const uint32_t off = chunk_off(TM, lane + 32 * i, p);
             if constexpr (TF32) {
               float4 hi, lo;
-              split_tf32(z[i][0], hi.x, lo.x); split_tf32(z[i][1], hi.y, lo.y);
-              split_tf32(z[i][2], hi.z, lo.z); split_tf32(z[i][3], hi.w, lo.w);
+              split_tf32_fast(z[i][0], hi.x, lo.x); split_tf32_fast(z[i][1], hi.y, lo.y);
+              split_tf32_fast(z[i][2], hi.z, lo.z); split_tf32_fast(z[i][3], hi.w, lo.w);
               *reinterpret_cast<float4*>(stage + off) = hi;
               *reinterpret_cast<float4*>(stage + C::A_TERM_BYTES + off) = lo;
             } else {
@@ -345,7 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const TcFwdJobs j
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem, C::TMEM_COLS);
+  if (warp == C::MMA_WARP) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 // out[net][row][o] = b3[o] + sum over slices of the partial layer-3 sums (fixed order)

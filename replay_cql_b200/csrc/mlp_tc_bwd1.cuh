@@ -38,9 +38,9 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32]) {
 }
 
 template <bool TF32, int IN, int OUT, bool WGRADS, bool DX>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb) {
-  using C = Cfg<TF32>;
-  using S = FwdSmem<TF32>;
+__global__ void __launch_bounds__(Pipe<TF32, BWD1_NPW>::THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb) {
+  using C = Pipe<TF32, BWD1_NPW>;
+  using S = FwdSmem<TF32, BWD1_NPW>;
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Bs = sm + S::OFF_B;
   uint8_t* As = sm + S::OFF_A;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
   const int item_lo = (int)((long long)total * blockIdx.x / gridDim.x);
   const int item_hi = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp == 12) {
+  if (warp == C::MMA_WARP) {
     tmem_alloc(slot, C::TMEM_COLS);
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::PIECES); mbar_init(&empty[s], 1); }
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
   tc_fence_after();
   const uint32_t tmem = *slot;
 
-  if (warp == 12) {
+  if (warp == C::MMA_WARP) {
     {
       const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TM, C::NS);
       const uint32_t a_lbo = TM * 16, b_lbo = C::NS * 16;
@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
       const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES;
       if (net_i != cur_net) {
         cur_net = net_i;
-        asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS));
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
         const float* net = jb.params + (size_t)net_i * NET_STRIDE;
         w3s[ptid] = make_float2(net[off_W3(IN) + ptid], OUT == 2 ? net[off_W3(IN) + H + ptid] : 0.f);
-        asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS));
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
       }
       float d0[4], d1[4];
       const float* h2r[4];
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd1_kernel(const Bwd1Job jb
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem, C::TMEM_COLS);
+  if (warp == C::MMA_WARP) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 // grads[net][idx] from the tensor-core partials: W2 <- pw2 (bwd2 splits); b2|W3|b3 <- small2 (bwd2 splits);

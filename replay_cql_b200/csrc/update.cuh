@@ -464,7 +464,7 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   CQL_REQUIRE(part_off <= h->part_floats, "internal: partial-sum scratch too small");
   if (items == 0) return;
   const int grid = items < h->num_sms ? items : h->num_sms;
-  tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::TC_THREADS, tc::FwdSmem<TF32>::BYTES, st>>>(tj);
+  tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
   CQL_LAUNCH_CHECK(h);
   for (int i = 0; i < jobs.n; ++i) {
     const FwdJob& j = jobs.j[i];
@@ -519,7 +519,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
   tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes, h->small1,
                  DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
-  tc::tc_bwd1_kernel<TF32, IN, OUT, WGRADS, DX><<<grid1, tc::TC_THREADS, tc::FwdSmem<TF32>::BYTES, st>>>(j1);
+  tc::tc_bwd1_kernel<TF32, IN, OUT, WGRADS, DX><<<grid1, tc::Pipe<TF32, tc::BWD1_NPW>::THREADS, tc::FwdSmem<TF32, tc::BWD1_NPW>::BYTES, st>>>(j1);
   CQL_LAUNCH_CHECK(h);
   if (!WGRADS) return;
   const int n_stage = (jb.rows + tc::B2Cfg<TF32>::RS - 1) / tc::B2Cfg<TF32>::RS;
