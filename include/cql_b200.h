@@ -169,7 +169,8 @@ int  cql_topk_filter_dev(cql_handle* h, const float* scores_dev, int64_t n_users
 int  cql_timed_update(cql_handle* h, float* out_ms8, void* stream);
 
 /* Self-test of the tensor-core building blocks (tcgen05.mma + TMEM + operand layout):
- * D[128][n] = A[128][k] * B[n][k]^T with `precision` = CQL_PREC_BF16 or CQL_PREC_TF32X3 (host pointers). */
+ * D[128][n] = A[128][k] * B[n][k]^T with `precision` = CQL_PREC_BF16 or CQL_PREC_TF32X3 (host pointers);
+ * add 0x100 to `precision` to stage operand A in tensor memory (tcgen05.st, "TS" MMA) instead of shared memory. */
 int  cql_selftest_umma(cql_handle* h, int precision, const float* A_host, const float* B_host,
                        int n, int k, float* D_host);
 

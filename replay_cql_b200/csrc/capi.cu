@@ -53,6 +53,8 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   const int f1 = (int)tc::FwdSmem<true, tc::BWD1_NPW>::BYTES, f0 = (int)tc::FwdSmem<false, tc::BWD1_NPW>::BYTES;
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_kernel<true, 3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f1));
@@ -413,6 +415,8 @@ int cql_selftest_umma(cql_handle* ch, int precision, const float* A_host, const 
                       float* D_host) {
   return guarded(ch, [&] {
     Handle& h = ch->h;
+    const bool a_in_tmem = (precision & 0x100) != 0;     // +0x100: stage A in tensor memory (TS mode)
+    precision &= 0xff;
     CQL_REQUIRE(precision == CQL_PREC_TF32X3 || precision == CQL_PREC_BF16, "cql_selftest_umma: precision must be tf32x3 or bf16");
     const bool tf32 = precision == CQL_PREC_TF32X3;
     CQL_REQUIRE(A_host && B_host && D_host, "cql_selftest_umma: NULL pointer");
@@ -427,7 +431,16 @@ int cql_selftest_umma(cql_handle* ch, int precision, const float* A_host, const 
     cudaStream_t st = h.own_stream;
     CQL_CUDA(cudaMemcpyAsync(dA, A_host, (size_t)128 * k * 4, cudaMemcpyHostToDevice, st));
     CQL_CUDA(cudaMemcpyAsync(dB, B_host, (size_t)n * k * 4, cudaMemcpyHostToDevice, st));
-    if (tf32) {
+    if (a_in_tmem) {
+      CQL_REQUIRE((tf32 ? 2 * k : k / 2) + n <= 512, "cql_selftest_umma: A + D do not fit in tensor memory");
+      if (tf32) {
+        CQL_CUDA(cudaFuncSetAttribute(tc::umma_ts_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::umma_ts_selftest_kernel<true><<<1, 128, smem, st>>>(dA, dB, dD, n, k);
+      } else {
+        CQL_CUDA(cudaFuncSetAttribute(tc::umma_ts_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::umma_ts_selftest_kernel<false><<<1, 128, smem, st>>>(dA, dB, dD, n, k);
+      }
+    } else if (tf32) {
       CQL_CUDA(cudaFuncSetAttribute(tc::umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc::umma_selftest_kernel<true><<<1, 128, smem, st>>>(dA, dB, dD, n, k);
     } else {

@@ -86,6 +86,90 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
+// Same product with the A operand staged in TENSOR MEMORY (tcgen05.st, thread = row) instead of shared memory --
+// the layout the fused kernels use so that operand A costs no shared-memory bandwidth.
+// TMEM columns: [0, KA) A hi, [KA, 2KA) A lo (tf32 only), then D; KA = K (tf32) or K/2 (bf16, two per column).
+template <bool TF32>
+__global__ void __launch_bounds__(128) umma_ts_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  constexpr int ES = TF32 ? 4 : 2, TERMS = TF32 ? 2 : 1, UK = 32 / ES;
+  const uint32_t b_bytes = (uint32_t)N * K * ES;
+  uint8_t* Bs = sm;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Bs + TERMS * b_bytes);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KA = TF32 ? K : K / 2;
+  const int d_col = TERMS * KA;
+
+  fill_operand<TF32>(B, N, K, Bs, Bs + b_bytes);
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc(slot, 512);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  {  // each thread stages its own row of A
+    const float* arow = A + (size_t)tid * K;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < KA; c0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (TF32) {
+          float h, l;
+          split_tf32(arow[c0 + i], h, l);
+          hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(l);
+        } else {
+          __nv_bfloat162 p = __floats2bfloat162_rn(arow[2 * (c0 + i)], arow[2 * (c0 + i) + 1]);
+          hi[i] = *reinterpret_cast<uint32_t*>(&p); lo[i] = 0;
+        }
+      }
+      tmem_st8(lane_base + c0, hi);
+      if (TF32) tmem_st8(lane_base + KA + c0, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, 128, N);
+    const uint32_t b_lbo = N * 16;
+    if (elect_one()) {
+      uint32_t acc = 0;
+      for (int j = 0; j < K / UK; ++j) {
+        const uint64_t b_hi = smem_desc(smem_u32(Bs) + 2 * j * b_lbo, b_lbo, 128);
+        const uint32_t a_hi = tmem + j * 8;               // 8 columns per MMA in both formats
+        if (TF32) {
+          const uint64_t b_lo = smem_desc(smem_u32(Bs + b_bytes) + 2 * j * b_lbo, b_lbo, 128);
+          umma_ts<TF32>(tmem + d_col, a_hi + KA, b_hi, idesc, acc); acc = 1;
+          umma_ts<TF32>(tmem + d_col, a_hi, b_lo, idesc, acc);
+          umma_ts<TF32>(tmem + d_col, a_hi, b_hi, idesc, acc);
+        } else {
+          umma_ts<TF32>(tmem + d_col, a_hi, b_hi, idesc, acc); acc = 1;
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + d_col + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < N) D[(size_t)(warp * 32 + lane) * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 inline size_t selftest_smem(bool tf32, int N, int K) {
   const size_t es = tf32 ? 4 : 2, terms = tf32 ? 2 : 1;
   return terms * (128 + (size_t)N) * K * es + 64;

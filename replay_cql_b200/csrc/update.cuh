@@ -7,6 +7,7 @@
 #pragma once
 #include "engine.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc_ts.cuh"
 #include "mlp_tc_bwd1.cuh"
 #include "mlp_tc_bwd2.cuh"
 
@@ -464,7 +465,10 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   CQL_REQUIRE(part_off <= h->part_floats, "internal: partial-sum scratch too small");
   if (items == 0) return;
   const int grid = items < h->num_sms ? items : h->num_sms;
-  tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
+  if constexpr (TF32)
+    tc::tc_fwd_ts_kernel<IN, OUT><<<grid, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(tj);
+  else
+    tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
   CQL_LAUNCH_CHECK(h);
   for (int i = 0; i < jobs.n; ++i) {
     const FwdJob& j = jobs.j[i];

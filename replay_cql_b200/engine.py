@@ -202,14 +202,14 @@ class CqlEngine:
         keys = ("critic_fwd", "critic_bwd1", "critic_bwd2", "update", "actor_step_fwd", "actor_bwd", "actor_fwd", "other")
         return dict(zip(keys, map(float, out)))
 
-    def selftest_umma(self, A: np.ndarray, B: np.ndarray, precision: str) -> np.ndarray:
+    def selftest_umma(self, A: np.ndarray, B: np.ndarray, precision: str, a_in_tmem: bool = False) -> np.ndarray:
         """D = A @ B.T on the tensor cores (A [128,k], B [n,k]); building-block self-test."""
         A, B = _f32(A), _f32(B)
         n, k = B.shape
         if A.shape != (128, k):
             raise ValueError("A must be [128, k]")
         D = np.empty((128, n), dtype=np.float32)
-        self._check(self._lib.cql_selftest_umma(self._h, PRECISIONS[precision], _ptr(A), _ptr(B), n, k, _ptr(D)),
+        self._check(self._lib.cql_selftest_umma(self._h, PRECISIONS[precision] + (0x100 if a_in_tmem else 0), _ptr(A), _ptr(B), n, k, _ptr(D)),
                     "cql_selftest_umma")
         return D
 

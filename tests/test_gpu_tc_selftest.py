@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("precision,n,k", [("bf16", 256, 256), ("bf16", 64, 64), ("bf16", 16, 32),
                                            ("tf32x3", 64, 128), ("tf32x3", 256, 64), ("tf32x3", 32, 32)])
-def test_umma_selftest(engine_factory, precision, n, k):
+@pytest.mark.parametrize("a_in_tmem", [False, True])
+def test_umma_selftest(engine_factory, precision, n, k, a_in_tmem):
     eng = engine_factory(batch_size=64)
     rng = np.random.default_rng(n * 1000 + k)
     A = rng.standard_normal((128, k)).astype(np.float32)
@@ -16,7 +17,7 @@ def test_umma_selftest(engine_factory, precision, n, k):
     # make layout mistakes loud: every row/column gets its own scale
     A *= (1 + np.arange(128, dtype=np.float32))[:, None] / 64
     B *= (1 + np.arange(n, dtype=np.float32))[:, None] / 32
-    D = eng.selftest_umma(A, B, precision)
+    D = eng.selftest_umma(A, B, precision, a_in_tmem=a_in_tmem)
     if precision == "bf16":
         import torch
         Ab = torch.from_numpy(A).bfloat16().double().numpy()
