@@ -7,7 +7,7 @@
 // from registers into TMEM with tcgen05.st -- a thread owns one row = one TMEM lane -- and the MMA takes
 // A from TMEM ("TS" form), so shared memory only serves the resident W2 slice: 64 B/clk.
 //
-// TMEM columns: [0,128) two 64-column accumulators; [128,384) four A stages of 32 K: hi[32] | lo[32].
+// TMEM columns: [0,128) two 64-column accumulators; [128,512) three A stages of 64 K: hi[64] | lo[64].
 // warps 0-3 epilogue, 4-19 producers (lane quarter = warp % 4, K eighth = (warp-4) / 4), 20 MMA issuer.
 #pragma once
 #include "mlp_tc.cuh"
@@ -17,8 +17,8 @@ namespace tc {
 
 struct TsCfg : Cfg<true> {
   static constexpr int NPW = 16;
-  static constexpr int KC = 32;                       // K per stage
-  static constexpr int STAGES = 4;
+  static constexpr int KC = 64;                       // K per stage
+  static constexpr int STAGES = 3;                    // 128 accumulator + 3 x 128 operand columns = all 512
   static constexpr int NCHUNK = H / KC;               // 8
   static constexpr int KPW = KC / (NPW / 4);          // K elements per producer warp per stage: 8
   static constexpr int MMA_WARP = 4 + NPW;
@@ -171,8 +171,11 @@ __global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_fwd_ts_kernel(const TcFw
         }
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);          // values are ready before the slot is: wait late
         tc_fence_after();
-        tmem_st8(lane_base + s * C::A_STAGE_COLS, hi);
-        tmem_st8(lane_base + s * C::A_STAGE_COLS + C::KC, lo);
+#pragma unroll
+        for (int q = 0; q < C::KPW; q += 8) {
+          tmem_st8(lane_base + s * C::A_STAGE_COLS + q, *reinterpret_cast<const uint32_t(*)[8]>(&hi[q]));
+          tmem_st8(lane_base + s * C::A_STAGE_COLS + C::KC + q, *reinterpret_cast<const uint32_t(*)[8]>(&lo[q]));
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

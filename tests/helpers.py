@@ -95,3 +95,11 @@ def digest(flat: np.ndarray, n_probe: int = 512, seed: int = 99) -> np.ndarray:
     parts += list(flat[n_slots * layout.NET_STRIDE:n_slots * layout.NET_STRIDE + 2])
     idx = np.random.default_rng(seed).integers(0, n_slots * layout.NET_STRIDE, size=n_probe)
     return np.concatenate([np.asarray(parts), flat[idx]])
+
+
+def rel_err_l2(a, b) -> float:
+    """||a - b||_2 / ||b||_2 (Frobenius)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.sqrt((b * b).sum())
+    num = np.sqrt(((a - b) ** 2).sum())
+    return float(num / den) if den > 0 else float(num)
