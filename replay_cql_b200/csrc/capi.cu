@@ -6,6 +6,7 @@
 #include "update.cuh"
 #include "score.cuh"
 #include "tc_selftest.cuh"
+#include "score_tc.cuh"
 
 using namespace cql;
 
@@ -21,6 +22,7 @@ struct cql_handle {
   float* part_s = nullptr;
   int* part_i = nullptr;
   size_t part_elems = 0;
+  uint8_t* packed_score = nullptr;   // tf32-packed W2 of actor + critics for the tensor-core scorer
 };
 
 static thread_local std::string g_create_error;
@@ -53,6 +55,7 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ScoreSmem::bytes(CQL_MAX_TOPK)));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   const int f1 = (int)tc::FwdSmem<true, tc::BWD1_NPW>::BYTES, f0 = (int)tc::FwdSmem<false, tc::BWD1_NPW>::BYTES;
@@ -206,6 +209,46 @@ void score_topk_dev_impl(cql_handle* ch, const int32_t* users, int64_t U, const 
     CQL_CUDA(cudaStreamSynchronize(st));
     return;
   }
+  if (h->cfg.precision != CQL_PREC_FP32) {   // tensor-core scorer (FP32-grade tf32 split in both TC modes)
+    using TC = tc::Cfg<true>;
+    if (!ch->packed_score) CQL_CUDA(cudaMalloc(&ch->packed_score, (size_t)(1 + h->C) * TC::PACKED_NET_BYTES));
+    const int chunks16 = H * (H / TC::EPC);
+    tc::k_pack_w2<true, false><<<dim3((chunks16 + 255) / 256, 1), 256, 0, st>>>(h->net_params(slot_actor()), 2, 1, ch->packed_score);
+    CQL_LAUNCH_CHECK(h);
+    tc::k_pack_w2<true, false><<<dim3((chunks16 + 255) / 256, h->C), 256, 0, st>>>(h->net_params(slot_critic(0)), 3, h->C,
+                                                                                   ch->packed_score + TC::PACKED_NET_BYTES);
+    CQL_LAUNCH_CHECK(h);
+    const int64_t tiles128 = (I + tc::TM - 1) / tc::TM;
+    const int chunks = (int)((tiles128 + tc::SC_CH - 1) / tc::SC_CH);
+    const size_t need = (size_t)U * chunks * k;
+    float* ps = out_scores;
+    int* pi = out_items;
+    if (chunks > 1) {
+      if (need > ch->part_elems) {
+        if (ch->part_s) CQL_CUDA(cudaFree(ch->part_s));
+        if (ch->part_i) CQL_CUDA(cudaFree(ch->part_i));
+        ch->part_s = nullptr; ch->part_i = nullptr; ch->part_elems = 0;
+        CQL_CUDA(cudaMalloc(&ch->part_s, need * sizeof(float)));
+        CQL_CUDA(cudaMalloc(&ch->part_i, need * sizeof(int)));
+        ch->part_elems = need;
+      }
+      ps = ch->part_s;
+      pi = ch->part_i;
+    }
+    tc::ScoreTcArgs a{h->params, ch->packed_score, users, items, seen_indptr, seen_items, U, I, h->C, k, mode, chunks, ps, pi};
+    const int64_t n_blocks = U * chunks;
+    const int grid = (int)std::min<int64_t>(n_blocks, h->num_sms);
+    const uint32_t smem = tc::ScoreSmem::bytes(k);
+    tc::tc_score_kernel<<<grid, tc::TsCfg::THREADS, smem, st>>>(a);
+    CQL_LAUNCH_CHECK(h);
+    if (chunks > 1) {
+      const int wpb = 4;
+      k_topk_merge<<<(unsigned)((U + wpb - 1) / wpb), wpb * 32, wpb * 2 * k * sizeof(float), st>>>(ps, pi, U, chunks, k,
+                                                                                                  out_scores, out_items);
+      CQL_LAUNCH_CHECK(h);
+    }
+    return;
+  }
   // enough CTAs to fill the machine a few times over, at most one chunk per tile
   int64_t want = (8ll * h->num_sms + U - 1) / U;
   int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, want));
@@ -280,6 +323,7 @@ void cql_destroy(cql_handle* ch) {
   for (int i = 0; i < 8; ++i) if (ch->sbuf[i]) cudaFree(ch->sbuf[i]);
   if (ch->part_s) cudaFree(ch->part_s);
   if (ch->part_i) cudaFree(ch->part_i);
+  if (ch->packed_score) cudaFree(ch->packed_score);
   ch->h.free_all();
   delete ch;
 }

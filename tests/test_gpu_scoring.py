@@ -32,10 +32,11 @@ def _lists_match(ti, ts, ri, rs):
         assert ti[r, c] in ri[r] or np.any(np.abs(rs[r] - ts[r, c]) <= TOL * scale)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", ["score_small.npz", "score_k1.npz"])
-def test_golden_scores(engine_factory, name):
+def test_golden_scores(engine_factory, name, precision):
     z = np.load(GOLD / name)
-    eng = engine_factory(batch_size=64)
+    eng = engine_factory(batch_size=64, precision=precision)
     eng.set_state(layout.init_state(2, int(z["init_seed"])))
     ti, ts = eng.score_topk(z["users"], z["items"], int(z["k"]), z["seen_indptr"], z["seen_items"], mode="q")
     _lists_match(ti, ts, z["top_items"], z["top_scores"])
@@ -49,10 +50,11 @@ def _oracle_state(seed):
     return flat, Hp.flat_to_oracle_state(flat, cfg)
 
 
-@pytest.mark.parametrize("U,I,k", [(5, 1000, 10), (700, 130, 7), (3, 63, 100), (2, 64, 64)])
-def test_random_against_brute_force(engine_factory, U, I, k):
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("U,I,k", [(5, 1000, 10), (700, 130, 7), (3, 63, 100), (2, 64, 64), (3, 5000, 10)])
+def test_random_against_brute_force(engine_factory, U, I, k, precision):
     flat, st = _oracle_state(11)
-    eng = engine_factory(batch_size=64)
+    eng = engine_factory(batch_size=64, precision=precision)
     eng.set_state(flat)
     rng = np.random.default_rng(U * 1000 + I)
     users = np.sort(rng.choice(6040, size=U, replace=False)).astype(np.int32)
