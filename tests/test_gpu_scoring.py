@@ -58,7 +58,7 @@ def test_random_against_brute_force(engine_factory, U, I, k, precision):
     eng.set_state(flat)
     rng = np.random.default_rng(U * 1000 + I)
     users = np.sort(rng.choice(6040, size=U, replace=False)).astype(np.int32)
-    items = np.sort(rng.choice(3706, size=I, replace=False)).astype(np.int32)
+    items = np.sort(rng.choice(max(3706, 2 * I), size=I, replace=False)).astype(np.int32)
     seen = {int(u): set(rng.choice(items, size=int(rng.integers(0, min(50, I))), replace=False).tolist()) for u in users}
     seen[int(users[0])] = set(items.tolist())          # a user who has seen everything
     indptr = np.zeros(int(users.max()) + 2, dtype=np.int64)
