@@ -38,8 +38,11 @@ FLOP_PER_UPDATE_PER_B = 269 * FLOP_PER_ROW       # 269 forward-equivalent rows p
 FLOP_PER_PAIR = 3 * FLOP_PER_ROW                 # 2 critics + actor = 399 360
 DTYPES = {"fp32": "f32", "tf32x3": "f32 (tf32x3: tensor-core 3-term split, fp32 accumulate, 1e-4 parity-gated)",
           "bf16": "bf16 (fp32 accumulate; non-parity variant)"}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from one `ncu --set full` capture
+# (profiles/r01_tc_fwd_ts_ncu_summary.txt); null where no capture exists for that variant
+KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "bf16": None}
 KERNEL_NAMES = {"fp32": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
-                "tf32x3": "tc_fwd_kernel<tf32x3,3,1> (critic forward, tcgen05 kind::tf32 3-term split)",
+                "tf32x3": "tc_fwd_ts_kernel<3,1> (critic forward: tcgen05 kind::tf32 3-term split, A operand in TMEM)",
                 "bf16": "tc_fwd_kernel<bf16,3,1> (critic forward, tcgen05 kind::f16)"}
 
 
@@ -152,7 +155,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    steps = max(1, args.steps)
+    steps = max(1, min(args.steps, 200))      # bounded sample: ~0.04-0.2 s per oracle update
     rate, dt, threads = cpu_update_rate(steps, max(1, min(args.warmup, 5)))
     srate, sdt, _ = cpu_scoring_rate(8)
     line = {
@@ -335,7 +338,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[args.precision],
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "peak_source": f"bf16_tflops_sustained ({pk_kind})", "traffic": None,
+                         "peak_source": f"bf16_tflops_sustained ({pk_kind})", "traffic": KERNEL_TRAFFIC[args.precision],
                          "flop_per_launch": fwd_flop, "ms_per_launch": tk["critic_fwd"],
                          "update_tflops": value / world * BATCH * FLOP_PER_UPDATE_PER_B / 1e12},
             "kernel_ms": tk,
@@ -359,8 +362,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=None, help="override the log size (debugging)")
     ap.add_argument("--precision", choices=["fp32", "tf32x3", "bf16"], default="tf32x3",
