@@ -118,8 +118,13 @@ int  cql_update_batch(cql_handle* h, const float* obs, const float* act, const f
  * back to back.  phase 0: sample + forward passes + temp/alpha grads
  *                phase 1: temp/alpha Adam, critic backward  -> critic grads
  *                phase 2: critic Adam + Polyak, actor passes -> actor grads
- *                phase 3: actor Adam + Polyak, step counter                    */
+ *                phase 3: actor Adam + Polyak, step counter
+ *                phase 4: phase 0 on the minibatch staged by cql_upload_batch  */
 int  cql_step_phase(cql_handle* h, int phase, void* stream);
+/* Data-parallel end-to-end variant: stage a caller-supplied host minibatch (B rows), then run the phases with
+ * phase 4 in place of phase 0 (same work, the uploaded batch instead of a sampled one). */
+int  cql_upload_batch(cql_handle* h, const float* obs, const float* act, const float* rew,
+                      const float* next_obs, const float* term, void* stream);
 enum { CQL_BUF_SCALAR_GRADS = 0,   /* 64 floats: [0]=d log_temp [1]=d log_alpha */
        CQL_BUF_CRITIC_GRADS = 1,   /* C*NET floats */
        CQL_BUF_ACTOR_GRADS = 2,    /* NET floats */

@@ -548,6 +548,23 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
   });
 }
 
+int cql_upload_batch(cql_handle* ch, const float* obs, const float* act, const float* rew, const float* next_obs,
+                     const float* term, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(obs && act && rew && next_obs && term, "cql_upload_batch: NULL batch pointer");
+    cudaStream_t st = pick_stream(&h, stream);
+    const int B = h.B;
+    CQL_CUDA(cudaStreamSynchronize(st));      // the staging buffer may still be in flight from the previous step
+    for (int b = 0; b < B; ++b) {
+      float* r = h.batch_host + (size_t)b * 8;
+      r[0] = obs[2 * b]; r[1] = obs[2 * b + 1]; r[2] = act[b]; r[3] = rew[b];
+      r[4] = next_obs[2 * b]; r[5] = next_obs[2 * b + 1]; r[6] = term[b]; r[7] = 0.f;
+    }
+    CQL_CUDA(cudaMemcpyAsync(h.batch, h.batch_host, (size_t)B * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+  });
+}
+
 int cql_step_phase(cql_handle* ch, int phase, void* stream) {
   return guarded(ch, [&] {
     Handle& h = ch->h;
@@ -557,7 +574,8 @@ int cql_step_phase(cql_handle* ch, int phase, void* stream) {
       case 1: phase1(&h, st); break;
       case 2: phase2(&h, st); break;
       case 3: phase3(&h, st); break;
-      default: throw Error{"cql_step_phase: phase must be 0..3"};
+      case 4: phase0(&h, st, BatchSource::Provided, NoiseSource::Philox); break;   // after cql_upload_batch
+      default: throw Error{"cql_step_phase: phase must be 0..4"};
     }
   });
 }

@@ -249,14 +249,22 @@ class CqlEngine:
     def step_phase(self, phase: int, stream: int | None = None) -> None:
         self._check(self._lib.cql_step_phase(self._h, phase, stream), "cql_step_phase")
 
-    def update_data_parallel(self, allreduce_mean: Callable[[int], None], stream: int | None = None) -> None:
+    def upload_batch(self, batch: Dict[str, np.ndarray], stream: int | None = None) -> None:
+        B = self.hp.batch_size
+        obs, nobs = _f32(batch["obs"], (B, 2)), _f32(batch["next_obs"], (B, 2))
+        act, rew, term = (_f32(np.reshape(batch[k], -1), (B,)) for k in ("act", "rew", "term"))
+        self._check(self._lib.cql_upload_batch(self._h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(nobs), _ptr(term), stream),
+                    "cql_upload_batch")
+
+    def update_data_parallel(self, allreduce_mean: Callable[[int], None], stream: int | None = None,
+                             uploaded_batch: bool = False) -> None:
         """One data-parallel update: the host averages the three gradient groups between phases.
 
         ``allreduce_mean(buffer_id)`` must average that device buffer over ranks on ``stream``
         (see ``parallel.GradAllReducer``).  Weights stay bit-identical across ranks because every
         rank applies the same Adam step to the same reduced gradient.
         """
-        self.step_phase(0, stream)
+        self.step_phase(4 if uploaded_batch else 0, stream)
         allreduce_mean(_lib.BUF_SCALAR_GRADS)
         self.step_phase(1, stream)
         allreduce_mean(_lib.BUF_CRITIC_GRADS)

@@ -176,15 +176,13 @@ class CQL(Recommender):
                 done += chunk
                 self.logger.debug("CQL epoch %d/%d %s", done // max(per_epoch, 1), self.n_epochs, self.last_metrics)
         else:
-            reducer = GradAllReducer(eng)
+            from .parallel import DataParallelStepper
             import torch
             with torch.cuda.device(eng.device):
-                side = torch.cuda.Stream()          # a real stream: kernels and NCCL are ordered on it
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    for _ in range(total):
-                        eng.update_data_parallel(reducer, stream=side.cuda_stream)
-                side.synchronize()
+                stepper = DataParallelStepper(eng)          # whole step (kernels + NCCL) as one CUDA graph
+                stepper.stream.wait_stream(torch.cuda.current_stream())
+                stepper.run(total)
+                stepper.stream.synchronize()
             self.last_metrics = eng.read_metrics()
 
     # ------------------------------------------------------------------ predict

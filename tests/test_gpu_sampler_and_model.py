@@ -110,3 +110,21 @@ def test_score_policy_mode(fitted):
         assert recs["relevance"].abs().max() <= 1.0     # tanh(mu)
     finally:
         model.score = "q"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_phase_split_equals_fused_update(engine_factory, precision):
+    """The four data-parallel phases (host all-reduce points in between; identity here) take exactly the
+    same step as the fused CUDA-graph update: bit-identical weights after 5 updates."""
+    log = make_log("tiny")
+    mdp = build_mdp(log, seed=1)
+    a = engine_factory(batch_size=64, seed=9, precision=precision)
+    b = engine_factory(batch_size=64, seed=9, precision=precision)
+    for e in (a, b):
+        e.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+    a.update(5)
+    for _ in range(5):
+        b.update_data_parallel(lambda buf: None)
+    torch.cuda.synchronize()
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert a.get_optimizer()[2] == b.get_optimizer()[2] == 5
