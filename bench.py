@@ -367,9 +367,23 @@ def run_ours(args):
                         "frac_of_hbm": gather_gbs / pk.get("hbm_gbs", 6650.0)},
         }
         print(json.dumps(line), flush=True)
+    # teardown: graphs first (NCCL communicators must not be destroyed under a live captured graph); a watchdog
+    # guarantees the process exits even if a collective teardown stalls -- the JSON line is already out
+    sys.stdout.flush()
+    wd = threading.Timer(45.0, lambda: os._exit(0))
+    wd.daemon = True
+    wd.start()
+    if stepper is not None:
+        stepper.graph = None
+    torch.cuda.synchronize(dev)
     eng.close()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+    wd.cancel()
 
 
 def main():
