@@ -6,6 +6,7 @@
 // reduce-scatter per 32-column chunk and then kept in registers across all tiles of the CTA.
 #pragma once
 #include "mlp_tc.cuh"
+#include "mlp_tc_ts.cuh"
 
 namespace cql {
 namespace tc {
@@ -286,6 +287,236 @@ __global__ void __launch_bounds__(Pipe<TF32, BWD1_NPW>::THREADS, 1) tc_bwd1_kern
   tc_fence_before();
   __syncthreads();
   if (warp == C::MMA_WARP) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// ---- FP32-grade variant with the A operand (dZ2 tile) staged in tensor memory, see mlp_tc_ts.cuh ------------
+template <int IN, int OUT, bool WGRADS, bool DX>
+__global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_bwd1_ts_kernel(const Bwd1Job jb) {
+  using C = TsCfg;
+  constexpr bool TF32 = true;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint8_t* Bs = sm + C::OFF_B;
+  float2* w3s = reinterpret_cast<float2*>(sm + C::OFF_W1);    // [256] (W3[0][j], W3[1][j])
+  float4* ebs = reinterpret_cast<float4*>(sm + C::OFF_EB);    // [NS]  (W1[k][0..2], b1[k]) of the slice's columns
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bload = tempty + 2;
+  uint64_t* drain = bload + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = (jb.rows + TM - 1) / TM;
+  const int tiles64 = (jb.rows + 63) / 64;
+  const int total = jb.n_nets * C::SLICES * tiles;
+  const int item_lo = (int)((long long)total * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == C::MMA_WARP) {
+    tmem_alloc(slot, C::TMEM_ALLOC);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::NPW); mbar_init(&empty[s], 1); }
+      for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4); }
+      mbar_init(bload, 1);
+      mbar_init(drain, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (warp == C::MMA_WARP) {
+    const uint32_t idesc = instr_desc(FMT_TF32, TM, C::NS);
+    const uint32_t b_lbo = C::NS * 16;
+    const uint32_t b_base = smem_u32(Bs);
+    int cur_pair = -1;
+    uint32_t it = 0, nb = 0, nd = 0, tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles;
+      if (pair != cur_pair) {
+        if (cur_pair >= 0) { if (elect_one()) umma_commit(drain); __syncwarp(); mbar_wait(drain, nd & 1); ++nd; }
+        const uint8_t* src = jb.packedT + (size_t)(pair / C::SLICES) * C::PACKED_NET_BYTES + (size_t)(pair % C::SLICES) * C::B_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bload, C::B_BYTES);
+          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+        }
+        __syncwarp();
+        mbar_wait(bload, nb & 1);
+        ++nb;
+        cur_pair = pair;
+      }
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + acc * C::NS;
+      for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        const uint32_t s = it % C::STAGES;
+        mbar_wait(&full[s], (it / C::STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_stage = tmem + C::A_COL0 + s * C::A_STAGE_COLS;
+#pragma unroll
+          for (int j = 0; j < C::KC / C::UK; ++j) {
+            const uint32_t g = c * (C::KC / C::UK) + j;
+            const uint64_t b_hi = smem_desc(b_base + 2 * g * b_lbo, b_lbo, 128);
+            const uint64_t b_lo = smem_desc(b_base + C::B_TERM_BYTES + 2 * g * b_lbo, b_lbo, 128);
+            const uint32_t a_hi = a_stage + j * C::UK, a_lo = a_hi + C::KC;
+            umma_ts<true>(d_tmem, a_lo, b_hi, idesc, (c == 0 && j == 0) ? 0u : 1u);
+            umma_ts<true>(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_ts<true>(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (c == C::NCHUNK - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+  } else if (warp >= 4) {
+    // ---------------- producers: dZ2 row -> TMEM ----------------
+    const int pw = warp - 4, ptid = tid - 128;
+    const int kq = pw >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + kq * C::KPW;
+    int cur_net = -1;
+    uint32_t it = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES;
+      if (net_i != cur_net) {
+        cur_net = net_i;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        for (int j = ptid; j < H; j += C::PROD_THREADS)
+          w3s[j] = make_float2(net[off_W3(IN) + j], OUT == 2 ? net[off_W3(IN) + H + j] : 0.f);
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+      }
+      const int r = tile * TM + (warp & 3) * 32 + lane;
+      const bool ok = r < jb.rows;
+      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT) : 0.f;
+      const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1) : 0.f;
+      const int rc = ok ? r : 0;
+      const float* h2r = jb.h2 + ((size_t)net_i * tiles64 + (rc >> 6)) * H * 64 + (rc & 63);
+      for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        const uint32_t s = it % C::STAGES;
+        const int j0 = c * C::KC + kq * C::KPW;
+        float hv[C::KPW];
+#pragma unroll
+        for (int e = 0; e < C::KPW; ++e) hv[e] = __ldg(h2r + (size_t)(j0 + e) * 64);
+        uint32_t hi[C::KPW], lo[C::KPW];
+#pragma unroll
+        for (int e = 0; e < C::KPW; ++e) {
+          const float2 w = w3s[j0 + e];
+          float g = d0 * w.x;
+          if (OUT == 2) g = fmaf(d1, w.y, g);
+          float h, l;
+          split_tf32_fast(hv[e] > 0.f ? g : 0.f, h, l);
+          hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
+        }
+        mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < C::KPW; q += 8) {
+          tmem_st8(lane_base + s * C::A_STAGE_COLS + q, *reinterpret_cast<const uint32_t(*)[8]>(&hi[q]));
+          tmem_st8(lane_base + s * C::A_STAGE_COLS + C::KC + q, *reinterpret_cast<const uint32_t(*)[8]>(&lo[q]));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: dZ1, dx, dW1/db1 ----------------
+    constexpr int NCH = C::NS / 32;
+    float a_b[NCH], a_w0[NCH], a_w1[NCH], a_w2[NCH];      // lane l <-> column chunk*32 + l of the current slice
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) { a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f; }
+    auto flush = [&](int pair) {
+      if (!WGRADS || pair < 0) return;
+      const int net_i = pair / C::SLICES, slice = pair % C::SLICES;
+      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 4 + warp) * SMALL_STRIDE;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int k = slice * C::NS + q * 32 + lane;
+        o[k * IN + 0] = a_w0[q];
+        o[k * IN + 1] = a_w1[q];
+        if (IN == 3) o[k * IN + 2] = a_w2[q];
+        o[H * IN + k] = a_b[q];
+        a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f;
+      }
+    };
+    int cur_pair = -1;
+    uint32_t tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES, slice = pair % C::SLICES;
+      if (pair != cur_pair) {
+        flush(cur_pair);
+        cur_pair = pair;
+        asm volatile("bar.sync 2, 128;");
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        for (int cidx = tid; cidx < C::NS; cidx += 128) {
+          const int k = slice * C::NS + cidx;
+          ebs[cidx] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
+                                  IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+        }
+        asm volatile("bar.sync 2, 128;");
+      }
+      const uint32_t acc = tcount & 1;
+      const int row = tile * TM + warp * 32 + lane;
+      const float4 x = row < jb.rows ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * C::NS + q * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 w = ebs[q * 32 + i];
+          float z = fmaf(x.y, w.y, x.x * w.x);
+          if (IN == 3) z = fmaf(x.z, w.z, z);
+          z += w.w;
+          const float d = z > 0.f ? v[i] : 0.f;
+          v[i] = d;
+          if (DX) {
+            dx0 = fmaf(d, w.x, dx0);
+            dx1 = fmaf(d, w.y, dx1);
+            if (IN == 3) dx2 = fmaf(d, w.z, dx2);
+          }
+        }
+        if (WGRADS) {
+          float t[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x.x;
+          a_w0[q] += warp_reduce_scatter32(t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x.y;
+          a_w1[q] += warp_reduce_scatter32(t);
+          if (IN == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = v[i] * x.z;
+            a_w2[q] += warp_reduce_scatter32(t);
+          }
+          a_b[q] += warp_reduce_scatter32(v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (DX && row < jb.rows)
+        jb.dX_part[((size_t)net_i * C::SLICES + slice) * jb.rows + row] = make_float4(dx0, dx1, dx2, 0.f);
+      ++tcount;
+    }
+    flush(cur_pair);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::MMA_WARP) tmem_dealloc(tmem, C::TMEM_ALLOC);
 }
 
 // grads[net][idx] from the tensor-core partials: W2 <- pw2 (bwd2 splits); b2|W3|b3 <- small2 (bwd2 splits);
