@@ -80,6 +80,40 @@ __global__ void k_pack_w2(const float* __restrict__ params, int in_dim, int n_ne
   }
 }
 
+// several networks / orientations in ONE launch (after an Adam step: critics fwd + critics^T + targets fwd)
+struct PackJobs {
+  struct J { const float* net; uint8_t* dst; int in_dim, transpose; } j[12];
+  int n;
+};
+template <bool TF32>
+__global__ void k_pack_multi(const PackJobs jobs) {
+  using C = Cfg<TF32>;
+  const PackJobs::J jb = jobs.j[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;        // 16-byte chunk id: n * (H/EPC) + kc
+  if (c >= H * (H / C::EPC)) return;
+  const int n = c / (H / C::EPC), kc = c % (H / C::EPC);
+  const float* W2 = jb.net + off_W2(jb.in_dim);
+  float v[C::EPC];
+#pragma unroll
+  for (int i = 0; i < C::EPC; ++i) {
+    const int k = kc * C::EPC + i;
+    v[i] = jb.transpose ? W2[(size_t)k * H + n] : W2[(size_t)n * H + k];
+  }
+  const int slice = n / C::NS, nl = n % C::NS;
+  uint8_t* base = jb.dst + (size_t)slice * C::B_BYTES + chunk_off(C::NS, nl, kc);
+  if constexpr (TF32) {
+    float4 h, l;
+    split_tf32(v[0], h.x, l.x); split_tf32(v[1], h.y, l.y); split_tf32(v[2], h.z, l.z); split_tf32(v[3], h.w, l.w);
+    *reinterpret_cast<float4*>(base) = h;
+    *reinterpret_cast<float4*>(base + C::B_TERM_BYTES) = l;
+  } else {
+    __nv_bfloat162 p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<uint4*>(p);
+  }
+}
+
 struct TcFwdJob {
   const float4* X;        // [rows]
   const float* params;    // fp32 slot of the first net (W1, b1, b2, W3, b3 are read from here)
@@ -386,6 +420,21 @@ __global__ void k_sum_partials(const float* __restrict__ part, const float* __re
   float s = 0.f;
   for (int sl = 0; sl < slices; ++sl) s += part[(((size_t)net * slices + sl) * rows + r) * OUT + o];
   out[i] = s + params[(size_t)net * NET_STRIDE + off_b3(IN, OUT) + o];
+}
+
+struct SumJobs {
+  struct J { const float* part; const float* params; float* out; int rows, n_nets; } j[4];
+  int n;
+};
+template <int IN, int OUT>
+__global__ void k_sum_partials_multi(const SumJobs jobs, int slices) {
+  const SumJobs::J jb = jobs.j[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= jb.n_nets * jb.rows * OUT) return;
+  const int o = i % OUT, r = (i / OUT) % jb.rows, net = i / (OUT * jb.rows);
+  float s = 0.f;
+  for (int sl = 0; sl < slices; ++sl) s += jb.part[(((size_t)net * slices + sl) * jb.rows + r) * OUT + o];
+  jb.out[i] = s + jb.params[(size_t)net * NET_STRIDE + off_b3(IN, OUT) + o];
 }
 
 }  // namespace tc

@@ -520,26 +520,45 @@ __global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_bwd1_ts_kernel(const Bwd
 }
 
 // grads[net][idx] from the tensor-core partials: W2 <- pw2 (bwd2 splits); b2|W3|b3 <- small2 (bwd2 splits);
-// W1|b1 <- small1 (bwd1 warp slots).  Fixed summation order.
+// W1|b1 <- small1 (bwd1 warp slots).  Fixed summation order.  One thread per 4 consecutive parameters,
+// 16-byte loads, 4 partials in flight (the partials were just written: L2-resident, latency-bound).
+__device__ __forceinline__ float4 sum_strided4(const float* __restrict__ p, int n, size_t stride) {
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * stride));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + (size_t)(i + 1) * stride));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)(i + 2) * stride));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p + (size_t)(i + 3) * stride));
+    s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+    s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+    s2.x += c.x; s2.y += c.y; s2.z += c.z; s2.w += c.w;
+    s3.x += d.x; s3.y += d.y; s3.z += d.z; s3.w += d.w;
+  }
+  for (; i < n; ++i) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * stride));
+    s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+  }
+  return make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y), (s0.z + s1.z) + (s2.z + s3.z),
+                     (s0.w + s1.w) + (s2.w + s3.w));
+}
+
 __global__ void k_reduce_grads_tc(const float* __restrict__ small1, int slots1, const float* __restrict__ small2,
                                   const float* __restrict__ pw2, int splits, int in_dim, int out_dim,
                                   float* __restrict__ grads) {
   const int net = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 4;       // every region boundary is a multiple of 4
   if (idx >= NET_STRIDE) return;
   const int w2_lo = off_W2(in_dim), w2_hi = w2_lo + H * H, total = net_floats(in_dim, out_dim);
-  float s = 0.f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (idx >= w2_lo && idx < w2_hi) {
-    const float* p = pw2 + (size_t)net * splits * H * H + (idx - w2_lo);
-    for (int i = 0; i < splits; ++i) s += p[(size_t)i * H * H];
+    s = sum_strided4(pw2 + (size_t)net * splits * H * H + (idx - w2_lo), splits, (size_t)H * H);
   } else if (idx < w2_lo) {
-    const float* p = small1 + (size_t)net * slots1 * SMALL_STRIDE + idx;
-    for (int i = 0; i < slots1; ++i) s += p[(size_t)i * SMALL_STRIDE];
-  } else if (idx < total) {
-    const float* p = small2 + (size_t)net * splits * SMALL_STRIDE + (idx - H * H);
-    for (int i = 0; i < splits; ++i) s += p[(size_t)i * SMALL_STRIDE];
+    s = sum_strided4(small1 + (size_t)net * slots1 * SMALL_STRIDE + idx, slots1, SMALL_STRIDE);
+  } else if (idx < total) {            // tail region: (idx - H*H) keeps 16-byte alignment; entries past `total` are zero
+    s = sum_strided4(small2 + (size_t)net * splits * SMALL_STRIDE + (idx - H * H), splits, SMALL_STRIDE);
   }
-  grads[(size_t)net * NET_STRIDE + idx] = s;
+  *reinterpret_cast<float4*>(grads + (size_t)net * NET_STRIDE + idx) = s;
 }
 
 }  // namespace tc

@@ -5,6 +5,7 @@
 // computed ONCE and shared by the temp step, both conservative-loss evaluations,
 // the TD target and the actor step (a result-preserving saving).
 #pragma once
+#include <algorithm>
 #include "engine.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc_ts.cuh"
@@ -102,6 +103,39 @@ __global__ void k_step_begin(const long long* step_dev, StepInfo* info, float be
   info->bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)t));
 }
 __global__ void k_step_end(long long* step_dev) { *step_dev += 1; }
+
+// sampled-update prologue in one launch: Adam bias corrections, replay gather (+ actor input rows), Philox noise
+__global__ void k_step_head(const float4* __restrict__ table, int64_t n_trans, const long long* __restrict__ step_dev,
+                            StepInfo* __restrict__ info, float beta1, float beta2, int B, int n, int rank, int world,
+                            uint64_t seed, float4* __restrict__ batch, float4* __restrict__ XA,
+                            float* __restrict__ noise, int64_t noise_total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long done = *step_dev;
+  if (i == 0) {
+    const long long t = done + 1;
+    info->step = t;
+    info->bc1 = 1.0 - pow((double)beta1, (double)t);
+    info->bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)t));
+  }
+  if (i < B) {
+    const int64_t p = ((int64_t)done * world + rank) * B + i;
+    const int64_t t = stream_index(p, n_trans, (int64_t)B * world, seed);
+    const float4 a = __ldg(table + 2 * t), b = __ldg(table + 2 * t + 1);
+    batch[2 * i] = a;
+    batch[2 * i + 1] = b;
+    XA[i] = make_float4(a.x, a.y, 0.f, 0.f);
+    XA[B + i] = make_float4(b.x, b.y, 0.f, 0.f);
+  }
+  if (i < noise_total) {
+    uint32_t r[4];
+    Philox::gen(seed ^ 0x5851F42D4C957F2Dull, ((uint64_t)done << 8) | (uint64_t)(rank & 0xff), (uint64_t)i, r);
+    const int64_t Bn = (int64_t)B * n;
+    const int64_t a = i - B;
+    const bool uniform = a >= 0 && a < 6 * Bn && ((a / Bn) % 3 == 2);
+    const float u1 = u01(r[0]), u2 = u01(r[1]);
+    noise[i] = uniform ? fmaf(2.f, u1, -1.f) : sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+  }
+}
 
 // ---------------------------------------------------------------- squashed Gaussian
 struct Sample { float a, logp, raw, t, std_; };
@@ -470,12 +504,16 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   else
     tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
   CQL_LAUNCH_CHECK(h);
+  tc::SumJobs sj{};
+  sj.n = jobs.n;
+  int max_n = 0;
   for (int i = 0; i < jobs.n; ++i) {
     const FwdJob& j = jobs.j[i];
-    const int n = j.n_nets * j.rows * OUT;
-    tc::k_sum_partials<IN, OUT><<<(n + 255) / 256, 256, 0, st>>>(part_of[i], j.params, j.rows, j.n_nets, C::SLICES, j.out);
-    CQL_LAUNCH_CHECK(h);
+    sj.j[i] = {part_of[i], j.params, j.out, j.rows, j.n_nets};
+    max_n = std::max(max_n, j.n_nets * j.rows * OUT);
   }
+  tc::k_sum_partials_multi<IN, OUT><<<dim3((max_n + 255) / 256, jobs.n), 256, 0, st>>>(sj, C::SLICES);
+  CQL_LAUNCH_CHECK(h);
 }
 
 template <int IN, int OUT>
@@ -485,30 +523,31 @@ inline void launch_fwd_any(Handle* h, FwdJobs& jobs, cudaStream_t st) {
   else launch_fwd<IN, OUT>(h, jobs, st);
 }
 
-// refresh the packed (tensor-core operand layout) copy of W2 for `n_slots` networks starting at `slot`
-inline void pack_weights(Handle* h, int slot, int n_slots, int in_dim, cudaStream_t st) {
-  if (h->cfg.precision == CQL_PREC_FP32) return;
-  const float* p = h->net_params(slot);
-  uint8_t* dst = h->packed_fwd + (size_t)slot * h->packed_net_bytes;
+// refresh the packed (tensor-core operand layout) copies of W2 -- forward orientation for every listed slot,
+// plus W2^T for the trainable ones (slot <= C) -- in ONE launch
+inline void pack_slots(Handle* h, const int* slots, int n_slots, cudaStream_t st) {
+  if (h->cfg.precision == CQL_PREC_FP32 || n_slots == 0) return;
+  tc::PackJobs jobs{};
+  for (int i = 0; i < n_slots; ++i) {
+    const int slot = slots[i];
+    const bool is_actor = slot == slot_actor() || slot == slot_targ_actor(h->C);
+    const int in_dim = is_actor ? 2 : 3;
+    jobs.j[jobs.n++] = {h->net_params(slot), h->packed_fwd + (size_t)slot * h->packed_net_bytes, in_dim, 0};
+    if (slot <= h->C) jobs.j[jobs.n++] = {h->net_params(slot), h->packed_bwd + (size_t)slot * h->packed_net_bytes, in_dim, 1};
+  }
   if (h->cfg.precision == CQL_PREC_TF32X3) {
     const int chunks = H * (H / tc::Cfg<true>::EPC);
-    tc::k_pack_w2<true, false><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dst);
+    tc::k_pack_multi<true><<<dim3((chunks + 255) / 256, jobs.n), 256, 0, st>>>(jobs);
   } else {
     const int chunks = H * (H / tc::Cfg<false>::EPC);
-    tc::k_pack_w2<false, false><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dst);
+    tc::k_pack_multi<false><<<dim3((chunks + 255) / 256, jobs.n), 256, 0, st>>>(jobs);
   }
   CQL_LAUNCH_CHECK(h);
-  if (slot <= h->C) {   // trainable nets also need W2^T for the backward
-    uint8_t* dt = h->packed_bwd + (size_t)slot * h->packed_net_bytes;
-    if (h->cfg.precision == CQL_PREC_TF32X3) {
-      const int chunks = H * (H / tc::Cfg<true>::EPC);
-      tc::k_pack_w2<true, true><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dt);
-    } else {
-      const int chunks = H * (H / tc::Cfg<false>::EPC);
-      tc::k_pack_w2<false, true><<<dim3((chunks + 255) / 256, n_slots), 256, 0, st>>>(p, in_dim, n_slots, dt);
-    }
-    CQL_LAUNCH_CHECK(h);
-  }
+}
+inline void pack_weights(Handle* h, int slot, int n_slots, int /*in_dim*/, cudaStream_t st) {
+  int slots[8];
+  for (int i = 0; i < n_slots; ++i) slots[i] = slot + i;
+  pack_slots(h, slots, n_slots, st);
 }
 
 // ---- tensor-core backward of one job: bwd1 (dH1, dW1, db1, dx) + bwd2 (dW2, db2, dW3, db3) + reduce
@@ -537,7 +576,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
   tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
   CQL_LAUNCH_CHECK(h);
-  tc::k_reduce_grads_tc<<<dim3((NET_STRIDE + 255) / 256, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
+  tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 255) / 256, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out);
   CQL_LAUNCH_CHECK(h);
 }
@@ -585,23 +624,33 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
   const int B = h->B, C = h->C, n3 = 3 * h->n;
   const cql_config& c = h->cfg;
   mark(h, st, 0);
-  k_step_begin<<<1, 1, 0, st>>>(h->step_dev, h->stepinfo, c.beta1, c.beta2);
-  CQL_LAUNCH_CHECK(h);
-  if (bs == BatchSource::Sampled) {
-    CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
-    k_sample<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4*>(h->table), h->n_trans, nullptr,
-                                              h->step_dev, 0, B, (int64_t)B * c.world_size, c.rank, c.world_size,
-                                              c.seed, reinterpret_cast<float4*>(h->batch));
-    CQL_LAUNCH_CHECK(h);
-  }
-  if (ns == NoiseSource::Philox) {
-    k_noise<<<(int)((h->noise_floats + 255) / 256), 256, 0, st>>>(h->noise, h->noise_floats, B, h->n, c.seed,
-                                                                  h->step_dev, c.rank);
-    CQL_LAUNCH_CHECK(h);
-  }
   const float4* batch4 = reinterpret_cast<const float4*>(h->batch);
-  k_actor_rows<<<(2 * B + 255) / 256, 256, 0, st>>>(batch4, B, h->XA);
-  CQL_LAUNCH_CHECK(h);
+  if (bs == BatchSource::Sampled && ns == NoiseSource::Philox) {
+    CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
+    const int64_t nthr = h->noise_floats > B ? h->noise_floats : B;
+    k_step_head<<<(int)((nthr + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(h->table), h->n_trans, h->step_dev,
+                                                          h->stepinfo, c.beta1, c.beta2, B, h->n, c.rank, c.world_size,
+                                                          c.seed, reinterpret_cast<float4*>(h->batch), h->XA, h->noise,
+                                                          h->noise_floats);
+    CQL_LAUNCH_CHECK(h);
+  } else {
+    k_step_begin<<<1, 1, 0, st>>>(h->step_dev, h->stepinfo, c.beta1, c.beta2);
+    CQL_LAUNCH_CHECK(h);
+    if (bs == BatchSource::Sampled) {
+      CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
+      k_sample<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4*>(h->table), h->n_trans, nullptr,
+                                                h->step_dev, 0, B, (int64_t)B * c.world_size, c.rank, c.world_size,
+                                                c.seed, reinterpret_cast<float4*>(h->batch));
+      CQL_LAUNCH_CHECK(h);
+    }
+    if (ns == NoiseSource::Philox) {
+      k_noise<<<(int)((h->noise_floats + 255) / 256), 256, 0, st>>>(h->noise, h->noise_floats, B, h->n, c.seed,
+                                                                    h->step_dev, c.rank);
+      CQL_LAUNCH_CHECK(h);
+    }
+    k_actor_rows<<<(2 * B + 255) / 256, 256, 0, st>>>(batch4, B, h->XA);
+    CQL_LAUNCH_CHECK(h);
+  }
   {
     FwdJobs jobs{};
     jobs.n = 2;
@@ -669,8 +718,11 @@ inline void phase2(Handle* h, cudaStream_t st) {
       h->net_params(slot_critic(0)), h->adam_m + (size_t)NET_STRIDE, h->adam_v + (size_t)NET_STRIDE, h->g_critics(),
       h->net_params(slot_targ_critic(C, 0)), cnt, c.critic_lr, c.beta1, c.beta2, c.adam_eps, c.tau, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
-  pack_weights(h, slot_critic(0), C, 3, st);
-  pack_weights(h, slot_targ_critic(C, 0), C, 3, st);
+  {
+    int slots[2 * CQL_MAX_CRITICS];
+    for (int i = 0; i < C; ++i) { slots[i] = slot_critic(i); slots[C + i] = slot_targ_critic(C, i); }
+    pack_slots(h, slots, 2 * C, st);
+  }
   {
     FwdJobs jobs{};
     jobs.n = 1;
