@@ -543,22 +543,39 @@ __device__ __forceinline__ float4 sum_strided4(const float* __restrict__ p, int 
                      (s0.w + s1.w) + (s2.w + s3.w));
 }
 
-__global__ void k_reduce_grads_tc(const float* __restrict__ small1, int slots1, const float* __restrict__ small2,
-                                  const float* __restrict__ pw2, int splits, int in_dim, int out_dim,
-                                  float* __restrict__ grads) {
+// block = 32 float4 groups (128 consecutive parameters) x 8 slot-chunks; chunk partials combined through shared
+// memory in chunk order, so the result is independent of scheduling
+__global__ void __launch_bounds__(256) k_reduce_grads_tc(const float* __restrict__ small1, int slots1,
+                                                         const float* __restrict__ small2, const float* __restrict__ pw2,
+                                                         int splits, int in_dim, int out_dim, float* __restrict__ grads) {
+  __shared__ float4 part[8][32];
   const int net = blockIdx.y;
-  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 4;       // every region boundary is a multiple of 4
-  if (idx >= NET_STRIDE) return;
+  const int g = threadIdx.x & 31, chunk = threadIdx.x >> 5;
+  const int idx = (blockIdx.x * 32 + g) * 4;                          // every region boundary is a multiple of 4
   const int w2_lo = off_W2(in_dim), w2_hi = w2_lo + H * H, total = net_floats(in_dim, out_dim);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (idx >= w2_lo && idx < w2_hi) {
-    s = sum_strided4(pw2 + (size_t)net * splits * H * H + (idx - w2_lo), splits, (size_t)H * H);
-  } else if (idx < w2_lo) {
-    s = sum_strided4(small1 + (size_t)net * slots1 * SMALL_STRIDE + idx, slots1, SMALL_STRIDE);
-  } else if (idx < total) {            // tail region: (idx - H*H) keeps 16-byte alignment; entries past `total` are zero
-    s = sum_strided4(small2 + (size_t)net * splits * SMALL_STRIDE + (idx - H * H), splits, SMALL_STRIDE);
+  if (idx < NET_STRIDE) {
+    const float* base = nullptr;
+    int n = 0;
+    size_t stride = 0;
+    if (idx >= w2_lo && idx < w2_hi) {
+      base = pw2 + (size_t)net * splits * H * H + (idx - w2_lo); n = splits; stride = (size_t)H * H;
+    } else if (idx < w2_lo) {
+      base = small1 + (size_t)net * slots1 * SMALL_STRIDE + idx; n = slots1; stride = SMALL_STRIDE;
+    } else if (idx < total) {         // tail: (idx - H*H) keeps 16-byte alignment; entries past `total` are zero
+      base = small2 + (size_t)net * splits * SMALL_STRIDE + (idx - H * H); n = splits; stride = SMALL_STRIDE;
+    }
+    const int per = (n + 7) / 8, lo = chunk * per, hi = min(n, lo + per);
+    if (base != nullptr && hi > lo) s = sum_strided4(base + (size_t)lo * stride, hi - lo, stride);
   }
-  *reinterpret_cast<float4*>(grads + (size_t)net * NET_STRIDE + idx) = s;
+  part[chunk][g] = s;
+  __syncthreads();
+  if (chunk == 0 && idx < NET_STRIDE) {
+    float4 t = part[0][g];
+#pragma unroll
+    for (int c = 1; c < 8; ++c) { const float4 v = part[c][g]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    *reinterpret_cast<float4*>(grads + (size_t)net * NET_STRIDE + idx) = t;
+  }
 }
 
 }  // namespace tc

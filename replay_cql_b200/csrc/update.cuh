@@ -576,7 +576,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
   tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
   CQL_LAUNCH_CHECK(h);
-  tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 255) / 256, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
+  tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out);
   CQL_LAUNCH_CHECK(h);
 }
