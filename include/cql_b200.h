@@ -91,6 +91,15 @@ int  cql_get_optimizer(cql_handle* h, float* host_m, float* host_v, int64_t n, i
 int  cql_load_transitions(cql_handle* h, const float* obs, const float* act,
                           const float* rew, const float* term, int64_t n);
 int64_t cql_num_transitions(const cql_handle* h);
+/* MDP builder on the GPU: interaction log columns (host, input order) -> replay table, one episode per user.
+ * order (user, timestamp, input order); reward = 1 for the user's top_k rows by (relevance desc, timestamp desc);
+ * terminal = user's last row; action = (float)relevance + noise.  action_noise (host, per ORIGINAL row, already
+ * scaled; may be NULL => seeded N(0,1)*noise_scale on the device).  Optional host outputs (all NULL or all set):
+ * obs_out [n][2], act_out/rew_out/term_out [n] in episode order; order_out [n] = original row of each step.
+ * replaces: MdpDatasetBuilder.build (two Spark window sorts + orderBy + toPandas) [EXT upstream RePlay CQL wrapper] */
+int  cql_build_mdp(cql_handle* h, const int32_t* user_idx, const int32_t* item_idx, const int64_t* timestamp,
+                   const double* relevance, const double* action_noise, int64_t n, int32_t top_k, float noise_scale,
+                   float* obs_out, float* act_out, float* rew_out, float* term_out, int64_t* order_out);
 /* stand-alone gather for the K1 roofline sweep: out_dev [count][8] floats.
  * idx_dev NULL => the handle's epoch permutation starting at position `pos`. */
 int  cql_sample_rows(cql_handle* h, const int64_t* idx_dev, int64_t pos, int64_t count,

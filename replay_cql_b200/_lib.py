@@ -52,6 +52,7 @@ SIGNATURES = {
     "cql_get_optimizer": (C.c_int, [_P, _P, _P, C.c_int64, _I64]),
     "cql_load_transitions": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64]),
     "cql_num_transitions": (C.c_int64, [_P]),
+    "cql_build_mdp": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
     "cql_sample_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
     "cql_update": (C.c_int, [_P, C.c_int64, _P, _P]),
     "cql_update_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -1,6 +1,6 @@
 """Builds the C-ABI CUDA library in-tree:  python -m replay_cql_b200.build
 
-One translation unit (csrc/capi.cu includes the kernel headers), compiled for
+Two translation units (csrc/capi.cu includes the kernel headers; csrc/mdp_gpu.cu the CUB sorts), compiled for
 sm_100a only.  The .so lands next to this file so it travels with the repo
 snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
 """
@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "capi.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "capi.cu"), str(CSRC / "mdp_gpu.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

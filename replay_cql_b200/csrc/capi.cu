@@ -27,6 +27,11 @@ struct cql_handle {
 
 static thread_local std::string g_create_error;
 
+// mdp_gpu.cu
+int64_t mdp_build_on_device(Handle& h, const int32_t* user_h, const int32_t* item_h, const int64_t* ts_h, const double* rel_h,
+                            const double* noise_h, int64_t n, int top_k, float noise_scale, float* obs_out, float* act_out,
+                            float* rew_out, float* term_out, int64_t* order_out);
+
 namespace {
 
 void* scratch(cql_handle* ch, int slot, size_t bytes) {
@@ -404,6 +409,18 @@ int cql_load_transitions(cql_handle* ch, const float* obs, const float* act, con
     CQL_CUDA(cudaFree(d_obs));
     CQL_CUDA(cudaFree(d_act));
     h.n_trans = n;
+    destroy_graph(ch);
+  });
+}
+
+int cql_build_mdp(cql_handle* ch, const int32_t* user_idx, const int32_t* item_idx, const int64_t* timestamp,
+                  const double* relevance, const double* action_noise, int64_t n, int32_t top_k, float noise_scale,
+                  float* obs_out, float* act_out, float* rew_out, float* term_out, int64_t* order_out) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(top_k >= 0, "cql_build_mdp: top_k < 0");
+    CQL_CUDA(cudaDeviceSynchronize());
+    ch->h.launches += mdp_build_on_device(ch->h, user_idx, item_idx, timestamp, relevance, action_noise, n, top_k,
+                                          noise_scale, obs_out, act_out, rew_out, term_out, order_out);
     destroy_graph(ch);
   });
 }

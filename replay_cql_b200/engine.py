@@ -164,6 +164,33 @@ class CqlEngine:
         self._check(self._lib.cql_load_transitions(self._h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(term), n),
                     "cql_load_transitions")
 
+    def build_mdp_on_device(self, user_idx, item_idx, timestamp, relevance, top_k: int = 10,
+                            action_randomization_scale: float = 1e-3, action_noise=None, want_outputs: bool = False):
+        """GPU MDP builder (stable radix sorts on the device) -> replay table resident in HBM.
+
+        Columns are in the log's input order.  ``action_noise`` (float64, per original row, already scaled)
+        overrides the seeded device draw.  With ``want_outputs`` returns (obs, act, rew, term, order) as numpy
+        arrays in episode order (for parity tests); otherwise None."""
+        user = np.ascontiguousarray(user_idx, dtype=np.int32)
+        item = np.ascontiguousarray(item_idx, dtype=np.int32)
+        ts = np.ascontiguousarray(timestamp, dtype=np.int64)
+        rel = np.ascontiguousarray(relevance, dtype=np.float64)
+        n = user.size
+        if not (item.size == ts.size == rel.size == n):
+            raise ValueError("log columns must have the same length")
+        if n == 0:
+            raise ValueError("empty log")
+        if n and (user.max() >= 2 ** 24 or item.max() >= 2 ** 24 or user.min() < 0 or item.min() < 0):
+            raise ValueError("user_idx/item_idx must be in [0, 2**24) to be exact in float32 observations")
+        nz = None if action_noise is None else np.ascontiguousarray(action_noise, dtype=np.float64)
+        outs = [None] * 5
+        if want_outputs:
+            outs = [np.empty((n, 2), np.float32), np.empty(n, np.float32), np.empty(n, np.float32),
+                    np.empty(n, np.float32), np.empty(n, np.int64)]
+        self._check(self._lib.cql_build_mdp(self._h, _ptr(user), _ptr(item), _ptr(ts), _ptr(rel), _ptr(nz), n, int(top_k),
+                                            float(action_randomization_scale), *[_ptr(o) for o in outs]), "cql_build_mdp")
+        return tuple(outs) if want_outputs else None
+
     @property
     def n_transitions(self) -> int:
         return int(self._lib.cql_num_transitions(self._h))

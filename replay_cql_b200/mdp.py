@@ -115,3 +115,17 @@ def seen_csr(log: Any, n_users_dim: int):
     indptr = np.zeros(n_users_dim + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     return indptr, i
+
+
+def build_mdp_on_device(engine, log: Any, top_k: int = 10, action_randomization_scale: float = 1e-3,
+                        action_noise: Optional[np.ndarray] = None, want_outputs: bool = False):
+    """Same semantics as :func:`build_mdp`, but sorted and expanded on the GPU (``cql_build_mdp``): the log
+    columns go host -> device once and the replay table never exists on the host."""
+    pdf = to_pandas(log)
+    for col in ("user_idx", "item_idx", "timestamp", "relevance"):
+        if col not in pdf.columns:
+            raise ValueError(f"log must have column {col}")
+    return engine.build_mdp_on_device(pdf["user_idx"].to_numpy(), pdf["item_idx"].to_numpy(),
+                                      timestamps_to_int64(pdf["timestamp"]), pdf["relevance"].to_numpy(),
+                                      top_k=top_k, action_randomization_scale=action_randomization_scale,
+                                      action_noise=action_noise, want_outputs=want_outputs)

@@ -15,7 +15,7 @@ import numpy as np
 import pandas as pd
 
 from .engine import CqlEngine, CqlHyperParams
-from .mdp import build_mdp, seen_csr
+from .mdp import build_mdp_on_device, seen_csr
 from .parallel import GradAllReducer, dist_info, gather_rows, shard_range
 from .recommender import Recommender, _rec_frame
 
@@ -155,18 +155,20 @@ class CQL(Recommender):
     # ------------------------------------------------------------------ fit
     def _fit(self, log: pd.DataFrame, user_features=None, item_features=None) -> None:
         """MDP build -> HBM replay table -> ``n_epochs`` x (N // (B*world)) fused updates."""
-        mdp = build_mdp(log, top_k=self.top_k, action_randomization_scale=self.action_randomization_scale,
-                        seed=self.seed)
         eng = self._make_engine()
-        eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+        if len(log) == 0:
+            self.logger.warning("CQL.fit: empty log")
+            return
+        build_mdp_on_device(eng, log, top_k=self.top_k, action_randomization_scale=self.action_randomization_scale)
+        n_rows = eng.n_transitions
         rank, world, _ = dist_info()
         per_epoch = self.n_steps_per_epoch
         if per_epoch is None:
-            per_epoch = len(mdp) // (self.batch_size * world)   # d3rlpy drops the last partial minibatch
+            per_epoch = n_rows // (self.batch_size * world)   # d3rlpy drops the last partial minibatch
         total = int(self.n_epochs) * int(per_epoch)
         if total == 0:
             self.logger.warning("CQL.fit: 0 update steps (log has %d rows, batch_size*world = %d)",
-                                len(mdp), self.batch_size * world)
+                                n_rows, self.batch_size * world)
             return
         if world == 1:
             done = 0

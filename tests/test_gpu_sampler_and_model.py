@@ -128,3 +128,41 @@ def test_phase_split_equals_fused_update(engine_factory, precision):
     torch.cuda.synchronize()
     assert np.array_equal(a.get_state(), b.get_state())
     assert a.get_optimizer()[2] == b.get_optimizer()[2] == 5
+
+
+@pytest.mark.parametrize("top_k", [0, 1, 3, 1000])
+def test_gpu_mdp_builder_bit_exact(engine_factory, top_k):
+    """cql_build_mdp (stable radix sorts on the device) == host builder == loop oracle, bit for bit,
+    including timestamp ties, shuffled rows and duplicate (user, item) rows."""
+    from oracle import mdp_oracle
+    from replay_cql_b200.mdp import build_mdp_on_device
+    rng = np.random.default_rng(11)
+    n = 5000
+    log = pd.DataFrame({"user_idx": rng.integers(0, 97, n), "item_idx": rng.integers(0, 300, n),
+                        "timestamp": rng.integers(0, 50, n), "relevance": rng.integers(1, 6, n).astype(float)})
+    noise = rng.standard_normal(n) * 1e-3
+    eng = engine_factory(batch_size=64)
+    obs, act, rew, term, order = build_mdp_on_device(eng, log, top_k=top_k, action_noise=noise, want_outputs=True)
+    host = build_mdp(log, top_k=top_k, action_noise=noise)
+    assert np.array_equal(order, host.order)
+    assert np.array_equal(obs, host.obs) and np.array_equal(act, host.act)
+    assert np.array_equal(rew, host.rew) and np.array_equal(term, host.term)
+    ref = mdp_oracle.build_mdp(log, top_k=top_k, action_noise=noise)
+    assert np.array_equal(obs, ref["obs"]) and np.array_equal(rew, ref["rew"][:, 0]) and np.array_equal(term, ref["term"][:, 0])
+    # the table itself: rows by explicit index == host expansion
+    tr = to_transitions(host)
+    full = np.concatenate([tr["obs"], tr["act"], tr["rew"], tr["next_obs"], tr["term"], np.zeros((n, 1), np.float32)], 1)
+    idx = rng.integers(0, n, 500)
+    assert np.array_equal(eng.sample_rows(500, idx=idx).cpu().numpy(), full[idx])
+
+
+def test_gpu_mdp_builder_datetime_and_seeded_noise(engine_factory):
+    from replay_cql_b200.mdp import build_mdp_on_device
+    log = make_log("tiny").sample(frac=1.0, random_state=5).reset_index(drop=True)
+    log["timestamp"] = pd.to_datetime(log["timestamp"], unit="s")
+    eng = engine_factory(batch_size=64, seed=3)
+    obs, act, rew, term, order = build_mdp_on_device(eng, log, top_k=10, want_outputs=True)
+    host = build_mdp(log, top_k=10, action_noise=np.zeros(len(log)))
+    assert np.array_equal(order, host.order) and np.array_equal(rew, host.rew) and np.array_equal(term, host.term)
+    d = act - host.act                       # seeded N(0, 1e-3) draw on the device
+    assert 5e-4 < d.std() < 2e-3 and abs(d.mean()) < 2e-4
