@@ -105,11 +105,9 @@ class ClockSampler:
 
 
 def build_workload(log_rows: int | None = None):
-    from replay_cql_b200.mdp import build_mdp
     from replay_cql_b200.synthetic import make_log, SHAPES
     log = make_log("ml20m", seed=12345, n_rows=log_rows)
-    mdp = build_mdp(log, top_k=K_TOP, action_randomization_scale=1e-3, seed=12345)
-    return log, mdp, SHAPES["ml20m"]
+    return log, SHAPES["ml20m"]
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -180,7 +178,7 @@ def run_ours(args):
     import torch.distributed as dist
     from replay_cql_b200 import _lib
     from replay_cql_b200.engine import CqlEngine, CqlHyperParams
-    from replay_cql_b200.mdp import seen_csr, to_transitions
+    from replay_cql_b200.mdp import seen_csr
     from replay_cql_b200.parallel import GradAllReducer, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -196,10 +194,21 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     pk, pk_kind = peaks()
 
-    log, mdp, shape = build_workload(args.rows)
+    from replay_cql_b200.mdp import build_mdp, build_mdp_on_device
+    log, shape = build_workload(args.rows)
     eng = CqlEngine(CqlHyperParams(batch_size=BATCH, seed=12345, precision=args.precision), device=local_rank,
                     rank=rank, world_size=world)
-    eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+    build_mdp_on_device(eng, log.iloc[:100_000], top_k=K_TOP)          # warm-up (CUB temp, allocator)
+    t0 = time.perf_counter()
+    build_mdp_on_device(eng, log, top_k=K_TOP, action_randomization_scale=1e-3)   # host columns in, table in HBM
+    mdp_gpu_s = time.perf_counter() - t0
+    n_rows = eng.n_transitions
+    mdp_host = None
+    if rank == 0 and world == 1 and not args.no_cpu:                    # host builder on a bounded 2M-row sample
+        sub = log.iloc[:2_000_000]
+        t0 = time.perf_counter()
+        build_mdp(sub, top_k=K_TOP, seed=12345)
+        mdp_host = {"rows": len(sub), "seconds": time.perf_counter() - t0}
     stream = torch.cuda.Stream(device=dev)
     sh = stream.cuda_stream
 
@@ -257,13 +266,14 @@ def run_ours(args):
     peak_tf = pk.get("bf16_tflops_sustained", 1400.0)
 
     # ---- e2e: host minibatch in, metrics out, every step ----
-    tr = to_transitions(mdp)
     rng = np.random.default_rng(rank)
     n_e2e = max(10, min(args.steps, 200))
     pool = []
-    for _ in range(8):
-        idx = rng.integers(0, len(mdp), BATCH)
-        pool.append({k: np.ascontiguousarray(v[idx]) for k, v in tr.items()})
+    for _ in range(8):          # host minibatches: rows read back from the replay table
+        rows = eng.sample_rows(BATCH, idx=rng.integers(0, n_rows, BATCH)).cpu().numpy()
+        pool.append({"obs": np.ascontiguousarray(rows[:, 0:2]), "act": np.ascontiguousarray(rows[:, 2:3]),
+                     "rew": np.ascontiguousarray(rows[:, 3:4]), "next_obs": np.ascontiguousarray(rows[:, 4:6]),
+                     "term": np.ascontiguousarray(rows[:, 6:7])})
     def e2e_step(i):
         if world == 1:
             eng.update_batch(pool[i % 8])
@@ -353,7 +363,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "users": shape["n_users"], "items": shape["n_items"],
-                       "rows": len(mdp), "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                       "rows": int(n_rows), "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "parallelism": f"dp{world}", "hidden": 256, "n_critics": 2, "n_action_samples": 10,
                        "precision": args.precision,
                        "l2": "inputs larger than L2: 640 MB replay table, fresh random gather every step; "
@@ -381,6 +391,8 @@ def run_ours(args):
                             "unit": "GB/s", "rows": int(users.size), "cols": shape["n_items"], "ms": topk_ms,
                             "bound": "hbm", "peak": pk.get("hbm_gbs", 6650.0), "frac": topk_gbs / pk.get("hbm_gbs", 6650.0),
                             "bytes_per_pair": 4},
+            "mdp_build": {"metric": "MDP builder: log columns (host) -> replay table (HBM)", "rows": int(n_rows),
+                          "gpu_seconds": mdp_gpu_s, "rows_per_s": n_rows / mdp_gpu_s, "host_numpy_sample": mdp_host},
             "sampler": {"metric": "replay gather", "value": gather_gbs, "unit": "GB/s", "rows": cnt,
                         "frac_of_hbm": gather_gbs / pk.get("hbm_gbs", 6650.0)},
         }
