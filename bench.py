@@ -311,13 +311,15 @@ def run_ours(args):
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l1 = eng.launch_count
+    SCORE_REPS = 3
     s0.record(stream)
     with torch.cuda.stream(stream):
-        eng.score_topk_device(d_users, d_items, K_TOP, d_ptr, d_seen, out_items=oi, out_scores=osc, stream=sh)
+        for _ in range(SCORE_REPS):
+            eng.score_topk_device(d_users, d_items, K_TOP, d_ptr, d_seen, out_items=oi, out_scores=osc, stream=sh)
     s1.record(stream)
     barrier()
-    score_ms = max_over_ranks(s0.elapsed_time(s1))
-    score_launches = eng.launch_count - l1
+    score_ms = max_over_ranks(s0.elapsed_time(s1)) / SCORE_REPS
+    score_launches = (eng.launch_count - l1) // SCORE_REPS
     users_per_s = n_score / (score_ms / 1e3)
     t0 = time.perf_counter()
     eng.score_topk(users, items, K_TOP, indptr, seen)

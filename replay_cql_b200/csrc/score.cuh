@@ -213,18 +213,23 @@ __global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ s
   const float* row = scores + (size_t)urow * n_items;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
   const int64_t nvec = vec_ok ? n_items / 4 : 0;
-  // vector body: 2 x float4 in flight per lane
-  for (int64_t v0 = (int64_t)warp * 64; v0 < nvec; v0 += (int64_t)nw * 64) {
-    float4 x[2];
-    int64_t vi[2];
+  // vector body: 4 x float4 in flight per lane; one warp vote per 16 values decides whether ANY of them can
+  // enter the list (after the first few hundred values almost none can), so the steady state is load + max
+  for (int64_t v0 = (int64_t)warp * 128; v0 < nvec; v0 += (int64_t)nw * 128) {
+    float4 x[4];
+    int64_t vi[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 4; ++q) {
       vi[q] = v0 + q * 32 + lane;
       x[q] = vi[q] < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi[q])
                           : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
+    float mx = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 4; ++q) mx = fmaxf(mx, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
+    if (!__any_sync(0xffffffffu, mx >= topS[k - 1])) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
       const float vals[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
