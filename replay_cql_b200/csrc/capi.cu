@@ -698,7 +698,7 @@ int cql_topk_filter_dev(cql_handle* ch, const float* scores_dev, int64_t n_users
     if (n_users == 0) return;
     cudaStream_t st = pick_stream(&h, stream);
     const int threads = 256;
-    k_topk_filter<<<(unsigned)n_users, threads, (threads / 32) * 2 * k * sizeof(float), st>>>(
+    k_topk_filter<<<(unsigned)n_users, threads, (threads / 32) * 2 * k * sizeof(float) + SEEN_CACHE * sizeof(int32_t), st>>>(
         scores_dev, n_items, users_dev, items_dev, seen_indptr, seen_items, k, out_scores, out_items);
     CQL_LAUNCH_CHECK(&h);
     if (!stream) CQL_CUDA(cudaStreamSynchronize(st));

@@ -26,6 +26,43 @@ __device__ __forceinline__ bool is_seen(const int32_t* __restrict__ seen, int64_
   return false;
 }
 
+// The lazy filter does one binary search per surviving candidate; from global memory that is ~8 dependent
+// L2 round trips (~4 us), which dominated the fold.  Users' seen lists are short (ML-20M: 144 on average), so
+// each CTA stages the current user's list in shared memory once and searches it there.
+constexpr int SEEN_CACHE = 4096;       // ints of shared memory per CTA; longer lists fall back to global memory
+struct SeenView {
+  const int32_t* g;      // global list [lo, hi)
+  const int32_t* s;      // shared-memory copy or nullptr
+  int64_t lo, hi;
+};
+__device__ __forceinline__ bool is_seen(const SeenView& v, int item) {
+  if (v.s != nullptr) {
+    int lo = 0, hi = (int)(v.hi - v.lo);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int x = v.s[mid];
+      if (x == item) return true;
+      if (x < item) lo = mid + 1; else hi = mid;
+    }
+    return false;
+  }
+  return is_seen(v.g, v.lo, v.hi, item);
+}
+// cooperative stage by `nthreads` threads (tid in [0, nthreads)); caller synchronises afterwards
+__device__ __forceinline__ SeenView stage_seen(const int64_t* __restrict__ indptr, const int32_t* __restrict__ seen,
+                                               int user, int32_t* cache, int tid, int nthreads) {
+  SeenView v{seen, nullptr, 0, 0};
+  if (indptr == nullptr) return v;
+  v.lo = indptr[user];
+  v.hi = indptr[user + 1];
+  const int64_t n = v.hi - v.lo;
+  if (n <= SEEN_CACHE) {
+    for (int64_t i = tid; i < n; i += nthreads) cache[i] = __ldg(seen + v.lo + i);
+    v.s = cache;
+  }
+  return v;
+}
+
 // Whole-warp insertion of (s,i) into the descending list top[0..k).  Caller guarantees
 // the candidate beats top[k-1].
 __device__ __forceinline__ void warp_topk_insert(float* topS, int* topI, int k, float s, int i) {
@@ -206,10 +243,10 @@ __global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ s
   int* topI = reinterpret_cast<int*>(topS + k);
   const int64_t urow = blockIdx.x;
   const int user = users ? users[urow] : (int)urow;
-  int64_t lo = 0, hi = 0;
-  if (seen_indptr) { lo = seen_indptr[user]; hi = seen_indptr[user + 1]; }
+  int32_t* cache = reinterpret_cast<int32_t*>(smem + (size_t)nw * 2 * k);
+  const SeenView sv = stage_seen(seen_indptr, seen_items, user, cache, threadIdx.x, blockDim.x);
   for (int e = lane; e < k; e += 32) { topS[e] = -INFINITY; topI[e] = -1; }
-  __syncwarp();
+  __syncthreads();
   const float* row = scores + (size_t)urow * n_items;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
   const int64_t nvec = vec_ok ? n_items / 4 : 0;
@@ -240,7 +277,7 @@ __global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ s
         if (cand) {
           item = items ? items[col] : (int)col;
           cand = better(s, item, topS[k - 1], topI[k - 1]);
-          if (cand && seen_indptr && is_seen(seen_items, lo, hi, item)) cand = false;
+          if (cand && seen_indptr && is_seen(sv, item)) cand = false;
         }
         unsigned m = __ballot_sync(0xffffffffu, cand);
         while (m) {
@@ -262,7 +299,7 @@ __global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ s
     if (cand) {
       item = items ? items[col] : (int)col;
       cand = better(s, item, topS[k - 1], topI[k - 1]);
-      if (cand && seen_indptr && is_seen(seen_items, lo, hi, item)) cand = false;
+      if (cand && seen_indptr && is_seen(sv, item)) cand = false;
     }
     unsigned m = __ballot_sync(0xffffffffu, cand);
     while (m) {

@@ -35,7 +35,8 @@ struct ScoreSmem : TsCfg {
   static constexpr uint32_t OFF_STQ = OFF_STA + SC_CH * TM * 4;            // float[CH*128] running sum
   static constexpr uint32_t OFF_SCORE = OFF_STQ + SC_CH * TM * 4;          // float[CH*128] final score
   static constexpr uint32_t OFF_AREADY = OFF_SCORE + SC_CH * TM * 4;       // mbarrier
-  static constexpr uint32_t OFF_TOP = OFF_AREADY + 16;                     // float[k] | int[k]
+  static constexpr uint32_t OFF_SEEN = OFF_AREADY + 16;                    // int[SEEN_CACHE] current user's seen list
+  static constexpr uint32_t OFF_TOP = OFF_SEEN + SEEN_CACHE * 4;           // float[k] | int[k]
   static inline uint32_t bytes(int k) { return OFF_TOP + (uint32_t)k * 8; }
 };
 
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_score_kernel(const Score
   float* st_q = reinterpret_cast<float*>(sm + C::OFF_STQ);
   float* score = reinterpret_cast<float*>(sm + C::OFF_SCORE);
   uint64_t* a_ready = reinterpret_cast<uint64_t*>(sm + C::OFF_AREADY);
+  int32_t* seen_cache = reinterpret_cast<int32_t*>(sm + C::OFF_SEEN);
   float* topS = reinterpret_cast<float*>(sm + C::OFF_TOP);
   int* topI = reinterpret_cast<int*>(topS + a.k);
 
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_score_kernel(const Score
     const int row_in_tile = warp * 32 + lane;
     uint32_t tcount = 0;
     int64_t cur_user_row = -1;
-    int64_t lo = 0, hi = 0;
+    SeenView sv{a.seen_items, nullptr, 0, 0};
     for (int64_t blk = blk_lo; blk < blk_hi; ++blk) {
       const int tb = tiles_of_block(blk);
       const int64_t urow = blk / a.chunks;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_score_kernel(const Score
       for (int e = tid; e < a.k; e += 128) { topS[e] = -INFINITY; topI[e] = -1; }
       if (urow != cur_user_row) {
         cur_user_row = urow;
-        if (a.seen_indptr) { const int user = a.users[urow]; lo = a.seen_indptr[user]; hi = a.seen_indptr[user + 1]; }
+        sv = stage_seen(a.seen_indptr, a.seen_items, a.users[urow], seen_cache, tid, 128);
       }
       asm volatile("bar.sync 2, 128;");
       if (tb > 0) {
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(TsCfg::THREADS, 1) tc_score_kernel(const Score
             const float s = r < rows ? score[r] : -INFINITY;
             const int item = r < rows ? a.items[i0 + r] : -1;
             bool cand = item >= 0 && better(s, item, topS[a.k - 1], topI[a.k - 1]);
-            if (cand && a.seen_indptr && is_seen(a.seen_items, lo, hi, item)) cand = false;
+            if (cand && a.seen_indptr && is_seen(sv, item)) cand = false;
             unsigned m = __ballot_sync(0xffffffffu, cand);
             while (m) {
               const int src = __ffs(m) - 1;
