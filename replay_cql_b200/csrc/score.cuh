@@ -326,4 +326,95 @@ __global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ s
   }
 }
 
+// ---- k <= 32, many rows: ONE warp per row, the top-k list lives in registers (lane e = e-th best) ----
+// Insert = one ballot + one shuffle; after the first ~2 k values of a row almost every 512-value batch is
+// rejected by a single vote, so the kernel streams the row at load speed (8 x 16-byte loads in flight per lane).
+constexpr int TKR_WARPS = 8;
+constexpr int TKR_SEEN = 512;          // per-warp shared-memory seen cache (ints)
+
+__global__ void __launch_bounds__(TKR_WARPS * 32) k_topk_filter_reg(const float* __restrict__ scores, int64_t n_users,
+                                                                    int64_t n_items, const int32_t* __restrict__ users,
+                                                                    const int32_t* __restrict__ items,
+                                                                    const int64_t* __restrict__ seen_indptr,
+                                                                    const int32_t* __restrict__ seen_items, int k,
+                                                                    float* __restrict__ out_s, int* __restrict__ out_i) {
+  __shared__ int32_t cache[TKR_WARPS][TKR_SEEN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t urow = (int64_t)blockIdx.x * TKR_WARPS + warp;
+  if (urow >= n_users) return;
+  const int user = users ? users[urow] : (int)urow;
+  SeenView sv{seen_items, nullptr, 0, 0};
+  if (seen_indptr) {
+    sv.lo = seen_indptr[user];
+    sv.hi = seen_indptr[user + 1];
+    if (sv.hi - sv.lo <= TKR_SEEN) {
+      for (int64_t i = lane; i < sv.hi - sv.lo; i += 32) cache[warp][i] = __ldg(seen_items + sv.lo + i);
+      sv.s = cache[warp];
+    }
+    __syncwarp();
+  }
+  float ms = -INFINITY;      // my list entry (lane e holds the e-th best); lanes >= k stay (-inf, -1)
+  int mi = -1;
+  float thr_s = -INFINITY;   // k-th best so far
+  int thr_i = -1;
+  auto offer = [&](float s, int item, bool valid) {
+    bool cand = valid && better(s, item, thr_s, thr_i);
+    if (cand && seen_indptr && is_seen(sv, item)) cand = false;
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float s2 = __shfl_sync(0xffffffffu, s, src);
+      const int i2 = __shfl_sync(0xffffffffu, item, src);
+      if (!better(s2, i2, thr_s, thr_i)) continue;
+      const int pos = __popc(__ballot_sync(0xffffffffu, better(ms, mi, s2, i2)));
+      const float us = __shfl_up_sync(0xffffffffu, ms, 1);
+      const int ui = __shfl_up_sync(0xffffffffu, mi, 1);
+      if (lane == pos) { ms = s2; mi = i2; }
+      else if (lane > pos && lane < k) { ms = us; mi = ui; }
+      thr_s = __shfl_sync(0xffffffffu, ms, k - 1);
+      thr_i = __shfl_sync(0xffffffffu, mi, k - 1);
+    }
+  };
+  const float* row = scores + (size_t)urow * n_items;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int64_t nvec = vec_ok ? n_items / 4 : 0;
+  constexpr int NV = 8;
+  for (int64_t v0 = 0; v0 < nvec; v0 += NV * 32) {
+    float4 x[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int64_t vi = v0 + q * 32 + lane;
+      x[q] = vi < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi)
+                       : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) mx = fmaxf(mx, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
+    if (!__any_sync(0xffffffffu, mx >= thr_s)) continue;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int64_t vi = v0 + q * 32 + lane;
+      const float qm = fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w));
+      if (!__any_sync(0xffffffffu, qm >= thr_s)) continue;
+      const float vals[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t col = vi * 4 + c;
+        const bool valid = vi < nvec && vals[c] >= thr_s;
+        const int item = valid ? (items ? items[col] : (int)col) : -1;
+        offer(vals[c], item, valid);
+      }
+    }
+  }
+  for (int64_t c0 = nvec * 4; c0 < n_items; c0 += 32) {
+    const int64_t col = c0 + lane;
+    const bool valid = col < n_items;
+    const float s = valid ? row[col] : -INFINITY;
+    const int item = valid ? (items ? items[col] : (int)col) : -1;
+    offer(s, item, valid);
+  }
+  if (lane < k) { out_s[urow * k + lane] = ms; out_i[urow * k + lane] = mi; }
+}
+
 }  // namespace cql

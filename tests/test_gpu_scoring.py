@@ -101,13 +101,15 @@ def test_score_pairs_and_edge_cases(engine_factory):
         eng.score_topk([1], [1], 5000)
 
 
-def test_standalone_topk_filter(engine_factory):
+@pytest.mark.parametrize("U,I,k", [(37, 5003, 10), (700, 2001, 10), (650, 4096, 32), (600, 333, 1)])
+def test_standalone_topk_filter(engine_factory, U, I, k):
+    """both kernels: CTA-per-row with shared-memory lists (few rows / k > 32) and warp-per-row with the list
+    in registers (>= 4 x SMs rows, k <= 32)"""
     eng = engine_factory(batch_size=64)
     rng = np.random.default_rng(3)
-    U, I, k = 37, 5003, 10
     scores = rng.standard_normal((U, I)).astype(np.float32)
     scores[:, ::7] = scores[:, 1::7]                            # plenty of exact ties
-    seen = {u: set(rng.choice(I, size=60, replace=False).tolist()) for u in range(U)}
+    seen = {u: set(rng.choice(I, size=int(rng.integers(0, 60)) if u % 7 else 700 % I, replace=False).tolist()) for u in range(U)}
     indptr = np.zeros(U + 1, dtype=np.int64)
     flat = []
     for u in range(U):
