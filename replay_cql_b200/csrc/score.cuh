@@ -357,16 +357,18 @@ __global__ void __launch_bounds__(TKR_WARPS * 32) k_topk_filter_reg(const float*
   int mi = -1;
   float thr_s = -INFINITY;   // k-th best so far
   int thr_i = -1;
-  auto offer = [&](float s, int item, bool valid) {
-    bool cand = valid && better(s, item, thr_s, thr_i);
-    if (cand && seen_indptr && is_seen(sv, item)) cand = false;
-    unsigned m = __ballot_sync(0xffffffffu, cand);
+  // candidates are detected on the score alone; the item id (a dependent global load) is fetched only for
+  // the handful of values that survive the vote -- one broadcast load per survivor
+  auto offer = [&](float s, int64_t col, bool valid) {
+    unsigned m = __ballot_sync(0xffffffffu, valid && s >= thr_s);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const float s2 = __shfl_sync(0xffffffffu, s, src);
-      const int i2 = __shfl_sync(0xffffffffu, item, src);
+      const int64_t c2 = __shfl_sync(0xffffffffu, col, src);
+      const int i2 = items ? __ldg(items + c2) : (int)c2;
       if (!better(s2, i2, thr_s, thr_i)) continue;
+      if (seen_indptr && is_seen(sv, i2)) continue;
       const int pos = __popc(__ballot_sync(0xffffffffu, better(ms, mi, s2, i2)));
       const float us = __shfl_up_sync(0xffffffffu, ms, 1);
       const int ui = __shfl_up_sync(0xffffffffu, mi, 1);
@@ -380,13 +382,21 @@ __global__ void __launch_bounds__(TKR_WARPS * 32) k_topk_filter_reg(const float*
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
   const int64_t nvec = vec_ok ? n_items / 4 : 0;
   constexpr int NV = 8;
+  const float4 NEG = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  float4 nx[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const int64_t vi = q * 32 + lane;
+    nx[q] = vi < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi) : NEG;
+  }
   for (int64_t v0 = 0; v0 < nvec; v0 += NV * 32) {
     float4 x[NV];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      const int64_t vi = v0 + q * 32 + lane;
-      x[q] = vi < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi)
-                       : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int q = 0; q < NV; ++q) x[q] = nx[q];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {          // prefetch the next batch while this one is examined
+      const int64_t vi = v0 + NV * 32 + q * 32 + lane;
+      nx[q] = vi < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi) : NEG;
     }
     float mx = -INFINITY;
 #pragma unroll
@@ -399,20 +409,13 @@ __global__ void __launch_bounds__(TKR_WARPS * 32) k_topk_filter_reg(const float*
       if (!__any_sync(0xffffffffu, qm >= thr_s)) continue;
       const float vals[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int64_t col = vi * 4 + c;
-        const bool valid = vi < nvec && vals[c] >= thr_s;
-        const int item = valid ? (items ? items[col] : (int)col) : -1;
-        offer(vals[c], item, valid);
-      }
+      for (int c = 0; c < 4; ++c) offer(vals[c], vi * 4 + c, vi < nvec);
     }
   }
   for (int64_t c0 = nvec * 4; c0 < n_items; c0 += 32) {
     const int64_t col = c0 + lane;
     const bool valid = col < n_items;
-    const float s = valid ? row[col] : -INFINITY;
-    const int item = valid ? (items ? items[col] : (int)col) : -1;
-    offer(s, item, valid);
+    offer(valid ? row[col] : -INFINITY, col, valid);
   }
   if (lane < k) { out_s[urow * k + lane] = ms; out_i[urow * k + lane] = mi; }
 }

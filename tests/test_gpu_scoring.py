@@ -108,7 +108,8 @@ def test_standalone_topk_filter(engine_factory, U, I, k):
     eng = engine_factory(batch_size=64)
     rng = np.random.default_rng(3)
     scores = rng.standard_normal((U, I)).astype(np.float32)
-    scores[:, ::7] = scores[:, 1::7]                            # plenty of exact ties
+    n7 = len(range(1, I, 7))
+    scores[:, 0:7 * n7:7] = scores[:, 1::7]                     # plenty of exact ties
     seen = {u: set(rng.choice(I, size=int(rng.integers(0, 60)) if u % 7 else 700 % I, replace=False).tolist()) for u in range(U)}
     indptr = np.zeros(U + 1, dtype=np.int64)
     flat = []
