@@ -698,7 +698,7 @@ int cql_topk_filter_dev(cql_handle* ch, const float* scores_dev, int64_t n_users
     if (n_users == 0) return;
     cudaStream_t st = pick_stream(&h, stream);
     if (k <= 32 && n_users >= 4 * (int64_t)h.num_sms) {     // enough rows: one warp per row, list in registers
-      k_topk_filter_reg<<<(unsigned)((n_users + TKR_WARPS - 1) / TKR_WARPS), TKR_WARPS * 32, 0, st>>>(
+      k_topk_filter_reg<<<(unsigned)((n_users + TKR_WARPS - 1) / TKR_WARPS), TKR_WARPS * 32, TKR_WARPS * TKR_SEEN * sizeof(int32_t), st>>>(
           scores_dev, n_users, n_items, users_dev, items_dev, seen_indptr, seen_items, k, out_scores, out_items);
       CQL_LAUNCH_CHECK(&h);
       if (!stream) CQL_CUDA(cudaStreamSynchronize(st));
