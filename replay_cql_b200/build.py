@@ -40,7 +40,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "capi.cu"), str(CSRC / "mdp_gpu.cu")]
+    extra = os.environ.get("CQL_EXTRA_NVCC", "").split()          # debugging only (e.g. -DTKS_TIMING)
+    digest = digest + "|" + " ".join(extra) if extra else digest
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(LIB), str(CSRC / "capi.cu"), str(CSRC / "mdp_gpu.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

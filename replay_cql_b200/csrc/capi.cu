@@ -7,6 +7,7 @@
 #include "score.cuh"
 #include "tc_selftest.cuh"
 #include "score_tc.cuh"
+#include "topk_staged.cuh"
 
 using namespace cql;
 
@@ -56,6 +57,7 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
   CQL_CUDA(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, score_smem(CQL_MAX_TOPK)));
   CQL_CUDA(cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  CQL_CUDA(cudaFuncSetAttribute(k_topk_filter_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TKS_SMEM));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<true, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
@@ -697,9 +699,15 @@ int cql_topk_filter_dev(cql_handle* ch, const float* scores_dev, int64_t n_users
     CQL_REQUIRE(k >= 1 && k <= 128, "cql_topk_filter_dev: k must be 1..128");
     if (n_users == 0) return;
     cudaStream_t st = pick_stream(&h, stream);
-    if (k <= 32 && n_users >= 4 * (int64_t)h.num_sms) {     // enough rows: one warp per row, list in registers
-      k_topk_filter_reg<<<(unsigned)((n_users + TKR_WARPS - 1) / TKR_WARPS), TKR_WARPS * 32, TKR_WARPS * TKR_SEEN * sizeof(int32_t), st>>>(
-          scores_dev, n_users, n_items, users_dev, items_dev, seen_indptr, seen_items, k, out_scores, out_items);
+    if (k <= 32) {     // streamed through a shared-memory ring (bulk copies), two-pass selection: topk_staged.cuh
+      TksArgs ta{};
+      ta.scores = scores_dev; ta.n_rows = n_users; ta.n_items = n_items; ta.users = users_dev; ta.items = items_dev;
+      ta.seen_indptr = seen_indptr; ta.seen_items = seen_items; ta.k = k; ta.out_s = out_scores; ta.out_i = out_items;
+      ta.chunk_len = TKS_CH;                                   // chunk starts stay multiples of TKS_WORKERS float4s
+      ta.nchunks = (int)((n_items + TKS_CH - 1) / TKS_CH);
+      ta.aligned = ((reinterpret_cast<uintptr_t>(scores_dev) & 15) == 0 && (n_items & 3) == 0) ? 1 : 0;
+      const unsigned grid = (unsigned)std::min<int64_t>(n_users, TKS_CTAS_PER_SM * (int64_t)h.num_sms);
+      k_topk_filter_staged<<<grid, TKS_THREADS, TKS_SMEM, st>>>(ta);
       CQL_LAUNCH_CHECK(&h);
       if (!stream) CQL_CUDA(cudaStreamSynchronize(st));
       return;

@@ -2,7 +2,7 @@ import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 from replay_cql_b200.engine import CqlEngine, CqlHyperParams
 eng = CqlEngine(CqlHyperParams(batch_size=64))
-U, I = 2048, 26744
+U, I = 8192, 26744
 dev = torch.device('cuda:0')
 sc = torch.randn((U, I), dtype=torch.float32, device=dev)
 users = torch.arange(U, dtype=torch.int32, device=dev)

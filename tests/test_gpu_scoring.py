@@ -123,3 +123,62 @@ def test_standalone_topk_filter(engine_factory, U, I, k):
                                     seen_items_t=torch.tensor(flat, dtype=torch.int32, device=dev))
     torch.cuda.synchronize()
     assert np.array_equal(ti.cpu().numpy(), ri) and np.array_equal(ts.cpu().numpy(), rs)   # bit-exact selection
+
+
+def _csr(seen: dict, n_ptr: int):
+    indptr = np.zeros(n_ptr + 1, dtype=np.int64)
+    flat = []
+    for u in range(n_ptr):
+        flat.extend(sorted(seen.get(u, ())))
+        indptr[u + 1] = len(flat)
+    return indptr, np.asarray(flat, dtype=np.int32)
+
+
+@pytest.mark.parametrize("case", ["aligned_multichunk", "popular_seen", "ties_overflow", "long_seen", "short_rows"])
+def test_staged_topk_filter_cases(engine_factory, case):
+    """topk_staged.cuh: bulk-copy ring path (16-byte aligned rows, several chunks per row), threshold retries
+    when the best-scored items are seen, candidate-list overflow on massive ties, seen lists longer than the
+    shared-memory cache, rows shorter than k; user ids / item ids through indirection arrays.  Bit-exact."""
+    eng = engine_factory(batch_size=64)
+    rng = np.random.default_rng(11)
+    U, I, k = 160, 26744, 10
+    n_user_ids = 1000
+    if case == "short_rows":
+        U, I, k = 50, 40, 32
+    if case == "ties_overflow":
+        U, I = 40, 9000
+    users = rng.choice(n_user_ids, size=U, replace=False).astype(np.int32)
+    items = rng.permutation(3 * I)[:I].astype(np.int32)                  # arbitrary ids, arbitrary order
+    scores = rng.standard_normal((U, I)).astype(np.float32)
+    seen = {}
+    for r, u in enumerate(users):
+        n = int(rng.integers(0, 200))
+        if case == "popular_seen":                                         # the user has seen their best-scored items
+            top = np.argsort(-scores[r])[: int(rng.integers(5, 120))]
+            seen[int(u)] = set(items[top].tolist())
+        elif case == "long_seen" and r % 3 == 0:
+            seen[int(u)] = set(items[rng.choice(I, size=3000, replace=False)].tolist())
+        elif case == "short_rows":
+            seen[int(u)] = set(items[rng.choice(I, size=int(rng.integers(0, 30)), replace=False)].tolist())
+        else:
+            seen[int(u)] = set(items[rng.choice(I, size=n, replace=False)].tolist())
+    if case == "ties_overflow":
+        scores = np.round(scores, 1)                                       # ~60 distinct values per row
+        scores[0, :] = 0.25                                                # a constant row
+        scores[1, :] = -np.inf
+    indptr, flat = _csr(seen, n_user_ids)
+    ri, rs = recs_oracle.brute_force_topk(lambda obs: scores[int(np.nonzero(users == int(obs[0, 0]))[0][0])],
+                                          users, items, seen, k)
+    dev = "cuda:0"
+    ti, ts = eng.topk_filter_device(torch.from_numpy(scores).to(dev), k,
+                                    users_t=torch.from_numpy(users).to(dev), items_t=torch.from_numpy(items).to(dev),
+                                    seen_indptr_t=torch.from_numpy(indptr).to(dev),
+                                    seen_items_t=torch.from_numpy(flat).to(dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(ts.cpu().numpy(), rs)
+    assert np.array_equal(ti.cpu().numpy(), ri)
+    # no users / items arrays, no filter: identity ids
+    ri2, rs2 = recs_oracle.brute_force_topk(lambda obs: scores[int(obs[0, 0])], np.arange(U), np.arange(I), {}, k)
+    ti2, ts2 = eng.topk_filter_device(torch.from_numpy(scores).to(dev), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(ti2.cpu().numpy(), ri2) and np.array_equal(ts2.cpu().numpy(), rs2)
