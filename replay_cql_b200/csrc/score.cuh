@@ -35,16 +35,19 @@ struct SeenView {
   const int32_t* s;      // shared-memory copy or nullptr
   int64_t lo, hi;
 };
+template <int MAXN = SEEN_CACHE>   // MAXN: power of two >= the longest cached list
 __device__ __forceinline__ bool is_seen(const SeenView& v, int item) {
   if (v.s != nullptr) {
-    int lo = 0, hi = (int)(v.hi - v.lo);
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const int x = v.s[mid];
-      if (x == item) return true;
-      if (x < item) lo = mid + 1; else hi = mid;
+    // branch-free lower bound with a fixed trip count: the lanes of a warp that search at the same time stay
+    // converged (a data-dependent loop serialises them -- measured 7 searching lanes ~ 3.5 k cycles)
+    const int n = (int)(v.hi - v.lo);
+    int lo = 0;
+#pragma unroll
+    for (int step = MAXN / 2; step >= 1; step >>= 1) {
+      const int p = lo + step;
+      if (p <= n && v.s[p - 1] < item) lo = p;
     }
-    return false;
+    return lo < n && v.s[lo] == item;
   }
   return is_seen(v.g, v.lo, v.hi, item);
 }
@@ -324,96 +327,6 @@ __global__ void __launch_bounds__(256) k_topk_filter(const float* __restrict__ s
     }
     for (int e = lane; e < k; e += 32) { out_s[urow * k + e] = topS[e]; out_i[urow * k + e] = topI[e]; }
   }
-}
-
-// ---- k <= 32, many rows: ONE warp per row, the top-k list lives in registers (lane e = e-th best) ----
-// Insert = one ballot + one shuffle; after the first ~2 k values of a row almost every 512-value batch is
-// rejected by a single vote, so the kernel streams the row at load speed (8 x 16-byte loads in flight per lane).
-constexpr int TKR_WARPS = 8;
-constexpr int TKR_SEEN = 1024;         // per-warp shared-memory seen cache (ints): 32 KB per CTA, 4 CTAs per SM
-
-__global__ void __launch_bounds__(TKR_WARPS * 32, 4) k_topk_filter_reg(const float* __restrict__ scores, int64_t n_users,
-                                                                    int64_t n_items, const int32_t* __restrict__ users,
-                                                                    const int32_t* __restrict__ items,
-                                                                    const int64_t* __restrict__ seen_indptr,
-                                                                    const int32_t* __restrict__ seen_items, int k,
-                                                                    float* __restrict__ out_s, int* __restrict__ out_i) {
-  extern __shared__ __align__(16) int32_t cache_all[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int32_t* cache_w = cache_all + warp * TKR_SEEN;
-  const int64_t urow = (int64_t)blockIdx.x * TKR_WARPS + warp;
-  if (urow >= n_users) return;
-  const int user = users ? users[urow] : (int)urow;
-  SeenView sv{seen_items, nullptr, 0, 0};
-  if (seen_indptr) {
-    sv.lo = seen_indptr[user];
-    sv.hi = seen_indptr[user + 1];
-    if (sv.hi - sv.lo <= TKR_SEEN) {
-      for (int64_t i = lane; i < sv.hi - sv.lo; i += 32) cache_w[i] = __ldg(seen_items + sv.lo + i);
-      sv.s = cache_w;
-    }
-    __syncwarp();
-  }
-  float ms = -INFINITY;      // my list entry (lane e holds the e-th best); lanes >= k stay (-inf, -1)
-  int mi = -1;
-  float thr_s = -INFINITY;   // k-th best so far
-  int thr_i = -1;
-  // candidates are detected on the score alone; the item id (a dependent global load) is fetched only for
-  // the handful of values that survive the vote -- one broadcast load per survivor
-  auto offer = [&](float s, int64_t col, bool valid) {
-    unsigned m = __ballot_sync(0xffffffffu, valid && s >= thr_s);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const float s2 = __shfl_sync(0xffffffffu, s, src);
-      const int64_t c2 = __shfl_sync(0xffffffffu, col, src);
-      const int i2 = items ? __ldg(items + c2) : (int)c2;
-      if (!better(s2, i2, thr_s, thr_i)) continue;
-      if (seen_indptr && is_seen(sv, i2)) continue;
-      const int pos = __popc(__ballot_sync(0xffffffffu, better(ms, mi, s2, i2)));
-      const float us = __shfl_up_sync(0xffffffffu, ms, 1);
-      const int ui = __shfl_up_sync(0xffffffffu, mi, 1);
-      if (lane == pos) { ms = s2; mi = i2; }
-      else if (lane > pos && lane < k) { ms = us; mi = ui; }
-      thr_s = __shfl_sync(0xffffffffu, ms, k - 1);
-      thr_i = __shfl_sync(0xffffffffu, mi, k - 1);
-    }
-  };
-  const float* row = scores + (size_t)urow * n_items;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-  const int64_t nvec = vec_ok ? n_items / 4 : 0;
-  // The row is too short for a rejection-dominated steady state (k ln(N/k) ~ 80 insert events per 27 k values), so
-  // the kernel is bound by the latency of those events, not by HBM: occupancy (many rows in flight per SM)
-  // matters more than deep per-row prefetch -> 4 loads in flight per lane, <= 64 registers, 4 CTAs per SM.
-  constexpr int NV = 4;
-  const float4 NEG = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  for (int64_t v0 = 0; v0 < nvec; v0 += NV * 32) {
-    float4 x[NV];
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      const int64_t vi = v0 + q * 32 + lane;
-      x[q] = vi < nvec ? __ldcs(reinterpret_cast<const float4*>(row) + vi) : NEG;
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) mx = fmaxf(mx, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
-    if (!__any_sync(0xffffffffu, mx >= thr_s)) continue;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      const int64_t vi = v0 + q * 32 + lane;
-      const float qm = fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w));
-      if (!__any_sync(0xffffffffu, qm >= thr_s)) continue;
-      const float vals[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) offer(vals[c], vi * 4 + c, vi < nvec);
-    }
-  }
-  for (int64_t c0 = nvec * 4; c0 < n_items; c0 += 32) {
-    const int64_t col = c0 + lane;
-    const bool valid = col < n_items;
-    offer(valid ? row[col] : -INFINITY, col, valid);
-  }
-  if (lane < k) { out_s[urow * k + lane] = ms; out_i[urow * k + lane] = mi; }
 }
 
 }  // namespace cql

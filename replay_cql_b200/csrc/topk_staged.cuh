@@ -40,12 +40,11 @@ constexpr int TKS_CAP = 256;          // candidates per collection round
 
 struct TksCtl {
   float t_lo, t_hi;
-  int ncand, done;
+  int ncand[2], done;      // candidate counters, double-buffered by row parity
   int seen_n;        // current row: length of the seen list, -1 = no filter
   int seen_cached;   // 1: the list sits in the row's shared-memory cache
   long long seen_lo; // current row: offset of the list in seen_items
   int cache_sel;     // which of the two caches
-  int pad;
 };
 
 constexpr size_t TKS_OFF_SEEN = (size_t)TKS_STAGES * TKS_CH * 4;
@@ -97,10 +96,14 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
   if (total == 0) return;
   auto row_of = [&](int64_t j) { return (int64_t)blockIdx.x + j * gridDim.x; };
   const bool items_al = (reinterpret_cast<uintptr_t>(a.items) & 15) == 0;
+  const int rank0 = min(32, k + 4 + (k >> 1));     // spare candidates so that seen items rarely force another round
 
   if (tid == 0) {
     for (int s = 0; s < TKS_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], TKS_WORKERS / 32); }
     tc::fence_mbar_init();
+    ctl->ncand[0] = 0;
+    ctl->ncand[1] = 0;
+    ctl->done = 0;
   }
   __syncthreads();
 
@@ -185,11 +188,28 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
 #pragma unroll
       for (int o = 1; o < TKS_GROUP; o <<= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
       if ((lane & (TKS_GROUP - 1)) == 0) gmax[warp * (32 / TKS_GROUP) + lane / TKS_GROUP] = g;
-      nbar_arrive(TKS_BAR_GM, TKS_SYNC);                  // group maxima are out
-      while (true) {
-        nbar_sync(TKS_BAR_TR, TKS_SYNC);                  // band (and the row info) or the verdict is in
-        if (ctl->done) break;
-        const float t_lo = ctl->t_lo, t_hi = ctl->t_hi;
+      nbar_sync(TKS_BAR_GM, TKS_SYNC);                    // group maxima (and the selector's row info) are out
+      // round 0: every warp derives the threshold itself = the rank0-th largest group maximum (rank by counting)
+      float t_lo, t_hi = INFINITY;
+      {
+        const float mine = gmax[lane];
+        int pos = 0;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float o = gmax[t];
+          pos += (o > mine || (o == mine && t < lane)) ? 1 : 0;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, pos == rank0 - 1);
+        t_lo = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+      }
+      volatile int* ncand = &ctl->ncand[j & 1];
+      for (int round = 0;; ++round) {
+        if (round > 0) {
+          nbar_sync(TKS_BAR_TR, TKS_SYNC);                // the selector's verdict, or the next band
+          if (ctl->done) break;
+          t_lo = ctl->t_lo;
+          t_hi = ctl->t_hi;
+        }
         if (m >= t_lo) {
           // pass 2: normally only the best float4 holds anything >= t_lo; rescan the share when the runner-up does too
           SeenView sv{a.seen_items, nullptr, 0, 0};
@@ -203,8 +223,8 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               if (gv * 4 + e >= a.n_items || !(sc4[e] >= t_lo && sc4[e] < t_hi)) continue;
-              if (seen_n >= 0 && is_seen(sv, it4[e])) continue;
-              const int p = atomicAdd(const_cast<int*>(&ctl->ncand), 1);
+              if (seen_n >= 0 && is_seen<TKS_SEEN>(sv, it4[e])) continue;
+              const int p = atomicAdd(const_cast<int*>(ncand), 1);
               if (p < TKS_CAP) { candS[p] = sc4[e]; candI[p] = it4[e]; }
             }
           };
@@ -236,14 +256,18 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (gv * 4 + e >= a.n_items || !(s4[e] >= t_lo && s4[e] < t_hi)) continue;
-                if (seen_n >= 0 && is_seen(sv, i4[e])) continue;
-                const int p = atomicAdd(const_cast<int*>(&ctl->ncand), 1);
+                if (seen_n >= 0 && is_seen<TKS_SEEN>(sv, i4[e])) continue;
+                const int p = atomicAdd(const_cast<int*>(ncand), 1);
                 if (p < TKS_CAP) { candS[p] = s4[e]; candI[p] = i4[e]; }
               }
             }
           }
         }
-        nbar_arrive(TKS_BAR_CD, TKS_SYNC);                // candidates of this round are out
+        nbar_sync(TKS_BAR_CD, TKS_SYNC);                  // candidates of this round are out
+        // k unseen candidates at or above t_lo settle the row (nothing below t_lo can enter the top-k): in that case
+        // nobody waits for the selector, which places the candidates while the next row streams in
+        const int n = *ncand;
+        if (round == 0 && n >= k && n <= TKS_CAP) break;
       }
     }
     return;
@@ -286,7 +310,6 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
     thr_s = __shfl_sync(0xffffffffu, ms, k - 1);
     thr_i = __shfl_sync(0xffffffffu, mi, k - 1);
   };
-  const int rank0 = min(32, k + 4 + (k >> 1));     // spare candidates so that seen items rarely force another round
 
   for (int64_t j = 0; j < nrows_cta; ++j) {
     const int64_t row = row_of(j);
@@ -328,13 +351,19 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
       gsorted[pos] = mine;
       __syncwarp();
     }
+    if (lane == 0) ctl->ncand[(j + 1) & 1] = 0;          // next row's counter (every worker has read its last value)
+    volatile int* ncand = &ctl->ncand[j & 1];
     int rank = rank0;
-    float t_hi = INFINITY, t_lo = gsorted[rank - 1];
+    float t_hi = INFINITY, t_lo = gsorted[rank - 1];     // round 0: the workers derived the same band themselves
+    bool settled = false;
     for (int round = 0;; ++round) {
-      if (lane == 0) { ctl->t_lo = t_lo; ctl->t_hi = t_hi; ctl->ncand = 0; ctl->done = 0; }
-      nbar_arrive(TKS_BAR_TR, TKS_SYNC);
+      if (round > 0) {
+        if (lane == 0) { ctl->t_lo = t_lo; ctl->t_hi = t_hi; *ncand = 0; ctl->done = 0; }
+        nbar_arrive(TKS_BAR_TR, TKS_SYNC);
+      }
       nbar_sync(TKS_BAR_CD, TKS_SYNC);
-      const int n = ctl->ncand;
+      const int n = *ncand;
+      if (round == 0 && n >= k && n <= TKS_CAP) settled = true;     // same predicate as the workers: no verdict needed
       if (n > TKS_CAP) {
         // overflow (massive ties): exact sequential scan of the band, straight from global memory
         for (int64_t base = 0; base < a.n_items; base += 128) {
@@ -401,8 +430,10 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
       t_hi = t_lo;
       t_lo = rank <= 32 ? gsorted[rank - 1] : -INFINITY;
     }
-    if (lane == 0) ctl->done = 1;
-    nbar_arrive(TKS_BAR_TR, TKS_SYNC);
+    if (!settled) {
+      if (lane == 0) ctl->done = 1;
+      nbar_arrive(TKS_BAR_TR, TKS_SYNC);
+    }
     if (lane < k) { a.out_s[row * k + lane] = ms; a.out_i[row * k + lane] = mi; }
     if (has_seen) {
       asm volatile("cp.async.wait_all;" ::: "memory");
