@@ -37,12 +37,14 @@ FLOP_PER_ROW = 2 * (3 * 256 + 256 * 256 + 256)   # f_c = 133 120
 FLOP_PER_UPDATE_PER_B = 269 * FLOP_PER_ROW       # 269 forward-equivalent rows per batch element
 FLOP_PER_PAIR = 3 * FLOP_PER_ROW                 # 2 critics + actor = 399 360
 DTYPES = {"fp32": "f32", "tf32x3": "f32 (tf32x3: tensor-core 3-term split, fp32 accumulate, 1e-4 parity-gated)",
+          "f16x3": "f32 (f16x3: tensor-core fp16 hi/lo 3-term split with exact power-of-two row scales, fp32 accumulate, 1e-4 parity-gated)",
           "bf16": "bf16 (fp32 accumulate; non-parity variant)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from one `ncu --set full` capture
 # (profiles/r01_tc_fwd_ts_ncu_summary.txt); null where no capture exists for that variant
-KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "bf16": None}
+KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": None, "bf16": None}
 KERNEL_NAMES = {"fp32": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
                 "tf32x3": "tc_fwd_ts_kernel<3,1> (critic forward: tcgen05 kind::tf32 3-term split, A operand in TMEM)",
+                "f16x3": "tc_fwd_h_kernel<3,1> (critic forward: tcgen05 kind::f16, fp16 hi/lo 3-term split, A operand in TMEM)",
                 "bf16": "tc_fwd_kernel<bf16,3,1> (critic forward, tcgen05 kind::f16)"}
 
 
@@ -427,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=None, help="override the log size (debugging)")
-    ap.add_argument("--precision", choices=["fp32", "tf32x3", "bf16"], default="tf32x3",
+    ap.add_argument("--precision", choices=["fp32", "tf32x3", "f16x3", "bf16"], default="tf32x3",
                     help="hidden-layer contraction: fp32 = CUDA-core FMA; tf32x3 = tcgen05 3-term split (FP32-grade, "
                          "default); bf16 = tcgen05 bf16 operands (non-parity variant)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

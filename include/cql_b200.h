@@ -38,7 +38,8 @@ extern "C" {
 /* precision of the 256x256 hidden-layer contraction */
 enum { CQL_PREC_FP32 = 0,      /* CUDA-core FP32 (exact-order reference path on the GPU) */
        CQL_PREC_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-term split, FP32-grade */
-       CQL_PREC_BF16 = 2 };    /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate) */
+       CQL_PREC_BF16 = 2,      /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate) */
+       CQL_PREC_F16X3 = 3 };   /* tcgen05 kind::f16, fp16 hi/lo 3-term split with exact power-of-two row scales, FP32-grade */
 
 enum { CQL_SQUASH_EPS = 0, CQL_SQUASH_SOFTPLUS = 1 };
 enum { CQL_SCORE_Q = 0,        /* mean_i Q_i(x, tanh(mu(x)))  (d3rlpy predict_value(x, predict(x))) */

@@ -11,7 +11,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libcql_b200.so"
 
-PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_BF16, PREC_F16X3 = 0, 1, 2, 3
 SQUASH_EPS, SQUASH_SOFTPLUS = 0, 1
 SCORE_Q, SCORE_POLICY = 0, 1
 BUF_SCALAR_GRADS, BUF_CRITIC_GRADS, BUF_ACTOR_GRADS, BUF_METRICS, BUF_PARAMS, BUF_ALL_GRADS = range(6)

@@ -63,6 +63,8 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ScoreSmem::bytes(CQL_MAX_TOPK)));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_ts_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
@@ -88,7 +90,8 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   CQL_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= (1 << 20), "cql_create: batch_size out of range");
   CQL_REQUIRE(cfg->n_critics >= 1 && cfg->n_critics <= CQL_MAX_CRITICS, "cql_create: n_critics must be 1..4");
   CQL_REQUIRE(cfg->n_action_samples >= 1 && cfg->n_action_samples <= 10, "cql_create: n_action_samples must be 1..10");
-  CQL_REQUIRE(cfg->precision == CQL_PREC_FP32 || cfg->precision == CQL_PREC_TF32X3 || cfg->precision == CQL_PREC_BF16,
+  CQL_REQUIRE(cfg->precision == CQL_PREC_FP32 || cfg->precision == CQL_PREC_TF32X3 || cfg->precision == CQL_PREC_BF16 ||
+                  cfg->precision == CQL_PREC_F16X3,
               "cql_create: bad precision");
   CQL_REQUIRE(cfg->squash == CQL_SQUASH_EPS || cfg->squash == CQL_SQUASH_SOFTPLUS, "cql_create: bad squash");
   CQL_REQUIRE(cfg->world_size >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world_size, "cql_create: bad rank/world_size");
@@ -155,13 +158,15 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   h.pw2C = h.dalloc<float>((size_t)C * h.splitsC * H * H);
   h.pw2A = h.dalloc<float>((size_t)h.splitsA * H * H);
   if (cfg->precision != CQL_PREC_FP32) {
-    h.packed_net_bytes = cfg->precision == CQL_PREC_TF32X3 ? tc::Cfg<true>::PACKED_NET_BYTES : tc::Cfg<false>::PACKED_NET_BYTES;
+    const bool bf = cfg->precision == CQL_PREC_BF16, f16 = cfg->precision == CQL_PREC_F16X3;
+    h.packed_net_bytes = f16 ? tc::HCfg::PACKED_NET_BYTES : (bf ? tc::Cfg<false>::PACKED_NET_BYTES : tc::Cfg<true>::PACKED_NET_BYTES);
+    h.packed_net_bytes_bwd = bf ? tc::Cfg<false>::PACKED_NET_BYTES : tc::Cfg<true>::PACKED_NET_BYTES;
     h.packed_fwd = h.dalloc<uint8_t>((size_t)(2 + 2 * C) * h.packed_net_bytes);
-    const int slices = cfg->precision == CQL_PREC_TF32X3 ? tc::Cfg<true>::SLICES : tc::Cfg<false>::SLICES;
+    const int slices = bf ? tc::Cfg<false>::SLICES : tc::Cfg<true>::SLICES;     // of the backward kernels; forward <= this
     h.part_floats = (size_t)C * slices * ((size_t)B * (2 * n3 + 2)) * 2 + 4096;
     h.part = h.dalloc<float>(h.part_floats);
     h.tc_slices = slices;
-    h.packed_bwd = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes);
+    h.packed_bwd = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes_bwd);
     h.slots1 = 4 * h.num_sms;
     h.splits_tc = h.num_sms;
     h.small1 = h.dalloc<float>((size_t)C * h.slots1 * SMALL_STRIDE);

@@ -75,7 +75,8 @@ struct Handle {
 
   // ---- tensor-core path (precision != FP32): packed W2 per slot, layer-3 partial sums ----
   uint8_t* packed_fwd = nullptr;   // [(2+2C) slots][PACKED_NET_BYTES]  B[n][k] = W2[n][k]
-  size_t packed_net_bytes = 0;
+  size_t packed_net_bytes = 0;     // stride of packed_fwd
+  size_t packed_net_bytes_bwd = 0; // stride of packed_bwd
   float* part = nullptr;           // scratch for [n_nets][SLICES][rows][OUT] partials
   size_t part_floats = 0;
   uint8_t* packed_bwd = nullptr;   // [(1+C) slots: actor, critics][PACKED_NET_BYTES]  B[n][k] = W2[k][n]

@@ -9,6 +9,8 @@
 #include "engine.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc_ts.cuh"
+#include "mlp_tc_h.cuh"
+#include <type_traits>
 #include "mlp_tc_bwd1.cuh"
 #include "mlp_tc_bwd2.cuh"
 
@@ -477,9 +479,9 @@ inline void launch_fwd(Handle* h, FwdJobs& jobs, cudaStream_t st) {
 }
 
 // ---- tensor-core forward: same job list, W2 from the packed copy, partial sums folded afterwards
-template <bool TF32, int IN, int OUT>
+template <bool TF32, int IN, int OUT, bool F16X3 = false>
 inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
-  using C = tc::Cfg<TF32>;
+  using C = std::conditional_t<F16X3, tc::HCfg, tc::Cfg<TF32>>;
   tc::TcFwdJobs tj{};
   tj.n = jobs.n;
   size_t part_off = 0;
@@ -499,7 +501,9 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   CQL_REQUIRE(part_off <= h->part_floats, "internal: partial-sum scratch too small");
   if (items == 0) return;
   const int grid = items < h->num_sms ? items : h->num_sms;
-  if constexpr (TF32)
+  if constexpr (F16X3)
+    tc::tc_fwd_h_kernel<IN, OUT><<<grid, tc::HCfg::THREADS, tc::HCfg::SMEM_BYTES, st>>>(tj);
+  else if constexpr (TF32)
     tc::tc_fwd_ts_kernel<IN, OUT><<<grid, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(tj);
   else
     tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
@@ -519,6 +523,7 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
 template <int IN, int OUT>
 inline void launch_fwd_any(Handle* h, FwdJobs& jobs, cudaStream_t st) {
   if (h->cfg.precision == CQL_PREC_TF32X3) launch_fwd_tc<true, IN, OUT>(h, jobs, st);
+  else if (h->cfg.precision == CQL_PREC_F16X3) launch_fwd_tc<true, IN, OUT, true>(h, jobs, st);
   else if (h->cfg.precision == CQL_PREC_BF16) launch_fwd_tc<false, IN, OUT>(h, jobs, st);
   else launch_fwd<IN, OUT>(h, jobs, st);
 }
@@ -527,15 +532,22 @@ inline void launch_fwd_any(Handle* h, FwdJobs& jobs, cudaStream_t st) {
 // plus W2^T for the trainable ones (slot <= C) -- in ONE launch
 inline void pack_slots(Handle* h, const int* slots, int n_slots, cudaStream_t st) {
   if (h->cfg.precision == CQL_PREC_FP32 || n_slots == 0) return;
-  tc::PackJobs jobs{};
+  tc::PackJobs jobs{}, jobs_h{};      // jobs_h: forward copies in the fp16 hi|lo layout (f16x3 mode)
+  const bool f16 = h->cfg.precision == CQL_PREC_F16X3;
   for (int i = 0; i < n_slots; ++i) {
     const int slot = slots[i];
     const bool is_actor = slot == slot_actor() || slot == slot_targ_actor(h->C);
     const int in_dim = is_actor ? 2 : 3;
-    jobs.j[jobs.n++] = {h->net_params(slot), h->packed_fwd + (size_t)slot * h->packed_net_bytes, in_dim, 0};
-    if (slot <= h->C) jobs.j[jobs.n++] = {h->net_params(slot), h->packed_bwd + (size_t)slot * h->packed_net_bytes, in_dim, 1};
+    tc::PackJobs& fj = f16 ? jobs_h : jobs;
+    fj.j[fj.n++] = {h->net_params(slot), h->packed_fwd + (size_t)slot * h->packed_net_bytes, in_dim, 0};
+    if (slot <= h->C) jobs.j[jobs.n++] = {h->net_params(slot), h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, in_dim, 1};
   }
-  if (h->cfg.precision == CQL_PREC_TF32X3) {
+  if (jobs_h.n) {
+    tc::k_pack_multi_h<<<dim3(H * 32 / 256, jobs_h.n), 256, 0, st>>>(jobs_h, 2);
+    CQL_LAUNCH_CHECK(h);
+  }
+  if (jobs.n == 0) return;
+  if (h->cfg.precision != CQL_PREC_BF16) {
     const int chunks = H * (H / tc::Cfg<true>::EPC);
     tc::k_pack_multi<true><<<dim3((chunks + 255) / 256, jobs.n), 256, 0, st>>>(jobs);
   } else {
@@ -560,7 +572,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   const int grid1 = items < h->num_sms ? items : h->num_sms;
   const int slots1 = 4 * grid1;
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
-  tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes, h->small1,
+  tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, h->small1,
                  DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
   if constexpr (TF32)
     tc::tc_bwd1_ts_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(j1);
@@ -694,7 +706,7 @@ inline void phase1(Handle* h, cudaStream_t st) {
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);
   if (h->cfg.precision != CQL_PREC_FP32) {
-    if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st);
+    if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st);
     else launch_bwd_tc<false, 3, 1, true, false>(h, jb, h->g_critics(), st);
     mark(h, st, 6);
     mark(h, st, 7);
@@ -736,7 +748,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
   CQL_LAUNCH_CHECK(h);
   {
     BwdJob jb{h->XP, h->dQP, h->h2P, h->net_params(slot_critic(0)), nullptr, h->dXP, nullptr, B, C, 1};
-    if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 3, 1, false, true>(h, jb, nullptr, st);
+    if (h->cfg.precision == CQL_PREC_TF32X3 || h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, false, true>(h, jb, nullptr, st);
     else if (h->cfg.precision == CQL_PREC_BF16) launch_bwd_tc<false, 3, 1, false, true>(h, jb, nullptr, st);
     else launch_bwd1<3, 1, false, true>(h, jb, st);
   }
@@ -748,7 +760,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
   BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
   mark(h, st, 10);
   if (tcm) {
-    if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 2, 2, true, false>(h, ja, h->g_actor(), st);
+    if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 2, 2, true, false>(h, ja, h->g_actor(), st);
     else launch_bwd_tc<false, 2, 2, true, false>(h, ja, h->g_actor(), st);
     mark(h, st, 11);
     return;

@@ -20,7 +20,8 @@ from . import _lib, layout
 METRIC_NAMES = ("temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss")
 NOISE_KEYS = ("temp_eps", "alpha_eps_t", "alpha_eps_t1", "alpha_u",
               "critic_eps_t", "critic_eps_t1", "critic_u", "actor_eps")
-PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "bf16": _lib.PREC_BF16}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "bf16": _lib.PREC_BF16,
+              "f16x3": _lib.PREC_F16X3}
 SQUASH = {"eps": _lib.SQUASH_EPS, "softplus": _lib.SQUASH_SOFTPLUS}
 SCORE_MODES = {"q": _lib.SCORE_Q, "policy": _lib.SCORE_POLICY}
 
