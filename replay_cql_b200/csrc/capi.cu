@@ -63,6 +63,11 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ScoreSmem::bytes(CQL_MAX_TOPK)));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2HCfg::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2HCfg::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
@@ -160,14 +165,14 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   if (cfg->precision != CQL_PREC_FP32) {
     const bool bf = cfg->precision == CQL_PREC_BF16, f16 = cfg->precision == CQL_PREC_F16X3;
     h.packed_net_bytes = f16 ? tc::HCfg::PACKED_NET_BYTES : (bf ? tc::Cfg<false>::PACKED_NET_BYTES : tc::Cfg<true>::PACKED_NET_BYTES);
-    h.packed_net_bytes_bwd = bf ? tc::Cfg<false>::PACKED_NET_BYTES : tc::Cfg<true>::PACKED_NET_BYTES;
+    h.packed_net_bytes_bwd = f16 ? tc::HCfg::PACKED_NET_BYTES : (bf ? tc::Cfg<false>::PACKED_NET_BYTES : tc::Cfg<true>::PACKED_NET_BYTES);
     h.packed_fwd = h.dalloc<uint8_t>((size_t)(2 + 2 * C) * h.packed_net_bytes);
-    const int slices = bf ? tc::Cfg<false>::SLICES : tc::Cfg<true>::SLICES;     // of the backward kernels; forward <= this
+    const int slices = f16 ? tc::HCfg::SLICES : (bf ? tc::Cfg<false>::SLICES : tc::Cfg<true>::SLICES);
     h.part_floats = (size_t)C * slices * ((size_t)B * (2 * n3 + 2)) * 2 + 4096;
     h.part = h.dalloc<float>(h.part_floats);
     h.tc_slices = slices;
     h.packed_bwd = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes_bwd);
-    h.slots1 = 4 * h.num_sms;
+    h.slots1 = (f16 ? tc::HCfg::NEW : 4) * h.num_sms;
     h.splits_tc = h.num_sms;
     h.small1 = h.dalloc<float>((size_t)C * h.slots1 * SMALL_STRIDE);
     h.small2 = h.dalloc<float>((size_t)C * h.splits_tc * SMALL_STRIDE);

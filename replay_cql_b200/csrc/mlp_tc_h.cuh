@@ -15,10 +15,13 @@
 // max(2^-22 |x|, 2^-39 max|row|), far inside the 1e-4 gates.
 //
 // TMEM columns: [0,256) two 128-column accumulators; [256,512) four A stages of 64 K: hi[32 cols] | lo[32 cols]
-// (two fp16 per 32-bit column).  warps 0-3 epilogue, 4-19 producers, 20 MMA issuer (as in mlp_tc_ts.cuh).
+// (two fp16 per 32-bit column).  warps 0-7 epilogue (group g = warp / 4 drains accumulator g, i.e. every other
+// work item -- the epilogue was the bottleneck with one group), 8-23 producers, 24 MMA issuer.
 #pragma once
 #include <cuda_fp16.h>
 #include "mlp_tc.cuh"
+#include "mlp_tc_bwd1.cuh"
+#include "mlp_tc_bwd2.cuh"
 
 namespace cql {
 namespace tc {
@@ -32,8 +35,9 @@ struct HCfg {
   static constexpr int STAGES = 4;
   static constexpr int NCHUNK = H / KC;               // 4
   static constexpr int KPW = KC / (NPW / 4);          // K elements per producer warp per stage: 16 = 8 columns
-  static constexpr int MMA_WARP = 4 + NPW;
-  static constexpr int THREADS = (5 + NPW) * 32;      // 672
+  static constexpr int NEW = 8;                       // epilogue warps: two groups of 4, one per TMEM accumulator
+  static constexpr int MMA_WARP = NEW + NPW;
+  static constexpr int THREADS = (NEW + 1 + NPW) * 32;   // 800
   static constexpr int PROD_THREADS = NPW * 32;
   static constexpr uint32_t B_TERM_BYTES = NS * H * ES;            // 64 KB
   static constexpr uint32_t B_BYTES = 2 * B_TERM_BYTES;            // 128 KB (hi | lo)
@@ -45,8 +49,8 @@ struct HCfg {
   static constexpr uint32_t TMEM_ALLOC = 512;
   static constexpr uint32_t OFF_B = 0;
   static constexpr uint32_t OFF_W1 = B_BYTES;                  // float4[256] pair-packed W1|b1
-  static constexpr uint32_t OFF_EB = OFF_W1 + H * 16;          // float4[NS]
-  static constexpr uint32_t OFF_BAR = OFF_EB + NS * 16;
+  static constexpr uint32_t OFF_EB = OFF_W1 + H * 16;          // float4[2][NS] (one copy per epilogue group)
+  static constexpr uint32_t OFF_BAR = OFF_EB + 2 * NS * 16;
   static constexpr uint32_t N_BARS = 2 * STAGES + 4 + 2;
   static constexpr uint32_t OFF_SLOT = OFF_BAR + N_BARS * 8;
   static constexpr uint32_t SMEM_BYTES = OFF_SLOT + 16;
@@ -73,6 +77,23 @@ __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint3
   const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Producer-side split, cheaper on the FMA pipe (which bounds the operand generators: 0.5 warp-instr/clk/SMSP):
+// hi = x truncated to an 11-bit significand by masking (ALU pipe, exactly representable in fp16 above 2^-14),
+// lo = rn_fp16(x - hi) with ONE packed subtraction.  x - hi has <= 13 significant bits, so |x - hi - lo| <= 2^-22 |x|.
+__device__ __forceinline__ void split_h2_trunc(float2 x, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+  float2 l;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(l.x), "=f"(l.y)
+      : "f"(x.x), "f"(x.y), "f"(h0), "f"(h1));
+  const __half2 hh = __floats2half2_rn(h0, h1);
+  const __half2 ll = __floats2half2_rn(l.x, l.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
 // packed fp32x2 multiply
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Bs = sm + C::OFF_B;
   float4* w1p = reinterpret_cast<float4*>(sm + C::OFF_W1);   // [k/2][2]: {wx_k,wx_k1,wy_k,wy_k1}, {wz_k,wz_k1,b_k,b_k1}
-  float4* ebs = reinterpret_cast<float4*>(sm + C::OFF_EB);   // [NS]: b2, w3_0, w3_1, 1/s_n
+  float4* ebs = reinterpret_cast<float4*>(sm + C::OFF_EB);   // [2][NS]: b2, w3_0, w3_1, 1 / s_n
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
@@ -240,14 +261,21 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
       }
       ++tcount;
     }
-  } else if (warp >= 4) {
+  } else if (warp >= C::NEW) {
     // =============================== producers: layer 1 -> scaled fp16 hi|lo -> TMEM ===============================
-    const int pw = warp - 4, ptid = tid - 128;
+    const int pw = warp - C::NEW, ptid = tid - C::NEW * 32;
     const int kq = pw >> 2;                                        // which K quarter of every stage
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + kq * (C::KPW / 2);
     int cur_netkey = -1;
     float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t it = 0;
+    auto load_x = [&](int item) {
+      const HItem ni = decode_item_h(jobs, item);
+      const TcFwdJob& nj = jobs.j[ni.job];
+      const int r = ni.tile * TM + (warp & 3) * 32 + lane;
+      return r < nj.rows ? __ldg(nj.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 x_next = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int item = item_lo; item < item_hi; ++item) {
       const HItem ii = decode_item_h(jobs, item);
       const TcFwdJob& jb = jobs.j[ii.job];
@@ -267,8 +295,9 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
         wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
         asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
       }
-      const int r = ii.tile * TM + (warp & 3) * 32 + lane;
-      const float4 x = r < jb.rows ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // this item's input row was prefetched while the previous item was generated; fetch the next one now
+      const float4 x = (item == item_lo) ? load_x(item) : x_next;
+      if (item + 1 < item_hi) x_next = load_x(item + 1);
       float sa, inv_sa;
       pow2_scale(h1_row_bound(x, wm), sa, inv_sa);
       const float2 xx = make_float2(x.x, x.x), xy = make_float2(x.y, x.y), xz = make_float2(x.z, x.z), ss = make_float2(sa, sa);
@@ -283,7 +312,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
           v = ffma2(xy, make_float2(wA.z, wA.w), v);
           if (IN == 3) v = ffma2(xz, make_float2(wB.x, wB.y), v);
           v = fmul2(make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)), ss);             // exact: power-of-two scale
-          split_h2(v.x, v.y, hi[pp], lo[pp]);
+          split_h2_trunc(v, hi[pp], lo[pp]);
         }
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);          // values are ready before the slot is: wait late
         tc_fence_after();
@@ -297,27 +326,29 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
     }
   } else {
     // =============================== epilogue: TMEM -> unscale -> layer 3 (+ H2) ===============================
+    const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;          // group = accumulator, qw = TMEM lane quarter
+    float4* ebg = ebs + grp * C::NS;
     int cur_pair = -1;
-    uint32_t tcount = 0;
-    const int row_in_tile = warp * 32 + lane;
+    const int row_in_tile = qw * 32 + lane;
     float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int item = item_lo; item < item_hi; ++item) {
+    for (int item = item_lo + grp; item < item_hi; item += 2) {
+      const uint32_t tcount = (uint32_t)(item - item_lo);
       const HItem ii = decode_item_h(jobs, item);
       const TcFwdJob& jb = jobs.j[ii.job];
       if (ii.pair_id != cur_pair) {
         cur_pair = ii.pair_id;
-        asm volatile("bar.sync 2, 128;");
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
         const float* net = jb.params + (size_t)ii.net * NET_STRIDE;
         const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
-        for (int cidx = tid; cidx < C::NS; cidx += 128) {
+        for (int cidx = gtid; cidx < C::NS; cidx += 128) {
           const int col = ii.slice * C::NS + cidx;
-          ebs[cidx] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col],
+          ebg[cidx] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col],
                                   OUT == 2 ? net[off_W3(IN) + H + col] : 0.f, __ldg(&meta->inv_s[col]));
         }
         wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
-        asm volatile("bar.sync 2, 128;");
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
       }
-      const uint32_t acc = tcount & 1;
+      const uint32_t acc = grp;
       const int row = ii.tile * TM + row_in_tile;
       const float4 x = row < jb.rows ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
       float sa, inv_sa;
@@ -332,11 +363,11 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
 #pragma unroll 1
       for (int c0 = 0; c0 < C::NS; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * C::NS + c0, v);
+        tmem_ld32(tmem + ((uint32_t)(qw * 32) << 16) + acc * C::NS + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float4 e = ebs[c0 + i];
+          const float4 e = ebg[c0 + i];
           const float hv = fmaxf(fmaf(v[i] * inv_sa, e.w, e.x), 0.f);
           v[i] = hv;
           q0 = fmaf(hv, e.y, q0);
@@ -355,12 +386,528 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
         o[0] = q0;
         if (OUT == 2) o[1] = q1;
       }
-      ++tcount;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == C::MMA_WARP) tmem_dealloc(tmem, C::TMEM_ALLOC);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Input gradient of the hidden layer on the same fp16 hi/lo path:  dH1 = dZ2 W2, then dZ1 = dH1 * relu'(Z1), dW1, db1
+// and (optionally) dx.  Structure of tc_bwd1_ts_kernel (mlp_tc_bwd1.cuh); differences: W2^T packed as scaled fp16
+// hi|lo in 128-column slices, the dZ2 row scaled by 2^e from the bound |dOut_0| max|W3_0| + |dOut_1| max|W3_1|,
+// two epilogue groups (one per accumulator), accumulator unscaled by 1/(s_m s_n) before the ReLU mask.
+template <int IN, int OUT, bool WGRADS, bool DX>
+__global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1Job jb) {
+  using C = HCfg;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint8_t* Bs = sm + C::OFF_B;
+  float2* w3s = reinterpret_cast<float2*>(sm + C::OFF_W1);    // [256] (W3[0][j], W3[1][j])
+  float4* ebs = reinterpret_cast<float4*>(sm + C::OFF_EB);    // [2][NS]  (W1[k][0..2], b1[k]) of the slice's columns
+  float* invs = reinterpret_cast<float*>(sm + C::OFF_W1 + H * 8);   // [2][NS] 1/s_n of the slice's columns (after w3s)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bload = tempty + 2;
+  uint64_t* drain = bload + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = (jb.rows + TM - 1) / TM;
+  const int tiles64 = (jb.rows + 63) / 64;
+  const int total = jb.n_nets * C::SLICES * tiles;
+  const int item_lo = (int)((long long)total * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == C::MMA_WARP) {
+    tmem_alloc(slot, C::TMEM_ALLOC);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::NPW); mbar_init(&empty[s], 1); }
+      for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4); }
+      mbar_init(bload, 1);
+      mbar_init(drain, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (warp == C::MMA_WARP) {
+    const uint32_t idesc = instr_desc(FMT_F16, TM, C::NS);
+    const uint32_t b_lbo = C::NS * 16;
+    const uint32_t b_base = smem_u32(Bs);
+    int cur_pair = -1;
+    uint32_t it = 0, nb = 0, nd = 0, tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles;
+      if (pair != cur_pair) {
+        if (cur_pair >= 0) { if (elect_one()) umma_commit(drain); __syncwarp(); mbar_wait(drain, nd & 1); ++nd; }
+        const uint8_t* src = jb.packedT + (size_t)(pair / C::SLICES) * C::PACKED_NET_BYTES + (size_t)(pair % C::SLICES) * C::B_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bload, C::B_BYTES);
+          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+        }
+        __syncwarp();
+        mbar_wait(bload, nb & 1);
+        ++nb;
+        cur_pair = pair;
+      }
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + acc * C::NS;
+      for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        const uint32_t s = it % C::STAGES;
+        mbar_wait(&full[s], (it / C::STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_stage = tmem + C::A_COL0 + s * C::A_STAGE_COLS;
+#pragma unroll
+          for (int j = 0; j < C::KC / C::UK; ++j) {
+            const uint32_t g = c * (C::KC / C::UK) + j;
+            const uint64_t b_hi = smem_desc(b_base + 2 * g * b_lbo, b_lbo, 128);
+            const uint64_t b_lo = smem_desc(b_base + C::B_TERM_BYTES + 2 * g * b_lbo, b_lbo, 128);
+            const uint32_t a_hi = a_stage + j * 8, a_lo = a_hi + C::A_LO_COLS;
+            umma_ts<false>(d_tmem, a_lo, b_hi, idesc, (c == 0 && j == 0) ? 0u : 1u);
+            umma_ts<false>(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_ts<false>(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (c == C::NCHUNK - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+  } else if (warp >= C::NEW) {
+    // ---------------- producers: dZ2 row -> scaled fp16 hi|lo -> TMEM ----------------
+    const int pw = warp - C::NEW, ptid = tid - C::NEW * 32;
+    const int kq = pw >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + kq * (C::KPW / 2);
+    int cur_net = -1;
+    float w3m0 = 0.f, w3m1 = 0.f;
+    uint32_t it = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES;
+      if (net_i != cur_net) {
+        cur_net = net_i;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        for (int j = ptid; j < H; j += C::PROD_THREADS)
+          w3s[j] = make_float2(net[off_W3(IN) + j], OUT == 2 ? net[off_W3(IN) + H + j] : 0.f);
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
+        w3m0 = __ldg(&meta->wmax[4]);
+        w3m1 = OUT == 2 ? __ldg(&meta->wmax[5]) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+      }
+      const int r = tile * TM + (warp & 3) * 32 + lane;
+      const bool ok = r < jb.rows;
+      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT) : 0.f;
+      const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1) : 0.f;
+      float sa, inv_sa;
+      pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);
+      const float d0s = d0 * sa, d1s = d1 * sa;                       // exact
+      const int rc = ok ? r : 0;
+      const float* h2r = jb.h2 + ((size_t)net_i * tiles64 + (rc >> 6)) * H * 64 + (rc & 63);
+      float hn[C::KPW];                                    // next stage's H2 values, loaded one stage ahead
+#pragma unroll
+      for (int e = 0; e < C::KPW; ++e) hn[e] = __ldg(h2r + (size_t)(kq * C::KPW + e) * 64);
+      for (int c = 0; c < C::NCHUNK; ++c, ++it) {
+        const uint32_t s = it % C::STAGES;
+        const int j0 = c * C::KC + kq * C::KPW;
+        float hv[C::KPW];
+#pragma unroll
+        for (int e = 0; e < C::KPW; ++e) hv[e] = hn[e];
+        if (c + 1 < C::NCHUNK) {
+#pragma unroll
+          for (int e = 0; e < C::KPW; ++e) hn[e] = __ldg(h2r + (size_t)(j0 + C::KC + e) * 64);
+        }
+        uint32_t hi[C::KPW / 2], lo[C::KPW / 2];
+#pragma unroll
+        for (int e = 0; e < C::KPW; e += 2) {
+          const float2 wa = w3s[j0 + e], wb = w3s[j0 + e + 1];
+          float ga = d0s * wa.x, gb = d0s * wb.x;
+          if (OUT == 2) { ga = fmaf(d1s, wa.y, ga); gb = fmaf(d1s, wb.y, gb); }
+          split_h2_trunc(make_float2(hv[e] > 0.f ? ga : 0.f, hv[e + 1] > 0.f ? gb : 0.f), hi[e / 2], lo[e / 2]);
+        }
+        mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+        tc_fence_after();
+        tmem_st8(lane_base + s * C::A_STAGE_COLS, hi);
+        tmem_st8(lane_base + s * C::A_STAGE_COLS + C::A_LO_COLS, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  } else {
+    // ---------------- epilogue (two groups): dZ1, dx, dW1/db1 ----------------
+    constexpr int NCH = C::NS / 32;
+    const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;
+    float4* ebg = ebs + grp * C::NS;
+    float* ivg = invs + grp * C::NS;
+    float a_b[NCH], a_w0[NCH], a_w1[NCH], a_w2[NCH];      // lane l <-> column chunk*32 + l of the current slice
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) { a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f; }
+    auto flush = [&](int pair) {
+      if (!WGRADS || pair < 0) return;
+      const int net_i = pair / C::SLICES, slice = pair % C::SLICES;
+      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * C::NEW + warp) * SMALL_STRIDE;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int k = slice * C::NS + q * 32 + lane;
+        o[k * IN + 0] = a_w0[q];
+        o[k * IN + 1] = a_w1[q];
+        if (IN == 3) o[k * IN + 2] = a_w2[q];
+        o[H * IN + k] = a_b[q];
+        a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f;
+      }
+    };
+    int cur_pair = -1;
+    float w3m0 = 0.f, w3m1 = 0.f;
+    for (int item = item_lo + grp; item < item_hi; item += 2) {
+      const uint32_t tcount = (uint32_t)(item - item_lo);
+      const int pair = item / tiles, tile = item % tiles, net_i = pair / C::SLICES, slice = pair % C::SLICES;
+      if (pair != cur_pair) {
+        flush(cur_pair);
+        cur_pair = pair;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
+        for (int cidx = gtid; cidx < C::NS; cidx += 128) {
+          const int k = slice * C::NS + cidx;
+          ebg[cidx] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
+                                  IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+          ivg[cidx] = __ldg(&meta->inv_s[k]);
+        }
+        w3m0 = __ldg(&meta->wmax[4]);
+        w3m1 = OUT == 2 ? __ldg(&meta->wmax[5]) : 0.f;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+      }
+      const uint32_t acc = grp;
+      const int row = tile * TM + qw * 32 + lane;
+      const bool ok = row < jb.rows;
+      const float4 x = ok ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT) : 0.f;
+      const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT + 1) : 0.f;
+      float sa, inv_sa;
+      pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);     // the producers' scale of this row
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(qw * 32) << 16) + acc * C::NS + q * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 w = ebg[q * 32 + i];
+          float z = fmaf(x.y, w.y, x.x * w.x);
+          if (IN == 3) z = fmaf(x.z, w.z, z);
+          z += w.w;
+          const float d = z > 0.f ? v[i] * inv_sa * ivg[q * 32 + i] : 0.f;
+          v[i] = d;
+          if (DX) {
+            dx0 = fmaf(d, w.x, dx0);
+            dx1 = fmaf(d, w.y, dx1);
+            if (IN == 3) dx2 = fmaf(d, w.z, dx2);
+          }
+        }
+        if (WGRADS) {
+          float t[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x.x;
+          a_w0[q] += warp_reduce_scatter32(t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x.y;
+          a_w1[q] += warp_reduce_scatter32(t);
+          if (IN == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = v[i] * x.z;
+            a_w2[q] += warp_reduce_scatter32(t);
+          }
+          a_b[q] += warp_reduce_scatter32(v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (DX && ok)
+        jb.dX_part[((size_t)net_i * C::SLICES + slice) * jb.rows + row] = make_float4(dx0, dx1, dx2, 0.f);
+    }
+    flush(cur_pair);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::MMA_WARP) tmem_dealloc(tmem, C::TMEM_ALLOC);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the hidden layer, dW2 = dZ2^T H1, on the fp16 hi/lo path.  Structure of tc_bwd2_kernel
+// (mlp_tc_bwd2.cuh): thread t owns hidden unit t and generates row t of BOTH operands on chip; the 256x256 FP32
+// accumulator fills the tensor memory.  The contraction runs over batch rows, so the scales are per operand ROW
+// (= per hidden unit = per thread), constant over the CTA's whole row range:
+//   s_A[t] from |W3[:,t]| . max_r |dOut[r,:]|,   s_B[t] from |W1[t,:]| . max_r |x[r,:]| + |b1[t]|
+// with the maxima taken in a pre-pass over the CTA's rows; the partial is unscaled by 1/(s_A[j] s_B[k]) on the way out.
+// A stage holds 32 rows (K = 32 = two MMAs), the same operand bytes as the tf32 kernel's 16 rows.
+struct B2HCfg {
+  static constexpr int ES = 2, EPC = 8, UK = 16;
+  static constexpr int RS = 32;                             // rows (K extent) per stage
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t OP_TERM_BYTES = H * RS * ES;    // 16 KB
+  static constexpr uint32_t OP_BYTES = 2 * OP_TERM_BYTES;   // 32 KB (hi | lo)
+  static constexpr uint32_t STAGE_BYTES = 2 * OP_BYTES;     // A then B: 64 KB
+  static constexpr uint32_t OFF_X = STAGES * STAGE_BYTES;       // float4[STAGES][RS]
+  static constexpr uint32_t OFF_DO = OFF_X + STAGES * RS * 16;  // float[STAGES][RS][2]
+  static constexpr uint32_t OFF_INV = OFF_DO + STAGES * RS * 8; // float invA[256] | invB[256]
+  static constexpr uint32_t OFF_MAX = OFF_INV + 2 * H * 4;      // int[8] row maxima (float bits)
+  static constexpr uint32_t OFF_BAR = OFF_MAX + 32;
+  static constexpr uint32_t OFF_SLOT = OFF_BAR + (2 * STAGES + 1) * 8;
+  static constexpr uint32_t BYTES = OFF_SLOT + 16;
+};
+
+template <int IN, int OUT>
+__global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job jb) {
+  using C = B2HCfg;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  float4* xs = reinterpret_cast<float4*>(sm + C::OFF_X);
+  float* dos = reinterpret_cast<float*>(sm + C::OFF_DO);
+  float* invA = reinterpret_cast<float*>(sm + C::OFF_INV);
+  float* invB = invA + H;
+  int* rmax = reinterpret_cast<int*>(sm + C::OFF_MAX);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* done = empty + C::STAGES;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, net_i = blockIdx.y;
+  const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+  const int tiles64 = (jb.rows + 63) / 64;
+  const int n_stage_total = (jb.rows + C::RS - 1) / C::RS;
+  const int st_lo = (int)((long long)n_stage_total * split / jb.splits);
+  const int st_hi = (int)((long long)n_stage_total * (split + 1) / jb.splits);
+
+  if (warp == B2_PROD_WARPS) {
+    tmem_alloc(slot, 512);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], B2_PROD_WARPS); mbar_init(&empty[s], 1); }
+      mbar_init(done, 1);
+      fence_mbar_init();
+    }
+  }
+  if (tid < 8) rmax[tid] = 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (warp == B2_PROD_WARPS) {
+    const uint32_t idesc = instr_desc(FMT_F16, 128, 256);
+    const uint32_t lbo = H * 16;
+    uint32_t it = 0;
+    for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
+      const uint32_t s = it % C::STAGES;
+      mbar_wait(&full[s], (it / C::STAGES) & 1);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sm + s * C::STAGE_BYTES);
+      const uint32_t b_base = a_base + C::OP_BYTES;
+      if (elect_one()) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int j = 0; j < C::RS / C::UK; ++j) {
+            const uint32_t acc = (it == 0 && j == 0) ? 0u : 1u;
+            const uint64_t a_hi = smem_desc(a_base + half * 2048 + 2 * j * lbo, lbo, 128);
+            const uint64_t b_hi = smem_desc(b_base + 2 * j * lbo, lbo, 128);
+            const uint64_t a_lo = smem_desc(a_base + C::OP_TERM_BYTES + half * 2048 + 2 * j * lbo, lbo, 128);
+            const uint64_t b_lo = smem_desc(b_base + C::OP_TERM_BYTES + 2 * j * lbo, lbo, 128);
+            const uint32_t d = tmem + half * 256;
+            umma<false>(d, a_lo, b_hi, idesc, acc);
+            umma<false>(d, a_hi, b_lo, idesc, 1u);
+            umma<false>(d, a_hi, b_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[s]);
+        if (sg == st_hi - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- producers: thread t = hidden unit t (A row j = t, B row k = t) ----------------
+    const int t = tid;   // 0..255
+    float w3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) w3[o] = net[off_W3(IN) + o * H + t];
+    const float w1x = net[off_W1(IN) + t * IN], w1y = net[off_W1(IN) + t * IN + 1];
+    const float w1z = IN == 3 ? net[off_W1(IN) + t * IN + 2] : 0.f;
+    const float b1v = net[off_b1(IN) + t];
+    // pre-pass: maxima of |x| components and |dOut| components over this CTA's rows -> per-unit scales
+    {
+      float mx0 = 0.f, mx1 = 0.f, mx2 = 0.f, md0 = 0.f, md1 = 0.f;
+      const int r_lo = st_lo * C::RS, r_hi = min(jb.rows, st_hi * C::RS);
+      for (int r = r_lo + t; r < r_hi; r += 256) {
+        const float4 x = __ldg(jb.X + r);
+        mx0 = fmaxf(mx0, fabsf(x.x)); mx1 = fmaxf(mx1, fabsf(x.y)); mx2 = fmaxf(mx2, fabsf(x.z));
+        md0 = fmaxf(md0, fabsf(__ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT)));
+        if (OUT == 2) md1 = fmaxf(md1, fabsf(__ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+        mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o)); md0 = fmaxf(md0, __shfl_xor_sync(0xffffffffu, md0, o));
+        md1 = fmaxf(md1, __shfl_xor_sync(0xffffffffu, md1, o));
+      }
+      if (lane == 0) {
+        atomicMax(&rmax[0], __float_as_int(mx0)); atomicMax(&rmax[1], __float_as_int(mx1)); atomicMax(&rmax[2], __float_as_int(mx2));
+        atomicMax(&rmax[3], __float_as_int(md0)); atomicMax(&rmax[4], __float_as_int(md1));
+      }
+      asm volatile("bar.sync 1, 256;");
+    }
+    float sA, sB;
+    {
+      float inv;
+      float bA = fabsf(w3[0]) * __int_as_float(rmax[3]);
+      if (OUT == 2) bA = fmaf(fabsf(w3[OUT - 1]), __int_as_float(rmax[4]), bA);
+      pow2_scale(bA, sA, inv);
+      invA[t] = inv;
+      const float bB = fmaf(fabsf(w1x), __int_as_float(rmax[0]), fmaf(fabsf(w1y), __int_as_float(rmax[1]),
+                       fmaf(fabsf(w1z), __int_as_float(rmax[2]), fabsf(b1v))));
+      pow2_scale(bB, sB, inv);
+      invB[t] = inv;
+    }
+    float s_db2 = 0.f, s_dw3[OUT], s_db3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) { s_dw3[o] = 0.f; s_db3[o] = 0.f; }
+    uint32_t it = 0;
+    auto h2_ptr = [&](int sg) {
+      const int row0 = sg * C::RS;
+      return jb.h2 + (((size_t)net_i * tiles64 + (row0 >> 6)) * H + t) * 64 + (row0 & 63);
+    };
+    // software pipeline: the next stage's H2 values (all threads) and x / dOut rows (threads < RS) are loaded into
+    // registers while the current stage is computed -- a stage's global-load latency is off the critical path
+    float4 hq[C::RS / 4], hn[C::RS / 4];
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dn[OUT];
+    auto prefetch = [&](int sg) {
+      const float* h2p = h2_ptr(sg);
+#pragma unroll
+      for (int q = 0; q < C::RS / 4; ++q) hn[q] = __ldg(reinterpret_cast<const float4*>(h2p) + q);
+      if (t < C::RS) {
+        const int r = sg * C::RS + t;
+        xn = r < jb.rows ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dn[o] = r < jb.rows ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + o) : 0.f;
+      }
+    };
+    if (st_lo < st_hi) prefetch(st_lo);
+    for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
+      const uint32_t s = it % C::STAGES;
+#pragma unroll
+      for (int q = 0; q < C::RS / 4; ++q) hq[q] = hn[q];
+      const float4 xc = xn;
+      float dc[OUT];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) dc[o] = dn[o];
+      if (sg + 1 < st_hi) prefetch(sg + 1);
+      mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+      float4* xst = xs + s * C::RS;
+      float* dost = dos + s * C::RS * 2;
+      if (t < C::RS) {
+        xst[t] = xc;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dost[t * 2 + o] = dc[o];
+      }
+      asm volatile("bar.sync 1, 256;");
+      uint8_t* Ast = sm + s * C::STAGE_BYTES;
+      uint8_t* Bst = Ast + C::OP_BYTES;
+#pragma unroll
+      for (int kc = 0; kc < C::RS / C::EPC; ++kc) {
+        float hv[8], dz[8], h1[8];
+        hv[0] = hq[2 * kc].x; hv[1] = hq[2 * kc].y; hv[2] = hq[2 * kc].z; hv[3] = hq[2 * kc].w;
+        hv[4] = hq[2 * kc + 1].x; hv[5] = hq[2 * kc + 1].y; hv[6] = hq[2 * kc + 1].z; hv[7] = hq[2 * kc + 1].w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int rl = kc * 8 + e;
+          float g = 0.f;
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) {
+            const float d = dost[rl * 2 + o];
+            g = fmaf(d, w3[o], g);
+            s_dw3[o] = fmaf(d, hv[e], s_dw3[o]);
+            if (t == 0) s_db3[o] += d;
+          }
+          dz[e] = hv[e] > 0.f ? g : 0.f;
+          s_db2 += dz[e];
+          const float4 x = xst[rl];
+          float z = fmaf(x.y, w1y, x.x * w1x);
+          if (IN == 3) z = fmaf(x.z, w1z, z);
+          h1[e] = fmaxf(z + b1v, 0.f);
+        }
+        const uint32_t off = chunk_off(H, t, kc);
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_h2_trunc(make_float2(dz[2 * e] * sA, dz[2 * e + 1] * sA), hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(Ast + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(Ast + C::OP_TERM_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_h2_trunc(make_float2(h1[2 * e] * sB, h1[2 * e + 1] * sB), hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(Bst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(Bst + C::OP_TERM_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    float* sm2 = jb.small2 + ((size_t)net_i * jb.splits + split) * SMALL_STRIDE;
+    sm2[H * IN + H + t] = s_db2;
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) sm2[H * IN + 2 * H + o * H + t] = s_dw3[o];
+    if (t == 0) {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) sm2[H * IN + 2 * H + OUT * H + o] = s_db3[o];
+    }
+  }
+  // ---------------- epilogue: unscale and dump the 256x256 accumulator as this split's partial ----------------
+  float* out = jb.pw2 + ((size_t)net_i * jb.splits + split) * H * H;
+  if (warp < 4) {
+    if (st_hi > st_lo) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int j = half * 128 + warp * 32 + lane;
+      const float ia = invA[j];
+      float* orow = out + (size_t)j * H;
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        float v[32];
+        if (st_hi > st_lo) {
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 256 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] * ia * invB[c0 + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == B2_PROD_WARPS) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc

@@ -30,6 +30,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// (a suspend-time hint -- CUTLASS passes 10 ms -- was measured here: it made the pipelined MLP kernels slower)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -9,10 +9,10 @@
 #include "engine.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc_ts.cuh"
-#include "mlp_tc_h.cuh"
 #include <type_traits>
 #include "mlp_tc_bwd1.cuh"
 #include "mlp_tc_bwd2.cuh"
+#include "mlp_tc_h.cuh"
 
 namespace cql {
 
@@ -540,7 +540,8 @@ inline void pack_slots(Handle* h, const int* slots, int n_slots, cudaStream_t st
     const int in_dim = is_actor ? 2 : 3;
     tc::PackJobs& fj = f16 ? jobs_h : jobs;
     fj.j[fj.n++] = {h->net_params(slot), h->packed_fwd + (size_t)slot * h->packed_net_bytes, in_dim, 0};
-    if (slot <= h->C) jobs.j[jobs.n++] = {h->net_params(slot), h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, in_dim, 1};
+    tc::PackJobs& bj = f16 ? jobs_h : jobs;
+    if (slot <= h->C) bj.j[bj.n++] = {h->net_params(slot), h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, in_dim, 1};
   }
   if (jobs_h.n) {
     tc::k_pack_multi_h<<<dim3(H * 32 / 256, jobs_h.n), 256, 0, st>>>(jobs_h, 2);
@@ -563,30 +564,36 @@ inline void pack_weights(Handle* h, int slot, int n_slots, int /*in_dim*/, cudaS
 }
 
 // ---- tensor-core backward of one job: bwd1 (dH1, dW1, db1, dx) + bwd2 (dW2, db2, dW3, db3) + reduce
-template <bool TF32, int IN, int OUT, bool WGRADS, bool DX>
+template <bool TF32, int IN, int OUT, bool WGRADS, bool DX, bool F16X3 = false>
 inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStream_t st) {
-  using C = tc::Cfg<TF32>;
+  using C = std::conditional_t<F16X3, tc::HCfg, tc::Cfg<TF32>>;
   const int slot = (int)((jb.params - h->params) / NET_STRIDE);
   const int tiles = (jb.rows + tc::TM - 1) / tc::TM;
   const int items = jb.n_nets * C::SLICES * tiles;
   const int grid1 = items < h->num_sms ? items : h->num_sms;
-  const int slots1 = 4 * grid1;
+  const int slots1 = (F16X3 ? tc::HCfg::NEW : 4) * grid1;
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
   tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, h->small1,
                  DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
-  if constexpr (TF32)
+  if constexpr (F16X3)
+    tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::HCfg::THREADS, tc::HCfg::SMEM_BYTES, st>>>(j1);
+  else if constexpr (TF32)
     tc::tc_bwd1_ts_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(j1);
   else
     tc::tc_bwd1_kernel<TF32, IN, OUT, WGRADS, DX><<<grid1, tc::Pipe<TF32, tc::BWD1_NPW>::THREADS, tc::FwdSmem<TF32, tc::BWD1_NPW>::BYTES, st>>>(j1);
   CQL_LAUNCH_CHECK(h);
   if (!WGRADS) return;
-  const int n_stage = (jb.rows + tc::B2Cfg<TF32>::RS - 1) / tc::B2Cfg<TF32>::RS;
+  constexpr int RS2 = F16X3 ? tc::B2HCfg::RS : tc::B2Cfg<TF32>::RS;
+  const int n_stage = (jb.rows + RS2 - 1) / RS2;
   int splits = h->num_sms / jb.n_nets;
   if (splits > n_stage) splits = n_stage;
   if (splits > h->splits_tc) splits = h->splits_tc;
   if (splits < 1) splits = 1;
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
-  tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
+  if constexpr (F16X3)
+    tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2HCfg::BYTES, st>>>(j2);
+  else
+    tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
   CQL_LAUNCH_CHECK(h);
   tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out);
@@ -706,7 +713,8 @@ inline void phase1(Handle* h, cudaStream_t st) {
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);
   if (h->cfg.precision != CQL_PREC_FP32) {
-    if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st);
+    if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, true, false, true>(h, jb, h->g_critics(), st);
+    else if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st);
     else launch_bwd_tc<false, 3, 1, true, false>(h, jb, h->g_critics(), st);
     mark(h, st, 6);
     mark(h, st, 7);
@@ -748,7 +756,8 @@ inline void phase2(Handle* h, cudaStream_t st) {
   CQL_LAUNCH_CHECK(h);
   {
     BwdJob jb{h->XP, h->dQP, h->h2P, h->net_params(slot_critic(0)), nullptr, h->dXP, nullptr, B, C, 1};
-    if (h->cfg.precision == CQL_PREC_TF32X3 || h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, false, true>(h, jb, nullptr, st);
+    if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, false, true, true>(h, jb, nullptr, st);
+    else if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 3, 1, false, true>(h, jb, nullptr, st);
     else if (h->cfg.precision == CQL_PREC_BF16) launch_bwd_tc<false, 3, 1, false, true>(h, jb, nullptr, st);
     else launch_bwd1<3, 1, false, true>(h, jb, st);
   }
@@ -760,7 +769,8 @@ inline void phase2(Handle* h, cudaStream_t st) {
   BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
   mark(h, st, 10);
   if (tcm) {
-    if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 2, 2, true, false>(h, ja, h->g_actor(), st);
+    if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 2, 2, true, false, true>(h, ja, h->g_actor(), st);
+    else if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 2, 2, true, false>(h, ja, h->g_actor(), st);
     else launch_bwd_tc<false, 2, 2, true, false>(h, ja, h->g_actor(), st);
     mark(h, st, 11);
     return;
