@@ -247,6 +247,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = eng.launch_count
+    r0 = stepper.replayed_steps if stepper is not None else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -254,7 +255,9 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launch_count - l0
+    launches = eng.launch_count - l0           # eager / library-graph launches are counted by the library itself
+    if stepper is not None:                    # graph replays: kernels captured per update x replayed updates
+        launches += stepper.launches_per_step * (stepper.replayed_steps - r0)
     clk = clocks.stop()
     value = world * args.steps / (ms / 1e3)
 
@@ -429,7 +432,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=None, help="override the log size (debugging)")
-    ap.add_argument("--precision", choices=["fp32", "tf32x3", "f16x3", "bf16"], default="tf32x3",
+    ap.add_argument("--precision", choices=["fp32", "tf32x3", "f16x3", "bf16"], default="f16x3",
                     help="hidden-layer contraction: fp32 = CUDA-core FMA; tf32x3 = tcgen05 3-term split (FP32-grade, "
                          "default); bf16 = tcgen05 bf16 operands (non-parity variant)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -7,6 +7,7 @@
 #include "score.cuh"
 #include "tc_selftest.cuh"
 #include "score_tc.cuh"
+#include "score_tc_h.cuh"
 #include "topk_staged.cuh"
 
 using namespace cql;
@@ -63,6 +64,7 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_kernel<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FwdSmem<false, tc::FWD_NPW>::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ScoreSmem::bytes(CQL_MAX_TOPK)));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_score_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ScoreSmemH::bytes(CQL_MAX_TOPK)));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2HCfg::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2HCfg::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
@@ -229,15 +231,26 @@ void score_topk_dev_impl(cql_handle* ch, const int32_t* users, int64_t U, const 
     CQL_CUDA(cudaStreamSynchronize(st));
     return;
   }
-  if (h->cfg.precision != CQL_PREC_FP32) {   // tensor-core scorer (FP32-grade tf32 split in both TC modes)
+  if (h->cfg.precision != CQL_PREC_FP32) {   // tensor-core scorer, FP32-grade: fp16 hi/lo split (f16x3) or tf32 split (other modes)
     using TC = tc::Cfg<true>;
-    if (!ch->packed_score) CQL_CUDA(cudaMalloc(&ch->packed_score, (size_t)(1 + h->C) * TC::PACKED_NET_BYTES));
-    const int chunks16 = H * (H / TC::EPC);
-    tc::k_pack_w2<true, false><<<dim3((chunks16 + 255) / 256, 1), 256, 0, st>>>(h->net_params(slot_actor()), 2, 1, ch->packed_score);
-    CQL_LAUNCH_CHECK(h);
-    tc::k_pack_w2<true, false><<<dim3((chunks16 + 255) / 256, h->C), 256, 0, st>>>(h->net_params(slot_critic(0)), 3, h->C,
-                                                                                   ch->packed_score + TC::PACKED_NET_BYTES);
-    CQL_LAUNCH_CHECK(h);
+    const bool f16 = h->cfg.precision == CQL_PREC_F16X3;
+    if (!ch->packed_score)
+      CQL_CUDA(cudaMalloc(&ch->packed_score, (size_t)(1 + h->C) * std::max<size_t>(TC::PACKED_NET_BYTES, tc::HCfg::PACKED_NET_BYTES)));
+    if (f16) {
+      tc::PackJobs pj{};
+      pj.j[pj.n++] = {h->net_params(slot_actor()), ch->packed_score, 2, 0};
+      for (int c = 0; c < h->C; ++c)
+        pj.j[pj.n++] = {h->net_params(slot_critic(c)), ch->packed_score + (size_t)(1 + c) * tc::HCfg::PACKED_NET_BYTES, 3, 0};
+      tc::k_pack_multi_h<<<dim3(H * 32 / 256, pj.n), 256, 0, st>>>(pj, 2);
+      CQL_LAUNCH_CHECK(h);
+    } else {
+      const int chunks16 = H * (H / TC::EPC);
+      tc::k_pack_w2<true, false><<<dim3((chunks16 + 255) / 256, 1), 256, 0, st>>>(h->net_params(slot_actor()), 2, 1, ch->packed_score);
+      CQL_LAUNCH_CHECK(h);
+      tc::k_pack_w2<true, false><<<dim3((chunks16 + 255) / 256, h->C), 256, 0, st>>>(h->net_params(slot_critic(0)), 3, h->C,
+                                                                                     ch->packed_score + TC::PACKED_NET_BYTES);
+      CQL_LAUNCH_CHECK(h);
+    }
     const int64_t tiles128 = (I + tc::TM - 1) / tc::TM;
     const int chunks = (int)((tiles128 + tc::SC_CH - 1) / tc::SC_CH);
     const size_t need = (size_t)U * chunks * k;
@@ -258,8 +271,8 @@ void score_topk_dev_impl(cql_handle* ch, const int32_t* users, int64_t U, const 
     tc::ScoreTcArgs a{h->params, ch->packed_score, users, items, seen_indptr, seen_items, U, I, h->C, k, mode, chunks, ps, pi};
     const int64_t n_blocks = U * chunks;
     const int grid = (int)std::min<int64_t>(n_blocks, h->num_sms);
-    const uint32_t smem = tc::ScoreSmem::bytes(k);
-    tc::tc_score_kernel<<<grid, tc::TsCfg::THREADS, smem, st>>>(a);
+    if (f16) tc::tc_score_h_kernel<<<grid, tc::HCfg4::THREADS, tc::ScoreSmemH::bytes(k), st>>>(a);
+    else tc::tc_score_kernel<<<grid, tc::TsCfg::THREADS, tc::ScoreSmem::bytes(k), st>>>(a);
     CQL_LAUNCH_CHECK(h);
     if (chunks > 1) {
       const int wpb = 4;

@@ -26,7 +26,8 @@
 namespace cql {
 namespace tc {
 
-struct HCfg {
+template <int NEW_>
+struct HCfgT {
   static constexpr int ES = 2, EPC = 8, UK = 16;
   static constexpr int NS = 128;                      // output columns per work item
   static constexpr int SLICES = H / NS;               // 2
@@ -35,7 +36,7 @@ struct HCfg {
   static constexpr int STAGES = 4;
   static constexpr int NCHUNK = H / KC;               // 4
   static constexpr int KPW = KC / (NPW / 4);          // K elements per producer warp per stage: 16 = 8 columns
-  static constexpr int NEW = 8;                       // epilogue warps: two groups of 4, one per TMEM accumulator
+  static constexpr int NEW = NEW_;                    // epilogue warps: 8 = two groups of 4, one per TMEM accumulator
   static constexpr int MMA_WARP = NEW + NPW;
   static constexpr int THREADS = (NEW + 1 + NPW) * 32;   // 800
   static constexpr int PROD_THREADS = NPW * 32;
@@ -55,6 +56,8 @@ struct HCfg {
   static constexpr uint32_t OFF_SLOT = OFF_BAR + N_BARS * 8;
   static constexpr uint32_t SMEM_BYTES = OFF_SLOT + 16;
 };
+using HCfg = HCfgT<8>;     // update kernels
+using HCfg4 = HCfgT<4>;    // scorer (one epilogue group keeps the per-row state)
 
 // meta block of a packed net
 struct HMeta {

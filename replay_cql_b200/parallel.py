@@ -95,6 +95,8 @@ class DataParallelStepper:
         self.stream = torch.cuda.Stream(device=self.device)
         self.graph = None
         self._warmup = warmup
+        self.launches_per_step = 0             # this library's kernel launches inside one captured update
+        self.replayed_steps = 0
 
     def _eager(self, n: int) -> None:
         import torch
@@ -107,8 +109,10 @@ class DataParallelStepper:
         self._eager(self._warmup)              # NCCL communicators / lazy state must exist before capture
         self.stream.synchronize()
         g = torch.cuda.CUDAGraph()
+        l0 = self.engine.launch_count
         with torch.cuda.graph(g, stream=self.stream):
             self.engine.update_data_parallel(self.reducer, stream=self.stream.cuda_stream)
+        self.launches_per_step = self.engine.launch_count - l0
         self.graph = g
 
     def run(self, n_steps: int) -> None:
@@ -123,5 +127,6 @@ class DataParallelStepper:
             with torch.cuda.stream(self.stream):
                 for _ in range(n_steps):
                     self.graph.replay()
+            self.replayed_steps += n_steps
         else:
             self._eager(n_steps)

@@ -112,7 +112,7 @@ def test_score_policy_mode(fitted):
         model.score = "q"
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "f16x3"])
 def test_phase_split_equals_fused_update(engine_factory, precision):
     """The four data-parallel phases (host all-reduce points in between; identity here) take exactly the
     same step as the fused CUDA-graph update: bit-identical weights after 5 updates."""

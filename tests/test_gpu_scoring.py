@@ -32,7 +32,7 @@ def _lists_match(ti, ts, ri, rs):
         assert ti[r, c] in ri[r] or np.any(np.abs(rs[r] - ts[r, c]) <= TOL * scale)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("name", ["score_small.npz", "score_k1.npz"])
 def test_golden_scores(engine_factory, name, precision):
     z = np.load(GOLD / name)
@@ -50,7 +50,7 @@ def _oracle_state(seed):
     return flat, Hp.flat_to_oracle_state(flat, cfg)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("U,I,k", [(5, 1000, 10), (700, 130, 7), (3, 63, 100), (2, 64, 64), (3, 5000, 10)])
 def test_random_against_brute_force(engine_factory, U, I, k, precision):
     flat, st = _oracle_state(11)
