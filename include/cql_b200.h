@@ -176,6 +176,18 @@ int  cql_topk_filter_dev(cql_handle* h, const float* scores_dev, int64_t n_users
                          const int64_t* seen_indptr, const int32_t* seen_items,
                          int32_t k, int32_t* out_items, float* out_scores, void* stream);
 
+/* Ranking metrics of a U x k_rec recommendation table against the ground truth, on the GPU (host pointers).
+ * replaces: Metric.__call__ -> get_enriched_recommendations + _get_metric_value_by_user,
+ *           replay/metrics/base_metric.py:102-140,178-200 and ndcg.py:51-61, hitrate.py, map.py, mrr.py,
+ *           precision.py, recall.py (the evaluation step of optimize(), replay/models/base_rec.py:150-274).
+ * rec_items [U][k_rec]: best first, padded with -1; users [U]: user id of each row (the ground-truth users --
+ * a user without recommendations is a row of -1 and scores 0); gt_indptr/gt_items: CSR over user id, items
+ * sorted ascending per user; ks [n_ks] (n_ks <= 8, each <= k_rec is not required).
+ * out_means [6][n_ks] in the order NDCG, HitRate, MAP, MRR, Precision, Recall (means over the U users). */
+int  cql_rank_metrics(cql_handle* h, const int32_t* rec_items, int64_t n_users, int32_t k_rec,
+                      const int32_t* users, const int64_t* gt_indptr, const int32_t* gt_items,
+                      const int32_t* ks, int32_t n_ks, double* out_means, void* stream);
+
 /* Measurement aid: runs ONE sampled update with CUDA events around the heavy launches and
  * returns their durations in milliseconds (synchronises).  out_ms[0] = critic forward (alpha +
  * critic + target rows), [1] = critic backward-1, [2] = critic backward-2 (dW2), [3] = whole

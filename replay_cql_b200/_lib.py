@@ -62,6 +62,7 @@ SIGNATURES = {
     "cql_score_topk": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "cql_score_topk_dev": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "cql_score_pairs": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "cql_rank_metrics": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "cql_topk_filter_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "cql_timed_update": (C.c_int, [_P, _P, _P]),
     "cql_selftest_umma": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),

@@ -9,6 +9,7 @@
 #include "score_tc.cuh"
 #include "score_tc_h.cuh"
 #include "topk_staged.cuh"
+#include "metrics.cuh"
 
 using namespace cql;
 
@@ -709,6 +710,49 @@ int cql_score_pairs(cql_handle* ch, const int32_t* users, const int32_t* items, 
     k_score_pairs<<<(unsigned)((n + BM - 1) / BM), NT, FWD_SMEM, st>>>(h.params, d_u, d_i, n, h.C, mode, d_o);
     CQL_LAUNCH_CHECK(&h);
     CQL_CUDA(cudaMemcpyAsync(out_scores, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int cql_rank_metrics(cql_handle* ch, const int32_t* rec_items, int64_t n_users, int32_t k_rec, const int32_t* users,
+                     const int64_t* gt_indptr, const int32_t* gt_items, const int32_t* ks, int32_t n_ks,
+                     double* out_means, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(n_users >= 0 && k_rec >= 1 && n_ks >= 1 && n_ks <= MET_MAX_KS && ks && out_means, "cql_rank_metrics: bad arguments");
+    for (int q = 0; q < n_ks; ++q) CQL_REQUIRE(ks[q] >= 1, "cql_rank_metrics: k must be >= 1");
+    if (n_users == 0) {
+      for (int i = 0; i < MET_COUNT * n_ks; ++i) out_means[i] = 0.0;
+      return;
+    }
+    CQL_REQUIRE(rec_items && users && gt_indptr, "cql_rank_metrics: NULL input");
+    cudaStream_t st = pick_stream(&h, stream);
+    int32_t mx = 0;
+    for (int64_t i = 0; i < n_users; ++i) {
+      CQL_REQUIRE(users[i] >= 0, "cql_rank_metrics: negative user id");
+      mx = std::max(mx, users[i]);
+    }
+    const int64_t np = (int64_t)mx + 2, ng = gt_indptr[np - 1];
+    CQL_REQUIRE(ng == 0 || gt_items, "cql_rank_metrics: gt_items is NULL");
+    int32_t* d_rec = (int32_t*)scratch(ch, 0, (size_t)n_users * k_rec * 4);
+    int32_t* d_users = (int32_t*)scratch(ch, 1, (size_t)n_users * 4);
+    int64_t* d_ptr = (int64_t*)scratch(ch, 4, (size_t)np * 8);
+    int32_t* d_gt = (int32_t*)scratch(ch, 5, (size_t)std::max<int64_t>(1, ng) * 4);
+    double* d_pu = (double*)scratch(ch, 2, (size_t)MET_COUNT * n_ks * n_users * 8);
+    double* d_out = (double*)scratch(ch, 3, (size_t)MET_COUNT * n_ks * 8);
+    CQL_CUDA(cudaMemcpyAsync(d_rec, rec_items, (size_t)n_users * k_rec * 4, cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(d_users, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, st));
+    CQL_CUDA(cudaMemcpyAsync(d_ptr, gt_indptr, (size_t)np * 8, cudaMemcpyHostToDevice, st));
+    if (ng) CQL_CUDA(cudaMemcpyAsync(d_gt, gt_items, (size_t)ng * 4, cudaMemcpyHostToDevice, st));
+    MetricArgs ma{};
+    ma.rec_items = d_rec; ma.users = d_users; ma.gt_indptr = d_ptr; ma.gt_items = d_gt;
+    ma.n_users = n_users; ma.k_rec = k_rec; ma.n_ks = n_ks; ma.per_user = d_pu;
+    for (int q = 0; q < n_ks; ++q) ma.ks[q] = ks[q];
+    k_rank_metrics<<<(unsigned)((n_users + 127) / 128), 128, 0, st>>>(ma);
+    CQL_LAUNCH_CHECK(&h);
+    k_metric_mean<<<MET_COUNT * n_ks, 256, 0, st>>>(d_pu, n_users, d_out);
+    CQL_LAUNCH_CHECK(&h);
+    CQL_CUDA(cudaMemcpyAsync(out_means, d_out, (size_t)MET_COUNT * n_ks * 8, cudaMemcpyDeviceToHost, st));
     CQL_CUDA(cudaStreamSynchronize(st));
   });
 }

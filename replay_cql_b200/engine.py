@@ -340,6 +340,32 @@ class CqlEngine:
                                               _ptr(out), None), "cql_score_pairs")
         return out
 
+    METRIC_NAMES = ("NDCG", "HitRate", "MAP", "MRR", "Precision", "Recall")
+
+    def rank_metrics(self, rec_items, users, gt_indptr, gt_items, ks) -> dict:
+        """Ranking metrics of a [U, k_rec] recommendation table (best first, -1 padded) against the ground truth
+        CSR (over user id, items sorted per user), computed on the GPU.  Returns {metric: {k: mean over users}}
+        with the reference's per-user definitions (replay/metrics/*.py ``_get_metric_value_by_user``)."""
+        rec_items = np.ascontiguousarray(rec_items, dtype=np.int32)
+        if rec_items.ndim != 2:
+            raise ValueError("rec_items must be [n_users, k_rec]")
+        users = np.ascontiguousarray(users, dtype=np.int32).reshape(-1)
+        if users.size != rec_items.shape[0]:
+            raise ValueError("one user id per row of rec_items")
+        gt_indptr = np.ascontiguousarray(gt_indptr, dtype=np.int64)
+        gt_items = np.ascontiguousarray(gt_items, dtype=np.int32)
+        ks = [int(k) for k in (ks if hasattr(ks, "__iter__") else [ks])]
+        if not ks or len(ks) > 8 or min(ks) < 1:
+            raise ValueError("ks: 1 to 8 cut-offs, each >= 1")
+        if users.size and gt_indptr.size < int(users.max()) + 2:
+            raise ValueError("gt_indptr must cover every user id")
+        ks_a = np.asarray(ks, dtype=np.int32)
+        out = np.zeros((len(self.METRIC_NAMES), len(ks)), dtype=np.float64)
+        self._check(self._lib.cql_rank_metrics(self._h, _ptr(rec_items), users.size, max(1, rec_items.shape[1]), _ptr(users),
+                                               _ptr(gt_indptr), _ptr(gt_items), _ptr(ks_a), len(ks), _ptr(out), None),
+                    "cql_rank_metrics")
+        return {name: {k: float(out[m, q]) for q, k in enumerate(ks)} for m, name in enumerate(self.METRIC_NAMES)}
+
     def score_topk_device(self, users_t, items_t, k: int, seen_indptr_t=None, seen_items_t=None, mode: str = "q",
                           out_items=None, out_scores=None, stream: int | None = None):
         """HBM-resident variant: every argument is a cuda tensor (int32 ids, int64 indptr)."""
