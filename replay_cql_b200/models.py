@@ -17,7 +17,7 @@ import pandas as pd
 from .engine import CqlEngine, CqlHyperParams
 from .mdp import build_mdp_on_device, seen_csr
 from .parallel import GradAllReducer, dist_info, gather_rows, shard_range
-from .recommender import Recommender, _rec_frame
+from .recommender import Recommender, _rec_frame, get_top_k_recs
 
 
 class CQL(Recommender):
@@ -222,6 +222,31 @@ class CQL(Recommender):
         it = pairs["item_idx"].to_numpy().astype(np.int32)
         rel = self.engine.score_pairs(u, it, mode=self.score) if u.size else np.zeros(0, dtype=np.float32)
         return _rec_frame(u, it, rel)
+
+    # ------------------------------------------------------------------ evaluation (the step right after predict)
+    def evaluate(self, recs: pd.DataFrame, ground_truth: pd.DataFrame, k) -> dict:
+        """Ranking metrics of a recommendation frame against ``ground_truth`` on the GPU:
+        ``{metric: {k: value}}`` for NDCG, HitRate, MAP, MRR, Precision, Recall with the reference's definitions
+        (``replay/metrics/*.py``; users = the ground-truth users, ``base_metric.py:102-140``).  Replaces the Spark
+        joins + Python UDFs that ``optimize`` trials run after every ``predict`` (``optuna_objective.py:80-111``)."""
+        if self.engine is None:
+            raise AttributeError("CQL model is not fitted or loaded")
+        ks = [int(x) for x in (k if hasattr(k, "__iter__") else [k])]
+        gt = ground_truth[["user_idx", "item_idx"]].drop_duplicates()
+        users = np.sort(gt["user_idx"].unique()).astype(np.int32)
+        if users.size == 0:
+            return {name: {kk: 0.0 for kk in ks} for name in self.engine.METRIC_NAMES}
+        gt_ptr, gt_items = seen_csr(gt, int(users.max()) + 1)
+        top = get_top_k_recs(recs, max(ks)) if len(recs) else recs
+        top = top[top["user_idx"].isin(users)].sort_values(["user_idx", "relevance", "item_idx"],
+                                                            ascending=[True, False, True], kind="stable")
+        k_rec = max(1, max(ks))
+        table = np.full((users.size, k_rec), -1, dtype=np.int32)
+        if len(top):
+            row = np.searchsorted(users, top["user_idx"].to_numpy())
+            pos = top.groupby("user_idx").cumcount().to_numpy()
+            table[row, pos] = top["item_idx"].to_numpy().astype(np.int32)
+        return self.engine.rank_metrics(table, users, gt_ptr, gt_items, ks)
 
     # ------------------------------------------------------------------ persistence (model_handler.py:38, :90)
     def _save_model(self, path: str) -> None:

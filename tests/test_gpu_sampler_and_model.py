@@ -102,6 +102,22 @@ def test_save_load_roundtrip(fitted, tmp_path):     # tests/models/test_save_loa
     loaded.engine.close()
 
 
+def test_evaluate_matches_metrics_oracle(fitted):
+    """CQL.evaluate (frames -> CSR -> cql_rank_metrics) == oracle on the model's own recommendations."""
+    from oracle import metrics_oracle as M
+    model, log = fitted
+    recs = model.predict(log, k=5, filter_seen_items=False)
+    gt = log.groupby("user_idx").tail(3)[["user_idx", "item_idx"]]
+    got = model.evaluate(recs, gt, [1, 3, 5])
+    recs_d = {int(u): g.sort_values(["relevance", "item_idx"], ascending=[False, True])["item_idx"].tolist()
+              for u, g in recs.groupby("user_idx")}
+    gt_d = {int(u): g["item_idx"].tolist() for u, g in gt.groupby("user_idx")}
+    ref = M.rank_metrics(recs_d, gt_d, [1, 3, 5])
+    for name in ref:
+        for k in (1, 3, 5):
+            assert got[name][k] == pytest.approx(ref[name][k], rel=1e-12, abs=1e-15), (name, k)
+
+
 def test_score_policy_mode(fitted):
     model, log = fitted
     model.score = "policy"
