@@ -19,6 +19,10 @@ struct cql_handle {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t graph_stream = nullptr;
   int64_t graph_launches = 0;
+  // same for the host-minibatch entry (cql_update_batch): [0] Philox noise, [1] caller-provided noise
+  cudaGraphExec_t batch_graph[2] = {nullptr, nullptr};
+  cudaStream_t batch_graph_stream[2] = {nullptr, nullptr};
+  int64_t batch_graph_launches[2] = {0, 0};
   // grow-only device scratch for the host-pointer scoring entry points
   void* sbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t sbuf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -191,6 +195,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
 
 void destroy_graph(cql_handle* ch) {
   if (ch->graph_exec) { cudaGraphExecDestroy(ch->graph_exec); ch->graph_exec = nullptr; }
+  for (auto& g : ch->batch_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
 
 template <typename F>
@@ -585,7 +590,33 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
       std::memcpy(h.noise_host, noise, h.noise_floats * sizeof(float));
       CQL_CUDA(cudaMemcpyAsync(h.noise, h.noise_host, h.noise_floats * sizeof(float), cudaMemcpyHostToDevice, st));
     }
-    run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+    // the 26 launches of the step replay as one CUDA graph (26 runtime launches cost ~100 us of host time per step)
+    const int gi = noise ? 1 : 0;
+    if (h.timing) {
+      run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+    } else {
+      if (!ch->batch_graph[gi] || ch->batch_graph_stream[gi] != st) {
+        if (ch->batch_graph[gi]) { cudaGraphExecDestroy(ch->batch_graph[gi]); ch->batch_graph[gi] = nullptr; }
+        cudaGraph_t g = nullptr;
+        const int64_t before = h.launches;
+        CQL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+          run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+        } catch (...) {
+          cudaStreamEndCapture(st, &g);
+          if (g) cudaGraphDestroy(g);
+          throw;
+        }
+        CQL_CUDA(cudaStreamEndCapture(st, &g));
+        ch->batch_graph_launches[gi] = h.launches - before;
+        h.launches = before;
+        CQL_CUDA(cudaGraphInstantiate(&ch->batch_graph[gi], g, 0));
+        CQL_CUDA(cudaGraphDestroy(g));
+        ch->batch_graph_stream[gi] = st;
+      }
+      CQL_CUDA(cudaGraphLaunch(ch->batch_graph[gi], st));
+      h.launches += ch->batch_graph_launches[gi];
+    }
     if (metrics6) CQL_CUDA(cudaMemcpyAsync(h.metrics_host, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (grads_out)
       CQL_CUDA(cudaMemcpyAsync(grads_out, h.grads, grad_floats(h.C) * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -665,26 +665,32 @@ struct B2HCfg {
   static constexpr int ES = 2, EPC = 8, UK = 16;
   static constexpr int RS = 32;                             // rows (K extent) per stage
   static constexpr int STAGES = 3;
+  static constexpr int PROD_WARPS = 16;                     // two threads per hidden unit, 16 rows of a stage each
+  static constexpr int PROD_THREADS = PROD_WARPS * 32;
+  static constexpr int THREADS = PROD_THREADS + 32;         // + MMA warp
+  static constexpr int RPT = RS / 2;                        // rows per thread per stage
   static constexpr uint32_t OP_TERM_BYTES = H * RS * ES;    // 16 KB
   static constexpr uint32_t OP_BYTES = 2 * OP_TERM_BYTES;   // 32 KB (hi | lo)
   static constexpr uint32_t STAGE_BYTES = 2 * OP_BYTES;     // A then B: 64 KB
   static constexpr uint32_t OFF_X = STAGES * STAGE_BYTES;       // float4[STAGES][RS]
   static constexpr uint32_t OFF_DO = OFF_X + STAGES * RS * 16;  // float[STAGES][RS][2]
   static constexpr uint32_t OFF_INV = OFF_DO + STAGES * RS * 8; // float invA[256] | invB[256]
-  static constexpr uint32_t OFF_MAX = OFF_INV + 2 * H * 4;      // int[8] row maxima (float bits)
+  static constexpr uint32_t OFF_SMALL = OFF_INV + 2 * H * 4;    // float[256][4]: second half's db2 | dW3[0..1] | -
+  static constexpr uint32_t OFF_MAX = OFF_SMALL + H * 16;       // int[8] row maxima (float bits)
   static constexpr uint32_t OFF_BAR = OFF_MAX + 32;
   static constexpr uint32_t OFF_SLOT = OFF_BAR + (2 * STAGES + 1) * 8;
   static constexpr uint32_t BYTES = OFF_SLOT + 16;
 };
 
 template <int IN, int OUT>
-__global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job jb) {
+__global__ void __launch_bounds__(B2HCfg::THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job jb) {
   using C = B2HCfg;
   extern __shared__ __align__(1024) uint8_t sm[];
   float4* xs = reinterpret_cast<float4*>(sm + C::OFF_X);
   float* dos = reinterpret_cast<float*>(sm + C::OFF_DO);
   float* invA = reinterpret_cast<float*>(sm + C::OFF_INV);
   float* invB = invA + H;
+  float4* small_h1 = reinterpret_cast<float4*>(sm + C::OFF_SMALL);
   int* rmax = reinterpret_cast<int*>(sm + C::OFF_MAX);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
   uint64_t* empty = full + C::STAGES;
@@ -698,10 +704,10 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
   const int st_lo = (int)((long long)n_stage_total * split / jb.splits);
   const int st_hi = (int)((long long)n_stage_total * (split + 1) / jb.splits);
 
-  if (warp == B2_PROD_WARPS) {
+  if (warp == C::PROD_WARPS) {
     tmem_alloc(slot, 512);
     if (lane == 0) {
-      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], B2_PROD_WARPS); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], C::PROD_WARPS); mbar_init(&empty[s], 1); }
       mbar_init(done, 1);
       fence_mbar_init();
     }
@@ -712,7 +718,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
   tc_fence_after();
   const uint32_t tmem = *slot;
 
-  if (warp == B2_PROD_WARPS) {
+  if (warp == C::PROD_WARPS) {
     const uint32_t idesc = instr_desc(FMT_F16, 128, 256);
     const uint32_t lbo = H * 16;
     uint32_t it = 0;
@@ -744,8 +750,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
       __syncwarp();
     }
   } else {
-    // ---------------- producers: thread t = hidden unit t (A row j = t, B row k = t) ----------------
-    const int t = tid;   // 0..255
+    // ---------------- producers: thread (t, rh): hidden unit t (A row j = t, B row k = t), rows rh*16 .. +16 of a stage
+    const int t = tid & (H - 1), rh = tid >> 8;
     float w3[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) w3[o] = net[off_W3(IN) + o * H + t];
@@ -756,7 +762,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
     {
       float mx0 = 0.f, mx1 = 0.f, mx2 = 0.f, md0 = 0.f, md1 = 0.f;
       const int r_lo = st_lo * C::RS, r_hi = min(jb.rows, st_hi * C::RS);
-      for (int r = r_lo + t; r < r_hi; r += 256) {
+      for (int r = r_lo + tid; r < r_hi; r += C::PROD_THREADS) {
         const float4 x = __ldg(jb.X + r);
         mx0 = fmaxf(mx0, fabsf(x.x)); mx1 = fmaxf(mx1, fabsf(x.y)); mx2 = fmaxf(mx2, fabsf(x.z));
         md0 = fmaxf(md0, fabsf(__ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT)));
@@ -772,39 +778,38 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
         atomicMax(&rmax[0], __float_as_int(mx0)); atomicMax(&rmax[1], __float_as_int(mx1)); atomicMax(&rmax[2], __float_as_int(mx2));
         atomicMax(&rmax[3], __float_as_int(md0)); atomicMax(&rmax[4], __float_as_int(md1));
       }
-      asm volatile("bar.sync 1, 256;");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
     }
     float sA, sB;
     {
-      float inv;
+      float ia, ib;
       float bA = fabsf(w3[0]) * __int_as_float(rmax[3]);
       if (OUT == 2) bA = fmaf(fabsf(w3[OUT - 1]), __int_as_float(rmax[4]), bA);
-      pow2_scale(bA, sA, inv);
-      invA[t] = inv;
+      pow2_scale(bA, sA, ia);
       const float bB = fmaf(fabsf(w1x), __int_as_float(rmax[0]), fmaf(fabsf(w1y), __int_as_float(rmax[1]),
                        fmaf(fabsf(w1z), __int_as_float(rmax[2]), fabsf(b1v))));
-      pow2_scale(bB, sB, inv);
-      invB[t] = inv;
+      pow2_scale(bB, sB, ib);
+      if (rh == 0) { invA[t] = ia; invB[t] = ib; }
     }
     float s_db2 = 0.f, s_dw3[OUT], s_db3[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) { s_dw3[o] = 0.f; s_db3[o] = 0.f; }
     uint32_t it = 0;
     auto h2_ptr = [&](int sg) {
-      const int row0 = sg * C::RS;
+      const int row0 = sg * C::RS + rh * C::RPT;
       return jb.h2 + (((size_t)net_i * tiles64 + (row0 >> 6)) * H + t) * 64 + (row0 & 63);
     };
     // software pipeline: the next stage's H2 values (all threads) and x / dOut rows (threads < RS) are loaded into
     // registers while the current stage is computed -- a stage's global-load latency is off the critical path
-    float4 hq[C::RS / 4], hn[C::RS / 4];
+    float4 hq[C::RPT / 4], hn[C::RPT / 4];
     float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
     float dn[OUT];
     auto prefetch = [&](int sg) {
       const float* h2p = h2_ptr(sg);
 #pragma unroll
-      for (int q = 0; q < C::RS / 4; ++q) hn[q] = __ldg(reinterpret_cast<const float4*>(h2p) + q);
-      if (t < C::RS) {
-        const int r = sg * C::RS + t;
+      for (int q = 0; q < C::RPT / 4; ++q) hn[q] = __ldg(reinterpret_cast<const float4*>(h2p) + q);
+      if (tid < C::RS) {
+        const int r = sg * C::RS + tid;
         xn = r < jb.rows ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int o = 0; o < OUT; ++o) dn[o] = r < jb.rows ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + o) : 0.f;
@@ -814,7 +819,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
     for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
       const uint32_t s = it % C::STAGES;
 #pragma unroll
-      for (int q = 0; q < C::RS / 4; ++q) hq[q] = hn[q];
+      for (int q = 0; q < C::RPT / 4; ++q) hq[q] = hn[q];
       const float4 xc = xn;
       float dc[OUT];
 #pragma unroll
@@ -823,19 +828,20 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
       mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
       float4* xst = xs + s * C::RS;
       float* dost = dos + s * C::RS * 2;
-      if (t < C::RS) {
-        xst[t] = xc;
+      if (tid < C::RS) {
+        xst[tid] = xc;
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) dost[t * 2 + o] = dc[o];
+        for (int o = 0; o < OUT; ++o) dost[tid * 2 + o] = dc[o];
       }
-      asm volatile("bar.sync 1, 256;");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
       uint8_t* Ast = sm + s * C::STAGE_BYTES;
       uint8_t* Bst = Ast + C::OP_BYTES;
 #pragma unroll
-      for (int kc = 0; kc < C::RS / C::EPC; ++kc) {
+      for (int kk = 0; kk < C::RPT / C::EPC; ++kk) {
+        const int kc = rh * (C::RPT / C::EPC) + kk;        // 16-byte K chunk (8 rows) of the stage
         float hv[8], dz[8], h1[8];
-        hv[0] = hq[2 * kc].x; hv[1] = hq[2 * kc].y; hv[2] = hq[2 * kc].z; hv[3] = hq[2 * kc].w;
-        hv[4] = hq[2 * kc + 1].x; hv[5] = hq[2 * kc + 1].y; hv[6] = hq[2 * kc + 1].z; hv[7] = hq[2 * kc + 1].w;
+        hv[0] = hq[2 * kk].x; hv[1] = hq[2 * kk].y; hv[2] = hq[2 * kk].z; hv[3] = hq[2 * kk].w;
+        hv[4] = hq[2 * kk + 1].x; hv[5] = hq[2 * kk + 1].y; hv[6] = hq[2 * kk + 1].z; hv[7] = hq[2 * kk + 1].w;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int rl = kc * 8 + e;
@@ -869,13 +875,22 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
     }
-    float* sm2 = jb.small2 + ((size_t)net_i * jb.splits + split) * SMALL_STRIDE;
-    sm2[H * IN + H + t] = s_db2;
-#pragma unroll
-    for (int o = 0; o < OUT; ++o) sm2[H * IN + 2 * H + o * H + t] = s_dw3[o];
-    if (t == 0) {
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) sm2[H * IN + 2 * H + OUT * H + o] = s_db3[o];
+    // small gradients of unit t: the two row-halves are added in a fixed order (first half + second half)
+    if (rh == 1) small_h1[t] = make_float4(s_db2, s_dw3[0], OUT == 2 ? s_dw3[OUT - 1] : 0.f, t == 0 ? s_db3[0] : 0.f);
+    float db3_1 = 0.f;
+    if (OUT == 2 && t == 0 && rh == 1) rmax[6] = __float_as_int(s_db3[OUT - 1]);   // (plain bit copy; slot unused otherwise)
+    asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+    if (rh == 0) {
+      const float4 o2 = small_h1[t];
+      if (OUT == 2 && t == 0) db3_1 = __int_as_float(rmax[6]);
+      float* sm2 = jb.small2 + ((size_t)net_i * jb.splits + split) * SMALL_STRIDE;
+      sm2[H * IN + H + t] = s_db2 + o2.x;
+      sm2[H * IN + 2 * H + t] = s_dw3[0] + o2.y;
+      if (OUT == 2) sm2[H * IN + 2 * H + H + t] = s_dw3[OUT - 1] + o2.z;
+      if (t == 0) {
+        sm2[H * IN + 2 * H + OUT * H] = s_db3[0] + o2.w;
+        if (OUT == 2) sm2[H * IN + 2 * H + OUT * H + 1] = s_db3[OUT - 1] + db3_1;
+      }
     }
   }
   // ---------------- epilogue: unscale and dump the 256x256 accumulator as this split's partial ----------------
@@ -910,7 +925,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) tc_bwd2_h_kernel(const Bwd2Job 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == B2_PROD_WARPS) tmem_dealloc(tmem, 512);
+  if (warp == C::PROD_WARPS) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc

@@ -586,12 +586,12 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   constexpr int RS2 = F16X3 ? tc::B2HCfg::RS : tc::B2Cfg<TF32>::RS;
   const int n_stage = (jb.rows + RS2 - 1) / RS2;
   int splits = h->num_sms / jb.n_nets;
-  if (splits > n_stage) splits = n_stage;
+  if (splits > n_stage) splits = n_stage;      // (fewer, longer splits for the small jobs were measured: slower)
   if (splits > h->splits_tc) splits = h->splits_tc;
   if (splits < 1) splits = 1;
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
   if constexpr (F16X3)
-    tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2HCfg::BYTES, st>>>(j2);
+    tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2HCfg::THREADS, tc::B2HCfg::BYTES, st>>>(j2);
   else
     tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
   CQL_LAUNCH_CHECK(h);
