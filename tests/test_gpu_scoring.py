@@ -78,6 +78,29 @@ def test_random_against_brute_force(engine_factory, U, I, k, precision):
     _lists_match(ti2, ts2, ri2, rs2)
 
 
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_stress_scale_ids(engine_factory, precision):
+    """BASELINE configs[4] magnitudes (user ids ~1e7, item ids ~1e6): the hidden activations reach ~5e6, far outside
+    the fp16 range -- the f16x3 path must follow them with its exact power-of-two row scales.  Reference = the
+    float64 oracle (the float32 oracle itself is ~1e-6 off at these magnitudes)."""
+    cfg = O.OracleConfig()
+    flat = layout.init_state(cfg.n_critics, 21)
+    st64 = Hp.flat_to_oracle_state(flat, cfg, dtype=torch.float64)
+    eng = engine_factory(batch_size=64, precision=precision)
+    eng.set_state(flat)
+    rng = np.random.default_rng(4)
+    users = np.sort(rng.choice(np.arange(9_000_000, 9_999_000), size=4, replace=False)).astype(np.int32)
+    items = np.sort(rng.choice(np.arange(900_000, 999_000), size=700, replace=False)).astype(np.int32)
+    k = 10
+    def score(obs):
+        return O.relevance(st64, torch.from_numpy(obs).double(), "q").float().numpy()
+    ri, rs = recs_oracle.brute_force_topk(score, users, items, {}, k)
+    ti, ts = eng.score_topk(users, items, k)
+    scale = float(np.max(np.abs(rs)))
+    assert np.max(np.abs(ts - rs)) <= 1e-5 * scale, (np.max(np.abs(ts - rs)), scale)
+    assert (ti == ri).mean() > 0.8           # near-ties may swap at these magnitudes
+
+
 def test_score_pairs_and_edge_cases(engine_factory):
     flat, st = _oracle_state(12)
     eng = engine_factory(batch_size=64)
