@@ -143,6 +143,19 @@ enum { CQL_BUF_SCALAR_GRADS = 0,   /* 64 floats: [0]=d log_temp [1]=d log_alpha 
        CQL_BUF_ALL_GRADS = 5 };    /* (1+C)*NET+64 floats: [actor | critics | scalars] */
 int  cql_device_buffer(cql_handle* h, int which, void** dev_ptr, int64_t* n_floats);
 
+/* Data-parallel gradient exchange over NVLink peer memory instead of a collective library call.
+ * cql_dp_attach: stage_ptrs[world] / signal_ptrs[world] are every rank's symmetric staging buffer (>= 2 x
+ *   stage_floats floats, stage_floats >= the CQL_BUF_ALL_GRADS size) and zero-initialised signal pad (>= world x 4
+ *   64-bit words), mapped into this process (e.g. torch.distributed._symmetric_memory handles); all ranks must attach
+ *   before the first exchange and call the exchanges in the same order.
+ * cql_dp_allreduce: mean over ranks of one gradient buffer (CQL_BUF_SCALAR_GRADS / _CRITIC_GRADS / _ACTOR_GRADS), in
+ *   place, one kernel on `stream` (publish + one-shot reduce in rank order: bit-identical on every rank).  Replaces the
+ *   torch.distributed.all_reduce between cql_step_phase calls.  cql_dp_error returns 1 after a wait timed out. */
+int  cql_dp_attach(cql_handle* h, int32_t world, int32_t rank, const void* const* stage_ptrs,
+                   const void* const* signal_ptrs, int64_t stage_floats);
+int  cql_dp_allreduce(cql_handle* h, int which, void* stream);
+int  cql_dp_error(cql_handle* h, int32_t* flag_out);
+
 /* ---- scoring (K5) ------------------------------------------------------ */
 /* For each user: relevance of every candidate item, minus the user's seen
  * items (CSR, sorted item ids per user; seen_indptr may be NULL = no filter),

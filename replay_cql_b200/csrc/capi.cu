@@ -10,6 +10,7 @@
 #include "score_tc_h.cuh"
 #include "topk_staged.cuh"
 #include "metrics.cuh"
+#include "dp_peer.cuh"
 
 using namespace cql;
 
@@ -30,6 +31,8 @@ struct cql_handle {
   int* part_i = nullptr;
   size_t part_elems = 0;
   uint8_t* packed_score = nullptr;   // tf32-packed W2 of actor + critics for the tensor-core scorer
+  DpPeer dp;                         // NVLink peer-memory gradient exchange (cql_dp_attach)
+  void* dp_local = nullptr;          // epochs | tickets | error flag
 };
 
 static thread_local std::string g_create_error;
@@ -363,6 +366,7 @@ void cql_destroy(cql_handle* ch) {
   if (ch->part_s) cudaFree(ch->part_s);
   if (ch->part_i) cudaFree(ch->part_i);
   if (ch->packed_score) cudaFree(ch->packed_score);
+  if (ch->dp_local) cudaFree(ch->dp_local);
   ch->h.free_all();
   delete ch;
 }
@@ -654,6 +658,60 @@ int cql_step_phase(cql_handle* ch, int phase, void* stream) {
       case 4: phase0(&h, st, BatchSource::Provided, NoiseSource::Philox); break;   // after cql_upload_batch
       default: throw Error{"cql_step_phase: phase must be 0..4"};
     }
+  });
+}
+
+int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const* stage_ptrs,
+                  const void* const* signal_ptrs, int64_t stage_floats) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "cql_dp_attach: bad world / rank");
+    CQL_REQUIRE(stage_ptrs && signal_ptrs, "cql_dp_attach: NULL pointer table");
+    const int64_t need = (int64_t)grad_floats(h.C);
+    CQL_REQUIRE(stage_floats >= need && stage_floats % 4 == 0, "cql_dp_attach: staging buffer too small (need the CQL_BUF_ALL_GRADS size, multiple of 4)");
+    DpPeer& p = ch->dp;
+    p.world = world; p.rank = rank; p.stage_floats = stage_floats;
+    for (int r = 0; r < world; ++r) {
+      CQL_REQUIRE(stage_ptrs[r] && signal_ptrs[r], "cql_dp_attach: NULL peer pointer");
+      p.stage[r] = (float*)stage_ptrs[r];
+      p.sig[r] = (unsigned long long*)signal_ptrs[r];
+    }
+    if (!ch->dp_local) CQL_CUDA(cudaMalloc(&ch->dp_local, 256));
+    CQL_CUDA(cudaMemset(ch->dp_local, 0, 256));
+    p.epoch = (unsigned long long*)ch->dp_local;
+    p.ticket = (unsigned int*)((char*)ch->dp_local + 64);
+    p.error = (int*)((char*)ch->dp_local + 128);
+    destroy_graph(ch);
+  });
+}
+
+int cql_dp_allreduce(cql_handle* ch, int which, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    DpPeer& p = ch->dp;
+    CQL_REQUIRE(p.world >= 1, "cql_dp_allreduce: call cql_dp_attach first");
+    float* buf = nullptr;
+    int64_t n = 0, off = 0;
+    int group = 0;
+    switch (which) {                      // staging offsets follow the CQL_BUF_ALL_GRADS layout [actor | critics | scalars]
+      case CQL_BUF_SCALAR_GRADS: buf = h.g_scalars(); n = SCALAR_SLOT; off = (int64_t)(1 + h.C) * NET_STRIDE; group = 0; break;
+      case CQL_BUF_CRITIC_GRADS: buf = h.g_critics(); n = (int64_t)h.C * NET_STRIDE; off = NET_STRIDE; group = 1; break;
+      case CQL_BUF_ACTOR_GRADS: buf = h.g_actor(); n = NET_STRIDE; off = 0; group = 2; break;
+      default: throw Error{"cql_dp_allreduce: which must be a CQL_BUF_*_GRADS group"};
+    }
+    if (p.world == 1) return;
+    cudaStream_t st = pick_stream(&h, stream);
+    const int grid = (int)std::min<int64_t>(h.num_sms, (n / 4 + 255) / 256);
+    k_dp_exchange<<<grid, 256, 0, st>>>(p, buf, off, n, group);      // grid <= SMs: every block resident while waiting
+    CQL_LAUNCH_CHECK(&h);
+  });
+}
+
+int cql_dp_error(cql_handle* ch, int32_t* flag_out) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(flag_out, "cql_dp_error: NULL output");
+    *flag_out = 0;
+    if (ch->dp_local) CQL_CUDA(cudaMemcpy(flag_out, (char*)ch->dp_local + 128, sizeof(int32_t), cudaMemcpyDeviceToHost));
   });
 }
 

@@ -284,6 +284,21 @@ class CqlEngine:
         self._check(self._lib.cql_upload_batch(self._h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(nobs), _ptr(term), stream),
                     "cql_upload_batch")
 
+    def dp_attach(self, world: int, rank: int, stage_ptrs, signal_ptrs, stage_floats: int) -> None:
+        """Hand the library every rank's symmetric staging buffer / signal pad (raw device pointers)."""
+        PtrArr = C.c_void_p * len(stage_ptrs)
+        self._check(self._lib.cql_dp_attach(self._h, int(world), int(rank), PtrArr(*[int(p) for p in stage_ptrs]),
+                                            PtrArr(*[int(p) for p in signal_ptrs]), int(stage_floats)), "cql_dp_attach")
+
+    def dp_allreduce(self, which: int, stream: int | None = None) -> None:
+        """Mean over ranks of one gradient buffer through NVLink peer memory (after ``dp_attach``)."""
+        self._check(self._lib.cql_dp_allreduce(self._h, int(which), self._torch_stream(stream)), "cql_dp_allreduce")
+
+    def dp_error(self) -> bool:
+        flag = C.c_int32(0)
+        self._check(self._lib.cql_dp_error(self._h, C.byref(flag)), "cql_dp_error")
+        return bool(flag.value)
+
     def update_data_parallel(self, allreduce_mean: Callable[[int], None], stream: int | None = None,
                              uploaded_batch: bool = False) -> None:
         """One data-parallel update: the host averages the three gradient groups between phases.

@@ -58,6 +58,54 @@ class GradAllReducer:
         allreduce_mean_(view, self.group)
 
 
+class PeerGradExchange:
+    """Gradient averaging through NVLink peer memory: the library's own one-shot all-reduce kernels
+    (``csrc/dp_peer.cuh``) on symmetric buffers from ``torch.distributed._symmetric_memory`` -- no collective
+    library call inside the update.  Same call signature as :class:`GradAllReducer`; construct it collectively
+    (every rank, same order).  Raises if symmetric memory cannot be set up, so callers can fall back to NCCL."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.engine = engine
+        pg = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        _, n = engine.device_buffer(_lib.BUF_ALL_GRADS)
+        self.stage_floats = (n + 3) // 4 * 4
+        dev = torch.device("cuda", engine.device)
+        self.buf = symm_mem.empty(2 * self.stage_floats, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, pg)
+        if self.handle.signal_pad_size < world * 4 * 8:
+            raise RuntimeError("symmetric-memory signal pad too small")
+        torch.cuda.synchronize(dev)
+        dist.barrier(pg)                                  # every staging buffer is zeroed before anyone publishes
+        engine.dp_attach(world, rank, list(self.handle.buffer_ptrs), list(self.handle.signal_pad_ptrs), self.stage_floats)
+        dist.barrier(pg)
+
+    def __call__(self, buffer_id: int) -> None:
+        self.engine.dp_allreduce(buffer_id)               # on torch's current stream
+
+
+def make_grad_exchange(engine, group=None, prefer_peer: bool = True):
+    """PeerGradExchange when every rank can set it up, else the NCCL/gloo reducer (decided collectively)."""
+    import torch
+    import torch.distributed as dist
+    ex, ok = None, 0
+    if prefer_peer and dist.get_backend(group) == "nccl" and os.environ.get("CQL_DP_EXCHANGE", "peer") == "peer":
+        try:
+            ex = PeerGradExchange(engine, group)
+            ok = 1
+        except Exception:                                  # no symmetric memory in this environment
+            ex, ok = None, 0
+        t = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", engine.device))
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        ok = int(t.item())
+    return ex if ok and ex is not None else GradAllReducer(engine, group)
+
+
 def gather_rows(local: np.ndarray, group=None) -> np.ndarray:
     """Concatenate per-rank arrays (ragged in dim 0) on every rank, in rank order."""
     import torch
@@ -90,7 +138,7 @@ class DataParallelStepper:
     def __init__(self, engine, group=None, warmup: int = 3):
         import torch
         self.engine = engine
-        self.reducer = GradAllReducer(engine, group)
+        self.reducer = make_grad_exchange(engine, group)
         self.device = torch.device("cuda", engine.device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.graph = None
