@@ -375,13 +375,17 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "users": shape["n_users"], "items": shape["n_items"],
                        "rows": int(n_rows), "batch_per_gpu": BATCH, "global_batch": BATCH * world,
-                       "parallelism": f"dp{world}", "hidden": 256, "n_critics": 2, "n_action_samples": 10,
+                       "parallelism": f"dp{world}",
+                       "grad_exchange": ("none" if world == 1 else
+                                         {"PeerGradExchange": "NVLink peer-memory one-shot all-reduce kernel (csrc/dp_peer.cuh), 3 per update",
+                                          "GradAllReducer": "NCCL all-reduce, 3 per update"}.get(type(reducer).__name__, type(reducer).__name__)),
+                       "hidden": 256, "n_critics": 2, "n_action_samples": 10,
                        "precision": args.precision,
                        "l2": "inputs larger than L2: 640 MB replay table, fresh random gather every step; "
                              "weights/activations are the step-to-step state of the algorithm"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": BATCH * 32,
                     "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batch (host minibatch in, metrics out)" if world == 1 else
-                           "cql_upload_batch + cql_step_phase x4 with NCCL all-reduce between phases + metrics D2H"},
+                           "cql_upload_batch + cql_step_phase x4 with the gradient exchange between phases + metrics D2H"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[args.precision],
