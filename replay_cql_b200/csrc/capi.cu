@@ -188,6 +188,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
     h.small2 = h.dalloc<float>((size_t)C * h.splits_tc * SMALL_STRIDE);
     h.pw2_tc = h.dalloc<float>((size_t)(h.num_sms + C) * H * H);
     h.dX_part = h.dalloc<float4>((size_t)C * slices * B);
+    h.b2_tickets = h.dalloc<unsigned int>((size_t)CQL_MAX_CRITICS * 64 + 64);
   }
   // scalars start at the configured initial values; networks are set by cql_set_weights
   float sc[SCALAR_SLOT] = {0};

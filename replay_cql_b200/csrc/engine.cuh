@@ -84,6 +84,7 @@ struct Handle {
   float* small2 = nullptr;         // [C][splits_tc][SMALL_STRIDE] bwd2 partials (b2 | W3 | b3)
   float* pw2_tc = nullptr;         // [C][splits_tc][H*H]
   float4* dX_part = nullptr;       // [C*SLICES][B]
+  unsigned int* b2_tickets = nullptr;   // [C][64] group tickets of the f16x3 bwd2 kernel
   int slots1 = 0, splits_tc = 0, tc_slices = 1;
 
   // optional event marks for cql_timed_update

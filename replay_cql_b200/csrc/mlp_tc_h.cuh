@@ -54,7 +54,8 @@ struct HCfgT {
   static constexpr uint32_t OFF_BAR = OFF_EB + 2 * NS * 16;
   static constexpr uint32_t N_BARS = 2 * STAGES + 4 + 2;
   static constexpr uint32_t OFF_SLOT = OFF_BAR + N_BARS * 8;
-  static constexpr uint32_t SMEM_BYTES = OFF_SLOT + 16;
+  static constexpr uint32_t OFF_FLUSH = OFF_SLOT + 16;         // bwd1: float[2 groups][4 warps][16][32] dW1/db1 partials
+  static constexpr uint32_t SMEM_BYTES = OFF_FLUSH + 2 * 4 * 16 * 32 * 4;
 };
 using HCfg = HCfgT<8>;     // update kernels
 using HCfg4 = HCfgT<4>;    // scorer (one epilogue group keeps the per-row state)
@@ -558,19 +559,36 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
     float a_b[NCH], a_w0[NCH], a_w1[NCH], a_w2[NCH];      // lane l <-> column chunk*32 + l of the current slice
 #pragma unroll
     for (int q = 0; q < NCH; ++q) { a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f; }
-    auto flush = [&](int pair) {
+    // The four warps of a group hold partial column sums over different rows: they are added through shared memory
+    // (fixed warp order) and ONE slot per (CTA, group) goes to global memory -- 4x fewer partials for the reduction.
+    float* flbuf = reinterpret_cast<float*>(sm + C::OFF_FLUSH) + grp * (4 * 16 * 32);
+    auto flush = [&](int pair) {                    // called uniformly by the 4 warps of the group
       if (!WGRADS || pair < 0) return;
       const int net_i = pair / C::SLICES, slice = pair % C::SLICES;
-      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * C::NEW + warp) * SMALL_STRIDE;
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
-        const int k = slice * C::NS + q * 32 + lane;
-        o[k * IN + 0] = a_w0[q];
-        o[k * IN + 1] = a_w1[q];
-        if (IN == 3) o[k * IN + 2] = a_w2[q];
-        o[H * IN + k] = a_b[q];
+        float* f = flbuf + (qw * 16 + q * 4) * 32 + lane;
+        f[0] = a_w0[q]; f[32] = a_w1[q]; f[64] = a_w2[q]; f[96] = a_b[q];
         a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f;
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 2 + grp) * SMALL_STRIDE;
+      // warp w of the group sums chunk q = w over the four warps (order 0..3) and writes that chunk's columns
+      {
+        const int q = qw;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float* f = flbuf + (w * 16 + q * 4) * 32 + lane;
+          t0 += f[0]; t1 += f[32]; t2 += f[64]; t3 += f[96];
+        }
+        const int k = slice * C::NS + q * 32 + lane;
+        o[k * IN + 0] = t0;
+        o[k * IN + 1] = t1;
+        if (IN == 3) o[k * IN + 2] = t2;
+        o[H * IN + k] = t3;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
     };
     int cur_pair = -1;
     float w3m0 = 0.f, w3m1 = 0.f;
@@ -661,6 +679,8 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
 //   s_A[t] from |W3[:,t]| . max_r |dOut[r,:]|,   s_B[t] from |W1[t,:]| . max_r |x[r,:]| + |b1[t]|
 // with the maxima taken in a pre-pass over the CTA's rows; the partial is unscaled by 1/(s_A[j] s_B[k]) on the way out.
 // A stage holds 32 rows (K = 32 = two MMAs), the same operand bytes as the tf32 kernel's 16 rows.
+constexpr int B2H_GROUP = 4;        // splits per in-kernel partial-sum group
+
 struct B2HCfg {
   static constexpr int ES = 2, EPC = 8, UK = 16;
   static constexpr int RS = 32;                             // rows (K extent) per stage
@@ -926,6 +946,34 @@ __global__ void __launch_bounds__(B2HCfg::THREADS, 1) tc_bwd2_h_kernel(const Bwd
   tc_fence_before();
   __syncthreads();
   if (warp == C::PROD_WARPS) tmem_dealloc(tmem, 512);
+  // ---------------- groups of B2H_GROUP splits: the last CTA to finish adds the group's partials (in split order, so the
+  // result does not depend on which CTA is last) into the first member's slot -- the reduction kernel then reads
+  // 4x fewer 256 KB partials
+  if (jb.tickets != nullptr) {
+    __shared__ int is_last;
+    const int g = split / B2H_GROUP, g_lo = g * B2H_GROUP, g_n = min(B2H_GROUP, jb.splits - g_lo);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int* tk = jb.tickets + net_i * 64 + g;
+      const unsigned int t = atomicAdd(tk, 1u);
+      is_last = (t == (unsigned)g_n - 1) ? 1 : 0;
+      if (is_last) *tk = 0;
+    }
+    __syncthreads();
+    if (is_last && g_n > 1) {
+      __threadfence();
+      float* first = jb.pw2 + ((size_t)net_i * jb.splits + g_lo) * H * H;
+      for (int i = tid * 4; i < H * H; i += C::THREADS * 4) {
+        float4 acc = __ldcg(reinterpret_cast<const float4*>(first + i));
+        for (int m = 1; m < g_n; ++m) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(first + (size_t)m * H * H + i));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(first + i) = acc;
+      }
+    }
+  }
 }
 
 }  // namespace tc

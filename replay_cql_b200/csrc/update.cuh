@@ -571,7 +571,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   const int tiles = (jb.rows + tc::TM - 1) / tc::TM;
   const int items = jb.n_nets * C::SLICES * tiles;
   const int grid1 = items < h->num_sms ? items : h->num_sms;
-  const int slots1 = (F16X3 ? tc::HCfg::NEW : 4) * grid1;
+  const int slots1 = (F16X3 ? 2 : 4) * grid1;      // f16x3: one slot per (CTA, epilogue group)
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
   tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, h->small1,
                  DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
@@ -590,13 +590,16 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   if (splits > h->splits_tc) splits = h->splits_tc;
   if (splits < 1) splits = 1;
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
+  constexpr bool GROUP_SUM = false;   // in-kernel group sums of the dW2 partials: measured slower (one CTA re-reads 1 MB at the tail)
+  if (F16X3 && GROUP_SUM) j2.tickets = h->b2_tickets;
   if constexpr (F16X3)
     tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2HCfg::THREADS, tc::B2HCfg::BYTES, st>>>(j2);
   else
     tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
   CQL_LAUNCH_CHECK(h);
   tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
-                                                                                  splits, IN, OUT, grads_out);
+                                                                                  splits, IN, OUT, grads_out,
+                                                                                  (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1);
   CQL_LAUNCH_CHECK(h);
 }
 
