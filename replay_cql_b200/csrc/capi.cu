@@ -126,6 +126,9 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   const int B = h.B, n = h.n, C = h.C, n3 = 3 * n;
   h.rsA = n3; h.rsC = n3 + 1;
   CQL_CUDA(cudaStreamCreateWithFlags(&h.own_stream, cudaStreamNonBlocking));
+  CQL_CUDA(cudaStreamCreateWithFlags(&h.side_stream, cudaStreamNonBlocking));
+  CQL_CUDA(cudaEventCreateWithFlags(&h.ev_fork, cudaEventDisableTiming));
+  CQL_CUDA(cudaEventCreateWithFlags(&h.ev_join, cudaEventDisableTiming));
   set_kernel_attrs();
 
   const int64_t S = state_floats(C);

@@ -18,6 +18,8 @@ struct Handle {
   cql_config cfg{};
   std::string err;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t side_stream = nullptr;            // fork/join branch for independent small launches (captured into the graphs)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int num_sms = 148;
   int64_t launches = 0;
 
@@ -109,6 +111,9 @@ struct Handle {
     if (batch_host) { cudaFreeHost(batch_host); batch_host = nullptr; }
     if (noise_host) { cudaFreeHost(noise_host); noise_host = nullptr; }
     if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
+    if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
+    if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+    if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   }
 

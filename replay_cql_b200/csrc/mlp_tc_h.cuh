@@ -914,22 +914,24 @@ __global__ void __launch_bounds__(B2HCfg::THREADS, 1) tc_bwd2_h_kernel(const Bwd
     }
   }
   // ---------------- epilogue: unscale and dump the 256x256 accumulator as this split's partial ----------------
+  // all 16 producer warps take part: warp w reads TMEM lane quarter w % 4 and every fourth 32-column chunk
   float* out = jb.pw2 + ((size_t)net_i * jb.splits + split) * H * H;
-  if (warp < 4) {
+  if (warp < C::PROD_WARPS) {
+    const int qw = warp & 3, part = warp >> 2;
     if (st_hi > st_lo) {
       mbar_wait(done, 0);
       tc_fence_after();
     }
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      const int j = half * 128 + warp * 32 + lane;
+      const int j = half * 128 + qw * 32 + lane;
       const float ia = invA[j];
       float* orow = out + (size_t)j * H;
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
+      for (int c0 = part * 32; c0 < H; c0 += 32 * (C::PROD_WARPS / 4)) {
         float v[32];
         if (st_hi > st_lo) {
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 256 + c0, v);
+          tmem_ld32(tmem + ((uint32_t)(qw * 32) << 16) + half * 256 + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = v[i] * ia * invB[c0 + i];

@@ -6,6 +6,7 @@
 // the TD target and the actor step (a result-preserving saving).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "engine.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc_ts.cuh"
@@ -575,6 +576,22 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
   tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, h->small1,
                  DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
+  // bwd1 and bwd2 of one job are independent (both only read X, dOut, H2).  For the small jobs (the actor's B rows:
+  // a few dozen CTAs each) they run side by side on a forked branch -- the fork/join is captured into the step graph.
+  constexpr int RS2 = F16X3 ? tc::B2HCfg::RS : tc::B2Cfg<TF32>::RS;
+  const int n_stage = (jb.rows + RS2 - 1) / RS2;
+  int splits = h->num_sms / jb.n_nets;
+  if (splits > n_stage) splits = n_stage;      // (fewer, longer splits for the small jobs were measured: slower)
+  if (splits > h->splits_tc) splits = h->splits_tc;
+  if (splits < 1) splits = 1;
+  static const bool no_fork = std::getenv("CQL_NO_FORK") != nullptr;      // A/B switch for measurements
+  const bool fork = WGRADS && !no_fork && !h->timing && h->side_stream != nullptr && grid1 + splits * jb.n_nets <= h->num_sms;
+  cudaStream_t st2 = st;
+  if (fork) {
+    CQL_CUDA(cudaEventRecord(h->ev_fork, st));
+    CQL_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    st2 = h->side_stream;
+  }
   if constexpr (F16X3)
     tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::HCfg::THREADS, tc::HCfg::SMEM_BYTES, st>>>(j1);
   else if constexpr (TF32)
@@ -583,20 +600,18 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     tc::tc_bwd1_kernel<TF32, IN, OUT, WGRADS, DX><<<grid1, tc::Pipe<TF32, tc::BWD1_NPW>::THREADS, tc::FwdSmem<TF32, tc::BWD1_NPW>::BYTES, st>>>(j1);
   CQL_LAUNCH_CHECK(h);
   if (!WGRADS) return;
-  constexpr int RS2 = F16X3 ? tc::B2HCfg::RS : tc::B2Cfg<TF32>::RS;
-  const int n_stage = (jb.rows + RS2 - 1) / RS2;
-  int splits = h->num_sms / jb.n_nets;
-  if (splits > n_stage) splits = n_stage;      // (fewer, longer splits for the small jobs were measured: slower)
-  if (splits > h->splits_tc) splits = h->splits_tc;
-  if (splits < 1) splits = 1;
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
   constexpr bool GROUP_SUM = false;   // in-kernel group sums of the dW2 partials: measured slower (one CTA re-reads 1 MB at the tail)
   if (F16X3 && GROUP_SUM) j2.tickets = h->b2_tickets;
   if constexpr (F16X3)
-    tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2HCfg::THREADS, tc::B2HCfg::BYTES, st>>>(j2);
+    tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2HCfg::THREADS, tc::B2HCfg::BYTES, st2>>>(j2);
   else
-    tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st>>>(j2);
+    tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st2>>>(j2);
   CQL_LAUNCH_CHECK(h);
+  if (fork) {
+    CQL_CUDA(cudaEventRecord(h->ev_join, st2));
+    CQL_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
   tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out,
                                                                                   (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1);
