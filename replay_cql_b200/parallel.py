@@ -135,10 +135,13 @@ class DataParallelStepper:
     phases cost more than the collectives themselves; capturing the whole step removes the host from the loop.
     """
 
-    def __init__(self, engine, group=None, warmup: int = 3):
+    def __init__(self, engine, group=None, warmup: int = 3, uploaded_batch: bool = False, reducer=None):
+        """``uploaded_batch``: the captured step consumes the minibatch last staged by ``engine.upload_batch`` instead
+        of sampling the replay table (end-to-end host-buffer path); ``reducer``: share another stepper's exchange."""
         import torch
         self.engine = engine
-        self.reducer = make_grad_exchange(engine, group)
+        self.uploaded_batch = uploaded_batch
+        self.reducer = reducer if reducer is not None else make_grad_exchange(engine, group)
         self.device = torch.device("cuda", engine.device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.graph = None
@@ -150,7 +153,8 @@ class DataParallelStepper:
         import torch
         with torch.cuda.stream(self.stream):
             for _ in range(n):
-                self.engine.update_data_parallel(self.reducer, stream=self.stream.cuda_stream)
+                self.engine.update_data_parallel(self.reducer, stream=self.stream.cuda_stream,
+                                                 uploaded_batch=self.uploaded_batch)
 
     def _capture(self) -> None:
         import torch
@@ -159,7 +163,8 @@ class DataParallelStepper:
         g = torch.cuda.CUDAGraph()
         l0 = self.engine.launch_count
         with torch.cuda.graph(g, stream=self.stream):
-            self.engine.update_data_parallel(self.reducer, stream=self.stream.cuda_stream)
+            self.engine.update_data_parallel(self.reducer, stream=self.stream.cuda_stream,
+                                             uploaded_batch=self.uploaded_batch)
         self.launches_per_step = self.engine.launch_count - l0
         self.graph = g
 
