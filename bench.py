@@ -321,12 +321,15 @@ def run_ours(args):
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l1 = eng.launch_count
     SCORE_REPS = 3
+    score_clocks = ClockSampler(local_rank)      # ~0.4 s of sustained tensor + CUDA-core load: the power cap may bite
+    score_clocks.start()
     s0.record(stream)
     with torch.cuda.stream(stream):
         for _ in range(SCORE_REPS):
             eng.score_topk_device(d_users, d_items, K_TOP, d_ptr, d_seen, out_items=oi, out_scores=osc, stream=sh)
     s1.record(stream)
     barrier()
+    score_clk = score_clocks.stop()
     score_ms = max_over_ranks(s0.elapsed_time(s1)) / SCORE_REPS
     score_launches = (eng.launch_count - l1) // SCORE_REPS
     users_per_s = n_score / (score_ms / 1e3)
@@ -402,7 +405,7 @@ def run_ours(args):
             "scoring": {"metric": "users scored top-10/sec", "value": users_per_s, "unit": "users/s",
                         "users": int(n_score), "items": shape["n_items"], "k": K_TOP, "filter_seen": True,
                         "ms": score_ms, "tflops": score_tf * world, "frac_of_peak": score_tf / peak_tf,
-                        "gpu_launches": int(score_launches),
+                        "gpu_launches": int(score_launches), "clocks": score_clk,
                         "e2e": {"value": n_score / score_e2e_s, "unit": "users/s",
                                 "h2d_bytes": int(users.nbytes + items.nbytes + indptr.nbytes + seen.nbytes),
                                 "d2h_bytes": int(users.size * K_TOP * 8), "api": "cql_score_topk (host ids + CSR in, top-k out)"}},
