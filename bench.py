@@ -78,9 +78,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_from: float | None = None, t_to: float | None = None):
+        """Summary of the samples taken in [t_from, t_to] (host clock); all samples if the window holds none."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -89,21 +90,31 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        win = [r for r in self.lines if (t_from is None or r[0] >= t_from) and (t_to is None or r[0] <= t_to + 0.12)]
+        sm, mx, reasons = summarise(win)
+        window = "timed region"
+        if not sm:                       # region shorter than the sampling period: report the neighbouring samples
+            sm, mx, reasons = summarise(self.lines)
+            window = "around the timed region"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def build_workload(log_rows: int | None = None):
@@ -246,23 +257,25 @@ def run_ours(args):
             stepper.run(k)
 
     # ---- HBM-resident updates/s ----
+    clocks = ClockSampler(local_rank)      # started before the warm-up so that it is already sampling in the timed region
+    clocks.start()
     do_steps(max(3, args.warmup))
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     l0 = eng.launch_count
     r0 = stepper.replayed_steps if stepper is not None else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_w0 = time.time()
     e0.record(stream)
     do_steps(args.steps)
     e1.record(stream)
     barrier()
+    t_w1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count - l0           # eager / library-graph launches are counted by the library itself
     if stepper is not None:                    # graph replays: kernels captured per update x replayed updates
         launches += stepper.launches_per_step * (stepper.replayed_steps - r0)
-    clk = clocks.stop()
+    clk = clocks.stop(t_w0, t_w1)
     value = world * args.steps / (ms / 1e3)
 
     # ---- per-kernel durations (events inside one real update), rank 0 reporting ----

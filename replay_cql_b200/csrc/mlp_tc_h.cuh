@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
+  grid_dep_wait();            // everything above overlapped the predecessor's tail (programmatic dependent launch)
 
   if (warp == C::MMA_WARP) {
     // =============================== MMA issuer ===============================
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
+  grid_dep_wait();            // everything above overlapped the predecessor's tail (programmatic dependent launch)
 
   if (warp == C::MMA_WARP) {
     const uint32_t idesc = instr_desc(FMT_F16, TM, C::NS);
@@ -737,6 +739,7 @@ __global__ void __launch_bounds__(B2HCfg::THREADS, 1) tc_bwd2_h_kernel(const Bwd
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
+  grid_dep_wait();            // everything above overlapped the predecessor's tail (programmatic dependent launch)
 
   if (warp == C::PROD_WARPS) {
     const uint32_t idesc = instr_desc(FMT_F16, 128, 256);

@@ -110,6 +110,121 @@ __device__ __forceinline__ void warp_fold_tile(float* topS, int* topI, int k, co
   }
 }
 
+// ---- order-independent fold of a block of scores into a (reset) top-k list, k <= 32, by 128 threads -------------
+// The sequential fold above inserts every candidate that beats the current k-th entry: with scores that grow along
+// the block (raw item ids as inputs make Q nearly monotone in the item index) EVERY item enters the list and the
+// fold costs as much as the MMAs (measured 205 ms vs 130 ms per 2048 users).  This variant is a two-pass selection
+// like topk_staged.cuh: thread maxima -> 32 group maxima -> threshold T = the (k + spare)-th largest -> only
+// elements >= T are looked up (item id, seen list) and inserted; if seen items ate the candidates T is lowered and
+// only the band [T_new, T_old) is collected.  Cost per block is ~constant.  Candidate overflow (massive ties)
+// falls back to the sequential fold of the band.  `scr` = 4 + 32 + 2*FB_CAP words of shared memory; all 128
+// threads call it (bar_id = their named barrier); the list topS/topI must be reset to (-inf, -1) by the caller.
+constexpr int FB_CAP = 96;
+constexpr int FB_SCRATCH_WORDS = 4 + 32 + 2 * FB_CAP;
+__device__ __forceinline__ void fold_block_select(const float* __restrict__ score, int rows, const int32_t* __restrict__ items,
+                                                  int64_t i0, const SeenView& sv, bool has_seen, int k, float* topS, int* topI,
+                                                  float* scr, int etid, int bar_id) {
+  volatile int* ncand = reinterpret_cast<volatile int*>(scr);
+  volatile int* done = reinterpret_cast<volatile int*>(scr) + 1;
+  volatile float* t_lo_s = scr + 2;
+  volatile float* t_hi_s = scr + 3;
+  float* gmax = scr + 4;
+  float* candS = scr + 36;
+  int* candI = reinterpret_cast<int*>(scr + 36 + FB_CAP);
+  const int lane = etid & 31, ew = etid >> 5;
+  // pass 1: thread maximum over its strided share, group maxima of 4 lanes
+  float m = -INFINITY;
+  for (int r = etid; r < rows; r += 128) m = fmaxf(m, score[r]);
+  float g = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, 2));
+  if ((lane & 3) == 0) gmax[ew * 8 + (lane >> 2)] = g;
+  if (etid == 0) { *ncand = 0; *done = 0; }
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id));
+  // every warp ranks the 32 group maxima itself (counting, no dependent chain)
+  const float mine = gmax[lane];
+  int pos = 0;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    const float o = gmax[t];
+    pos += (o > mine || (o == mine && t < lane)) ? 1 : 0;
+  }
+  int rank = min(32, k + 4 + (k >> 1));
+  float t_hi = INFINITY;
+  float t_lo = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, pos == rank - 1)) - 1);
+  while (true) {
+    // pass 2: elements of the band, unseen, with their item ids
+    if (m >= t_lo) {
+      for (int r = etid; r < rows; r += 128) {
+        const float s = score[r];
+        if (!(s >= t_lo && s < t_hi)) continue;
+        const int item = __ldg(items + i0 + r);
+        if (has_seen && is_seen(sv, item)) continue;
+        const int p = atomicAdd(const_cast<int*>(ncand), 1);
+        if (p < FB_CAP) { candS[p] = s; candI[p] = item; }
+      }
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id));
+    if (ew == 0) {
+      const int n = *ncand;
+      if (n > FB_CAP) {                               // overflow: sequential fold of the band
+        for (int base = 0; base < rows; base += 32) {
+          const int r = base + lane;
+          const float s = r < rows ? score[r] : -INFINITY;
+          const int item = r < rows ? __ldg(items + i0 + r) : -1;
+          bool cand = item >= 0 && s >= t_lo && s < t_hi && better(s, item, topS[k - 1], topI[k - 1]);
+          if (cand && has_seen && is_seen(sv, item)) cand = false;
+          unsigned mm = __ballot_sync(0xffffffffu, cand);
+          while (mm) {
+            const int src = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const float s2 = __shfl_sync(0xffffffffu, s, src);
+            const int i2 = __shfl_sync(0xffffffffu, item, src);
+            if (better(s2, i2, topS[k - 1], topI[k - 1])) warp_topk_insert(topS, topI, k, s2, i2);
+          }
+        }
+      } else {
+        for (int e = 0; e < n; ++e) {                  // ~k + 8 inserts, whatever the order of the scores
+          const float s2 = candS[e];
+          const int i2 = candI[e];
+          if (better(s2, i2, topS[k - 1], topI[k - 1])) warp_topk_insert(topS, topI, k, s2, i2);
+        }
+      }
+      __syncwarp();
+      // nothing below t_lo can belong to the top-k once the k-th entry reaches t_lo
+      const bool settled = (topI[k - 1] >= 0 && topS[k - 1] >= t_lo) || t_lo == -INFINITY;
+      if (lane == 0) {
+        if (settled) {
+          *done = 1;
+        } else {
+          int n_ok = 0;
+          for (int e = 0; e < k; ++e) n_ok += (topI[e] >= 0 && topS[e] >= t_lo) ? 1 : 0;
+          int rk = rank + max(2, 2 * (k - n_ok));
+          // (gmax is unsorted: the new threshold is recomputed by every warp from `rank`, published here)
+          *t_hi_s = t_lo;
+          *t_lo_s = __int_as_float(rk);                // carries the new rank; every warp derives t_lo from it
+          *ncand = 0;
+        }
+      }
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id));
+    if (*done) break;
+    rank = __float_as_int(*t_lo_s);
+    t_hi = *t_hi_s;
+    // skip group maxima equal to the old threshold (they were collected already)
+    {
+      float nt = -INFINITY;
+      bool found = false;
+      while (rank <= 32 && !found) {
+        const unsigned hit = __ballot_sync(0xffffffffu, pos == rank - 1);
+        nt = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+        if (nt < t_hi) found = true; else ++rank;
+      }
+      t_lo = found ? nt : -INFINITY;
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id));     // every thread has read the round's control words
+  }
+}
+
 struct ScoreArgs {
   const float* params;        // flat state
   const int32_t* users;       // [U]

@@ -25,7 +25,8 @@ struct ScoreSmemH : HCfg4 {
   static constexpr uint32_t OFF_AREADY = OFF_SCORE + SC_CH * TM * 4;       // mbarrier
   static constexpr uint32_t OFF_SEEN = OFF_AREADY + 16;                    // int[SEEN_CACHE] current user's seen list
   static constexpr uint32_t OFF_TOP = OFF_SEEN + SEEN_CACHE * 4;           // float[k] | int[k]
-  static inline uint32_t bytes(int k) { return OFF_TOP + (uint32_t)k * 8; }
+  __host__ __device__ static inline uint32_t off_fold(int k) { return OFF_TOP + (uint32_t)k * 8; }     // fold_block_select scratch
+  static inline uint32_t bytes(int k) { return off_fold(k) + FB_SCRATCH_WORDS * 4; }
 };
 
 __global__ void __launch_bounds__(HCfg4::THREADS, 1) tc_score_h_kernel(const ScoreTcArgs a) {
@@ -283,22 +284,27 @@ __global__ void __launch_bounds__(HCfg4::THREADS, 1) tc_score_h_kernel(const Sco
         }
         // fold the block into the (user, chunk) top-k list
         asm volatile("bar.sync 2, 128;");
-        if (warp == 0) {
+        {
           const int64_t i0 = (int64_t)chunk * SC_CH * TM;
           const int rows = (int)min((int64_t)tb * TM, a.n_items - i0);
-          for (int base = 0; base < rows; base += 32) {
-            const int r = base + lane;
-            const float s = r < rows ? score[r] : -INFINITY;
-            const int item = r < rows ? a.items[i0 + r] : -1;
-            bool cand = item >= 0 && better(s, item, topS[a.k - 1], topI[a.k - 1]);
-            if (cand && a.seen_indptr && is_seen(sv, item)) cand = false;
-            unsigned m = __ballot_sync(0xffffffffu, cand);
-            while (m) {
-              const int src = __ffs(m) - 1;
-              m &= m - 1;
-              const float s2 = __shfl_sync(0xffffffffu, s, src);
-              const int i2 = __shfl_sync(0xffffffffu, item, src);
-              if (better(s2, i2, topS[a.k - 1], topI[a.k - 1])) warp_topk_insert(topS, topI, a.k, s2, i2);
+          if (a.k <= 32) {       // order-independent two-pass selection by all four epilogue warps (score.cuh)
+            fold_block_select(score, rows, a.items, i0, sv, a.seen_indptr != nullptr, a.k, topS, topI,
+                              reinterpret_cast<float*>(sm + C::off_fold(a.k)), tid, 2);
+          } else if (warp == 0) {
+            for (int base = 0; base < rows; base += 32) {
+              const int r = base + lane;
+              const float s = r < rows ? score[r] : -INFINITY;
+              const int item = r < rows ? a.items[i0 + r] : -1;
+              bool cand = item >= 0 && better(s, item, topS[a.k - 1], topI[a.k - 1]);
+              if (cand && a.seen_indptr && is_seen(sv, item)) cand = false;
+              unsigned m = __ballot_sync(0xffffffffu, cand);
+              while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float s2 = __shfl_sync(0xffffffffu, s, src);
+                const int i2 = __shfl_sync(0xffffffffu, item, src);
+                if (better(s2, i2, topS[a.k - 1], topI[a.k - 1])) warp_topk_insert(topS, topI, a.k, s2, i2);
+              }
             }
           }
         }

@@ -6,6 +6,7 @@
 // the TD target and the actor step (a result-preserving saving).
 #pragma once
 #include <algorithm>
+#include <utility>
 #include <cstdlib>
 #include "engine.cuh"
 #include "mlp_tc.cuh"
@@ -461,6 +462,22 @@ __global__ void k_adam_polyak(float* __restrict__ p, float* __restrict__ m, floa
 }
 
 // ---------------------------------------------------------------- launch helpers
+// Programmatic dependent launch: the kernel may start (barrier init, TMEM allocation) while its predecessor in the
+// stream drains; it executes `griddepcontrol.wait` before touching anything the predecessor wrote.  Only used for
+// kernels that contain that wait (the f16x3 tensor-core kernels).  CQL_NO_PDL=1 switches it off (A/B measurements).
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl = std::getenv("CQL_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  CQL_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 template <int IN, int OUT>
 inline void launch_fwd(Handle* h, FwdJobs& jobs, cudaStream_t st) {
   int t = 0;
@@ -503,7 +520,7 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   if (items == 0) return;
   const int grid = items < h->num_sms ? items : h->num_sms;
   if constexpr (F16X3)
-    tc::tc_fwd_h_kernel<IN, OUT><<<grid, tc::HCfg::THREADS, tc::HCfg::SMEM_BYTES, st>>>(tj);
+    launch_pdl(tc::tc_fwd_h_kernel<IN, OUT>, dim3(grid), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, tj);
   else if constexpr (TF32)
     tc::tc_fwd_ts_kernel<IN, OUT><<<grid, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(tj);
   else
@@ -593,7 +610,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     st2 = h->side_stream;
   }
   if constexpr (F16X3)
-    tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::HCfg::THREADS, tc::HCfg::SMEM_BYTES, st>>>(j1);
+    launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX>, dim3(grid1), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, j1);
   else if constexpr (TF32)
     tc::tc_bwd1_ts_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(j1);
   else
@@ -604,7 +621,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   constexpr bool GROUP_SUM = false;   // in-kernel group sums of the dW2 partials: measured slower (one CTA re-reads 1 MB at the tail)
   if (F16X3 && GROUP_SUM) j2.tickets = h->b2_tickets;
   if constexpr (F16X3)
-    tc::tc_bwd2_h_kernel<IN, OUT><<<dim3(splits, jb.n_nets), tc::B2HCfg::THREADS, tc::B2HCfg::BYTES, st2>>>(j2);
+    launch_pdl(tc::tc_bwd2_h_kernel<IN, OUT>, dim3(splits, jb.n_nets), dim3(tc::B2HCfg::THREADS), tc::B2HCfg::BYTES, st2, j2);
   else
     tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st2>>>(j2);
   CQL_LAUNCH_CHECK(h);
