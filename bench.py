@@ -330,6 +330,7 @@ def run_ours(args):
         oi = torch.empty((users.size, K_TOP), dtype=torch.int32, device=dev)
         osc = torch.empty((users.size, K_TOP), dtype=torch.float32, device=dev)
         eng.score_topk_device(d_users[:64], d_items, K_TOP, d_ptr, d_seen, out_items=oi[:64], out_scores=osc[:64], stream=sh)
+        eng.score_topk_device(d_users, d_items, K_TOP, d_ptr, d_seen, out_items=oi, out_scores=osc, stream=sh)   # full-size warm-up pass
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l1 = eng.launch_count

@@ -428,6 +428,8 @@ struct SumJobs {
 };
 template <int IN, int OUT>
 __global__ void k_sum_partials_multi(const SumJobs jobs, int slices) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const SumJobs::J jb = jobs.j[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= jb.n_nets * jb.rows * OUT) return;

@@ -551,6 +551,8 @@ __global__ void __launch_bounds__(256) k_reduce_grads_tc(const float* __restrict
                                                          const float* __restrict__ small2, const float* __restrict__ pw2,
                                                          int splits, int in_dim, int out_dim, float* __restrict__ grads,
                                                          int w2_group = 1) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   __shared__ float4 part[8][32];
   const int net = blockIdx.y;
   const int g = threadIdx.x & 31, chunk = threadIdx.x >> 5;

@@ -114,6 +114,8 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 // then HMeta.  One WARP per operand row n (32 lanes = the 32 K-chunks), so the row maximum is a warp reduction.
 // transpose=0: B[n][k] = W2[n][k] (forward);  1: B[n][k] = W2[k][n] (backward dH1 = dZ2 W2).
 __global__ void __launch_bounds__(256) k_pack_multi_h(const PackJobs jobs, int out_dim_actor) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   using C = HCfg;
   const PackJobs::J jb = jobs.j[blockIdx.y];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;        // 16-byte chunk id: n * 32 + kc

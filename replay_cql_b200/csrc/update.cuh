@@ -106,13 +106,17 @@ __global__ void k_step_begin(const long long* step_dev, StepInfo* info, float be
   info->bc1 = 1.0 - pow((double)beta1, (double)t);
   info->bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)t));
 }
-__global__ void k_step_end(long long* step_dev) { *step_dev += 1; }
+__global__ void k_step_end(long long* step_dev) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+  *step_dev += 1; }
 
 // sampled-update prologue in one launch: Adam bias corrections, replay gather (+ actor input rows), Philox noise
 __global__ void k_step_head(const float4* __restrict__ table, int64_t n_trans, const long long* __restrict__ step_dev,
                             StepInfo* __restrict__ info, float beta1, float beta2, int B, int n, int rank, int world,
                             uint64_t seed, float4* __restrict__ batch, float4* __restrict__ XA,
                             float* __restrict__ noise, int64_t noise_total) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const long long done = *step_dev;
   if (i == 0) {
@@ -184,6 +188,8 @@ __global__ void k_prep(const float4* __restrict__ batch, const float* __restrict
                        float4* __restrict__ XAl, float* __restrict__ offAl,
                        float4* __restrict__ XC, float* __restrict__ offC,
                        float4* __restrict__ XT, float4* __restrict__ XP, float4* __restrict__ perb) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = g >> 6, l = g & 63;
   if (b >= B) return;
@@ -282,6 +288,8 @@ __global__ void __launch_bounds__(256) k_lse(const float4* __restrict__ batch, c
                                              const float* __restrict__ offAl, const float* __restrict__ QC,
                                              const float* __restrict__ offC, const float* __restrict__ QT, LossConsts k,
                                              float* __restrict__ dQ, PairVals* __restrict__ pairv) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= k.C * k.B) return;
   const int c = p / k.B, b = p % k.B;
@@ -308,6 +316,8 @@ __global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict
                                                         const float* __restrict__ scalars, LossConsts k,
                                                         float* __restrict__ g_scalars, float* __restrict__ sums,
                                                         float* __restrict__ metrics) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   __shared__ float red[32];
   float st = 0.f;
   for (int b = threadIdx.x; b < k.B; b += 1024) st += perb[b].x;
@@ -348,6 +358,8 @@ __device__ __forceinline__ float adam_scalar(float p, float g, float& m, float& 
 __global__ void k_scalar_adam(float* __restrict__ scalars, float* __restrict__ sc_m, float* __restrict__ sc_v,
                               const float* __restrict__ g_scalars, const StepInfo* __restrict__ si, LossConsts k,
                               float* __restrict__ sums, float* __restrict__ metrics) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float lt = scalars[0], la = scalars[1];
   if (k.temp_lr > 0.f) { float m = sc_m[0], v = sc_v[0]; lt = adam_scalar(lt, g_scalars[0], m, v, k.temp_lr, k, *si); sc_m[0] = m; sc_v[0] = v; scalars[0] = lt; }
@@ -365,6 +377,8 @@ __global__ void k_scalar_adam(float* __restrict__ scalars, float* __restrict__ s
 
 __global__ void k_dq(const PairVals* __restrict__ pairv, const float* __restrict__ sums, LossConsts k,
                      float* __restrict__ dQ) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rsC = 3 * k.n + 1;
   if (i >= (int64_t)k.C * k.B * rsC) return;
@@ -378,6 +392,8 @@ __global__ void k_dq(const PairVals* __restrict__ pairv, const float* __restrict
 __global__ void __launch_bounds__(1024) k_actor_dq(const float* __restrict__ QP, const float4* __restrict__ perb,
                                                    const float* __restrict__ scalars, int B, int C,
                                                    float* __restrict__ dQP, float* __restrict__ metrics) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   __shared__ float red[32];
   const float T = expf(scalars[0]);
   float s = 0.f;
@@ -399,6 +415,8 @@ __global__ void __launch_bounds__(1024) k_actor_dq(const float* __restrict__ QP,
 __global__ void k_actor_dout(const float* __restrict__ outA, const float* __restrict__ noise_actor,
                              const float4* __restrict__ dXP, const float* __restrict__ scalars, int B, int n_parts,
                              int squash, float* __restrict__ dOutA) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float da = 0.f;
@@ -447,6 +465,8 @@ __global__ void k_reduce_grads(const float* __restrict__ small, const float* __r
 __global__ void k_adam_polyak(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                               const float* __restrict__ g, float* __restrict__ targ, int64_t count, float lr,
                               float beta1, float beta2, float eps, float tau, const StepInfo* __restrict__ si) {
+  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
+ 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const float step_size = (float)((double)lr / si->bc1);
@@ -534,7 +554,7 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
     sj.j[i] = {part_of[i], j.params, j.out, j.rows, j.n_nets};
     max_n = std::max(max_n, j.n_nets * j.rows * OUT);
   }
-  tc::k_sum_partials_multi<IN, OUT><<<dim3((max_n + 255) / 256, jobs.n), 256, 0, st>>>(sj, C::SLICES);
+  launch_pdl(tc::k_sum_partials_multi<IN, OUT>, dim3(dim3((max_n + 255) / 256, jobs.n)), dim3(256), 0, st, sj, C::SLICES);
   CQL_LAUNCH_CHECK(h);
 }
 
@@ -562,7 +582,7 @@ inline void pack_slots(Handle* h, const int* slots, int n_slots, cudaStream_t st
     if (slot <= h->C) bj.j[bj.n++] = {h->net_params(slot), h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, in_dim, 1};
   }
   if (jobs_h.n) {
-    tc::k_pack_multi_h<<<dim3(H * 32 / 256, jobs_h.n), 256, 0, st>>>(jobs_h, 2);
+    launch_pdl(tc::k_pack_multi_h, dim3(dim3(H * 32 / 256, jobs_h.n)), dim3(256), 0, st, jobs_h, 2);
     CQL_LAUNCH_CHECK(h);
   }
   if (jobs.n == 0) return;
@@ -629,7 +649,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     CQL_CUDA(cudaEventRecord(h->ev_join, st2));
     CQL_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
-  tc::k_reduce_grads_tc<<<dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets), 256, 0, st>>>(h->small1, slots1, h->small2, h->pw2_tc,
+  launch_pdl(tc::k_reduce_grads_tc, dim3(dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets)), dim3(256), 0, st, h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out,
                                                                                   (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1);
   CQL_LAUNCH_CHECK(h);
@@ -682,7 +702,7 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
   if (bs == BatchSource::Sampled && ns == NoiseSource::Philox) {
     CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
     const int64_t nthr = h->noise_floats > B ? h->noise_floats : B;
-    k_step_head<<<(int)((nthr + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(h->table), h->n_trans, h->step_dev,
+    launch_pdl(k_step_head, dim3((int)((nthr + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(h->table), h->n_trans, h->step_dev,
                                                           h->stepinfo, c.beta1, c.beta2, B, h->n, c.rank, c.world_size,
                                                           c.seed, reinterpret_cast<float4*>(h->batch), h->XA, h->noise,
                                                           h->noise_floats);
@@ -714,7 +734,7 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     launch_fwd_any<2, 2>(h, jobs, st);
     mark(h, st, 2);
   }
-  k_prep<<<(B * 64 + 255) / 256, 256, 0, st>>>(batch4, h->outA, h->noise, B, h->n, c.squash, h->XAl, h->offAl, h->XC,
+  launch_pdl(k_prep, dim3((B * 64 + 255) / 256), dim3(256), 0, st, batch4, h->outA, h->noise, B, h->n, c.squash, h->XAl, h->offAl, h->XC,
                                                h->offC, h->XT, h->XP, reinterpret_cast<float4*>(h->perb));
   CQL_LAUNCH_CHECK(h);
   {
@@ -727,10 +747,10 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     launch_fwd_any<3, 1>(h, jobs, st);
     mark(h, st, 4);
   }
-  k_lse<<<(C * B * 32 + 255) / 256, 256, 0, st>>>(batch4, h->QAl, h->offAl, h->QC, h->offC, h->QT, loss_consts(h), h->dQ,
+  launch_pdl(k_lse, dim3((C * B * 32 + 255) / 256), dim3(256), 0, st, batch4, h->QAl, h->offAl, h->QC, h->offC, h->QT, loss_consts(h), h->dQ,
                                                  reinterpret_cast<PairVals*>(h->pairv));
   CQL_LAUNCH_CHECK(h);
-  k_scalar_reduce<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
+  launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
                                       h->scalars(), loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics);
   CQL_LAUNCH_CHECK(h);
 }
@@ -739,10 +759,10 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
 inline void phase1(Handle* h, cudaStream_t st) {
   const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
   const int64_t so = scalars_off(C);
-  k_scalar_adam<<<1, 32, 0, st>>>(h->scalars(), h->adam_m + so, h->adam_v + so, h->g_scalars(), h->stepinfo,
+  launch_pdl(k_scalar_adam, dim3(1), dim3(32), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so, h->g_scalars(), h->stepinfo,
                                  loss_consts(h), h->loss_sums, h->metrics);
   CQL_LAUNCH_CHECK(h);
-  k_dq<<<(int)(((int64_t)C * rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<const PairVals*>(h->pairv), h->loss_sums,
+  launch_pdl(k_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const PairVals*>(h->pairv), h->loss_sums,
                                                               loss_consts(h), h->dQ);
   CQL_LAUNCH_CHECK(h);
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
@@ -769,7 +789,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
   const int B = h->B, C = h->C;
   const cql_config& c = h->cfg;
   const int64_t cnt = (int64_t)C * NET_STRIDE;
-  k_adam_polyak<<<(int)((cnt + 255) / 256), 256, 0, st>>>(
+  launch_pdl(k_adam_polyak, dim3((int)((cnt + 255) / 256)), dim3(256), 0, st, 
       h->net_params(slot_critic(0)), h->adam_m + (size_t)NET_STRIDE, h->adam_v + (size_t)NET_STRIDE, h->g_critics(),
       h->net_params(slot_targ_critic(C, 0)), cnt, c.critic_lr, c.beta1, c.beta2, c.adam_eps, c.tau, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
@@ -786,7 +806,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
     launch_fwd_any<3, 1>(h, jobs, st);
     mark(h, st, 9);
   }
-  k_actor_dq<<<1, 1024, 0, st>>>(h->QP, reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
+  launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, h->QP, reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
                                  h->metrics);
   CQL_LAUNCH_CHECK(h);
   {
@@ -797,7 +817,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
     else launch_bwd1<3, 1, false, true>(h, jb, st);
   }
   const bool tcm = h->cfg.precision != CQL_PREC_FP32;
-  k_actor_dout<<<(B + 127) / 128, 128, 0, st>>>(h->outA, h->noise + B + 6 * (int64_t)B * h->n,
+  launch_pdl(k_actor_dout, dim3((B + 127) / 128), dim3(128), 0, st, h->outA, h->noise + B + 6 * (int64_t)B * h->n,
                                                 tcm ? h->dX_part : h->dXP, h->scalars(), B,
                                                 tcm ? C * h->tc_slices : C, c.squash, h->dOutA);
   CQL_LAUNCH_CHECK(h);
@@ -821,13 +841,13 @@ inline void phase2(Handle* h, cudaStream_t st) {
 // phase 3: actor Adam + Polyak of the target policy, step counter
 inline void phase3(Handle* h, cudaStream_t st) {
   const cql_config& c = h->cfg;
-  k_adam_polyak<<<(NET_STRIDE + 255) / 256, 256, 0, st>>>(h->net_params(slot_actor()), h->adam_m, h->adam_v,
+  launch_pdl(k_adam_polyak, dim3((NET_STRIDE + 255) / 256), dim3(256), 0, st, h->net_params(slot_actor()), h->adam_m, h->adam_v,
                                                          h->g_actor(), h->net_params(slot_targ_actor(h->C)),
                                                          (int64_t)NET_STRIDE, c.actor_lr, c.beta1, c.beta2, c.adam_eps,
                                                          c.tau, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
   pack_weights(h, slot_actor(), 1, 2, st);
-  k_step_end<<<1, 1, 0, st>>>(h->step_dev);
+  launch_pdl(k_step_end, dim3(1), dim3(1), 0, st, h->step_dev);
   CQL_LAUNCH_CHECK(h);
   mark(h, st, 12);
 }
