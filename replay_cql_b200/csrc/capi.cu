@@ -593,15 +593,18 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
       r[0] = obs[2 * b]; r[1] = obs[2 * b + 1]; r[2] = act[b]; r[3] = rew[b];
       r[4] = next_obs[2 * b]; r[5] = next_obs[2 * b + 1]; r[6] = term[b]; r[7] = 0.f;
     }
-    CQL_CUDA(cudaMemcpyAsync(h.batch, h.batch_host, (size_t)B * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (noise) {
-      std::memcpy(h.noise_host, noise, h.noise_floats * sizeof(float));
-      CQL_CUDA(cudaMemcpyAsync(h.noise, h.noise_host, h.noise_floats * sizeof(float), cudaMemcpyHostToDevice, st));
-    }
-    // the 26 launches of the step replay as one CUDA graph (26 runtime launches cost ~100 us of host time per step)
+    if (noise) std::memcpy(h.noise_host, noise, h.noise_floats * sizeof(float));
+    // pinned staging -> device, the 26 launches of the step and the metrics read-back replay as ONE CUDA graph
+    // (26 runtime launches + 3 copies cost ~100 us of host time per step)
+    auto enqueue = [&] {
+      CQL_CUDA(cudaMemcpyAsync(h.batch, h.batch_host, (size_t)B * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+      if (noise) CQL_CUDA(cudaMemcpyAsync(h.noise, h.noise_host, h.noise_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+      run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+      CQL_CUDA(cudaMemcpyAsync(h.metrics_host, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    };
     const int gi = noise ? 1 : 0;
     if (h.timing) {
-      run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+      enqueue();
     } else {
       if (!ch->batch_graph[gi] || ch->batch_graph_stream[gi] != st) {
         if (ch->batch_graph[gi]) { cudaGraphExecDestroy(ch->batch_graph[gi]); ch->batch_graph[gi] = nullptr; }
@@ -609,7 +612,7 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
         const int64_t before = h.launches;
         CQL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
-          run_full_step(&h, st, BatchSource::Provided, noise ? NoiseSource::Provided : NoiseSource::Philox);
+          enqueue();
         } catch (...) {
           cudaStreamEndCapture(st, &g);
           if (g) cudaGraphDestroy(g);
@@ -625,7 +628,6 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
       CQL_CUDA(cudaGraphLaunch(ch->batch_graph[gi], st));
       h.launches += ch->batch_graph_launches[gi];
     }
-    if (metrics6) CQL_CUDA(cudaMemcpyAsync(h.metrics_host, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (grads_out)
       CQL_CUDA(cudaMemcpyAsync(grads_out, h.grads, grad_floats(h.C) * sizeof(float), cudaMemcpyDeviceToHost, st));
     CQL_CUDA(cudaStreamSynchronize(st));
