@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(HCfg4::THREADS, 1) tc_score_h_kernel(const Sco
             const HMeta* meta = reinterpret_cast<const HMeta*>(a.packed + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
             if (tid < C::NS) {
               const int col = slice * C::NS + tid;
-              ebs[tid] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col], 0.f, __ldg(&meta->inv_s[col]));   // actor: W3 row 0 = mu
+              // column scale folded into the constants (exact: powers of two): relu(v/(s_m s_n) + b2) w3 =
+              // relu(v/s_m + b2 s_n) (w3/s_n); two columns per 16-byte word.  actor: W3 row 0 = mu
+              const float inv_n = __ldg(&meta->inv_s[col]);
+              reinterpret_cast<float2*>(ebs)[tid] = make_float2(net[off_b2(IN) + col] / inv_n, net[off_W3(IN) + col] * inv_n);
             }
             wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), __ldg(&meta->wmax[2]), __ldg(&meta->wmax[3]));
           }
@@ -256,9 +259,10 @@ __global__ void __launch_bounds__(HCfg4::THREADS, 1) tc_score_h_kernel(const Sco
               tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * C::NS + c0, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float4 e = ebs[c0 + i];
-                q0 = fmaf(fmaxf(fmaf(v[i] * inv_sa, e.w, e.x), 0.f), e.y, q0);
+              for (int i = 0; i < 32; i += 2) {
+                const float4 e = ebs[(c0 + i) >> 1];           // (b2 s_n, w3 / s_n) of columns c0+i, c0+i+1
+                q0 = fmaf(fmaxf(fmaf(v[i], inv_sa, e.x), 0.f), e.y, q0);
+                q0 = fmaf(fmaxf(fmaf(v[i + 1], inv_sa, e.z), 0.f), e.w, q0);
               }
             }
             tc_fence_before();
