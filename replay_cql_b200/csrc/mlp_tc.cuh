@@ -127,6 +127,7 @@ struct TcFwdJobs {
   TcFwdJob j[3];
   int n;
   int item_begin[4];      // prefix sums of items per job; item = (net, slice, tile)
+  int h2_cost = 0;        // f16x3 kernel: relative cost of an item that stores H2 (plain item = 10); 0 = default
 };
 
 struct ItemInfo { int job, net, slice, tile, pair_id; };

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(256) k_pack_multi_h(const PackJobs jobs, int o
   }
 }
 
+constexpr int FWD_H2_COST = 13;     // relative cost of a forward item that stores H2 (plain item = 10)
+
 struct HItem { int job, net, slice, tile, pair_id; };
 __device__ __forceinline__ HItem decode_item_h(const TcFwdJobs& jobs, int item) {
   HItem it;
@@ -194,9 +196,27 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int total = jobs.item_begin[jobs.n];
-  const int item_lo = (int)((long long)total * blockIdx.x / gridDim.x);
-  const int item_hi = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+  // contiguous item range per CTA, balanced by COST: an item whose epilogue also stores H2 is ~30 % more expensive,
+  // and those items are contiguous (one job), so an equal-count split leaves their CTAs as the tail of the launch
+  int item_lo, item_hi;
+  {
+    long long cb[4];
+    int wj[3];
+    cb[0] = 0;
+    for (int j = 0; j < jobs.n; ++j) {
+      wj[j] = jobs.j[j].h2 != nullptr ? (jobs.h2_cost > 0 ? jobs.h2_cost : FWD_H2_COST) : 10;
+      cb[j + 1] = cb[j] + (long long)(jobs.item_begin[j + 1] - jobs.item_begin[j]) * wj[j];
+    }
+    auto item_at = [&](long long cost) {
+      int j = 0;
+      while (j + 1 < jobs.n && cost >= cb[j + 1]) ++j;
+      const int it = jobs.item_begin[j] + (int)((cost - cb[j]) / wj[j]);
+      return it < jobs.item_begin[j + 1] ? it : jobs.item_begin[j + 1];
+    };
+    const long long total_cost = cb[jobs.n];
+    item_lo = blockIdx.x == 0 ? 0 : item_at(total_cost * blockIdx.x / gridDim.x);
+    item_hi = blockIdx.x == gridDim.x - 1 ? jobs.item_begin[jobs.n] : item_at(total_cost * (blockIdx.x + 1) / gridDim.x);
+  }
 
   if (warp == C::MMA_WARP) {
     tmem_alloc(slot, C::TMEM_ALLOC);
@@ -335,6 +355,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
     // =============================== epilogue: TMEM -> unscale -> layer 3 (+ H2) ===============================
     const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;          // group = accumulator, qw = TMEM lane quarter
     float4* ebg = ebs + grp * C::NS;
+    float2* efg = reinterpret_cast<float2*>(sm + C::OFF_FLUSH) + grp * C::NS;   // folded constants (region used by bwd1 only)
     int cur_pair = -1;
     const int row_in_tile = qw * 32 + lane;
     float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -349,8 +370,12 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
         const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
         for (int cidx = gtid; cidx < C::NS; cidx += 128) {
           const int col = ii.slice * C::NS + cidx;
+          const float inv_n = __ldg(&meta->inv_s[col]);
           ebg[cidx] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col],
-                                  OUT == 2 ? net[off_W3(IN) + H + col] : 0.f, __ldg(&meta->inv_s[col]));
+                                  OUT == 2 ? net[off_W3(IN) + H + col] : 0.f, inv_n);
+          // folded form for items that do not store H2 (exact, powers of two):
+          // relu(v/(s_m s_n) + b2) w3 = relu(v/s_m + b2 s_n) (w3/s_n); two columns per 16-byte word
+          if (OUT == 1) efg[cidx] = make_float2(net[off_b2(IN) + col] / inv_n, net[off_W3(IN) + col] * inv_n);
         }
         wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
@@ -367,6 +392,20 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
       float* h2row = store_h2 ? jb.h2 + (((size_t)ii.net * tiles64 + (row >> 6)) * H + ii.slice * C::NS) * 64 + (row & 63)
                               : nullptr;
       float q0 = 0.f, q1 = 0.f;
+      if (OUT == 1 && !store_h2) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::NS; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem + ((uint32_t)(qw * 32) << 16) + acc * C::NS + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float4 e = reinterpret_cast<const float4*>(efg)[(c0 + i) >> 1];
+            q0 = fmaf(fmaxf(fmaf(v[i], inv_sa, e.x), 0.f), e.y, q0);
+            q0 = fmaf(fmaxf(fmaf(v[i + 1], inv_sa, e.z), 0.f), e.w, q0);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < C::NS; c0 += 32) {
         float v[32];

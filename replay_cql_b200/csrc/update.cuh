@@ -536,6 +536,7 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
                            j.n_nets};
   }
   tj.item_begin[jobs.n] = items;
+  { static const char* hc = std::getenv("CQL_H2_COST"); if (hc) tj.h2_cost = std::atoi(hc); }   // tuning knob
   CQL_REQUIRE(part_off <= h->part_floats, "internal: partial-sum scratch too small");
   if (items == 0) return;
   const int grid = items < h->num_sms ? items : h->num_sms;
