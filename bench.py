@@ -41,7 +41,7 @@ DTYPES = {"fp32": "f32", "tf32x3": "f32 (tf32x3: tensor-core 3-term split, fp32 
           "bf16": "bf16 (fp32 accumulate; non-parity variant)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from one `ncu --set full` capture
 # (profiles/r01_tc_fwd_ts_ncu_summary.txt, profiles/r01_f16x3_fwd_h_ncu_summary.txt); null where no capture exists for that variant
-KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": 2.136064e6 + 7.964416e6, "bf16": None}
+KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": 2.136832e6 + 13.496576e6, "bf16": None}
 KERNEL_NAMES = {"fp32": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
                 "tf32x3": "tc_fwd_ts_kernel<3,1> (critic forward: tcgen05 kind::tf32 3-term split, A operand in TMEM)",
                 "f16x3": "tc_fwd_h_kernel<3,1> (critic forward: tcgen05 kind::f16, fp16 hi/lo 3-term split, A operand in TMEM)",
