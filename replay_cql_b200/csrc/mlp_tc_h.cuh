@@ -681,10 +681,12 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float4 w = ebg[q * 32 + i];
-          float z = fmaf(x.y, w.y, x.x * w.x);
+          // layer-1 pre-activation in the FORWARD's order (chain starts from the bias): the ReLU mask agrees with
+          // the forward bit for bit
+          float z = fmaf(x.y, w.y, fmaf(x.x, w.x, w.w));
           if (IN == 3) z = fmaf(x.z, w.z, z);
-          z += w.w;
-          const float d = z > 0.f ? v[i] * inv_sa * ivg[q * 32 + i] : 0.f;
+          // without dx the column scale 1/s_n is applied once per column sum instead of once per element
+          const float d = z > 0.f ? (DX ? v[i] * inv_sa * ivg[q * 32 + i] : v[i] * inv_sa) : 0.f;
           v[i] = d;
           if (DX) {
             dx0 = fmaf(d, w.x, dx0);
@@ -710,7 +712,9 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
             if (IN == 3) s2 = fmaf(dv, xr.z, s2);
             sb += dv;
           }
-          a_w0[q] += s0; a_w1[q] += s1; a_w2[q] += s2; a_b[q] += sb;
+          const float cs = DX ? 1.f : ivg[q * 32 + lane];
+          a_w0[q] = fmaf(s0, cs, a_w0[q]); a_w1[q] = fmaf(s1, cs, a_w1[q]); a_w2[q] = fmaf(s2, cs, a_w2[q]);
+          a_b[q] = fmaf(sb, cs, a_b[q]);
         }
       }
       tc_fence_before();
@@ -933,9 +937,9 @@ __global__ void __launch_bounds__(B2HCfg::THREADS, 1) tc_bwd2_h_kernel(const Bwd
           dz[e] = hv[e] > 0.f ? g : 0.f;
           s_db2 += dz[e];
           const float4 x = xst[rl];
-          float z = fmaf(x.y, w1y, x.x * w1x);
+          float z = fmaf(x.y, w1y, fmaf(x.x, w1x, b1v));        // the forward's order: chain starts from the bias
           if (IN == 3) z = fmaf(x.z, w1z, z);
-          h1[e] = fmaxf(z + b1v, 0.f);
+          h1[e] = fmaxf(z, 0.f);
         }
         const uint32_t off = chunk_off(H, t, kc);
         uint32_t hi[4], lo[4];
