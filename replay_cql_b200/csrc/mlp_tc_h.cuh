@@ -298,15 +298,16 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
     int cur_netkey = -1;
     float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t it = 0;
-    auto load_x = [&](int item) {
-      const HItem ni = decode_item_h(jobs, item);
+    auto load_x = [&](const HItem& ni) {
       const TcFwdJob& nj = jobs.j[ni.job];
       const int r = ni.tile * TM + (warp & 3) * 32 + lane;
       return r < nj.rows ? __ldg(nj.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     float4 x_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    HItem ii_next = item_lo < item_hi ? decode_item_h(jobs, item_lo) : HItem{};   // one decode (integer division) per item
     for (int item = item_lo; item < item_hi; ++item) {
-      const HItem ii = decode_item_h(jobs, item);
+      const HItem ii = ii_next;
+      if (item + 1 < item_hi) ii_next = decode_item_h(jobs, item + 1);
       const TcFwdJob& jb = jobs.j[ii.job];
       const int netkey = ii.job * 64 + ii.net;
       if (netkey != cur_netkey) {
@@ -325,8 +326,8 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
         asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
       }
       // this item's input row was prefetched while the previous item was generated; fetch the next one now
-      const float4 x = (item == item_lo) ? load_x(item) : x_next;
-      if (item + 1 < item_hi) x_next = load_x(item + 1);
+      const float4 x = (item == item_lo) ? load_x(ii) : x_next;
+      if (item + 1 < item_hi) x_next = load_x(ii_next);
       float sa, inv_sa;
       pow2_scale(h1_row_bound(x, wm), sa, inv_sa);
       const float2 xx = make_float2(x.x, x.x), xy = make_float2(x.y, x.y), xz = make_float2(x.z, x.z), ss = make_float2(sa, sa);
