@@ -158,8 +158,11 @@ __global__ void __launch_bounds__(HCfg4::THREADS, 1) tc_score_h_kernel(const Sco
             const int k = 2 * pr;
             const float* wa = net + off_W1(IN) + k * IN;
             const float* wb = wa + IN;
+            // the whole block belongs to one user: the first link of the layer-1 chain, b + u * w_user, is taken here once
+            // per (block, network) instead of once per pair (same operation, so bit-identical)
             w1p[2 * pr] = make_float4(wa[0], wb[0], wa[1], wb[1]);
-            w1p[2 * pr + 1] = make_float4(IN == 3 ? wa[2] : 0.f, IN == 3 ? wb[2] : 0.f, net[off_b1(IN) + k], net[off_b1(IN) + k + 1]);
+            w1p[2 * pr + 1] = make_float4(IN == 3 ? wa[2] : 0.f, IN == 3 ? wb[2] : 0.f, fmaf(uf, wa[0], net[off_b1(IN) + k]),
+                                          fmaf(uf, wb[0], net[off_b1(IN) + k + 1]));
           }
           const HMeta* meta = reinterpret_cast<const HMeta*>(a.packed + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
           wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), __ldg(&meta->wmax[2]), __ldg(&meta->wmax[3]));
@@ -181,9 +184,8 @@ __global__ void __launch_bounds__(HCfg4::THREADS, 1) tc_score_h_kernel(const Sco
             for (int pp = 0; pp < C::KPW / 2; ++pp) {
               const int pr = (c * C::KC + kq * C::KPW) / 2 + pp;
               const float4 wA = w1p[2 * pr], wB = w1p[2 * pr + 1];
-              float2 v = ffma2(xx, make_float2(wA.x, wA.y), make_float2(wB.z, wB.w));
-              v = ffma2(xy, make_float2(wA.z, wA.w), v);
-              v = ffma2(xz, make_float2(wB.x, wB.y), v);      // actor: wz = 0
+              float2 v = ffma2(xy, make_float2(wA.z, wA.w), make_float2(wB.z, wB.w));   // chain starts from b + u * w_user
+              if (net_i != 0) v = ffma2(xz, make_float2(wB.x, wB.y), v);                // the actor has no action input
               v = fmul2(make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)), ss);
               split_h2_trunc(v, hi[pp], lo[pp]);
             }
