@@ -124,10 +124,10 @@ def test_score_pairs_and_edge_cases(engine_factory):
         eng.score_topk([1], [1], 5000)
 
 
-@pytest.mark.parametrize("U,I,k", [(37, 5003, 10), (700, 2001, 10), (650, 4096, 32), (600, 333, 1)])
+@pytest.mark.parametrize("U,I,k", [(37, 5003, 10), (700, 2001, 10), (650, 4096, 32), (600, 333, 1), (20, 3000, 40)])
 def test_standalone_topk_filter(engine_factory, U, I, k):
-    """both kernels: CTA-per-row with shared-memory lists (few rows / k > 32) and warp-per-row with the list
-    in registers (>= 4 x SMs rows, k <= 32)"""
+    """both kernels: the staged two-pass kernel (k <= 32; aligned and unaligned rows) and the CTA-per-row kernel with
+    shared-memory lists (k > 32)"""
     eng = engine_factory(batch_size=64)
     rng = np.random.default_rng(3)
     scores = rng.standard_normal((U, I)).astype(np.float32)
