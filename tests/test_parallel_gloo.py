@@ -40,6 +40,9 @@ def _worker(rank, world, port, out_dir):
         from replay_cql_b200.parallel import allreduce_mean_, dist_info, gather_rows
         from tests import helpers as Hp
         assert dist_info()[:2] == (rank, world)
+        # 0. without NCCL the gradient exchange falls back (collectively) to the all-reduce reducer
+        from replay_cql_b200.parallel import GradAllReducer, make_grad_exchange
+        assert isinstance(make_grad_exchange(object()), GradAllReducer)
         # 1. allreduce_mean_
         t = torch.full((5,), float(rank + 1))
         allreduce_mean_(t)
