@@ -123,6 +123,14 @@ int  cql_update_batch(cql_handle* h, const float* obs, const float* act, const f
                       const float* next_obs, const float* term, const float* noise,
                       float* metrics6, float* grads_out, void* stream);
 
+/* n_batches consecutive updates on caller-supplied minibatches (host buffers, n_batches x B rows each, Philox noise):
+ * the host loop of an offline trainer that owns its batches.  Per step the minibatch goes host -> pinned ring -> device
+ * and the six metrics come back; copies and steps are pipelined on `stream` (the host runs up to 8 steps ahead) and the
+ * call returns after the last step.  metrics_out (host, may be NULL): [n_batches][6].
+ * replaces: the per-step loop of d3rlpy LearnableBase.fit over TransitionMiniBatch objects [EXT d3rlpy/base.py] */
+int  cql_update_batches(cql_handle* h, int64_t n_batches, const float* obs, const float* act, const float* rew,
+                        const float* next_obs, const float* term, float* metrics_out, void* stream);
+
 /* Data-parallel split of one update.  The host all-reduces (mean) the exposed
  * gradient buffer between phases; with world_size==1 the phases can be called
  * back to back.  phase 0: sample + forward passes + temp/alpha grads

@@ -31,6 +31,14 @@ struct cql_handle {
   int* part_i = nullptr;
   size_t part_elems = 0;
   uint8_t* packed_score = nullptr;   // tf32-packed W2 of actor + critics for the tensor-core scorer
+  // cql_update_batches: the bare step (minibatch already on the device) as a graph, pinned staging ring, metrics rows
+  cudaGraphExec_t step_graph = nullptr;
+  cudaStream_t step_graph_stream = nullptr;
+  int64_t step_graph_launches = 0;
+  float* ring = nullptr;             // pinned [8][B*8]
+  cudaEvent_t ring_ev[8] = {};
+  float* metrics_rows = nullptr;     // pinned [metrics_rows_cap][8]
+  int64_t metrics_rows_cap = 0;
   DpPeer dp;                         // NVLink peer-memory gradient exchange (cql_dp_attach)
   void* dp_local = nullptr;          // epochs | tickets | error flag
 };
@@ -203,6 +211,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
 void destroy_graph(cql_handle* ch) {
   if (ch->graph_exec) { cudaGraphExecDestroy(ch->graph_exec); ch->graph_exec = nullptr; }
   for (auto& g : ch->batch_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  if (ch->step_graph) { cudaGraphExecDestroy(ch->step_graph); ch->step_graph = nullptr; }
 }
 
 template <typename F>
@@ -371,6 +380,9 @@ void cql_destroy(cql_handle* ch) {
   if (ch->part_i) cudaFree(ch->part_i);
   if (ch->packed_score) cudaFree(ch->packed_score);
   if (ch->dp_local) cudaFree(ch->dp_local);
+  if (ch->ring) cudaFreeHost(ch->ring);
+  if (ch->metrics_rows) cudaFreeHost(ch->metrics_rows);
+  for (auto& e : ch->ring_ev) if (e) cudaEventDestroy(e);
   ch->h.free_all();
   delete ch;
 }
@@ -632,6 +644,69 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
       CQL_CUDA(cudaMemcpyAsync(grads_out, h.grads, grad_floats(h.C) * sizeof(float), cudaMemcpyDeviceToHost, st));
     CQL_CUDA(cudaStreamSynchronize(st));
     if (metrics6) std::memcpy(metrics6, h.metrics_host, 6 * sizeof(float));
+  });
+}
+
+int cql_update_batches(cql_handle* ch, int64_t n_batches, const float* obs, const float* act, const float* rew,
+                       const float* next_obs, const float* term, float* metrics_out, void* stream) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(n_batches >= 0, "cql_update_batches: n_batches < 0");
+    if (n_batches == 0) return;
+    CQL_REQUIRE(obs && act && rew && next_obs && term, "cql_update_batches: NULL batch pointer");
+    cudaStream_t st = pick_stream(&h, stream);
+    const int B = h.B;
+    constexpr int RING = 8;
+    const size_t row_floats = (size_t)B * 8;
+    if (!ch->ring) {
+      CQL_CUDA(cudaMallocHost(&ch->ring, RING * row_floats * sizeof(float)));
+      for (auto& e : ch->ring_ev) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (ch->metrics_rows_cap < n_batches) {
+      if (ch->metrics_rows) CQL_CUDA(cudaFreeHost(ch->metrics_rows));
+      ch->metrics_rows = nullptr; ch->metrics_rows_cap = 0;
+      CQL_CUDA(cudaMallocHost(&ch->metrics_rows, (size_t)n_batches * 8 * sizeof(float)));
+      ch->metrics_rows_cap = n_batches;
+    }
+    if (!ch->step_graph || ch->step_graph_stream != st) {          // the step alone: minibatch already in h.batch
+      if (ch->step_graph) { cudaGraphExecDestroy(ch->step_graph); ch->step_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      const int64_t before = h.launches;
+      CQL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        run_full_step(&h, st, BatchSource::Provided, NoiseSource::Philox);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CQL_CUDA(cudaStreamEndCapture(st, &g));
+      ch->step_graph_launches = h.launches - before;
+      h.launches = before;
+      CQL_CUDA(cudaGraphInstantiate(&ch->step_graph, g, 0));
+      CQL_CUDA(cudaGraphDestroy(g));
+      ch->step_graph_stream = st;
+    }
+    for (int64_t i = 0; i < n_batches; ++i) {
+      const int slot = (int)(i % RING);
+      if (i >= RING) CQL_CUDA(cudaEventSynchronize(ch->ring_ev[slot]));     // that slot's host->device copy has run
+      float* stage = ch->ring + (size_t)slot * row_floats;
+      const float *o = obs + (size_t)i * B * 2, *a = act + (size_t)i * B, *r = rew + (size_t)i * B,
+                  *no = next_obs + (size_t)i * B * 2, *t = term + (size_t)i * B;
+      for (int b = 0; b < B; ++b) {
+        float* w = stage + (size_t)b * 8;
+        w[0] = o[2 * b]; w[1] = o[2 * b + 1]; w[2] = a[b]; w[3] = r[b];
+        w[4] = no[2 * b]; w[5] = no[2 * b + 1]; w[6] = t[b]; w[7] = 0.f;
+      }
+      CQL_CUDA(cudaMemcpyAsync(h.batch, stage, row_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+      CQL_CUDA(cudaEventRecord(ch->ring_ev[slot], st));
+      CQL_CUDA(cudaGraphLaunch(ch->step_graph, st));
+      h.launches += ch->step_graph_launches;
+      CQL_CUDA(cudaMemcpyAsync(ch->metrics_rows + (size_t)i * 8, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CQL_CUDA(cudaStreamSynchronize(st));
+    if (metrics_out)
+      for (int64_t i = 0; i < n_batches; ++i) std::memcpy(metrics_out + i * 6, ch->metrics_rows + i * 8, 6 * sizeof(float));
   });
 }
 

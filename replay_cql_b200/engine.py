@@ -263,6 +263,25 @@ class CqlEngine:
         metrics = dict(zip(METRIC_NAMES, map(float, m)))
         return metrics, (layout.unpack_grads(g, self.hp.n_critics) if want_grads else None)
 
+    def update_batches(self, batches, stream: int | None = None):
+        """Consecutive updates on host minibatches (Philox noise), pipelined inside the library: per step the batch goes
+        host -> pinned ring -> device and the six metrics come back.  ``batches``: a sequence of batch dicts, or one dict of
+        stacked arrays ``obs [n,B,2], act [n,B], rew [n,B], next_obs [n,B,2], term [n,B]``.  -> list of metric dicts."""
+        B = self.hp.batch_size
+        if not isinstance(batches, dict):
+            if len(batches) == 0:
+                return []
+            batches = {k: np.stack([np.reshape(np.asarray(b[k], dtype=np.float32), (B, -1)) for b in batches])
+                       for k in ("obs", "act", "rew", "next_obs", "term")}
+        n = int(np.asarray(batches["act"]).reshape(-1, B).shape[0])
+        obs = _f32(np.reshape(batches["obs"], (n * B, 2)), (n * B, 2))
+        nobs = _f32(np.reshape(batches["next_obs"], (n * B, 2)), (n * B, 2))
+        act, rew, term = (_f32(np.reshape(batches[k], -1), (n * B,)) for k in ("act", "rew", "term"))
+        m = np.zeros((n, 6), dtype=np.float32)
+        self._check(self._lib.cql_update_batches(self._h, n, _ptr(obs), _ptr(act), _ptr(rew), _ptr(nobs), _ptr(term),
+                                                 _ptr(m), stream), "cql_update_batches")
+        return [dict(zip(METRIC_NAMES, map(float, row))) for row in m]
+
     def device_buffer(self, which: int):
         ptr, n = C.c_void_p(), C.c_int64()
         self._check(self._lib.cql_device_buffer(self._h, which, C.byref(ptr), C.byref(n)), "cql_device_buffer")

@@ -146,6 +146,24 @@ def test_phase_split_equals_fused_update(engine_factory, precision):
     assert a.get_optimizer()[2] == b.get_optimizer()[2] == 5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+def test_update_batches_equals_single_calls(engine_factory, precision):
+    """cql_update_batches (pinned ring, pipelined copies, one graph per step) takes exactly the steps of repeated
+    cql_update_batch calls: bit-identical state and per-step metrics, also when the ring wraps (n > 8)."""
+    from tests import helpers as Hp
+    B, n = 64, 11
+    a = engine_factory(batch_size=B, seed=3, precision=precision)
+    b = engine_factory(batch_size=B, seed=3, precision=precision)
+    batches = [Hp.batch_to_numpy(Hp.make_batch(B, seed=300 + i, scale=1e-3)) for i in range(n)]
+    single = [a.update_batch(bt)[0] for bt in batches]
+    multi = b.update_batches(batches)
+    torch.cuda.synchronize()
+    assert np.array_equal(a.get_state(), b.get_state())
+    for s1, s2 in zip(single, multi):
+        assert s1 == s2
+    assert b.update_batches([]) == []
+
+
 @pytest.mark.parametrize("top_k", [0, 1, 3, 1000])
 def test_gpu_mdp_builder_bit_exact(engine_factory, top_k):
     """cql_build_mdp (stable radix sorts on the device) == host builder == loop oracle, bit for bit,
