@@ -2,7 +2,7 @@
 // (reference: `_filter_seen` replay/models/base_rec.py:417-464 followed by `get_top_k` replay/utils.py:100-109,
 // here as one HBM-bound pass: 4 bytes read per (user, item) pair).
 //
-// Design (k <= 32).  Persistent CTAs (5 per SM) walk rows round-robin; warp-specialised:
+// Design (k <= 32).  Persistent CTAs (6 per SM) walk rows round-robin; warp-specialised:
 //  * producer warp: streams the row, cut into chunks of <= CH floats, into a STAGES-deep shared-memory ring
 //    with 1-D bulk copies (TMA, cp.async.bulk + full/empty mbarriers) -- loads never wait for the selection;
 //  * 8 worker warps, pass 1: every thread keeps the three best float4 maxima of its strided share of the
@@ -27,14 +27,14 @@
 namespace cql {
 
 constexpr int TKS_WORKERS = 128;      // 4 worker warps + selector warp + producer warp
-constexpr int TKS_CTAS_PER_SM = 5;
+constexpr int TKS_CTAS_PER_SM = 6;
 constexpr int TKS_GROUP = TKS_WORKERS / 32;   // lanes per group maximum (32 groups per CTA)
 constexpr int TKS_SEL_WARP = TKS_WORKERS / 32;
 constexpr int TKS_PROD_WARP = TKS_SEL_WARP + 1;
 constexpr int TKS_THREADS = TKS_WORKERS + 64;
 constexpr int TKS_SYNC = TKS_WORKERS + 32;   // participants of the worker <-> selector barriers
 constexpr int TKS_STAGES = 2;
-constexpr int TKS_CH = 4096;          // floats per stage: 2 x 16 KB ring, 5 CTAs per SM (measured: 4.72 TB/s; 3 stages x 4 CTAs: 4.54)
+constexpr int TKS_CH = 3072;          // floats per stage: 2 x 12 KB ring, 6 CTAs per SM (measured 5.03 TB/s; 2 x 16 KB x 5 CTAs: 4.72; 3 x 16 KB x 4: 4.54)
 constexpr int TKS_SEEN = 512;         // ints per seen cache (two caches: current row / next row)
 constexpr int TKS_CAP = 256;          // candidates per collection round
 
