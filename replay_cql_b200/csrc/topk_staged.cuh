@@ -51,7 +51,8 @@ constexpr size_t TKS_OFF_SEEN = (size_t)TKS_STAGES * TKS_CH * 4;
 constexpr size_t TKS_OFF_CS = TKS_OFF_SEEN + 2 * TKS_SEEN * 4;
 constexpr size_t TKS_OFF_CI = TKS_OFF_CS + TKS_CAP * 4;
 constexpr size_t TKS_OFF_G = TKS_OFF_CI + TKS_CAP * 4;       // gmax[32] | sorted[32] | listS[32] | listI[32]
-constexpr size_t TKS_OFF_CTL = TKS_OFF_G + 128 * 4;
+constexpr size_t TKS_OFF_BEST = TKS_OFF_G + 128 * 4;   // float4 best[2][TKS_WORKERS]: every worker's best two float4s of the row
+constexpr size_t TKS_OFF_CTL = TKS_OFF_BEST + 2 * TKS_WORKERS * 16;
 constexpr size_t TKS_OFF_BAR = TKS_OFF_CTL + 64;
 constexpr size_t TKS_SMEM = TKS_OFF_BAR + 2 * TKS_STAGES * 8;
 
@@ -129,15 +130,8 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
 
   if (warp < TKS_SEL_WARP) {
     // =========================== workers: pass 1 (maxima) and pass 2 (candidates) ===========================
-    auto fetch4 = [&](const float* rowp, int64_t gv, float* sc, int* it) {   // scores and item ids of float4 `gv` of a row
+    auto fetch_ids = [&](int64_t gv, int* it) {                              // item ids of float4 `gv` of a row
       const int64_t col0 = gv * 4;
-      if (a.aligned) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(rowp) + gv);
-        sc[0] = x.x; sc[1] = x.y; sc[2] = x.z; sc[3] = x.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sc[e] = col0 + e < a.n_items ? __ldg(rowp + col0 + e) : -INFINITY;
-      }
       if (a.items != nullptr && items_al && col0 + 3 < a.n_items) {
         const int4 y = __ldg(reinterpret_cast<const int4*>(a.items) + gv);
         it[0] = y.x; it[1] = y.y; it[2] = y.z; it[3] = y.w;
@@ -147,12 +141,28 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
           it[e] = a.items ? (col0 + e < a.n_items ? __ldg(a.items + col0 + e) : -1) : (int)(col0 + e);
       }
     };
+    auto fetch4 = [&](const float* rowp, int64_t gv, float* sc, int* it) {   // scores and item ids of float4 `gv` of a row
+      const int64_t col0 = gv * 4;
+      if (a.aligned) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(rowp) + gv);
+        sc[0] = x.x; sc[1] = x.y; sc[2] = x.z; sc[3] = x.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[e] = col0 + e < a.n_items ? __ldg(rowp + col0 + e) : -INFINITY;
+      }
+      fetch_ids(gv, it);
+    };
+    // the best two float4s of the share are stashed in shared memory as they are found (a handful of stores per
+    // row): re-reading them from global memory after the row missed L2 (ncu: +6.5 % DRAM reads) and put a DRAM
+    // round trip on the row's hand-over
+    float4* best = reinterpret_cast<float4*>(tks_sm + TKS_OFF_BEST) + tid;
     int64_t q = 0;
     for (int64_t j = 0; j < nrows_cta; ++j) {
       const float* rowp = a.scores + (size_t)row_of(j) * a.n_items;
       // pass 1 over the whole row: best and second-best float4 maximum of this thread's strided share
       float m = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // best / second / third float4 maximum of the share
       int gvbest = 0, gv2 = 0;                                // float4 index (within the row) of the best two
+      int sb = 0;                                             // stash slot of the best (the runner-up sits in the other)
       for (int c = 0; c < a.nchunks; ++c, ++q) {
         const int64_t c0 = (int64_t)c * a.chunk_len;
         const int len = (int)min((int64_t)a.chunk_len, a.n_items - c0);
@@ -170,8 +180,8 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
         for (int v = tid; v < nvec; v += TKS_WORKERS) {
           const float4 x = b4[v];
           const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-          if (mx > m) { m3 = m2; m2 = m; gv2 = gvbest; m = mx; gvbest = gv0 + v; }
-          else if (mx > m2) { m3 = m2; m2 = mx; gv2 = gv0 + v; }
+          if (mx > m) { m3 = m2; m2 = m; gv2 = gvbest; m = mx; gvbest = gv0 + v; sb ^= 1; best[sb * TKS_WORKERS] = x; }
+          else if (mx > m2) { m3 = m2; m2 = mx; gv2 = gv0 + v; best[(sb ^ 1) * TKS_WORKERS] = x; }
           else m3 = fmaxf(m3, mx);
         }
         if (a.aligned) {
@@ -179,11 +189,17 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
           if (lane == 0) tc::mbar_arrive(&empty[q % TKS_STAGES]);
         }
       }
-      // speculative re-read of the best two float4s and their item ids (L2 hits), overlapped with the threshold hand-over
+      // the best two float4s come back from the stash (slots never written hold garbage, but then m / m2 = -inf and
+      // they are not offered); their item ids are read speculatively (L2 hits), overlapped with the threshold hand-over
       float sc[8];
       int it[8];
-      fetch4(rowp, gvbest, sc, it);
-      fetch4(rowp, gv2, sc + 4, it + 4);
+      {
+        const float4 x = best[sb * TKS_WORKERS], y = best[(sb ^ 1) * TKS_WORKERS];
+        sc[0] = x.x; sc[1] = x.y; sc[2] = x.z; sc[3] = x.w;
+        sc[4] = y.x; sc[5] = y.y; sc[6] = y.z; sc[7] = y.w;
+      }
+      fetch_ids(gvbest, it);
+      fetch_ids(gv2, it + 4);
       float g = m;
 #pragma unroll
       for (int o = 1; o < TKS_GROUP; o <<= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
