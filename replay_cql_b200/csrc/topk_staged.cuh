@@ -235,18 +235,31 @@ __global__ void __launch_bounds__(TKS_THREADS, TKS_CTAS_PER_SM) k_topk_filter_st
             sv.hi = sv.lo + seen_n;
             if (ctl->seen_cached) sv.s = seen_cache + ctl->cache_sel * TKS_SEEN;
           }
-          auto offer4 = [&](int64_t gv, const float* sc4, const int* it4) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (gv * 4 + e >= a.n_items || !(sc4[e] >= t_lo && sc4[e] < t_hi)) continue;
-              if (seen_n >= 0 && is_seen<TKS_SEEN>(sv, it4[e])) continue;
-              const int p = atomicAdd(const_cast<int*>(ncand), 1);
-              if (p < TKS_CAP) { candS[p] = sc4[e]; candI[p] = it4[e]; }
-            }
-          };
           if (m3 < t_lo) {
-            offer4(gvbest, sc, it);
-            if (m2 >= t_lo) offer4(gv2, sc + 4, it + 4);
+            // in-band elements of the best two float4s as a bit mask, then ONE search per set bit: searching inside a
+            // loop over the 8 elements made every warp run the 9-step seen search up to 8 times in a row (the lanes'
+            // hits sit at different positions), ~1.5 us per row that the 2-stage ring could not hide
+            unsigned band = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int64_t col = (int64_t)(e < 4 ? gvbest : gv2) * 4 + (e & 3);
+              const bool in = col < a.n_items && sc[e] >= t_lo && sc[e] < t_hi && (e < 4 || m2 >= t_lo);
+              band |= in ? 1u << e : 0u;
+            }
+            while (band) {
+              const int e = __ffs(band) - 1;
+              band &= band - 1;
+              float s = sc[0];
+              int item = it[0];
+#pragma unroll
+              for (int u = 1; u < 8; ++u) {
+                s = u == e ? sc[u] : s;
+                item = u == e ? it[u] : item;
+              }
+              if (seen_n >= 0 && is_seen<TKS_SEEN>(sv, item)) continue;
+              const int p = atomicAdd(const_cast<int*>(ncand), 1);
+              if (p < TKS_CAP) { candS[p] = s; candI[p] = item; }
+            }
           }
         }
         // three or more float4s of a thread's share reach the band (a few % of the rows): the warp rescans that
