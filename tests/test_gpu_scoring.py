@@ -181,6 +181,9 @@ def test_staged_topk_filter_cases(engine_factory, case):
             seen[int(u)] = set(items[top].tolist())
         elif case == "long_seen" and r % 3 == 0:
             seen[int(u)] = set(items[rng.choice(I, size=3000, replace=False)].tolist())
+        elif case == "long_seen" and r % 3 == 1:                          # a long list that holds the best-scored items:
+            top = np.argsort(-scores[r])[: int(rng.integers(513, 2600))]   # every candidate is found through the sampled
+            seen[int(u)] = set(items[top].tolist())                        # cache + one global window (stride 2..6)
         elif case == "short_rows":
             seen[int(u)] = set(items[rng.choice(I, size=int(rng.integers(0, 30)), replace=False)].tolist())
         else:
