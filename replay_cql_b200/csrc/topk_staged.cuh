@@ -5,13 +5,13 @@
 // Design (k <= 32).  Persistent CTAs (6 per SM) walk rows round-robin; warp-specialised:
 //  * producer warp: streams the row, cut into chunks of <= CH floats, into a STAGES-deep shared-memory ring
 //    with 1-D bulk copies (TMA, cp.async.bulk + full/empty mbarriers) -- loads never wait for the selection;
-//  * 8 worker warps, pass 1: every thread keeps the three best float4 maxima of its strided share of the
-//    WHOLE row (and where the best two are); nothing else happens per chunk.  At the end of the row
-//    8-lane groups reduce to 32 group maxima;
+//  * 4 worker warps, pass 1: every thread keeps the three best float4 maxima of its strided share of the
+//    WHOLE row, where the best two are, and a copy of those two float4s in shared memory; nothing else happens per
+//    chunk.  At the end of the row 4-lane groups reduce to 32 group maxima;
 //  * selector warp: sorts the 32 group maxima; the (k + spare)-th largest is a threshold T reached by at
 //    least k + spare elements;
-//  * workers, pass 2: only threads whose maximum reaches T revisit their best (two) float4s (16-byte re-reads
-//    that hit L2; their whole share only if the third-best reaches T too), resolve the item id, drop seen items (binary search
+//  * workers, pass 2: only threads whose maximum reaches T revisit their best (two) float4s (from the shared-memory
+//    stash; their whole share, from global memory, only if the third-best reaches T too), resolve the item id, drop seen items (binary search
 //    in a shared-memory copy of the user's seen list -- sampled, plus one window of global memory, for lists over
 //    512 items) and push (score, item) candidates -- about k + 8 per row;
 //  * selector: places the candidates by rank (no serial insertion on the common path) and verifies: if the
