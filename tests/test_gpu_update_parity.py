@@ -75,6 +75,48 @@ def test_update_steps_match_oracle(engine_factory, B, scale, squash, precision):
     assert abs(gpu["log_alpha"] - ref["log_alpha"]) <= 1e-6
 
 
+@pytest.mark.parametrize("B", [1024, 8192])
+def test_headline_and_stress_batch_sizes(engine_factory, B):
+    """BASELINE.json batch sizes: 1024 (headline metric) and 8192 (stress configuration), one update of the bench's
+    default precision (f16x3): losses within 1e-4 of the float32 oracle; updated tensors within 1e-4 of the float32
+    oracle, or -- where the float32 oracle itself is further than that from the float64 oracle -- as close to the
+    float64 oracle as the float32 oracle is (x4).  (The first Adam step moves a weight by lr * g / (|g| + 1e-8): on
+    the thousands of W2 entries whose gradient is ~0 the sign of a 1e-10 rounding residue decides the step, and the
+    CPU float32 oracle differs from the float64 one by 1.7e-4 of max|W2| on exactly the tensor where the GPU does.)
+    The bf16 variant is held to its stated 2e-2 on the losses."""
+    cfg = O.OracleConfig()
+    st = O.init_state(cfg, seed=7)
+    st64 = O.cast_state(st, torch.float64)
+    batch = Hp.make_batch(B, seed=300, scale=1e-3)
+    noise = O.make_noise(B, cfg.n_action_samples, seed=400)
+    m_ref, _ = O.update(cfg, st, batch, noise)
+    eng = engine_factory(batch_size=B, precision="f16x3")
+    eng.set_state(Hp.oracle_state_to_flat(O.init_state(cfg, seed=7)))
+    m_gpu, _ = eng.update_batch(Hp.batch_to_numpy(batch), Hp.noise_to_numpy(noise))
+    for name in ("temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss"):
+        assert abs(m_gpu[name] - m_ref[name]) <= TOL * max(1.0, abs(m_ref[name])), (name, m_gpu[name], m_ref[name])
+    ref = layout.unpack_state(Hp.oracle_state_to_flat(st), cfg.n_critics)
+    gpu = layout.unpack_state(eng.get_state(), cfg.n_critics)
+    pairs = [((grp, k), gpu[grp][k], ref[grp][k], lambda s_, grp=grp, k=k: s_[grp][k])
+             for grp in ("actor", "targ_actor") for k in layout.NET_KEYS]
+    pairs += [((grp, c, k), gpu[grp][c][k], ref[grp][c][k], lambda s_, grp=grp, c=c, k=k: s_[grp][c][k])
+              for grp in ("critics", "targ_critics") for c in range(cfg.n_critics) for k in layout.NET_KEYS]
+    ref64 = None
+    for tag, a, b, pick in pairs:
+        if Hp.rel_err(a, b) <= TOL:
+            continue
+        if ref64 is None:                      # float64 twin of the same update, only when a tensor needs the budget
+            O.update(cfg, st64, {k: v.double() for k, v in batch.items()}, {k: v.double() for k, v in noise.items()})
+            ref64 = layout.unpack_state(Hp.oracle_state_to_flat(O.cast_state(st64, torch.float32)), cfg.n_critics)
+        b64 = pick(ref64)
+        assert Hp.rel_err(a, b64) <= max(TOL, 4 * Hp.rel_err(b, b64)), (tag, Hp.rel_err(a, b), Hp.rel_err(a, b64), Hp.rel_err(b, b64))
+    eng16 = engine_factory(batch_size=B, precision="bf16")
+    eng16.set_state(Hp.oracle_state_to_flat(O.init_state(cfg, seed=7)))
+    m16, _ = eng16.update_batch(Hp.batch_to_numpy(batch), Hp.noise_to_numpy(noise))
+    for k in m16:
+        assert abs(m16[k] - m_ref[k]) <= 2e-2 * max(1.0, abs(m_ref[k])), (k, m16[k], m_ref[k])
+
+
 def _f64_budget(v32, v64):
     return abs(v32 - v64)
 
