@@ -11,7 +11,10 @@ Per-user bodies restated from the mounted checkout (``_get_metric_value_by_user`
 
 and the user set of ``get_enriched_recommendations`` (``replay/metrics/base_metric.py:102-140``): a RIGHT join on
 the ground-truth users, missing predictions filled with an empty list; the metric is the mean over those users
-(``base_metric.py`` ``_mean``).  Pinned by the doctest vectors of the reference files (tests/test_metrics_oracle.py).
+(``base_metric.py`` ``_mean``).  With ``ground_truth_users`` the reference right-joins the ground truth on those users
+(``preprocess_gt``, ``base_metric.py:73-97``): callers model that by passing exactly those users as keys, with an empty
+collection for a user without test items.  Pinned by the doctest vectors of the reference files and by the golden values
+of the reference's ``tests/test_metrics.py`` (tests/test_metrics_oracle.py).
 """
 from __future__ import annotations
 
