@@ -153,3 +153,58 @@ def test_cql_init_args_roundtrip_json():
         CQL(use_gpu=False)
     with pytest.raises(ValueError):
         CQL(soft_q_backup=True)
+
+
+class PopSaved(PopLike):
+    """PopLike with the persistence hooks of a real model: one constructor argument, one data frame
+    (the reference's PopRec keeps `item_popularity` in `_dataframes`, replay/models/pop_rec.py)."""
+
+    def __init__(self, alpha: float = 0.0):
+        self.alpha = alpha
+
+    @property
+    def _init_args(self):
+        return {"alpha": self.alpha}
+
+    @property
+    def _dataframes(self):
+        return {"item_popularity": self.item_popularity}
+
+    def _fit(self, log, user_features=None, item_features=None):
+        super()._fit(log)
+        self.item_popularity = (self.pop + self.alpha).rename("relevance").reset_index()
+
+    def _predict(self, log, k, users, items, user_features=None, item_features=None, filter_seen_items=True):
+        self.pop = self.item_popularity.set_index("item_idx")["relevance"]
+        return super()._predict(log, k, users, items)
+
+    def _save_model(self, path):
+        with open(path, "w") as f:
+            f.write("opaque")
+
+    def _load_model(self, path):
+        with open(path) as f:
+            assert f.read() == "opaque"
+
+
+def test_save_load_layout_and_equal_preds(tmp_path, monkeypatch):   # test_save_load_models.py:48-70, model_handler.py:29-92
+    import json
+    import os
+
+    from replay_cql_b200 import model_handler, models
+    monkeypatch.setattr(models, "PopSaved", PopSaved, raising=False)       # load() resolves the class by name (:69)
+    model = PopSaved(alpha=0.25)
+    model.fit(LOG)
+    base = model.predict(LOG, 2)
+    path = str(tmp_path / "test")
+    os.makedirs(path)
+    open(os.path.join(path, "stale"), "w").close()                         # prepare_dir wipes an existing directory (:19-26)
+    model_handler.save(model, path)
+    assert sorted(os.listdir(path)) == ["dataframes", "init_args.json", "model", "study"]
+    assert sorted(os.listdir(os.path.join(path, "dataframes"))) == ["fit_items", "fit_users", "item_popularity"]
+    with open(os.path.join(path, "init_args.json")) as f:
+        assert json.load(f) == {"alpha": 0.25, "_model_name": "PopSaved"}
+    loaded = model_handler.load(path)
+    assert isinstance(loaded, PopSaved) and loaded.alpha == 0.25 and loaded.study is None
+    assert loaded.users_count == model.users_count and loaded.items_count == model.items_count
+    pd.testing.assert_frame_equal(loaded.predict(LOG, 2).reset_index(drop=True), base.reset_index(drop=True))
