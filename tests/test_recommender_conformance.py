@@ -208,3 +208,51 @@ def test_save_load_layout_and_equal_preds(tmp_path, monkeypatch):   # test_save_
     assert isinstance(loaded, PopSaved) and loaded.alpha == 0.25 and loaded.study is None
     assert loaded.users_count == model.users_count and loaded.items_count == model.items_count
     pd.testing.assert_frame_equal(loaded.predict(LOG, 2).reset_index(drop=True), base.reset_index(drop=True))
+
+
+LONG_LOG = pd.DataFrame([  # reference fixture `long_log_with_features`, tests/utils.py:77-98
+    [0, 0, datetime(2019, 1, 1), 1.0], [0, 3, datetime(2019, 1, 5), 3.0], [0, 1, datetime(2019, 1, 1), 2.0],
+    [0, 4, datetime(2019, 1, 1), 4.0], [1, 0, datetime(2020, 1, 5), 4.0], [1, 2, datetime(2018, 1, 1), 2.0],
+    [1, 6, datetime(2019, 1, 1), 4.0], [1, 7, datetime(2020, 1, 1), 4.0], [2, 8, datetime(2019, 1, 1), 3.0],
+    [2, 1, datetime(2019, 1, 1), 2.0], [2, 5, datetime(2020, 3, 1), 1.0], [2, 6, datetime(2019, 1, 1), 5.0]],
+    columns=["user_idx", "item_idx", "timestamp", "relevance"])
+
+
+def _fit_predict_selected(model, train_log, inf_log, users):   # test_all_models.py:281-286
+    model.fit(train_log)
+    return model.predict(log=inf_log, users=users, k=1)
+
+
+def test_predict_new_users():   # test_all_models.py:289-317: a user absent from training but present in the predict log
+    model = PopLike()
+    model.can_predict_cold_users = True
+    pred = _fit_predict_selected(model, LONG_LOG[LONG_LOG["user_idx"] != 0], LONG_LOG, [0])
+    assert len(pred) == 1 and pred["user_idx"].iloc[0] == 0
+
+
+def test_predict_cold_users():   # test_all_models.py:320-345: the user appears in neither log
+    model = PopLike()
+    model.can_predict_cold_users = True
+    warm = LONG_LOG[LONG_LOG["user_idx"] != 0]
+    pred = _fit_predict_selected(model, warm, warm, [0])
+    assert len(pred) == 1 and pred["user_idx"].iloc[0] == 0
+
+
+def test_predict_cold_and_new_filter_out():   # test_all_models.py:348-390: models that cannot score cold users drop them
+    model = PopLike()
+    assert model.can_predict_cold_users is False
+    pred = _fit_predict_selected(model, LONG_LOG[LONG_LOG["user_idx"] != 0], LONG_LOG, [0, 3])
+    assert len(pred) == 0
+    model.can_predict_cold_users = True
+    assert 1 <= len(_fit_predict_selected(model, LONG_LOG[LONG_LOG["user_idx"] != 0], LONG_LOG, [0, 3])) <= 2
+
+
+def test_predict_and_predict_pairs_to_file(tmp_path):   # test_all_models.py:393-447
+    model = PopLike()
+    path = str(tmp_path / "pred.parquet")
+    assert model.fit_predict(LONG_LOG, k=10, recs_file_path=path) is None
+    pd.testing.assert_frame_equal(model.predict(LONG_LOG, k=10).reset_index(drop=True), pd.read_parquet(path))
+    pairs = LONG_LOG.loc[LONG_LOG["user_idx"] == 1, ["user_idx", "item_idx"]]
+    path2 = str(tmp_path / "pairs.parquet")
+    assert model.predict_pairs(pairs=pairs, log=LONG_LOG, recs_file_path=path2) is None
+    pd.testing.assert_frame_equal(model.predict_pairs(pairs=pairs, log=LONG_LOG).reset_index(drop=True), pd.read_parquet(path2))
