@@ -248,6 +248,10 @@ class CQL(Recommender):
             table[row, pos] = top["item_idx"].to_numpy().astype(np.int32)
         return self.engine.rank_metrics(table, users, gt_ptr, gt_items, ks)
 
+    def _default_criterion(self):
+        """``optimize`` trials score NDCG@k on the GPU (``cql_rank_metrics``) instead of the pandas criterion."""
+        return lambda recs, test, k: self.evaluate(recs, test, k)["NDCG"][int(k)]
+
     # ------------------------------------------------------------------ persistence (model_handler.py:38, :90)
     def _save_model(self, path: str) -> None:
         os.makedirs(path, exist_ok=True)

@@ -12,8 +12,10 @@ importable) Spark DataFrames; results come back in the flavour of the input.
 from __future__ import annotations
 
 import logging
+import math
 from abc import ABC, abstractmethod
-from typing import Any, Dict, Iterable, Optional, Union
+from copy import deepcopy
+from typing import Any, Callable, Dict, Iterable, List, Optional, Union
 
 import numpy as np
 import pandas as pd
@@ -43,6 +45,111 @@ def get_top_k(df: pd.DataFrame, partition_by: str, order_by: list, ascending: li
 def get_top_k_recs(recs: pd.DataFrame, k: int) -> pd.DataFrame:
     """``replay/utils.py:112-127``.  Spark leaves ties arbitrary; here ties go to the lower item_idx."""
     return get_top_k(recs, "user_idx", ["relevance", "item_idx"], [False, True], k)
+
+
+def ndcg_at_k(recs: pd.DataFrame, ground_truth: pd.DataFrame, k: int) -> float:
+    """Default ``optimize`` criterion: the reference's ``NDCG()(recs, test, k)`` on pandas -- per-user body of
+    ``replay/metrics/ndcg.py:51-61``, users = the ground-truth users with missing predictions counted as zero
+    (``replay/metrics/base_metric.py:102-140``), ``k`` best predictions by ``get_top_k_recs``."""
+    gt = ground_truth.groupby("user_idx")["item_idx"].agg(lambda x: set(x.tolist()))
+    if len(gt) == 0:
+        return 0.0
+    top = get_top_k_recs(recs, k) if len(recs) else recs
+    top = top.sort_values(["user_idx", "relevance", "item_idx"], ascending=[True, False, True], kind="stable")
+    pred = top.groupby("user_idx")["item_idx"].agg(list) if len(top) else pd.Series(dtype=object)
+    total = 0.0
+    for user, truth in gt.items():
+        items = pred.get(user, [])
+        if not items or not truth:
+            continue
+        dcg = sum(1.0 / math.log2(i + 2) for i, item in enumerate(items[:k]) if item in truth)
+        idcg = sum(1.0 / math.log2(i + 2) for i in range(min(k, len(truth))))
+        total += dcg / idcg
+    return total / len(gt)
+
+
+class _Trial:
+    """What ``suggest_params`` needs from an optuna trial (``replay/optuna_objective.py:47-73``)."""
+
+    def __init__(self, rng: np.random.Generator, fixed: Optional[dict] = None):
+        self.rng, self.fixed, self.params, self.value = rng, fixed or {}, {}, None
+
+    def _keep(self, name, value):
+        self.params[name] = self.fixed.get(name, value)
+        return self.params[name]
+
+    def suggest_uniform(self, name, low, high):
+        return self._keep(name, low if low == high else float(self.rng.uniform(low, high)))
+
+    def suggest_loguniform(self, name, low, high):     # a pinned parameter ([v, v]) comes back bit-identical
+        return self._keep(name, low if low == high else float(math.exp(self.rng.uniform(math.log(low), math.log(high)))))
+
+    def suggest_int(self, name, low, high, log=False):
+        if low == high:
+            return self._keep(name, low)
+        if log:
+            return self._keep(name, int(min(high, max(low, round(math.exp(self.rng.uniform(math.log(low), math.log(high + 1)) - 0.5))))))
+        return self._keep(name, int(self.rng.integers(low, high + 1)))
+
+    def suggest_categorical(self, name, choices):
+        return self._keep(name, choices[int(self.rng.integers(len(choices)))])
+
+
+class RandomSearchStudy:
+    """Stand-in for ``optuna.create_study(direction="maximize")`` when optuna is not installed: the same members
+    ``optimize`` touches (``enqueue_trial``, ``optimize(objective, n_trials)``, ``trials[i].params``, ``best_params``,
+    ``best_value``), seeded random sampling instead of TPE.  Picklable, so ``save`` / ``load`` keep it as ``study``."""
+
+    def __init__(self, seed: int = 0):
+        self.rng = np.random.default_rng(seed)
+        self.trials: List[_Trial] = []
+        self._queue: List[dict] = []
+
+    def enqueue_trial(self, params: dict) -> None:
+        self._queue.append(dict(params))
+
+    def optimize(self, objective: Callable, n_trials: int) -> None:
+        for _ in range(n_trials):
+            trial = _Trial(self.rng, self._queue.pop(0) if self._queue else None)
+            trial.value = float(objective(trial))
+            self.trials.append(trial)
+
+    @property
+    def best_trial(self) -> _Trial:
+        if not self.trials:
+            raise ValueError("No trials are completed yet.")
+        return max(self.trials, key=lambda t: t.value)
+
+    @property
+    def best_params(self) -> dict:
+        return dict(self.best_trial.params)
+
+    @property
+    def best_value(self) -> float:
+        return self.best_trial.value
+
+
+def _create_study():
+    try:                                      # the reference's study (base_rec.py:116-119) when optuna is there
+        from optuna import create_study
+        from optuna.samplers import TPESampler
+        return create_study(direction="maximize", sampler=TPESampler())
+    except ImportError:
+        return RandomSearchStudy()
+
+
+def suggest_params(trial, search_space: Dict[str, Dict[str, Any]]) -> Dict[str, Any]:
+    """``replay/optuna_objective.py:47-73``."""
+    suggest = {"uniform": trial.suggest_uniform, "int": trial.suggest_int, "loguniform": trial.suggest_loguniform,
+               "loguniform_int": lambda name, low, high: trial.suggest_int(name, low, high, log=True)}
+    res = {}
+    for param, spec in search_space.items():
+        if spec["type"] == "categorical":
+            res[param] = trial.suggest_categorical(param, spec["args"])
+        else:
+            low, high = spec["args"]
+            res[param] = suggest[spec["type"]](param, low, high)
+    return res
 
 
 class Recommender(ABC):
@@ -94,6 +201,90 @@ class Recommender(ABC):
         for param, value in params.items():
             setattr(self, param, value)
         self._clear_cache()
+
+    # ------------------------------------------------------------ hyper-parameter search (base_rec.py:80-274, 938-952)
+    def _default_criterion(self) -> Callable[[pd.DataFrame, pd.DataFrame, int], float]:
+        return ndcg_at_k
+
+    def optimize(self, train: Any, test: Any, user_features=None, item_features=None,
+                 param_borders: Optional[Dict[str, List[Any]]] = None, criterion: Optional[Callable] = None,
+                 k: int = 10, budget: int = 10, new_study: bool = True) -> Optional[Dict[str, Any]]:
+        """``base_rec.py:80-141``: search ``_search_space`` (narrowed by ``param_borders``) for the parameters that
+        maximise ``criterion(recs, test, k)`` (default NDCG) of ``fit(train)`` + ``predict`` for the test users and
+        items; the initial parameters are tried first if they lie inside the space; the best ones are set on the
+        model and returned."""
+        if self._search_space is None:
+            self.logger.warning("%s has no hyper parameters to optimize", str(self))
+            return None
+        if self.study is None or new_study:
+            self.study = _create_study()
+        search_space = self._prepare_param_borders(param_borders)
+        if self._init_params_in_search_space(search_space) and not self._params_tried():
+            self.study.enqueue_trial({p: v for p, v in self._init_args.items() if p in search_space})
+        train_pd, test_pd = to_pandas(train), to_pandas(test)
+        users = test_pd[["user_idx"]].drop_duplicates()
+        items = test_pd[["item_idx"]].drop_duplicates()
+        metric = criterion if criterion is not None else self._default_criterion()
+
+        def objective(trial) -> float:            # optuna_objective.py:76-134 (eval_quality, scenario_objective_calculator)
+            self.set_params(**suggest_params(trial, search_space))
+            self._fit_wrap(train_pd, user_features, item_features)
+            recs = self._predict_wrap(log=train_pd, k=k, users=users, items=items,
+                                      user_features=user_features, item_features=item_features)
+            return float(metric(recs, test_pd, k))
+
+        self.study.optimize(objective, budget)
+        best_params = self.study.best_params
+        self.set_params(**best_params)
+        return best_params
+
+    def _init_params_in_search_space(self, search_space: Dict[str, Dict[str, Any]]) -> bool:
+        """``base_rec.py:151-182``."""
+        outside = {}
+        for param, value in self._init_args.items():
+            if param not in search_space:
+                continue
+            borders, kind = search_space[param]["args"], search_space[param]["type"]
+            if (kind == "categorical" and value not in borders) or \
+                    (kind != "categorical" and (value < borders[0] or value > borders[1])):
+                outside[param] = {"borders": borders, "value": value}
+        if outside:
+            self.logger.debug("Model is initialized with parameters outside the search space: %s."
+                              "Initial parameters will not be evaluated during optimization."
+                              "Change search spare with 'param_borders' argument if necessary", outside)
+            return False
+        return True
+
+    def _prepare_param_borders(self, param_borders: Optional[Dict[str, List[Any]]] = None) -> Dict[str, Dict[str, Any]]:
+        """``base_rec.py:184-221``: parameters without user borders are pinned to their current value."""
+        search_space = deepcopy(self._search_space)
+        if param_borders is None:
+            return search_space
+        for param, borders in param_borders.items():
+            self._check_borders(param, borders)
+            search_space[param]["args"] = borders
+        args = self._init_args
+        for param in search_space:
+            if param not in param_borders:
+                value = args[param]
+                search_space[param]["args"] = [value] if search_space[param]["type"] == "categorical" else [value, value]
+        return search_space
+
+    def _check_borders(self, param: str, borders: Any) -> None:
+        """``base_rec.py:223-241``."""
+        if param not in self._search_space:
+            raise ValueError(f"Hyper parameter {param} is not defined for {str(self)}")
+        if not isinstance(borders, list):
+            raise ValueError(f"Parameter {param} borders are not a list")
+        if self._search_space[param]["type"] != "categorical" and len(borders) != 2:
+            raise ValueError(f"Hyper parameter {param} is numerical but bounds are not in ([lower, upper]) format")
+
+    def _params_tried(self) -> bool:
+        """``base_rec.py:938-952``."""
+        if self.study is None:
+            return False
+        params = {name: value for name, value in self._init_args.items() if name in self._search_space}
+        return any(params == trial.params for trial in self.study.trials)
 
     def __str__(self) -> str:
         return type(self).__name__
