@@ -173,9 +173,12 @@ def run_reference(args):
         "impl": "reference", "metric": "CQL updates/sec (batch 1024)", "value": rate, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": BATCH, "hidden": 256, "n_critics": 2, "n_action_samples": 10,
+        "config": {"workload": WORKLOAD, "users": 138_493, "items": 26_744, "rows": 20_000_263,
+                   "batch_per_gpu": BATCH, "global_batch": BATCH, "parallelism": "cpu", "grad_exchange": "none",
+                   "hidden": 256, "n_critics": 2, "n_action_samples": 10, "precision": "fp32 (PyTorch CPU)",
                    "note": "CPU oracle = eager PyTorch restatement of d3rlpy CQL._update (d3rlpy and Spark are not "
-                           "installable here); batches pre-built in host memory"},
+                           "installable here); minibatches of the same shape and id ranges pre-built in host memory "
+                           "(the cost of an update does not depend on the log it was sampled from)"},
         "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} updates at batch 1024 after warm-up, torch threads={threads}"},
         "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
