@@ -183,8 +183,9 @@ class CQL(Recommender):
             with torch.cuda.device(eng.device):
                 stepper = DataParallelStepper(eng)          # whole step (kernels + NCCL) as one CUDA graph
                 stepper.stream.wait_stream(torch.cuda.current_stream())
-                stepper.run(total)
-                stepper.stream.synchronize()
+                stepper.run(total)                          # exactly `total` updates (warm-up steps included)
+                stepper.finish()                            # raises if a gradient exchange timed out
+                assert stepper.steps_done == total
             self.last_metrics = eng.read_metrics()
 
     # ------------------------------------------------------------------ predict

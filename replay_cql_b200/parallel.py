@@ -148,6 +148,7 @@ class DataParallelStepper:
         self._warmup = warmup
         self.launches_per_step = 0             # this library's kernel launches inside one captured update
         self.replayed_steps = 0
+        self.eager_steps = 0
 
     def _eager(self, n: int) -> None:
         import torch
@@ -155,10 +156,12 @@ class DataParallelStepper:
             for _ in range(n):
                 self.engine.update_data_parallel(self.reducer, stream=self.stream.cuda_stream,
                                                  uploaded_batch=self.uploaded_batch)
+        self.eager_steps += n
 
     def _capture(self) -> None:
+        """Capture ONE update as a CUDA graph.  No update runs here: the eager warm-up steps (NCCL communicators /
+        lazy state must exist before capture) are taken by ``run`` out of the caller's step budget."""
         import torch
-        self._eager(self._warmup)              # NCCL communicators / lazy state must exist before capture
         self.stream.synchronize()
         g = torch.cuda.CUDAGraph()
         l0 = self.engine.launch_count
@@ -169,9 +172,18 @@ class DataParallelStepper:
         self.graph = g
 
     def run(self, n_steps: int) -> None:
-        """Enqueue ``n_steps`` updates on ``self.stream`` (asynchronous)."""
+        """Enqueue EXACTLY ``n_steps`` updates on ``self.stream`` (asynchronous).  The first ``warmup`` of them run
+        eagerly (they are real updates and count), the rest replay the captured graph."""
         import torch
+        n_steps = int(n_steps)
+        if n_steps <= 0:
+            return
         if self.graph is None:
+            w = min(max(self._warmup - self.eager_steps, 0), n_steps)
+            self._eager(w)
+            n_steps -= w
+            if n_steps == 0:
+                return
             try:
                 self._capture()
             except Exception:                  # capture unsupported in this build: stay eager
@@ -183,3 +195,16 @@ class DataParallelStepper:
             self.replayed_steps += n_steps
         else:
             self._eager(n_steps)
+
+    @property
+    def steps_done(self) -> int:
+        """updates enqueued so far (eager + replayed)"""
+        return self.eager_steps + self.replayed_steps
+
+    def finish(self) -> None:
+        """Wait for the enqueued updates and fail loudly if a peer-memory exchange timed out: after a timeout the
+        ranks no longer hold the same averaged gradients, so the replicas have diverged and training must stop."""
+        self.stream.synchronize()
+        if isinstance(self.reducer, PeerGradExchange) and self.engine.dp_error():
+            raise RuntimeError("data-parallel gradient exchange timed out (a peer rank stalled for too long); "
+                               "replicas are no longer identical -- restart from the last checkpoint")

@@ -200,3 +200,25 @@ def test_gpu_mdp_builder_datetime_and_seeded_noise(engine_factory):
     assert np.array_equal(order, host.order) and np.array_equal(rew, host.rew) and np.array_equal(term, host.term)
     d = act - host.act                       # seeded N(0, 1e-3) draw on the device
     assert 5e-4 < d.std() < 2e-3 and abs(d.mean()) < 2e-4
+
+
+def test_data_parallel_stepper_takes_exactly_n_steps(engine_factory):
+    """the stepper's eager warm-up updates are REAL updates and must come out of the requested budget
+    (the N>1 fit used to take total + 3 steps).  World 1 with a no-op gradient exchange: the 4 phases + graph capture
+    are the product path; the result must be bit-identical to the single-GPU `cql_update` loop of the same length."""
+    from replay_cql_b200.parallel import DataParallelStepper
+    log = make_log("tiny")
+    mdp = build_mdp(log, seed=1)
+    ref = engine_factory(batch_size=64, seed=5, precision="f16x3")
+    ref.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+    ref.update(17)
+    for first, second in ((17, 0), (2, 15), (5, 12)):
+        eng = engine_factory(batch_size=64, seed=5, precision="f16x3")
+        eng.load_transitions(mdp.obs, mdp.act, mdp.rew, mdp.term)
+        stepper = DataParallelStepper(eng, reducer=lambda buffer_id: None)
+        stepper.run(first)
+        stepper.run(second)
+        stepper.finish()
+        assert stepper.steps_done == 17 and stepper.eager_steps == 3
+        assert eng.get_optimizer()[2] == 17
+        assert np.array_equal(eng.get_state(), ref.get_state())
