@@ -424,19 +424,26 @@ __global__ void k_actor_dout(const float* __restrict__ outA, const float* __rest
   const float mu = outA[2 * b], ls_raw = outA[2 * b + 1], ls = clamp_ls(ls_raw);
   const float eps = noise_actor[b];
   const Sample s = policy_sample(mu, ls, eps, squash);
-  const float w = expf(scalars[0]) / (float)B;   // d loss / d logp
+  const float w = __fdiv_rn(expf(scalars[0]), (float)B);   // d loss / d logp
+  // Every product and sum below is rounded separately (no FMA contraction), in autograd's order.  With raw indices
+  // as observations the policy saturates: a = +-1 exactly, 1 - a^2 = 0, and the reference's gradient through the mean
+  // head is EXACTLY zero because -dt/std and +dt/std cancel bit for bit.  A contracted fma(w, t/std, g_raw) leaves the
+  // product's rounding residue (~1e-7 of the batch gradient) instead, which the first Adam steps normalise to full
+  // +-lr moves on weights whose true gradient is zero.
   const float one_m_a2 = __fsub_rn(1.f, __fmul_rn(s.a, s.a));
-  float g_raw = w * (-s.t / s.std_);
+  const float dt_std = __fmul_rn(w, __fdiv_rn(s.t, s.std_));     // -(d loss / d t) / std = w t / std
+  float g_tanh;                                                  // d loss / d raw through the squashing terms
   if (squash == CQL_SQUASH_EPS) {
-    const float g_a = da + w * (2.f * s.a / __fadd_rn(one_m_a2, 1e-6f));
-    g_raw += g_a * one_m_a2;
+    const float g_a = __fadd_rn(da, __fmul_rn(w, __fdiv_rn(__fmul_rn(2.f, s.a), __fadd_rn(one_m_a2, 1e-6f))));
+    g_tanh = __fmul_rn(g_a, one_m_a2);
   } else {
-    const float sig = 1.f / (1.f + expf(2.f * s.raw));  // sigmoid(-2 raw)
-    g_raw += w * (2.f - 4.f * sig) + da * one_m_a2;
+    const float sig = __fdiv_rn(1.f, __fadd_rn(1.f, expf(__fmul_rn(2.f, s.raw))));  // sigmoid(-2 raw)
+    g_tanh = __fadd_rn(__fmul_rn(w, __fsub_rn(2.f, __fmul_rn(4.f, sig))), __fmul_rn(da, one_m_a2));
   }
-  const float g_mu = g_raw + w * (s.t / s.std_);
-  const float g_std = g_raw * eps + w * (s.t * s.t / s.std_);
-  const float g_ls = g_std * s.std_ - w;
+  const float g_raw = __fadd_rn(g_tanh, -dt_std);                // tanh branch + (raw - mu) / std branch
+  const float g_mu = __fadd_rn(g_raw, dt_std);                   // raw = mu + std eps  and  -(raw - mu) / std
+  const float g_std = __fadd_rn(__fmul_rn(g_raw, eps), __fmul_rn(w, __fdiv_rn(__fmul_rn(s.t, s.t), s.std_)));
+  const float g_ls = __fsub_rn(__fmul_rn(g_std, s.std_), w);
   dOutA[2 * b] = g_mu;
   dOutA[2 * b + 1] = (ls_raw >= -20.f && ls_raw <= 2.f) ? g_ls : 0.f;
 }

@@ -46,7 +46,7 @@ class CqlHyperParams:
     beta1: float = 0.9
     beta2: float = 0.999
     adam_eps: float = 1e-8
-    precision: str = "fp32"
+    precision: str = "f16x3"   # tcgen05 fp16 hi/lo 3-term split, FP32-grade (1e-4 gates); "fp32" = CUDA-core FMA
     squash: str = "eps"
     seed: int = 12345
 

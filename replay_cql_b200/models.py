@@ -63,7 +63,7 @@ class CQL(Recommender):
         n_action_samples: int = 10,
         soft_q_backup: bool = False,
         use_gpu: bool = True,
-        precision: str = "fp32",
+        precision: str = "f16x3",
         score: str = "q",
         squash: str = "eps",
         seed: int = 12345,
