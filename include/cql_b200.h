@@ -222,6 +222,12 @@ int  cql_timed_update(cql_handle* h, float* out_ms8, void* stream);
 int  cql_selftest_umma(cql_handle* h, int precision, const float* A_host, const float* B_host,
                        int n, int k, float* D_host);
 
+/* Measurement aid: issue rate of back-to-back tcgen05.mma kind::f16 K=16 instructions.
+ * mode bit 0: A operand in tensor memory (else shared memory); bit 1: N = 256 (else 128); bit 2: cta_group::2 on a
+ * CTA pair, M = 256 (else one CTA, M = 128); bit 3: alternate operand addresses in the 3-term pattern.
+ * out_clk2[0] = SM clocks to ISSUE `iters` MMAs, [1] = clocks until the last one has retired. */
+int  cql_mma_bench(cql_handle* h, int mode, int iters, int64_t* out_clk2);
+
 /* number of kernels this library has launched on the handle (bench "gpu_launches") */
 int64_t cql_launch_count(const cql_handle* h);
 

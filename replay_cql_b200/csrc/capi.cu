@@ -11,6 +11,7 @@
 #include "topk_staged.cuh"
 #include "metrics.cuh"
 #include "dp_peer.cuh"
+#include "mma_bench.cuh"
 
 using namespace cql;
 
@@ -88,6 +89,11 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2Cfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2Cfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h2_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2B1Cfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h2_kernel<3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2B1Cfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h2_kernel<2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2B1Cfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_ts_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_ts_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TsCfg::SMEM_BYTES));
@@ -193,6 +199,12 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
     h.part = h.dalloc<float>(h.part_floats);
     h.tc_slices = slices;
     h.packed_bwd = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes_bwd);
+    if (f16) {
+      h.packed_net_bytes2 = tc::H2Cfg::PACKED_NET_BYTES;
+      h.packed_fwd2 = h.dalloc<uint8_t>((size_t)(2 + 2 * C) * h.packed_net_bytes2);
+      h.packed_bwd2 = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes2);
+      if (const char* sw = std::getenv("CQL_PAIR_SWAP")) h.pair_swap_b = std::atoi(sw);
+    }
     h.slots1 = (f16 ? tc::HCfg::NEW : 4) * h.num_sms;
     h.splits_tc = h.num_sms;
     h.small1 = h.dalloc<float>((size_t)C * h.slots1 * SMALL_STRIDE);
@@ -569,6 +581,32 @@ int cql_selftest_umma(cql_handle* ch, int precision, const float* A_host, const 
   });
 }
 
+int cql_mma_bench(cql_handle* ch, int mode, int iters, int64_t* out_clk2) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(out_clk2 && iters > 0 && mode >= 0 && mode < 16, "cql_mma_bench: bad arguments");
+    long long* d = nullptr;
+    CQL_CUDA(cudaMalloc(&d, 16));
+    const size_t smem = 64 * 1024 + 64;
+    CQL_CUDA(cudaFuncSetAttribute(tc::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    const bool pair = mode & 4;
+    cfg.gridDim = dim3(pair ? 2 : 1); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = h.own_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    CQL_CUDA(cudaLaunchKernelEx(&cfg, tc::mma_bench_kernel, mode, iters, d));
+    CQL_LAUNCH_CHECK(&h);
+    long long hst[2];
+    CQL_CUDA(cudaStreamSynchronize(h.own_stream));
+    CQL_CUDA(cudaMemcpy(hst, d, 16, cudaMemcpyDeviceToHost));
+    CQL_CUDA(cudaFree(d));
+    out_clk2[0] = hst[0]; out_clk2[1] = hst[1];
+  });
+}
+
 int cql_timed_update(cql_handle* ch, float* out_ms8, void* stream) {
   return guarded(ch, [&] {
     Handle& h = ch->h;
@@ -578,13 +616,16 @@ int cql_timed_update(cql_handle* ch, float* out_ms8, void* stream) {
     for (int i = 0; i < 13; ++i)
       if (!h.ev[i]) CQL_CUDA(cudaEventCreate(&h.ev[i]));
     h.timing = true;
+    g_timing_no_pdl = true;      // events between kernels only separate their durations without PDL overlap
     try {
       run_full_step(&h, st, BatchSource::Sampled, NoiseSource::Philox);
     } catch (...) {
       h.timing = false;
+      g_timing_no_pdl = false;
       throw;
     }
     h.timing = false;
+    g_timing_no_pdl = false;
     CQL_CUDA(cudaStreamSynchronize(st));
     auto ms = [&](int a, int b) { float t = 0.f; CQL_CUDA(cudaEventElapsedTime(&t, h.ev[a], h.ev[b])); return t; };
     out_ms8[0] = ms(3, 4); out_ms8[1] = ms(5, 6); out_ms8[2] = ms(6, 7); out_ms8[3] = ms(0, 12);

@@ -1,0 +1,809 @@
+// mlp_tc_h2.cuh -- the f16x3 hidden-layer kernels on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Why: in the one-CTA kernels (mlp_tc_h.cuh) a 128-row H1 tile is generated TWICE -- once per 128-column W2 slice,
+// because a whole W2 (256 columns, fp16 hi|lo = 256 KB) does not fit one SM's shared memory -- and that CUDA-core
+// operand generation, not the tensor pipe, bounds them (ncu r01: 62 % of all executed instructions are the producers',
+// tensor pipe 45 %).  A CTA pair holds W2 JOINTLY: each CTA keeps 64 of the 128 operand rows of either pass
+// (2 passes x hi|lo x 64 rows x 256 K = 128 KB per CTA), and one `tcgen05.mma.cta_group::2` of shape
+// M = 256 (128 rows per CTA), N = 128 reads both halves.  Each CTA's producers therefore generate its 128-row
+// H1 tile ONCE (into its own tensor memory, 4 stages of 64 K = the whole K = 256) and the tile feeds both passes:
+//   pass 0: D[:, 0:128]   += A(chunks 0..3) x W2[0:128, :]^T     (stages stay full)
+//   pass 1: D[:, 128:256] += A(chunks 0..3) x W2[128:256, :]^T   (each stage is released after its pass-1 MMAs)
+// The two 128-column accumulators are drained by two epilogue groups, each while the OTHER pass computes, so the
+// tensor pipe does not wait for an epilogue; producers refill stage c of the next tile while pass 1 still runs.
+//
+// Roles per CTA (800 threads): warps 0-7 epilogue (group g = pass g), 8-23 producers, 24 = MMA issuer in the leader
+// CTA (cluster rank 0) / W2 loader in the peer.  Cross-CTA signalling: producers and epilogue warps of the peer
+// arrive on the LEADER's mbarriers through `mapa` + `mbarrier.arrive.shared::cluster`; the leader's
+// `tcgen05.commit ... multicast::cluster` arrives on the same barrier offset in BOTH CTAs.
+#pragma once
+#include "mlp_tc_h.cuh"
+
+namespace cql {
+namespace tc {
+
+// ---- cluster / cta_group::2 PTX wrappers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster (the CUTLASS ClusterBarrier form).
+// No cluster-scope release/acquire qualifiers on purpose: what the barriers order here lives in tensor memory and in
+// the async proxy (tcgen05.st / tcgen05.mma / bulk copies, ordered by tcgen05.wait + tcgen05.fence), and an
+// `.acquire.cluster` wait makes ptxas emit CCTL.IVALL -- an L1 invalidation -- after EVERY wait (measured: the pair
+// kernel was slower than the one-CTA kernel with them).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {   // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, 256 x N over the pair] (+)= A[tmem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T ; leader CTA issues
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// all MMAs issued so far arrive (once complete) on the barrier at this offset in the CTAs of `mask`
+__device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// x (scaled; ReLU NOT yet applied) -> fp16 hi and lo of relu(x): hi = x truncated to 11 significant bits (mask), lo =
+// x - hi (same sign as x: truncation is toward zero), both converted with .relu -- a negative x gives hi = lo = +0, so
+// the two FMNMX of the plain path are folded into the conversions (the ALU pipe is the producers' busiest).
+__device__ __forceinline__ void split_h2_trunc_relu(float2 x, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+  float2 l;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(l.x), "=f"(l.y)
+      : "f"(x.x), "f"(x.y), "f"(h0), "f"(h1));
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h1), "f"(h0));     // first source -> upper half
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l.y), "f"(l.x));
+}
+
+struct H2Cfg {
+  static constexpr int NPW = 16, NEW = 8;
+  static constexpr int KC = 64, STAGES = 4, NCHUNK = H / KC, UK = 16;
+  static constexpr int KPW = KC / (NPW / 4);             // 16 K elements per producer warp per stage
+  static constexpr int NP = 128;                         // output columns per pass (UMMA N)
+  static constexpr int NLOC = NP / 2;                    // operand rows of a pass held by ONE CTA
+  static constexpr int PASSES = H / NP;                  // 2
+  static constexpr int TMP = 2 * TM;                     // rows per pair tile (UMMA M)
+  static constexpr int MMA_WARP = NEW + NPW;
+  static constexpr int THREADS = (NEW + NPW + 1) * 32;   // 800
+  static constexpr int PROD_THREADS = NPW * 32;
+  static constexpr uint32_t B_TERM_BYTES = NLOC * H * 2;             // 32 KB
+  static constexpr uint32_t B_PASS_BYTES = 2 * B_TERM_BYTES;         // 64 KB (hi | lo)
+  static constexpr uint32_t B_BYTES = PASSES * B_PASS_BYTES;         // 128 KB per CTA
+  // packed net (global): [cta rank 2][pass 2][term 2][kchunk 32][64 rows][16 B], then HMeta
+  static constexpr size_t META_OFF = 2 * (size_t)B_BYTES;
+  static constexpr size_t PACKED_NET_BYTES = META_OFF + 2048;
+  static constexpr uint32_t A_COL0 = 256, A_STAGE_COLS = KC, A_LO_COLS = KC / 2;
+  static constexpr uint32_t OFF_B = 0;
+  static constexpr uint32_t OFF_W1 = B_BYTES;                        // float4[256] pair-packed W1|b1
+  static constexpr uint32_t OFF_EB = OFF_W1 + H * 16;                // float4[2 passes][128]: b2, w3_0, w3_1, 1/s_n
+  static constexpr uint32_t OFF_EF = OFF_EB + PASSES * NP * 16;      // float2[2 passes][128] folded constants
+  static constexpr uint32_t OFF_BAR = OFF_EF + PASSES * NP * 8;
+  static constexpr uint32_t N_BARS = 2 * STAGES + 2 + 2 + 3;         // full, empty, tfull, tempty, bload, bready, drain
+  static constexpr uint32_t OFF_SLOT = OFF_BAR + N_BARS * 8;
+  static constexpr uint32_t SMEM_BYTES = OFF_SLOT + 16;
+};
+
+// byte offset of the 16-byte chunk (operand row n of 256, K chunk kc, term) inside a pair-packed net
+__host__ __device__ constexpr size_t pair_chunk_off(int n, int kc, int term) {
+  return (size_t)((n & 127) >> 6) * H2Cfg::B_BYTES + (size_t)(n >> 7) * H2Cfg::B_PASS_BYTES +
+         (size_t)term * H2Cfg::B_TERM_BYTES + chunk_off(H2Cfg::NLOC, n & 63, kc);
+}
+
+// Same packing as k_pack_multi_h (one warp per operand row: row maximum -> exact power-of-two scale, fp16 hi|lo) into
+// the pair layout.  transpose: 0 -> B[n][k] = W2[n][k] (forward), 1 -> B[n][k] = W2[k][n] (dH1 = dZ2 W2).
+__global__ void __launch_bounds__(256) k_pack_pair_h(const PackJobs jobs, int out_dim_actor) {
+  grid_dep_wait();
+  using C = H2Cfg;
+  const PackJobs::J jb = jobs.j[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;        // 16-byte chunk id: n * 32 + kc
+  const int n = c >> 5, kc = c & 31;
+  const float* W2 = jb.net + off_W2(jb.in_dim);
+  float v[8];
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = kc * 8 + i;
+    v[i] = jb.transpose ? W2[(size_t)k * H + n] : W2[(size_t)n * H + k];
+    mx = fmaxf(mx, fabsf(v[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float s, inv_s;
+  pow2_scale(mx, s, inv_s);
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_h2(v[2 * i] * s, v[2 * i + 1] * s, hi[i], lo[i]);
+  *reinterpret_cast<uint4*>(jb.dst + pair_chunk_off(n, kc, 0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(jb.dst + pair_chunk_off(n, kc, 1)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  HMeta* meta = reinterpret_cast<HMeta*>(jb.dst + C::META_OFF);
+  if (kc == 0) meta->inv_s[n] = inv_s;
+  if (blockIdx.x == 0) {                                      // maxima of the small layers (scales of the A rows)
+    __shared__ int wm[8];
+    if (threadIdx.x < 8) wm[threadIdx.x] = 0;
+    __syncthreads();
+    const int out_dim = jb.in_dim == 2 ? out_dim_actor : 1;
+    const int k = threadIdx.x;
+    const float* W1 = jb.net + off_W1(jb.in_dim);
+    for (int cc = 0; cc < jb.in_dim; ++cc) atomicMax(&wm[cc], __float_as_int(fabsf(W1[k * jb.in_dim + cc])));
+    atomicMax(&wm[3], __float_as_int(fabsf(jb.net[off_b1(jb.in_dim) + k])));
+    for (int o = 0; o < out_dim; ++o) atomicMax(&wm[4 + o], __float_as_int(fabsf(jb.net[off_W3(jb.in_dim) + o * H + k])));
+    __syncthreads();
+    if (threadIdx.x < 8) meta->wmax[threadIdx.x] = __int_as_float(wm[threadIdx.x]);
+  }
+}
+
+// pair items: (job, net, pair tile of 256 rows); a cluster takes a contiguous, cost-balanced range
+struct H2Item { int job, net, tp, netkey; };
+__device__ __forceinline__ int pair_tiles(int rows) { return (rows + H2Cfg::TMP - 1) / H2Cfg::TMP; }
+__device__ __forceinline__ H2Item decode_item_h2(const TcFwdJobs& jobs, const int* pbeg, int item) {
+  H2Item it;
+  it.job = 0;
+  while (it.job + 1 < jobs.n && item >= pbeg[it.job + 1]) ++it.job;
+  const int local = item - pbeg[it.job];
+  const int tiles = pair_tiles(jobs.j[it.job].rows);
+  it.net = local / tiles;
+  it.tp = local % tiles;
+  it.netkey = it.job * 64 + it.net;
+  return it;
+}
+
+template <int IN, int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) tc_fwd_h2_kernel(const TcFwdJobs jobs, int swap_b) {
+  using C = H2Cfg;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint8_t* Bs = sm + C::OFF_B;
+  float4* w1p = reinterpret_cast<float4*>(sm + C::OFF_W1);
+  float4* ebs = reinterpret_cast<float4*>(sm + C::OFF_EB);
+  float2* efs = reinterpret_cast<float2*>(sm + C::OFF_EF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+  uint64_t* full = bars;                         // [STAGES] leader: 2 x NPW producer warps
+  uint64_t* empty = bars + C::STAGES;            // [STAGES] both CTAs: multicast commit
+  uint64_t* tfull = bars + 2 * C::STAGES;        // [2] both CTAs: multicast commit
+  uint64_t* tempty = tfull + 2;                  // [2] leader: 2 x 4 epilogue warps
+  uint64_t* bload = tempty + 2;                  // own W2 half landed
+  uint64_t* bready = bload + 1;                  // leader: both halves landed
+  uint64_t* drain = bready + 1;                  // both CTAs: every MMA issued so far has retired
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  // contiguous pair-item range of this cluster, balanced by cost (items that store H2 are more expensive)
+  int pbeg[4];
+  int item_lo, item_hi;
+  {
+    long long cb[4];
+    int wj[3];
+    cb[0] = 0;
+    pbeg[0] = 0;
+    for (int j = 0; j < jobs.n; ++j) {
+      pbeg[j + 1] = pbeg[j] + jobs.j[j].n_nets * pair_tiles(jobs.j[j].rows);
+      wj[j] = jobs.j[j].h2 != nullptr ? (jobs.h2_cost > 0 ? jobs.h2_cost : FWD_H2_COST) : 10;
+      cb[j + 1] = cb[j] + (long long)(pbeg[j + 1] - pbeg[j]) * wj[j];
+    }
+    auto item_at = [&](long long cost) {
+      int j = 0;
+      while (j + 1 < jobs.n && cost >= cb[j + 1]) ++j;
+      const int it = pbeg[j] + (int)((cost - cb[j]) / wj[j]);
+      return it < pbeg[j + 1] ? it : pbeg[j + 1];
+    };
+    const long long total_cost = cb[jobs.n];
+    item_lo = cluster_id == 0 ? 0 : item_at(total_cost * cluster_id / n_clusters);
+    item_hi = cluster_id == n_clusters - 1 ? pbeg[jobs.n] : item_at(total_cost * (cluster_id + 1) / n_clusters);
+  }
+
+  if (warp == C::MMA_WARP) {
+    tmem_alloc2(slot, 512);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 2 * C::NPW); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+      mbar_init(bload, 1);
+      mbar_init(bready, 2);
+      mbar_init(drain, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();           // both CTAs' barriers are initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  grid_dep_wait();              // everything above overlapped the predecessor's tail (programmatic dependent launch)
+
+  if (warp == C::MMA_WARP) {
+    // ============ leader: W2-half loader + MMA issuer;  peer: W2-half loader ============
+    const uint32_t idesc = instr_desc(FMT_F16, C::TMP, C::NP);
+    const uint32_t b_lbo = C::NLOC * 16;
+    const uint32_t b_base = smem_u32(Bs);
+    int cur_key = -1;
+    uint32_t nb = 0, nd = 0, tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const H2Item ii = decode_item_h2(jobs, pbeg, item);
+      if (ii.netkey != cur_key) {
+        if (cur_key >= 0) {                         // the old W2 must not be overwritten while MMAs still read it
+          if (leader && elect_one()) umma_commit2(drain, 3);
+          __syncwarp();
+          mbar_wait_cluster(drain, nd & 1);
+          ++nd;
+        }
+        const TcFwdJob& jb = jobs.j[ii.job];
+        const uint8_t* src = jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + (size_t)(rank ^ (uint32_t)swap_b) * C::B_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bload, C::B_BYTES);
+          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+        }
+        __syncwarp();
+        mbar_wait(bload, nb & 1);
+        if (elect_one()) mbar_arrive_cluster(bready, 0);
+        __syncwarp();
+        if (leader) mbar_wait_cluster(bready, nb & 1);
+        ++nb;
+        cur_key = ii.netkey;
+      }
+      if (!leader) continue;
+      for (int p = 0; p < C::PASSES; ++p) {
+        mbar_wait_cluster(&tempty[p], (tcount & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + p * C::NP;
+        const uint32_t bp = b_base + p * C::B_PASS_BYTES;
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          if (p == 0) {
+            mbar_wait_cluster(&full[c], tcount & 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint32_t a_stage = tmem + C::A_COL0 + c * C::A_STAGE_COLS;
+#pragma unroll
+            for (int j = 0; j < C::KC / C::UK; ++j) {
+              const uint32_t g = c * (C::KC / C::UK) + j;
+              const uint64_t b_hi = smem_desc(bp + 2 * g * b_lbo, b_lbo, 128);
+              const uint64_t b_lo = smem_desc(bp + C::B_TERM_BYTES + 2 * g * b_lbo, b_lbo, 128);
+              const uint32_t a_hi = a_stage + j * 8, a_lo = a_hi + C::A_LO_COLS;
+              umma_ts2(d_tmem, a_lo, b_hi, idesc, (c == 0 && j == 0) ? 0u : 1u);
+              umma_ts2(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_ts2(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            if (p == C::PASSES - 1) umma_commit2(&empty[c], 3);      // stage reusable in both CTAs
+            if (c == C::NCHUNK - 1) umma_commit2(&tfull[p], 3);      // accumulator p complete in both CTAs
+          }
+          __syncwarp();
+        }
+      }
+      ++tcount;
+    }
+  } else if (warp >= C::NEW) {
+    // ============ producers (both CTAs): layer 1 of the CTA's 128 rows -> scaled fp16 hi|lo -> own TMEM ============
+    const int pw = warp - C::NEW, ptid = tid - C::NEW * 32;
+    const int kq = pw >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + kq * (C::KPW / 2);
+    int cur_key = -1;
+    float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t tcount = 0;
+    auto load_x = [&](const H2Item& ni) {
+      const TcFwdJob& nj = jobs.j[ni.job];
+      const int r = ni.tp * C::TMP + (int)rank * TM + (warp & 3) * 32 + lane;
+      return r < nj.rows ? __ldg(nj.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 x_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    H2Item ii_next = item_lo < item_hi ? decode_item_h2(jobs, pbeg, item_lo) : H2Item{};
+    for (int item = item_lo; item < item_hi; ++item, ++tcount) {
+      const H2Item ii = ii_next;
+      if (item + 1 < item_hi) ii_next = decode_item_h2(jobs, pbeg, item + 1);
+      const TcFwdJob& jb = jobs.j[ii.job];
+      if (ii.netkey != cur_key) {
+        cur_key = ii.netkey;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+        const float* net = jb.params + (size_t)ii.net * NET_STRIDE;
+        for (int pr = ptid; pr < H / 2; pr += C::PROD_THREADS) {
+          const int k = 2 * pr;
+          const float* wa = net + off_W1(IN) + k * IN;
+          const float* wb = wa + IN;
+          w1p[2 * pr] = make_float4(wa[0], wb[0], wa[1], wb[1]);
+          w1p[2 * pr + 1] = make_float4(IN == 3 ? wa[2] : 0.f, IN == 3 ? wb[2] : 0.f, net[off_b1(IN) + k], net[off_b1(IN) + k + 1]);
+        }
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
+        wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+      }
+      const float4 x = (item == item_lo) ? load_x(ii) : x_next;
+      if (item + 1 < item_hi) x_next = load_x(ii_next);
+      float sa, inv_sa;
+      pow2_scale(h1_row_bound(x, wm), sa, inv_sa);
+      const float2 xx = make_float2(x.x, x.x), xy = make_float2(x.y, x.y), xz = make_float2(x.z, x.z), ss = make_float2(sa, sa);
+      for (int c = 0; c < C::NCHUNK; ++c) {
+        uint32_t hi[C::KPW / 2], lo[C::KPW / 2];
+#pragma unroll
+        for (int pp = 0; pp < C::KPW / 2; ++pp) {
+          const int pr = (c * C::KC + kq * C::KPW) / 2 + pp;
+          const float4 wA = w1p[2 * pr], wB = w1p[2 * pr + 1];
+          float2 v = ffma2(xx, make_float2(wA.x, wA.y), make_float2(wB.z, wB.w));   // chain starts from the bias
+          v = ffma2(xy, make_float2(wA.z, wA.w), v);
+          if (IN == 3) v = ffma2(xz, make_float2(wB.x, wB.y), v);
+          split_h2_trunc_relu(fmul2(v, ss), hi[pp], lo[pp]);                         // exact: power-of-two scale; ReLU in the cvt
+        }
+        mbar_wait_cluster(&empty[c], (tcount & 1) ^ 1);           // values are ready before the stage is: wait late
+        tc_fence_after();
+        tmem_st8(lane_base + c * C::A_STAGE_COLS, hi);
+        tmem_st8(lane_base + c * C::A_STAGE_COLS + C::A_LO_COLS, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&full[c], 0);
+      }
+    }
+    // the leader's last multicast commits land in THIS CTA's barriers: do not exit before they have
+    if (item_hi > item_lo)
+      for (int c = 0; c < C::NCHUNK; ++c) mbar_wait_cluster(&empty[c], (tcount & 1) ^ 1);
+  } else {
+    // ============ epilogue (both CTAs): group g drains pass g: unscale -> +b2 -> ReLU -> layer 3 (+ H2) ============
+    const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;
+    float4* ebg = ebs + grp * C::NP;
+    float2* efg = efs + grp * C::NP;
+    int cur_key = -1;
+    const int row_in_tile = (int)rank * TM + qw * 32 + lane;
+    float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item, ++tcount) {
+      const H2Item ii = decode_item_h2(jobs, pbeg, item);
+      const TcFwdJob& jb = jobs.j[ii.job];
+      if (ii.netkey != cur_key) {
+        cur_key = ii.netkey;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        const float* net = jb.params + (size_t)ii.net * NET_STRIDE;
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
+        for (int cidx = gtid; cidx < C::NP; cidx += 128) {
+          const int col = grp * C::NP + cidx;
+          const float inv_n = __ldg(&meta->inv_s[col]);
+          ebg[cidx] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col],
+                                  OUT == 2 ? net[off_W3(IN) + H + col] : 0.f, inv_n);
+          // folded form for items that do not store H2 (exact, powers of two):
+          // relu(v/(s_m s_n) + b2) w3 = relu(v/s_m + b2 s_n) (w3/s_n)
+          if (OUT == 1) {                 // pairs of columns: (b2'_c, b2'_c+1, w3'_c, w3'_c+1) -- natural fp32x2 operands
+            float* ef = reinterpret_cast<float*>(efg) + (cidx >> 1) * 4 + (cidx & 1);
+            ef[0] = net[off_b2(IN) + col] / inv_n;
+            ef[2] = net[off_W3(IN) + col] * inv_n;
+          }
+        }
+        wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+      }
+      const int row = ii.tp * C::TMP + row_in_tile;
+      const float4 x = row < jb.rows ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float sa, inv_sa;
+      pow2_scale(h1_row_bound(x, wm), sa, inv_sa);                 // the producers' scale of this row, recomputed
+      mbar_wait_cluster(&tfull[grp], tcount & 1);
+      tc_fence_after();
+      const bool store_h2 = jb.h2 != nullptr;
+      const int tiles64 = (jb.rows + 63) / 64;
+      float* h2row = store_h2 ? jb.h2 + (((size_t)ii.net * tiles64 + (row >> 6)) * H + grp * C::NP) * 64 + (row & 63)
+                              : nullptr;
+      const uint32_t t_acc = tmem + ((uint32_t)(qw * 32) << 16) + grp * C::NP;
+      float q0 = 0.f, q1 = 0.f;
+      // The per-column constants are warp-uniform shared-memory loads.  They are fetched in BATCHES (8 x LDS.128 issued
+      // back to back, together with the TMEM load) before the math of a step: interleaved one by one each LDS exposed
+      // its ~30-clock latency inside the dependent chain and a 128-column epilogue took ~6 k clocks (ncu r02), three
+      // times the 3 k clocks the other pass leaves it.
+      if (OUT == 1 && !store_h2) {
+        const float2 isa2 = make_float2(inv_sa, inv_sa);
+        const float4* ef4 = reinterpret_cast<const float4*>(efg);   // [64]: (b2'_c, b2'_c+1, w3'_c, w3'_c+1)
+        float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::NP; c0 += 16) {
+          float v[16];
+          float4 e[8];
+          tmem_ld16(t_acc + c0, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = ef4[(c0 >> 1) + j];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float2 ha = ffma2(make_float2(v[2 * j], v[2 * j + 1]), isa2, make_float2(e[j].x, e[j].y));
+            float2 hb = ffma2(make_float2(v[2 * j + 2], v[2 * j + 3]), isa2, make_float2(e[j + 1].x, e[j + 1].y));
+            ha.x = fmaxf(ha.x, 0.f); ha.y = fmaxf(ha.y, 0.f);
+            hb.x = fmaxf(hb.x, 0.f); hb.y = fmaxf(hb.y, 0.f);
+            qa = ffma2(ha, make_float2(e[j].z, e[j].w), qa);
+            qb = ffma2(hb, make_float2(e[j + 1].z, e[j + 1].w), qb);
+          }
+        }
+        q0 = (qa.x + qa.y) + (qb.x + qb.y);
+      } else {
+        float q0b = 0.f, q1b = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::NP; c0 += 8) {
+          float v[8];
+          float4 e[8];
+          tmem_ld8(t_acc + c0, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ebg[c0 + i];
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float ha = fmaxf(fmaf(v[i] * inv_sa, e[i].w, e[i].x), 0.f);
+            const float hb = fmaxf(fmaf(v[i + 1] * inv_sa, e[i + 1].w, e[i + 1].x), 0.f);
+            v[i] = ha;
+            v[i + 1] = hb;
+            q0 = fmaf(ha, e[i].y, q0);
+            q0b = fmaf(hb, e[i + 1].y, q0b);
+            if (OUT == 2) { q1 = fmaf(ha, e[i].z, q1); q1b = fmaf(hb, e[i + 1].z, q1b); }
+          }
+          if (store_h2 && (row >> 6) < tiles64) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h2row[(size_t)(c0 + i) * 64] = v[i];
+          }
+        }
+        q0 += q0b;
+        q1 += q1b;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty[grp], 0);
+      if (row < jb.rows) {
+        float* o = jb.out_part + (((size_t)ii.net * C::PASSES + grp) * jb.rows + row) * OUT;
+        o[0] = q0;
+        if (OUT == 2) o[1] = q1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();           // the peer's TMEM / barriers stay alive until the leader's last MMA has retired
+  if (warp == C::MMA_WARP) tmem_dealloc2(tmem, 512);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Input gradient of the hidden layer on CTA pairs: dH1 = dZ2 W2 (A = the CTA's 128 dZ2 rows, generated ONCE per pair
+// tile from dOut, W3 and the stored H2; B = W2^T in the pair layout), then dZ1 = dH1 * relu'(Z1), dW1/db1 column sums
+// and (optionally) dx -- the epilogue of tc_bwd1_h_kernel, group g on the columns of pass g.
+struct H2B1Cfg : H2Cfg {
+  static constexpr uint32_t OFF_W3 = B_BYTES;                        // float2[256] (W3[0][j], W3[1][j])
+  static constexpr uint32_t OFF_EB = OFF_W3 + H * 8;                 // float4[2 passes][128]: W1[k][0..2], b1[k]
+  static constexpr uint32_t OFF_IV = OFF_EB + PASSES * NP * 16;      // float[2][128] 1/s_n
+  static constexpr uint32_t OFF_BAR = OFF_IV + PASSES * NP * 4;
+  static constexpr uint32_t OFF_SLOT = OFF_BAR + 128;                // (N_BARS * 8 = 120, rounded up: what follows holds float4)
+  static constexpr uint32_t OFF_FLUSH = OFF_SLOT + 16;               // float[2 groups][4 warps][16][32]
+  static constexpr uint32_t OFF_RED = OFF_FLUSH + 2 * 4 * 16 * 32 * 4;
+  static constexpr uint32_t RED_WARP_BYTES = 32 * 33 * 4 + 32 * 16;
+  static constexpr uint32_t SMEM_BYTES = OFF_RED + NEW * RED_WARP_BYTES;
+};
+
+template <int IN, int OUT, bool WGRADS, bool DX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) tc_bwd1_h2_kernel(const Bwd1Job jb, int swap_b) {
+  using C = H2B1Cfg;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint8_t* Bs = sm + C::OFF_B;
+  float2* w3s = reinterpret_cast<float2*>(sm + C::OFF_W3);
+  float4* ebs = reinterpret_cast<float4*>(sm + C::OFF_EB);
+  float* invs = reinterpret_cast<float*>(sm + C::OFF_IV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bload = tempty + 2;
+  uint64_t* bready = bload + 1;
+  uint64_t* drain = bready + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int tiles = pair_tiles(jb.rows);
+  const int tiles64 = (jb.rows + 63) / 64;
+  const int total = jb.n_nets * tiles;
+  const int item_lo = (int)((long long)total * cluster_id / n_clusters);
+  const int item_hi = (int)((long long)total * (cluster_id + 1) / n_clusters);
+
+  if (warp == C::MMA_WARP) {
+    tmem_alloc2(slot, 512);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 2 * C::NPW); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+      mbar_init(bload, 1);
+      mbar_init(bready, 2);
+      mbar_init(drain, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  grid_dep_wait();
+
+  if (warp == C::MMA_WARP) {
+    const uint32_t idesc = instr_desc(FMT_F16, C::TMP, C::NP);
+    const uint32_t b_lbo = C::NLOC * 16;
+    const uint32_t b_base = smem_u32(Bs);
+    int cur_net = -1;
+    uint32_t nb = 0, nd = 0, tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int net_i = item / tiles;
+      if (net_i != cur_net) {
+        if (cur_net >= 0) {
+          if (leader && elect_one()) umma_commit2(drain, 3);
+          __syncwarp();
+          mbar_wait_cluster(drain, nd & 1);
+          ++nd;
+        }
+        const uint8_t* src = jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + (size_t)(rank ^ (uint32_t)swap_b) * C::B_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bload, C::B_BYTES);
+          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
+        }
+        __syncwarp();
+        mbar_wait(bload, nb & 1);
+        if (elect_one()) mbar_arrive_cluster(bready, 0);
+        __syncwarp();
+        if (leader) mbar_wait_cluster(bready, nb & 1);
+        ++nb;
+        cur_net = net_i;
+      }
+      if (!leader) continue;
+      for (int p = 0; p < C::PASSES; ++p) {
+        mbar_wait_cluster(&tempty[p], (tcount & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + p * C::NP;
+        const uint32_t bp = b_base + p * C::B_PASS_BYTES;
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          if (p == 0) {
+            mbar_wait_cluster(&full[c], tcount & 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint32_t a_stage = tmem + C::A_COL0 + c * C::A_STAGE_COLS;
+#pragma unroll
+            for (int j = 0; j < C::KC / C::UK; ++j) {
+              const uint32_t g = c * (C::KC / C::UK) + j;
+              const uint64_t b_hi = smem_desc(bp + 2 * g * b_lbo, b_lbo, 128);
+              const uint64_t b_lo = smem_desc(bp + C::B_TERM_BYTES + 2 * g * b_lbo, b_lbo, 128);
+              const uint32_t a_hi = a_stage + j * 8, a_lo = a_hi + C::A_LO_COLS;
+              umma_ts2(d_tmem, a_lo, b_hi, idesc, (c == 0 && j == 0) ? 0u : 1u);
+              umma_ts2(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_ts2(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            if (p == C::PASSES - 1) umma_commit2(&empty[c], 3);
+            if (c == C::NCHUNK - 1) umma_commit2(&tfull[p], 3);
+          }
+          __syncwarp();
+        }
+      }
+      ++tcount;
+    }
+  } else if (warp >= C::NEW) {
+    // ---------------- producers: the CTA's 128 dZ2 rows -> scaled fp16 hi|lo -> own TMEM (once per pair tile) ----------------
+    const int pw = warp - C::NEW, ptid = tid - C::NEW * 32;
+    const int kq = pw >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + kq * (C::KPW / 2);
+    int cur_net = -1;
+    float w3m0 = 0.f, w3m1 = 0.f;
+    uint32_t tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item, ++tcount) {
+      const int net_i = item / tiles, tp = item % tiles;
+      if (net_i != cur_net) {
+        cur_net = net_i;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        for (int j = ptid; j < H; j += C::PROD_THREADS)
+          w3s[j] = make_float2(net[off_W3(IN) + j], OUT == 2 ? net[off_W3(IN) + H + j] : 0.f);
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
+        w3m0 = __ldg(&meta->wmax[4]);
+        w3m1 = OUT == 2 ? __ldg(&meta->wmax[5]) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+      }
+      const int r = tp * C::TMP + (int)rank * TM + (warp & 3) * 32 + lane;
+      const bool ok = r < jb.rows;
+      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT) : 0.f;
+      const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1) : 0.f;
+      float sa, inv_sa;
+      pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);
+      const float d0s = d0 * sa, d1s = d1 * sa;                       // exact
+      const int rc = ok ? r : 0;
+      const float* h2r = jb.h2 + ((size_t)net_i * tiles64 + (rc >> 6)) * H * 64 + (rc & 63);
+      float hn[C::KPW];                                    // next stage's H2 values, loaded one stage ahead
+#pragma unroll
+      for (int e = 0; e < C::KPW; ++e) hn[e] = __ldg(h2r + (size_t)(kq * C::KPW + e) * 64);
+      for (int c = 0; c < C::NCHUNK; ++c) {
+        const int j0 = c * C::KC + kq * C::KPW;
+        float hv[C::KPW];
+#pragma unroll
+        for (int e = 0; e < C::KPW; ++e) hv[e] = hn[e];
+        if (c + 1 < C::NCHUNK) {
+#pragma unroll
+          for (int e = 0; e < C::KPW; ++e) hn[e] = __ldg(h2r + (size_t)(j0 + C::KC + e) * 64);
+        }
+        uint32_t hi[C::KPW / 2], lo[C::KPW / 2];
+#pragma unroll
+        for (int e = 0; e < C::KPW; e += 2) {
+          const float2 wa = w3s[j0 + e], wb = w3s[j0 + e + 1];
+          float ga = d0s * wa.x, gb = d0s * wb.x;
+          if (OUT == 2) { ga = fmaf(d1s, wa.y, ga); gb = fmaf(d1s, wb.y, gb); }
+          split_h2_trunc(make_float2(hv[e] > 0.f ? ga : 0.f, hv[e + 1] > 0.f ? gb : 0.f), hi[e / 2], lo[e / 2]);
+        }
+        mbar_wait_cluster(&empty[c], (tcount & 1) ^ 1);
+        tc_fence_after();
+        tmem_st8(lane_base + c * C::A_STAGE_COLS, hi);
+        tmem_st8(lane_base + c * C::A_STAGE_COLS + C::A_LO_COLS, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&full[c], 0);
+      }
+    }
+    if (item_hi > item_lo)
+      for (int c = 0; c < C::NCHUNK; ++c) mbar_wait_cluster(&empty[c], (tcount & 1) ^ 1);
+  } else {
+    // ---------------- epilogue: group g = pass g = columns [128 g, 128 g + 128): dZ1, dx, dW1/db1 ----------------
+    constexpr int NCH = C::NP / 32;
+    const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;
+    float4* ebg = ebs + grp * C::NP;
+    float* ivg = invs + grp * C::NP;
+    float a_b[NCH], a_w0[NCH], a_w1[NCH], a_w2[NCH];      // lane l <-> column chunk*32 + l of the group's pass
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) { a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f; }
+    float* flbuf = reinterpret_cast<float*>(sm + C::OFF_FLUSH) + grp * (4 * 16 * 32);
+    float* red_t = reinterpret_cast<float*>(sm + C::OFF_RED + warp * C::RED_WARP_BYTES);       // [32][33]
+    float4* red_x = reinterpret_cast<float4*>(red_t + 32 * 33);                                 // [32] this item's input rows
+    auto flush = [&](int net_i) {                    // called uniformly by the 4 warps of the group
+      if (!WGRADS || net_i < 0) return;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        float* f = flbuf + (qw * 16 + q * 4) * 32 + lane;
+        f[0] = a_w0[q]; f[32] = a_w1[q]; f[64] = a_w2[q]; f[96] = a_b[q];
+        a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 2 + grp) * SMALL_STRIDE;
+      {
+        const int q = qw;                            // warp w sums chunk q = w over the four warps (order 0..3)
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float* f = flbuf + (w * 16 + q * 4) * 32 + lane;
+          t0 += f[0]; t1 += f[32]; t2 += f[64]; t3 += f[96];
+        }
+        const int k = grp * C::NP + q * 32 + lane;
+        o[k * IN + 0] = t0;
+        o[k * IN + 1] = t1;
+        if (IN == 3) o[k * IN + 2] = t2;
+        o[H * IN + k] = t3;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+    };
+    int cur_net = -1;
+    float w3m0 = 0.f, w3m1 = 0.f;
+    uint32_t tcount = 0;
+    for (int item = item_lo; item < item_hi; ++item, ++tcount) {
+      const int net_i = item / tiles, tp = item % tiles;
+      if (net_i != cur_net) {
+        flush(cur_net);
+        cur_net = net_i;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
+        for (int cidx = gtid; cidx < C::NP; cidx += 128) {
+          const int k = grp * C::NP + cidx;
+          ebg[cidx] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
+                                  IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+          ivg[cidx] = __ldg(&meta->inv_s[k]);
+        }
+        w3m0 = __ldg(&meta->wmax[4]);
+        w3m1 = OUT == 2 ? __ldg(&meta->wmax[5]) : 0.f;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+      }
+      const int row = tp * C::TMP + (int)rank * TM + qw * 32 + lane;
+      const bool ok = row < jb.rows;
+      const float4 x = ok ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT) : 0.f;
+      const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT + 1) : 0.f;
+      float sa, inv_sa;
+      pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);     // the producers' scale of this row
+      if (WGRADS) {
+        __syncwarp();
+        red_x[lane] = x;                                                      // rows beyond jb.rows are zero
+      }
+      mbar_wait_cluster(&tfull[grp], tcount & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem + ((uint32_t)(qw * 32) << 16) + grp * C::NP;
+      float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {                   // (unrolled: a_w*[q] must stay in registers)
+        if (WGRADS) __syncwarp();                       // the previous chunk's column sums have read red_t
+        // 8 columns per step: the TMEM load and the step's constants (warp-uniform LDS) are issued together, then the
+        // math -- one LDS per column inside the dependent chain made this epilogue latency-bound (ncu r02)
+#pragma unroll 1
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          float v[8];
+          float4 w[8];
+          float iv[8];
+          tmem_ld8(t_acc + q * 32 + c8, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = ebg[q * 32 + c8 + i];
+          if (DX) {
+            const float4 i0 = *reinterpret_cast<const float4*>(ivg + q * 32 + c8);
+            const float4 i1 = *reinterpret_cast<const float4*>(ivg + q * 32 + c8 + 4);
+            iv[0] = i0.x; iv[1] = i0.y; iv[2] = i0.z; iv[3] = i0.w; iv[4] = i1.x; iv[5] = i1.y; iv[6] = i1.z; iv[7] = i1.w;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // layer-1 pre-activation in the FORWARD's order (chain starts from the bias): same ReLU mask bit for bit
+            float z = fmaf(x.y, w[i].y, fmaf(x.x, w[i].x, w[i].w));
+            if (IN == 3) z = fmaf(x.z, w[i].z, z);
+            // without dx the column scale 1/s_n is applied once per column sum instead of once per element
+            const float d = z > 0.f ? (DX ? v[i] * inv_sa * iv[i] : v[i] * inv_sa) : 0.f;
+            if (DX) {
+              dx0 = fmaf(d, w[i].x, dx0);
+              dx1 = fmaf(d, w[i].y, dx1);
+              if (IN == 3) dx2 = fmaf(d, w[i].z, dx2);
+            }
+            if (WGRADS) red_t[lane * 33 + c8 + i] = d;
+          }
+        }
+        if (WGRADS) {
+          // column sums over the warp's 32 rows through the transposed shared-memory tile (fixed row order)
+          __syncwarp();
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, sb = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float dv = red_t[r * 33 + lane];
+            const float4 xr = red_x[r];
+            s0 = fmaf(dv, xr.x, s0);
+            s1 = fmaf(dv, xr.y, s1);
+            if (IN == 3) s2 = fmaf(dv, xr.z, s2);
+            sb += dv;
+          }
+          const float cs = DX ? 1.f : ivg[q * 32 + lane];
+          a_w0[q] = fmaf(s0, cs, a_w0[q]); a_w1[q] = fmaf(s1, cs, a_w1[q]); a_w2[q] = fmaf(s2, cs, a_w2[q]);
+          a_b[q] = fmaf(sb, cs, a_b[q]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty[grp], 0);
+      if (DX && ok)
+        jb.dX_part[((size_t)net_i * C::PASSES + grp) * jb.rows + row] = make_float4(dx0, dx1, dx2, 0.f);
+    }
+    flush(cur_net);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == C::MMA_WARP) tmem_dealloc2(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace cql

@@ -15,6 +15,7 @@
 #include "mlp_tc_bwd1.cuh"
 #include "mlp_tc_bwd2.cuh"
 #include "mlp_tc_h.cuh"
+#include "mlp_tc_h2.cuh"
 
 namespace cql {
 
@@ -492,11 +493,30 @@ __global__ void k_adam_polyak(float* __restrict__ p, float* __restrict__ m, floa
 // Programmatic dependent launch: the kernel may start (barrier init, TMEM allocation) while its predecessor in the
 // stream drains; it executes `griddepcontrol.wait` before touching anything the predecessor wrote.  Only used for
 // kernels that contain that wait (the f16x3 tensor-core kernels).  CQL_NO_PDL=1 switches it off (A/B measurements).
+// cql_timed_update switches PDL off for its one timed step: with PDL a kernel's prologue starts under its predecessor,
+// so a CUDA event recorded between two kernels no longer separates their durations (r01: bwd1 0.118 ms / bwd2 0.003 ms)
+inline bool g_timing_no_pdl = false;
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  static const bool no_pdl = std::getenv("CQL_NO_PDL") != nullptr;
+  static const bool no_pdl_env = std::getenv("CQL_NO_PDL") != nullptr;
+  const bool no_pdl = no_pdl_env || g_timing_no_pdl;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  CQL_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
+// same for a kernel compiled with __cluster_dims__(2, 1, 1): grid = 2 x clusters
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_pair(void (*kernel)(KArgs...), int clusters, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl_env = std::getenv("CQL_NO_PDL") != nullptr;
+  const bool no_pdl = no_pdl_env || g_timing_no_pdl;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -529,6 +549,14 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   using C = std::conditional_t<F16X3, tc::HCfg, tc::Cfg<TF32>>;
   tc::TcFwdJobs tj{};
   tj.n = jobs.n;
+  // big launches of the f16x3 path run on CTA pairs (one H1 tile feeds all 256 output columns); CQL_NO_PAIR=1 = A/B switch
+  bool pair = false;
+  if constexpr (F16X3) {
+    static const bool no_pair = std::getenv("CQL_NO_PAIR") != nullptr;
+    int pair_items = 0;
+    for (int i = 0; i < jobs.n; ++i) pair_items += jobs.j[i].n_nets * ((jobs.j[i].rows + 2 * tc::TM - 1) / (2 * tc::TM));
+    pair = !no_pair && pair_items >= h->num_sms / 2;
+  }
   size_t part_off = 0;
   int items = 0;
   float* part_of[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -539,17 +567,19 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
     items += j.n_nets * C::SLICES * ((j.rows + tc::TM - 1) / tc::TM);
     part_of[i] = h->part + part_off;
     part_off += (size_t)j.n_nets * C::SLICES * j.rows * OUT;
-    tj.j[i] = tc::TcFwdJob{j.X, j.params, h->packed_fwd + (size_t)slot * h->packed_net_bytes, part_of[i], j.h2, j.rows,
-                           j.n_nets};
+    tj.j[i] = tc::TcFwdJob{j.X, j.params,
+                           pair ? h->packed_fwd2 + (size_t)slot * h->packed_net_bytes2 : h->packed_fwd + (size_t)slot * h->packed_net_bytes,
+                           part_of[i], j.h2, j.rows, j.n_nets};
   }
   tj.item_begin[jobs.n] = items;
   { static const char* hc = std::getenv("CQL_H2_COST"); if (hc) tj.h2_cost = std::atoi(hc); }   // tuning knob
   CQL_REQUIRE(part_off <= h->part_floats, "internal: partial-sum scratch too small");
   if (items == 0) return;
   const int grid = items < h->num_sms ? items : h->num_sms;
-  if constexpr (F16X3)
-    launch_pdl(tc::tc_fwd_h_kernel<IN, OUT>, dim3(grid), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, tj);
-  else if constexpr (TF32)
+  if constexpr (F16X3) {
+    if (pair) launch_pdl_pair(tc::tc_fwd_h2_kernel<IN, OUT>, h->num_sms / 2, dim3(tc::H2Cfg::THREADS), tc::H2Cfg::SMEM_BYTES, st, tj, h->pair_swap_b);
+    else launch_pdl(tc::tc_fwd_h_kernel<IN, OUT>, dim3(grid), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, tj);
+  } else if constexpr (TF32)
     tc::tc_fwd_ts_kernel<IN, OUT><<<grid, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(tj);
   else
     tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
@@ -592,6 +622,18 @@ inline void pack_slots(Handle* h, const int* slots, int n_slots, cudaStream_t st
   if (jobs_h.n) {
     launch_pdl(tc::k_pack_multi_h, dim3(dim3(H * 32 / 256, jobs_h.n)), dim3(256), 0, st, jobs_h, 2);
     CQL_LAUNCH_CHECK(h);
+    tc::PackJobs jp{};                // the same operands in the CTA-pair layout
+    for (int i = 0; i < n_slots; ++i) {
+      const int slot = slots[i];
+      const bool is_actor = slot == slot_actor() || slot == slot_targ_actor(h->C);
+      if (is_actor) continue;         // the actor's launches are small: one-CTA kernels only
+      jp.j[jp.n++] = {h->net_params(slot), h->packed_fwd2 + (size_t)slot * h->packed_net_bytes2, 3, 0};
+      if (slot <= h->C) jp.j[jp.n++] = {h->net_params(slot), h->packed_bwd2 + (size_t)slot * h->packed_net_bytes2, 3, 1};
+    }
+    if (jp.n) {
+      launch_pdl(tc::k_pack_pair_h, dim3(dim3(H * 32 / 256, jp.n)), dim3(256), 0, st, jp, 2);
+      CQL_LAUNCH_CHECK(h);
+    }
   }
   if (jobs.n == 0) return;
   if (h->cfg.precision != CQL_PREC_BF16) {
@@ -611,16 +653,23 @@ inline void pack_weights(Handle* h, int slot, int n_slots, int /*in_dim*/, cudaS
 
 // ---- tensor-core backward of one job: bwd1 (dH1, dW1, db1, dx) + bwd2 (dW2, db2, dW3, db3) + reduce
 template <bool TF32, int IN, int OUT, bool WGRADS, bool DX, bool F16X3 = false>
-inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStream_t st) {
+inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStream_t st, int mark_mid = -1, int mark_end = -1) {
   using C = std::conditional_t<F16X3, tc::HCfg, tc::Cfg<TF32>>;
   const int slot = (int)((jb.params - h->params) / NET_STRIDE);
   const int tiles = (jb.rows + tc::TM - 1) / tc::TM;
   const int items = jb.n_nets * C::SLICES * tiles;
-  const int grid1 = items < h->num_sms ? items : h->num_sms;
+  // big launches of the f16x3 path run on CTA pairs (mlp_tc_h2.cuh): one dZ2 tile feeds all 256 columns of dH1
+  bool pair = false;
+  if constexpr (F16X3) {
+    static const bool no_pair = std::getenv("CQL_NO_PAIR") != nullptr || std::getenv("CQL_NO_PAIR_BWD1") != nullptr;
+    pair = !no_pair && IN == 3 && jb.n_nets * ((jb.rows + 2 * tc::TM - 1) / (2 * tc::TM)) >= h->num_sms / 2;
+  }
+  const int grid1 = pair ? 2 * (h->num_sms / 2) : (items < h->num_sms ? items : h->num_sms);
   const int slots1 = (F16X3 ? 2 : 4) * grid1;      // f16x3: one slot per (CTA, epilogue group)
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
-  tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params, h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd, h->small1,
-                 DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
+  tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params,
+                 pair ? h->packed_bwd2 + (size_t)slot * h->packed_net_bytes2 : h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd,
+                 h->small1, DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
   // bwd1 and bwd2 of one job are independent (both only read X, dOut, H2).  For the small jobs (the actor's B rows:
   // a few dozen CTAs each) they run side by side on a forked branch -- the fork/join is captured into the step graph.
   constexpr int RS2 = F16X3 ? tc::B2HCfg::RS : tc::B2Cfg<TF32>::RS;
@@ -637,13 +686,15 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     CQL_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     st2 = h->side_stream;
   }
-  if constexpr (F16X3)
-    launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX>, dim3(grid1), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, j1);
-  else if constexpr (TF32)
+  if constexpr (F16X3) {
+    if (pair) launch_pdl_pair(tc::tc_bwd1_h2_kernel<IN, OUT, WGRADS, DX>, h->num_sms / 2, dim3(tc::H2Cfg::THREADS), tc::H2B1Cfg::SMEM_BYTES, st, j1, h->pair_swap_b);
+    else launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX>, dim3(grid1), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, j1);
+  } else if constexpr (TF32)
     tc::tc_bwd1_ts_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(j1);
   else
     tc::tc_bwd1_kernel<TF32, IN, OUT, WGRADS, DX><<<grid1, tc::Pipe<TF32, tc::BWD1_NPW>::THREADS, tc::FwdSmem<TF32, tc::BWD1_NPW>::BYTES, st>>>(j1);
   CQL_LAUNCH_CHECK(h);
+  if (mark_mid >= 0) mark(h, st, mark_mid);
   if (!WGRADS) return;
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
   constexpr bool GROUP_SUM = false;   // in-kernel group sums of the dW2 partials: measured slower (one CTA re-reads 1 MB at the tail)
@@ -657,6 +708,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     CQL_CUDA(cudaEventRecord(h->ev_join, st2));
     CQL_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
+  if (mark_end >= 0) mark(h, st, mark_end);
   launch_pdl(tc::k_reduce_grads_tc, dim3(dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets)), dim3(256), 0, st, h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out,
                                                                                   (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1);
@@ -776,11 +828,9 @@ inline void phase1(Handle* h, cudaStream_t st) {
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);
   if (h->cfg.precision != CQL_PREC_FP32) {
-    if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, true, false, true>(h, jb, h->g_critics(), st);
-    else if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st);
-    else launch_bwd_tc<false, 3, 1, true, false>(h, jb, h->g_critics(), st);
-    mark(h, st, 6);
-    mark(h, st, 7);
+    if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, true, false, true>(h, jb, h->g_critics(), st, 6, 7);
+    else if (h->cfg.precision != CQL_PREC_BF16) launch_bwd_tc<true, 3, 1, true, false>(h, jb, h->g_critics(), st, 6, 7);
+    else launch_bwd_tc<false, 3, 1, true, false>(h, jb, h->g_critics(), st, 6, 7);
     return;
   }
   launch_bwd1<3, 1, true, false>(h, jb, st);

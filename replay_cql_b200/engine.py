@@ -216,6 +216,17 @@ class CqlEngine:
                                               stream), "cql_sample_rows")
         return out
 
+    def export_transitions(self, chunk: int = 1 << 22) -> np.ndarray:
+        """The replay table back on the host, [n, 8] float32 rows in table order (checkpointing)."""
+        import torch
+        n = self.n_transitions
+        out = np.empty((n, 8), dtype=np.float32)
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            idx = torch.arange(lo, hi, dtype=torch.int64, device=f"cuda:{self.device}")
+            out[lo:hi] = self.sample_rows(hi - lo, idx=idx).cpu().numpy()
+        return out
+
     # ------------------------------------------------------------------ updates
     def update(self, n_steps: int = 1, want_metrics: bool = True, stream: int | None = None) -> Optional[Dict[str, float]]:
         """``n_steps`` updates with on-device sampling + Philox noise (CUDA-graph replay)."""
@@ -229,6 +240,12 @@ class CqlEngine:
         self._check(self._lib.cql_timed_update(self._h, _ptr(out), stream), "cql_timed_update")
         keys = ("critic_fwd", "critic_bwd1", "critic_bwd2", "update", "actor_step_fwd", "actor_bwd", "actor_fwd", "other")
         return dict(zip(keys, map(float, out)))
+
+    def mma_bench(self, mode: int, iters: int = 512):
+        """Issue-rate microbenchmark of tcgen05.mma kind::f16 (see ``cql_mma_bench``): -> (clocks to issue, clocks to retire)."""
+        out = np.zeros(2, dtype=np.int64)
+        self._check(self._lib.cql_mma_bench(self._h, int(mode), int(iters), _ptr(out)), "cql_mma_bench")
+        return int(out[0]), int(out[1])
 
     def selftest_umma(self, A: np.ndarray, B: np.ndarray, precision: str, a_in_tmem: bool = False) -> np.ndarray:
         """D = A @ B.T on the tensor cores (A [128,k], B [n,k]); building-block self-test."""

@@ -68,6 +68,8 @@ class CQL(Recommender):
         squash: str = "eps",
         seed: int = 12345,
         n_steps_per_epoch: Optional[int] = None,
+        save_replay_table: bool = False,
+        log_every: int = 1000,
     ):
         if soft_q_backup:
             raise ValueError("soft_q_backup=True is not supported (d3rlpy default False is restated)")
@@ -100,6 +102,8 @@ class CQL(Recommender):
         self.squash = squash
         self.seed = seed
         self.n_steps_per_epoch = n_steps_per_epoch
+        self.save_replay_table = save_replay_table
+        self.log_every = log_every
         self.engine: Optional[CqlEngine] = None
         self.last_metrics: Optional[Dict[str, float]] = None
 
@@ -129,6 +133,8 @@ class CQL(Recommender):
             "squash": self.squash,
             "seed": self.seed,
             "n_steps_per_epoch": self.n_steps_per_epoch,
+            "save_replay_table": self.save_replay_table,
+            "log_every": self.log_every,
         }
 
     # ------------------------------------------------------------------ engine
@@ -170,23 +176,64 @@ class CQL(Recommender):
             self.logger.warning("CQL.fit: 0 update steps (log has %d rows, batch_size*world = %d)",
                                 n_rows, self.batch_size * world)
             return
-        if world == 1:
-            done = 0
-            while done < total:
-                chunk = min(per_epoch, total - done)
-                self.last_metrics = eng.update(chunk)
-                done += chunk
-                self.logger.debug("CQL epoch %d/%d %s", done // max(per_epoch, 1), self.n_epochs, self.last_metrics)
-        else:
+        self._run_steps(total, per_epoch)
+
+    def _run_steps(self, total: int, per_epoch: Optional[int] = None) -> None:
+        """``total`` updates on the engine's replay table, continuing from its step counter (which fixes the position
+        in the epoch permutation and the Philox counters).  The six losses of d3rlpy's progress line (temp_loss, temp,
+        alpha_loss, alpha, critic_loss, actor_loss) are logged at DEBUG every ``log_every`` steps on every world size,
+        in the house style of ``replay/models/base_rec.py:639-646`` (``self.logger``)."""
+        eng = self.engine
+        rank, world, _ = dist_info()
+        every = max(1, int(self.log_every or total))
+        if per_epoch:
+            every = min(every, max(1, int(per_epoch)))
+        first = eng.get_optimizer()[2]
+        stepper = None
+        if world > 1:
             from .parallel import DataParallelStepper
             import torch
-            with torch.cuda.device(eng.device):
-                stepper = DataParallelStepper(eng)          # whole step (kernels + NCCL) as one CUDA graph
-                stepper.stream.wait_stream(torch.cuda.current_stream())
-                stepper.run(total)                          # exactly `total` updates (warm-up steps included)
+            torch.cuda.set_device(eng.device)
+            stepper = DataParallelStepper(eng)              # whole step (kernels + gradient exchanges) as one CUDA graph
+            stepper.stream.wait_stream(torch.cuda.current_stream())
+        done = 0
+        while done < total:
+            chunk = min(every, total - done)
+            if stepper is None:
+                self.last_metrics = eng.update(chunk)
+            else:
+                stepper.run(chunk)                          # exactly `chunk` updates (eager warm-up steps included)
                 stepper.finish()                            # raises if a gradient exchange timed out
-                assert stepper.steps_done == total
-            self.last_metrics = eng.read_metrics()
+                self.last_metrics = eng.read_metrics()
+            done += chunk
+            self.logger.debug("CQL step %d (rank %d/%d)%s %s", first + done, rank, world,
+                              f" epoch {(done - 1) // per_epoch + 1}/{self.n_epochs}" if per_epoch else "",
+                              " ".join(f"{k}={v:.6g}" for k, v in self.last_metrics.items()))
+        if stepper is not None:
+            assert stepper.steps_done == total
+            stepper.graph = None
+
+    def resume(self, log: Optional[pd.DataFrame] = None, n_steps: Optional[int] = None,
+               n_epochs: Optional[int] = None) -> "CQL":
+        """Continue training a fitted or loaded model EXACTLY where it stopped: weights, targets, the
+        Adam moments and the step counter come from the engine (``save``/``load`` persist them); the step counter fixes
+        the position in the epoch permutation and the Philox counters, so ``fit(N) -> save -> load -> resume(M)`` is
+        bit-identical to ``fit(N + M)``.  The replay table is taken from the checkpoint when it was saved with
+        ``save_replay_table=True``; otherwise it is rebuilt from ``log`` (the MDP builder is deterministic: stable
+        sorts + action noise seeded per original row)."""
+        if self.engine is None:
+            raise AttributeError("CQL model is not fitted or loaded")
+        eng = self.engine
+        if eng.n_transitions == 0:
+            if log is None or len(log) == 0:
+                raise ValueError("resume: the checkpoint holds no replay table (save_replay_table=False) -- pass the log")
+            build_mdp_on_device(eng, log, top_k=self.top_k, action_randomization_scale=self.action_randomization_scale)
+        _, world, _ = dist_info()
+        per_epoch = self.n_steps_per_epoch or eng.n_transitions // (self.batch_size * world)
+        total = int(n_steps) if n_steps is not None else int(n_epochs if n_epochs is not None else self.n_epochs) * per_epoch
+        if total > 0:
+            self._run_steps(total, per_epoch)
+        return self
 
     # ------------------------------------------------------------------ predict
     def _predict(self, log: Optional[pd.DataFrame], k: int, users: pd.DataFrame, items: pd.DataFrame,
@@ -262,8 +309,11 @@ class CQL(Recommender):
             return
         m, v, step = self.engine.get_optimizer()
         np.savez(os.path.join(path, "state.npz"), state=self.engine.get_state(), adam_m=m, adam_v=v)
+        n_rows = self.engine.n_transitions if self.save_replay_table else 0
+        if n_rows:                                          # [n, 8] rows: obs.x obs.y act rew next.x next.y term pad
+            np.save(os.path.join(path, "replay_table.npy"), self.engine.export_transitions())
         with open(os.path.join(path, "meta.json"), "w") as f:
-            json.dump({"fitted": True, "step": step, "format": 1}, f)
+            json.dump({"fitted": True, "step": step, "format": 2, "replay_rows": int(n_rows)}, f)
 
     def _load_model(self, path: str) -> None:
         with open(os.path.join(path, "meta.json")) as f:
@@ -274,3 +324,6 @@ class CQL(Recommender):
         eng = self._make_engine()
         eng.set_state(data["state"])
         eng.set_optimizer(data["adam_m"], data["adam_v"], int(meta["step"]))
+        if meta.get("replay_rows"):
+            rows = np.load(os.path.join(path, "replay_table.npy"))
+            eng.load_transitions(rows[:, 0:2], rows[:, 2], rows[:, 3], rows[:, 6])
