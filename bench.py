@@ -32,7 +32,7 @@ sys.path.insert(0, str(ROOT))
 BATCH = 1024
 K_TOP = 10
 WORKLOAD = "ml20m-train"          # BASELINE.json configs[2]: 138 493 users x 26 744 items, 20 000 263 rows
-SCORE_USERS = 2048                # users scored per timed scoring pass (bounded sample of configs[3])
+SCORE_WARM_USERS = 2048           # users of the untimed warm-up scoring pass (the timed pass scores ALL users, configs[3])
 FLOP_PER_ROW = 2 * (3 * 256 + 256 * 256 + 256)   # f_c = 133 120
 FLOP_PER_UPDATE_PER_B = 269 * FLOP_PER_ROW       # 269 forward-equivalent rows per batch element
 FLOP_PER_PAIR = 3 * FLOP_PER_ROW                 # 2 critics + actor = 399 360
@@ -41,10 +41,12 @@ DTYPES = {"fp32": "f32", "tf32x3": "f32 (tf32x3: tensor-core 3-term split, fp32 
           "bf16": "bf16 (fp32 accumulate; non-parity variant)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from one `ncu --set full` capture
 # (profiles/r01_tc_fwd_ts_ncu_summary.txt, profiles/r01_f16x3_fwd_h_ncu_summary.txt); null where no capture exists for that variant
-KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": 2.136832e6 + 13.496576e6, "bf16": None}
+KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": 2.136832e6 + 15.324416e6, "bf16": None}
+TRAFFIC_SOURCE = {"fp32": None, "tf32x3": "ncu --set full capture profiles/r01_tc_fwd_ts_ncu_summary.txt (not measured in this run)",
+                  "f16x3": "ncu --set full capture profiles/r02_pair_fwd_ncu_summary.txt (not measured in this run)", "bf16": None}
 KERNEL_NAMES = {"fp32": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
                 "tf32x3": "tc_fwd_ts_kernel<3,1> (critic forward: tcgen05 kind::tf32 3-term split, A operand in TMEM)",
-                "f16x3": "tc_fwd_h_kernel<3,1> (critic forward: tcgen05 kind::f16, fp16 hi/lo 3-term split, A operand in TMEM)",
+                "f16x3": "tc_fwd_h2_kernel<3,1> (critic forward on CTA pairs: tcgen05 cta_group::2 kind::f16, fp16 hi/lo 3-term split, A operand in TMEM)",
                 "bf16": "tc_fwd_kernel<bf16,3,1> (critic forward, tcgen05 kind::f16)"}
 
 
@@ -80,11 +82,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout: float = 5.0):
+        """Block until nvidia-smi has delivered a sample (it can take seconds to start when 8 ranks launch it at once):
+        a timed region shorter than the sampling period otherwise ends before the first line arrives."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self, t_from: float | None = None, t_to: float | None = None):
         """Summary of the samples taken in [t_from, t_to] (host clock); all samples if the window holds none."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        n0, t0 = len(self.lines), time.time()
+        while len(self.lines) == n0 and time.time() - t0 < 1.0:      # one more sample after the region
+            time.sleep(0.02)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -263,6 +274,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)      # started before the warm-up so that it is already sampling in the timed region
     clocks.start()
     do_steps(max(3, args.warmup))
+    clocks.wait_first()
     barrier()
     l0 = eng.launch_count
     r0 = stepper.replayed_steps if stepper is not None else 0
@@ -329,14 +341,15 @@ def run_ours(args):
         e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n_e2e / e2e_s
 
-    # ---- scoring: users sharded over ranks, all items, seen filter, k=10 ----
-    n_score = SCORE_USERS * world
-    users_all = np.sort(np.random.default_rng(1).choice(shape["n_users"], size=n_score, replace=False)).astype(np.int32)
+    # ---- scoring (BASELINE configs[3]): ALL users sharded over ranks, all items, seen filter, k=10 ----
+    n_score = shape["n_users"]
+    users_all = np.arange(n_score, dtype=np.int32)
     lo, hi = shard_range(n_score, rank, world)
     users = users_all[lo:hi]
     items = np.arange(shape["n_items"], dtype=np.int32)
-    sub = log[log["user_idx"].isin(users)]
-    indptr, seen = seen_csr(sub, shape["n_users"])
+    lo_row, hi_row = np.searchsorted(log["user_idx"].to_numpy(), [lo, hi])      # the generator's log is user-major
+    indptr, seen = seen_csr(log.iloc[lo_row:hi_row], shape["n_users"])
+    n_warm = min(SCORE_WARM_USERS, users.size)
     with torch.cuda.stream(stream):
         d_users = torch.from_numpy(users).to(dev)
         d_items = torch.from_numpy(items).to(dev)
@@ -345,13 +358,14 @@ def run_ours(args):
         oi = torch.empty((users.size, K_TOP), dtype=torch.int32, device=dev)
         osc = torch.empty((users.size, K_TOP), dtype=torch.float32, device=dev)
         eng.score_topk_device(d_users[:64], d_items, K_TOP, d_ptr, d_seen, out_items=oi[:64], out_scores=osc[:64], stream=sh)
-        eng.score_topk_device(d_users, d_items, K_TOP, d_ptr, d_seen, out_items=oi, out_scores=osc, stream=sh)   # full-size warm-up pass
+        eng.score_topk_device(d_users[:n_warm], d_items, K_TOP, d_ptr, d_seen, out_items=oi[:n_warm], out_scores=osc[:n_warm], stream=sh)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l1 = eng.launch_count
-    SCORE_REPS = 3
-    score_clocks = ClockSampler(local_rank)      # ~0.4 s of sustained tensor + CUDA-core load: the power cap may bite
+    SCORE_REPS = 1
+    score_clocks = ClockSampler(local_rank)      # seconds of sustained tensor + CUDA-core load: the power cap may bite
     score_clocks.start()
+    score_clocks.wait_first()
     s0.record(stream)
     with torch.cuda.stream(stream):
         for _ in range(SCORE_REPS):
@@ -362,18 +376,21 @@ def run_ours(args):
     score_ms = max_over_ranks(s0.elapsed_time(s1)) / SCORE_REPS
     score_launches = (eng.launch_count - l1) // SCORE_REPS
     users_per_s = n_score / (score_ms / 1e3)
-    eng.score_topk(users, items, K_TOP, indptr, seen)                 # warm-up of the host-buffer entry (scratch allocation at full size)
+    top_dev = oi.cpu().numpy()
+    assert (top_dev[:, 0] >= 0).all() and not np.isin(top_dev[0], seen[indptr[users[0]]:indptr[users[0] + 1]]).any()
+    eng.score_topk(users[:n_warm], items, K_TOP, indptr, seen)         # warm-up of the host-buffer entry (scratch allocation)
     barrier()
     t0 = time.perf_counter()
-    eng.score_topk(users, items, K_TOP, indptr, seen)
+    top_host, _ = eng.score_topk(users, items, K_TOP, indptr, seen)   # host ids + CSR in, top-k out: every user of this rank
     score_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert np.array_equal(top_host, top_dev)
     pairs = float(users.size) * shape["n_items"]
     score_tf = pairs * FLOP_PER_PAIR / (score_ms / 1e3) / 1e12
 
     # ---- stand-alone top-k + lazy seen filter over a MATERIALISED score matrix (HBM-bound: 4 B/pair read) ----
-    TOPK_ROWS = 4 * users.size                                       # 8192 rows x 26744 fp32 = 876 MB >> L2
+    TOPK_ROWS = 8192                                                 # 8192 rows x 26744 fp32 = 876 MB >> L2
     sc_mat = torch.randn((TOPK_ROWS, shape["n_items"]), dtype=torch.float32, device=dev)
-    tk_users = d_users.repeat(4)
+    tk_users = d_users[torch.randint(0, users.size, (TOPK_ROWS,), device=dev)]
     with torch.cuda.stream(stream):
         eng.topk_filter_device(sc_mat, K_TOP, users_t=tk_users, items_t=d_items, seen_indptr_t=d_ptr, seen_items_t=d_seen, stream=sh)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -398,6 +415,28 @@ def run_ours(args):
         g1.record(stream)
     torch.cuda.synchronize(dev)
     gather_gbs = 10 * cnt * 64 / (g0.elapsed_time(g1) / 1e3) / 1e9    # 32 B read + 32 B written per row
+
+    # ---- the product path: replay.models.CQL().fit(log) / .predict(log, 10) through the Recommender API (pandas in / out) ----
+    product = None
+    if world == 1:
+        from replay_cql_b200.models import CQL
+        n_fit = max(50, min(args.steps, 2000))
+        model = CQL(n_epochs=1, n_steps_per_epoch=n_fit, batch_size=BATCH, seed=12345)      # every default incl. precision
+        t0 = time.perf_counter()
+        model.fit(log)                                   # fit_users/fit_items, MDP build on the GPU, n_fit updates
+        torch.cuda.synchronize(dev)
+        fit_s = time.perf_counter() - t0
+        pu = log[["user_idx"]].drop_duplicates().iloc[:: max(1, shape["n_users"] // 4096)]
+        t0 = time.perf_counter()
+        recs = model.predict(log, K_TOP, users=pu, filter_seen_items=True)
+        pred_s = time.perf_counter() - t0
+        assert len(recs) == len(pu) * K_TOP
+        product = {"api": "replay_cql_b200.models.CQL(n_epochs=1, n_steps_per_epoch=%d).fit(log); .predict(log, 10, users=<%d users>)" % (n_fit, len(pu)),
+                   "precision": model.precision, "fit_seconds": fit_s, "fit_updates": n_fit,
+                   "fit_note": "wall clock of the whole call: distinct users/items (pandas), host columns -> HBM + GPU MDP build, updates",
+                   "predict_seconds": pred_s, "predict_users": int(len(pu)), "predict_users_per_s": len(pu) / pred_s,
+                   "predict_note": "wall clock incl. pandas cold filter, seen CSR build from the 20M-row log, fused scoring, result frame"}
+        model.engine.close()
 
     if rank == 0:
         cpu = None
@@ -427,12 +466,18 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[args.precision],
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": f"bf16_tflops_sustained ({pk_kind})", "traffic": KERNEL_TRAFFIC[args.precision],
+                         "traffic_source": TRAFFIC_SOURCE[args.precision],
                          "flop_per_launch": fwd_flop, "ms_per_launch": tk["critic_fwd"],
                          "update_tflops": value / world * BATCH * FLOP_PER_UPDATE_PER_B / 1e12},
             "kernel_ms": tk,
+            "kernel_ms_note": "one eager update with CUDA events between the launches and programmatic dependent launch "
+                              "switched OFF (with PDL a kernel's prologue overlaps its predecessor and events no longer "
+                              "separate them); 'update' here is therefore longer than ms_per_step (graph replay, PDL on)",
             "cpu_baseline": cpu,
+            "product_path": product,
             "scoring": {"metric": "users scored top-10/sec", "value": users_per_s, "unit": "users/s",
-                        "users": int(n_score), "items": shape["n_items"], "k": K_TOP, "filter_seen": True,
+                        "users": int(n_score), "users_note": "every user of the ML-20M shape, sharded over the ranks (configs[3])",
+                        "items": shape["n_items"], "k": K_TOP, "filter_seen": True,
                         "ms": score_ms, "tflops": score_tf * world, "frac_of_peak": score_tf / peak_tf,
                         "gpu_launches": int(score_launches), "clocks": score_clk,
                         "e2e": {"value": n_score / score_e2e_s, "unit": "users/s",
@@ -468,6 +513,136 @@ def run_ours(args):
     wd.cancel()
 
 
+# ----------------------------------------------------------------------------- BASELINE configs[0,1]: ML-1M fit + predict
+def run_ml1m(args):
+    """fit + predict wall clock on the ML-1M-shaped log (6 040 x 3 706, 1 000 209 rows) through the Recommender API with
+    default hyper-parameters -- the `fit_pred_time` protocol of the reference's leaderboard
+    (docs/pages/useful_data/res_1m.csv:1-15) -- next to the CPU path (oracle updates + per-user scoring loop in the style of
+    replay/models/neuromf.py:394-438), which is timed on a bounded sample and extrapolated (stated)."""
+    import torch
+    from replay_cql_b200.models import CQL
+    from replay_cql_b200.synthetic import make_log, SHAPES
+    shape = SHAPES["ml1m"]
+    log = make_log("ml1m", seed=12345)
+    dev = torch.device("cuda", 0)
+    CQL(n_epochs=1, n_steps_per_epoch=3, batch_size=BATCH).fit(log.iloc[:50_000]).engine.close()     # context / allocator warm-up
+    model = CQL(n_epochs=1, batch_size=BATCH, seed=12345)
+    clocks = ClockSampler(0); clocks.start(); clocks.wait_first()
+    t0 = time.perf_counter()
+    model.fit(log)
+    torch.cuda.synchronize(dev)
+    fit_s = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    recs = model.predict(log, K_TOP, filter_seen_items=True)
+    pred_s = time.perf_counter() - t1
+    clk = clocks.stop()
+    n_updates = model.engine.get_optimizer()[2]
+    launches = model.engine.launch_count
+    assert recs.groupby("user_idx").size().max() <= K_TOP and recs["user_idx"].nunique() == shape["n_users"]
+    model.engine.close()
+    cpu = None
+    if not args.no_cpu:
+        rate, dt, threads = cpu_update_rate(40, 3)
+        srate, sdt, _ = cpu_scoring_rate(24, n_items=shape["n_items"])
+        cpu = {"value": n_updates / rate + shape["n_users"] / srate, "unit": "s (extrapolated fit+predict)", "cores": threads, "kind": "port",
+               "sample": f"40 oracle updates at batch 1024 ({dt:.1f} s) -> {rate:.1f} updates/s x {n_updates} updates; "
+                         f"24 users x {shape['n_items']} items per-user loop ({sdt:.1f} s) -> {srate:.2f} users/s x {shape['n_users']} users"}
+    line = {"metric": "CQL fit+predict wall clock, ML-1M shape (fit_pred_time)", "value": fit_s + pred_s, "unit": "s", "n_gpus": 1,
+            "steps": int(n_updates), "warmup": 3, "ms_per_step": 1e3 * fit_s / max(1, n_updates), "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[model.precision], "data": "synthetic",
+            "config": {"workload": "ml1m-fit-predict", "users": shape["n_users"], "items": shape["n_items"], "rows": shape["n_rows"],
+                       "batch_per_gpu": BATCH, "n_epochs": 1, "k": K_TOP, "filter_seen_items": True, "precision": model.precision,
+                       "api": "replay_cql_b200.models.CQL().fit(log); .predict(log, 10)"},
+            "fit_seconds": fit_s, "predict_seconds": pred_s, "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu,
+            "e2e": {"value": fit_s + pred_s, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "the whole measurement IS end to end: pandas frames in, pandas frame out"}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[4]: stress shape, scaled
+def run_stress(args):
+    """10M users x 1M items, 1e9-row replay table (32 GB) resident in HBM, batch 8192, the bf16 tensor-core critic variant
+    (stated tolerance 2e-2 on losses, not a parity mode).  The table is generated ON the device (`cql_synth_table`): the
+    log's 24 GB of columns are not worth moving through the host.  Scoring: a stated user sample x all 1M items."""
+    import torch
+    import torch.distributed as dist
+    from replay_cql_b200.engine import CqlEngine, CqlHyperParams
+    from replay_cql_b200.parallel import DataParallelStepper, shard_range
+    from replay_cql_b200.synthetic import SHAPES
+    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    shape = dict(SHAPES["stress"]); shape["n_rows"] = args.stress_rows
+    B = 8192
+    prec = "bf16" if args.precision == "f16x3" else args.precision
+    eng = CqlEngine(CqlHyperParams(batch_size=B, seed=12345, precision=prec), device=local_rank, rank=rank, world_size=world)
+    t0 = time.perf_counter()
+    eng.synth_table(shape["n_rows"], shape["n_users"], shape["n_items"], seed=12345)
+    synth_s = time.perf_counter() - t0
+    stepper = DataParallelStepper(eng) if world > 1 else None
+    stream = stepper.stream if stepper else torch.cuda.Stream(device=dev)
+    def do_steps(k):
+        if stepper: stepper.run(k)
+        else:
+            with torch.cuda.stream(stream): eng.update(k, want_metrics=False, stream=stream.cuda_stream)
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1: dist.barrier()
+    steps = max(20, min(args.steps, 300))
+    clocks = ClockSampler(local_rank); clocks.start()
+    do_steps(max(3, min(args.warmup, 10))); clocks.wait_first(); barrier()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); do_steps(steps); e1.record(stream); barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    clk = clocks.stop()
+    m = eng.read_metrics()
+    assert all(np.isfinite(v) for v in m.values()), m
+    n_su = 64                                           # users scored per rank: 64 x 1e6 pairs each
+    rng = np.random.default_rng(7 + rank)
+    users = np.sort(rng.choice(shape["n_users"], size=n_su, replace=False)).astype(np.int32)
+    items = np.arange(shape["n_items"], dtype=np.int32)
+    eng.score_topk(users[:4], items, K_TOP)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    ti, _ = eng.score_topk(users, items, K_TOP)         # host ids in, top-k out (no seen filter: the synthetic table has no log)
+    score_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([score_s], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); score_s = float(t.item())
+    if rank == 0:
+        pk, pk_kind = peaks()
+        value = world * steps / (ms / 1e3)
+        line = {"metric": "CQL updates/sec (batch 8192, stress shape)", "value": value, "unit": "updates/s", "n_gpus": world, "steps": steps,
+                "warmup": max(3, min(args.warmup, 10)), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": DTYPES[prec], "data": "synthetic (generated on the device, cql_synth_table)",
+                "config": {"workload": "stress", "users": shape["n_users"], "items": shape["n_items"], "rows": int(shape["n_rows"]),
+                           "table_gb": shape["n_rows"] * 32 / 1e9, "table": "replicated on every rank", "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": f"dp{world}", "precision": prec, "table_generation_seconds": synth_s,
+                           "l2": "32 GB replay table >> L2, fresh random gather every step"},
+                "gpu_launches": int(eng.launch_count - l0) + (stepper.launches_per_step * stepper.replayed_steps if stepper else 0),
+                "clocks": clk, "update_tflops": value / world * B * FLOP_PER_UPDATE_PER_B / 1e12,
+                "update_frac_of_bf16_sustained": value / world * B * FLOP_PER_UPDATE_PER_B / 1e12 / pk.get("bf16_tflops_sustained", 1400.0),
+                "last_metrics": m,
+                "scoring": {"metric": "users scored top-10/sec over 1e6 items", "value": world * n_su / score_s, "unit": "users/s",
+                            "users": world * n_su, "sample": f"{n_su} random users per rank x all 1 000 000 items (of 10M users: a bounded sample)",
+                            "tflops": world * n_su * shape["n_items"] * FLOP_PER_PAIR / score_s / 1e12, "api": "cql_score_topk (host ids in, top-k out)"},
+                "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if stepper: stepper.graph = None
+    torch.cuda.synchronize(dev)
+    eng.close()
+    if world > 1:
+        try:
+            dist.barrier(); dist.destroy_process_group()
+        except Exception:
+            pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -479,9 +654,17 @@ def main():
                     help="hidden-layer contraction: fp32 = CUDA-core FMA; tf32x3 = tcgen05 3-term split (FP32-grade, "
                          "default); bf16 = tcgen05 bf16 operands (non-parity variant)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", choices=["ml20m", "ml1m", "stress"], default="ml20m",
+                    help="ml20m = the headline line (BASELINE configs[2,3]); ml1m = fit+predict wall clock beside the CPU "
+                         "per-user path (configs[0,1]); stress = 1e9-row table, batch 8192, bf16 (configs[4], scaled scoring)")
+    ap.add_argument("--stress-rows", type=int, default=1_000_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ml1m":
+        run_ml1m(args)
+    elif args.workload == "stress":
+        run_stress(args)
     else:
         run_ours(args)
 

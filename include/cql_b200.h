@@ -101,6 +101,12 @@ int64_t cql_num_transitions(const cql_handle* h);
 int  cql_build_mdp(cql_handle* h, const int32_t* user_idx, const int32_t* item_idx, const int64_t* timestamp,
                    const double* relevance, const double* action_noise, int64_t n, int32_t top_k, float noise_scale,
                    float* obs_out, float* act_out, float* rew_out, float* term_out, int64_t* order_out);
+/* Synthetic replay table of a BASELINE.json shape generated IN PLACE on the device (measurement aid for the stress
+ * configuration: 1e9 rows x 32 B = 32 GB): user-major episodes of fixed length ceil(n / n_users), Zipf-like items,
+ * ML-like ratings + N(0, 1e-3) as actions, ~10 rewarded rows per episode, terminal on each episode's last row.
+ * Row i depends only on (seed, i).  replaces: nothing in the reference -- stands in for SURVEY 8d's generator where
+ * the log itself (24 GB of columns) is not worth moving through the host. */
+int  cql_synth_table(cql_handle* h, int64_t n_rows, int64_t n_users, int64_t n_items, uint64_t seed);
 /* stand-alone gather for the K1 roofline sweep: out_dev [count][8] floats.
  * idx_dev NULL => the handle's epoch permutation starting at position `pos`. */
 int  cql_sample_rows(cql_handle* h, const int64_t* idx_dev, int64_t pos, int64_t count,

@@ -70,6 +70,7 @@ SIGNATURES = {
     "cql_topk_filter_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "cql_timed_update": (C.c_int, [_P, _P, _P]),
     "cql_mma_bench": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "cql_synth_table": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_uint64]),
     "cql_selftest_umma": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "cql_launch_count": (C.c_int64, [_P]),
 }

@@ -1,0 +1,212 @@
+// adam_pack.cuh -- Adam + Polyak + operand packing of one group of networks in ONE launch (f16x3 path).
+//
+// After an Adam step every tensor-core operand copy of W2 must be refreshed: forward orientation (one-CTA and CTA-pair
+// layouts) of the network and of its target copy, and the transposed orientation (both layouts) for the backward.
+// Round 1 ran k_adam_polyak, then a pack kernel (now two, with the pair layouts): three dependent launches twice per
+// update.  Here a CTA owns 8 consecutive W2 rows: it applies Adam + Polyak to them, packs them (row maximum by a warp
+// reduction -> exact power-of-two row scale) for the forward layouts of network and target, and -- through a
+// shared-memory tile -- writes the one 16-byte K chunk those 8 rows contribute to EVERY operand row of the transposed
+// layouts.  A transposed operand row spans all 256 W2 rows (owned by 32 different CTAs), so its scale cannot be a row
+// maximum here; it is ONE power of two per network from a bound on max|W2|: the maximum seen in the previous step
+// (tracked with atomicMax in three rotating slots: read / accumulate / clear) plus 4 lr (an Adam step moves an entry by
+// at most ~3.2 lr), with one spare binade.  The scale only has to keep fp16 in range: entries 2^-15 of the maximum are
+// still represented to 2^-24 of the maximum (fp16 subnormals), far inside the 1e-4 gates.
+// The last CTA of each network handles the small tensors (W1, b1, b2, W3, b3) and the layer maxima (HMeta::wmax).
+#pragma once
+#include "mlp_tc_h2.cuh"
+
+namespace cql {
+namespace tc {
+
+struct AdamPackNet {
+  float* p;            // network slot (fp32 parameters)
+  float* m;
+  float* v;
+  const float* g;
+  float* targ;         // target slot
+  uint8_t* fwd;        // packed forward, one-CTA layout (HCfg)            -- never null
+  uint8_t* fwd2;       // packed forward, pair layout (H2Cfg)              -- null for the actor
+  uint8_t* bwd;        // packed transposed, one-CTA layout                -- never null
+  uint8_t* bwd2;       // packed transposed, pair layout                   -- null for the actor
+  uint8_t* tfwd;       // target: packed forward, one-CTA layout
+  uint8_t* tfwd2;      // target: packed forward, pair layout              -- null for the actor
+  int* w2max;          // [3] rotating slots: float bits of max|W2|
+};
+struct AdamPackJobs {
+  AdamPackNet n[CQL_MAX_CRITICS];
+  int in_dim, out_dim;
+  float lr, beta1, beta2, eps, tau;
+  long long* step_inc;      // the update's LAST launch: completed-steps counter to increment (else null)
+};
+
+__device__ __forceinline__ float adam_one(float& p, float& m, float& v, float g, float step_size, float bc2s, float beta1,
+                                          float beta2, float eps) {
+  const float mi = m + (g - m) * (1.f - beta1);
+  const float vi = v * beta2 + (1.f - beta2) * g * g;
+  m = mi;
+  v = vi;
+  p = p - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+  return p;
+}
+
+// one 16-byte chunk (8 consecutive K values of operand row n) -> hi|lo in the one-CTA and (optionally) the pair layout
+__device__ __forceinline__ void store_chunk(const float (&x)[8], float s, uint8_t* one, uint8_t* pair, int n, int kc) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_h2(x[2 * i] * s, x[2 * i + 1] * s, hi[i], lo[i]);
+  const uint4 h4 = make_uint4(hi[0], hi[1], hi[2], hi[3]), l4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  uint8_t* b = one + (size_t)(n / HCfg::NS) * HCfg::B_BYTES + chunk_off(HCfg::NS, n % HCfg::NS, kc);
+  *reinterpret_cast<uint4*>(b) = h4;
+  *reinterpret_cast<uint4*>(b + HCfg::B_TERM_BYTES) = l4;
+  if (pair != nullptr) {
+    *reinterpret_cast<uint4*>(pair + pair_chunk_off(n, kc, 0)) = h4;
+    *reinterpret_cast<uint4*>(pair + pair_chunk_off(n, kc, 1)) = l4;
+  }
+}
+
+constexpr int AP_ROWS = 8;                    // W2 rows per CTA
+constexpr int AP_W2_BLOCKS = H / AP_ROWS;     // 32
+
+__global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, const StepInfo* __restrict__ si) {
+  grid_dep_wait();
+  __shared__ float tile[AP_ROWS][H + 4];
+  __shared__ int wm[16];
+  const AdamPackNet nt = jobs.n[blockIdx.y];
+  const int in_dim = jobs.in_dim, out_dim = jobs.out_dim;
+  const float step_size = (float)((double)jobs.lr / si->bc1), bc2s = (float)si->bc2_sqrt;
+  const int slot_rd = (int)(si->step % 3), slot_acc = (int)((si->step + 1) % 3), slot_clr = (int)((si->step + 2) % 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (blockIdx.x < AP_W2_BLOCKS) {
+    // ---------------- 8 rows of W2: Adam + Polyak, forward packs, then the transposed K chunk ----------------
+    const int n = blockIdx.x * AP_ROWS + (tid >> 5), kc = lane;
+    const size_t off = (size_t)off_W2(in_dim) + (size_t)n * H + kc * 8;
+    float p[8], t[8];
+    {
+      const float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
+      float4 m0 = *reinterpret_cast<const float4*>(nt.m + off), m1 = *reinterpret_cast<const float4*>(nt.m + off + 4);
+      float4 v0 = *reinterpret_cast<const float4*>(nt.v + off), v1 = *reinterpret_cast<const float4*>(nt.v + off + 4);
+      const float4 p0 = *reinterpret_cast<const float4*>(nt.p + off), p1 = *reinterpret_cast<const float4*>(nt.p + off + 4);
+      const float4 t0 = *reinterpret_cast<const float4*>(nt.targ + off), t1 = *reinterpret_cast<const float4*>(nt.targ + off + 4);
+      p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
+      t[0] = t0.x; t[1] = t0.y; t[2] = t0.z; t[3] = t0.w; t[4] = t1.x; t[5] = t1.y; t[6] = t1.z; t[7] = t1.w;
+      float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        adam_one(p[i], mm[i], vv[i], gg[i], step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
+        t[i] = t[i] * (1.f - jobs.tau) + jobs.tau * p[i];
+      }
+      *reinterpret_cast<float4*>(nt.m + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(nt.m + off + 4) = make_float4(mm[4], mm[5], mm[6], mm[7]);
+      *reinterpret_cast<float4*>(nt.v + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(nt.v + off + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+      *reinterpret_cast<float4*>(nt.p + off) = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(nt.p + off + 4) = make_float4(p[4], p[5], p[6], p[7]);
+      *reinterpret_cast<float4*>(nt.targ + off) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(nt.targ + off + 4) = make_float4(t[4], t[5], t[6], t[7]);
+    }
+    float* trow = &tile[tid >> 5][kc * 8];
+    *reinterpret_cast<float4*>(trow) = make_float4(p[0], p[1], p[2], p[3]);
+    *reinterpret_cast<float4*>(trow + 4) = make_float4(p[4], p[5], p[6], p[7]);
+    // forward orientation: operand row n = W2 row n, scale from the row maximum (this warp = this row)
+    float mx = 0.f, mt = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mx = fmaxf(mx, fabsf(p[i])); mt = fmaxf(mt, fabsf(t[i])); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+    }
+    float s, inv_s, st, inv_st;
+    pow2_scale(mx, s, inv_s);
+    pow2_scale(mt, st, inv_st);
+    store_chunk(p, s, nt.fwd, nt.fwd2, n, kc);
+    store_chunk(t, st, nt.tfwd, nt.tfwd2, n, kc);
+    if (lane == 0) {
+      reinterpret_cast<HMeta*>(nt.fwd + HCfg::META_OFF)->inv_s[n] = inv_s;
+      reinterpret_cast<HMeta*>(nt.tfwd + HCfg::META_OFF)->inv_s[n] = inv_st;
+      if (nt.fwd2) reinterpret_cast<HMeta*>(nt.fwd2 + H2Cfg::META_OFF)->inv_s[n] = inv_s;
+      if (nt.tfwd2) reinterpret_cast<HMeta*>(nt.tfwd2 + H2Cfg::META_OFF)->inv_s[n] = inv_st;
+      atomicMax(&nt.w2max[slot_acc], __float_as_int(mx));
+    }
+    __syncthreads();
+    // transposed orientation: operand row n' = W2 column n', K index = W2 row: these 8 rows are K chunk blockIdx.x of
+    // EVERY operand row.  One power-of-two scale per network (see the header of this file).
+    {
+      const float bound = 2.f * (__int_as_float(nt.w2max[slot_rd]) + 4.f * jobs.lr);
+      float sT, inv_sT;
+      pow2_scale(bound, sT, inv_sT);
+      const int np = tid;
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = tile[i][np];
+      store_chunk(x, sT, nt.bwd, nt.bwd2, np, (int)blockIdx.x);
+      if (blockIdx.x == 0) {
+        reinterpret_cast<HMeta*>(nt.bwd + HCfg::META_OFF)->inv_s[np] = inv_sT;
+        if (nt.bwd2) reinterpret_cast<HMeta*>(nt.bwd2 + H2Cfg::META_OFF)->inv_s[np] = inv_sT;
+      }
+    }
+    return;
+  }
+  // ---------------- the small tensors: W1 | b1, b2, W3 | b3 (+ layer maxima for the operand generators) ----------------
+  if (tid < 16) wm[tid] = 0;
+  if (tid == 0) nt.w2max[slot_clr] = 0;
+  __syncthreads();
+  auto upd = [&](int idx) {
+    float pp = nt.p[idx], mm = nt.m[idx], vv = nt.v[idx];
+    adam_one(pp, mm, vv, nt.g[idx], step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
+    const float tt = nt.targ[idx] * (1.f - jobs.tau) + jobs.tau * pp;
+    nt.p[idx] = pp; nt.m[idx] = mm; nt.v[idx] = vv; nt.targ[idx] = tt;
+    return make_float2(pp, tt);
+  };
+  const int k = tid;                                        // 256 threads = 256 hidden units
+  for (int c = 0; c < in_dim; ++c) {
+    const float2 r = upd(off_W1(in_dim) + k * in_dim + c);
+    atomicMax(&wm[c], __float_as_int(fabsf(r.x)));
+    atomicMax(&wm[8 + c], __float_as_int(fabsf(r.y)));
+  }
+  {
+    const float2 r = upd(off_b1(in_dim) + k);
+    atomicMax(&wm[3], __float_as_int(fabsf(r.x)));
+    atomicMax(&wm[8 + 3], __float_as_int(fabsf(r.y)));
+  }
+  upd(off_b2(in_dim) + k);
+  for (int o = 0; o < out_dim; ++o) {
+    const float2 r = upd(off_W3(in_dim) + o * H + k);
+    atomicMax(&wm[4 + o], __float_as_int(fabsf(r.x)));
+    atomicMax(&wm[8 + 4 + o], __float_as_int(fabsf(r.y)));
+  }
+  if (tid < out_dim) upd(off_b3(in_dim, out_dim) + tid);
+  __syncthreads();
+  if (tid < 8) {
+    const float w = __int_as_float(wm[tid]), wt = __int_as_float(wm[8 + tid]);
+    reinterpret_cast<HMeta*>(nt.fwd + HCfg::META_OFF)->wmax[tid] = w;
+    reinterpret_cast<HMeta*>(nt.bwd + HCfg::META_OFF)->wmax[tid] = w;
+    reinterpret_cast<HMeta*>(nt.tfwd + HCfg::META_OFF)->wmax[tid] = wt;
+    if (nt.fwd2) reinterpret_cast<HMeta*>(nt.fwd2 + H2Cfg::META_OFF)->wmax[tid] = w;
+    if (nt.bwd2) reinterpret_cast<HMeta*>(nt.bwd2 + H2Cfg::META_OFF)->wmax[tid] = w;
+    if (nt.tfwd2) reinterpret_cast<HMeta*>(nt.tfwd2 + H2Cfg::META_OFF)->wmax[tid] = wt;
+  }
+  // the step counter (position in the epoch permutation, Philox stream); nothing in this launch reads it
+  if (jobs.step_inc != nullptr && blockIdx.y == 0 && tid == 0) *jobs.step_inc += 1;
+}
+
+// after the weights were set from the host: every rotating slot of every network = its true max|W2|
+__global__ void __launch_bounds__(256) k_w2max_init(const float* __restrict__ params, int n_slots, int* __restrict__ w2max) {
+  const int slot = blockIdx.x;
+  if (slot >= n_slots) return;
+  const bool is_actor = slot == 0 || slot == n_slots / 2;      // [actor | critics | targ_actor | targ_critics]
+  const float* W2 = params + (size_t)slot * NET_STRIDE + off_W2(is_actor ? 2 : 3);
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) mx = fmaxf(mx, fabsf(W2[i]));
+  __shared__ int sm;
+  if (threadIdx.x == 0) sm = 0;
+  __syncthreads();
+  atomicMax(&sm, __float_as_int(mx));
+  __syncthreads();
+  if (threadIdx.x < 3) w2max[slot * 4 + threadIdx.x] = sm;
+}
+
+}  // namespace tc
+}  // namespace cql

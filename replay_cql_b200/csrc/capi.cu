@@ -84,11 +84,18 @@ void set_kernel_attrs() {
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_score_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ScoreSmemH::bytes(CQL_MAX_TOPK)));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2HCfg::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2HCfg::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2PCfg::BYTES));
+  CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd2_h2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::B2PCfg::BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h_kernel<2, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfg::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute((tc::tc_fwd_h_kernel<3, 1, tc::HCfgS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfgS::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute((tc::tc_fwd_h_kernel<2, 2, tc::HCfgS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfgS::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute((tc::tc_bwd1_h_kernel<3, 1, true, false, tc::HCfgS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfgS::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute((tc::tc_bwd1_h_kernel<3, 1, false, true, tc::HCfgS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfgS::SMEM_BYTES));
+  CQL_CUDA(cudaFuncSetAttribute((tc::tc_bwd1_h_kernel<2, 2, true, false, tc::HCfgS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HCfgS::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2Cfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_fwd_h2_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2Cfg::SMEM_BYTES));
   CQL_CUDA(cudaFuncSetAttribute(tc::tc_bwd1_h2_kernel<3, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::H2B1Cfg::SMEM_BYTES));
@@ -182,7 +189,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   h.dOutA = h.dalloc<float>(2 * (size_t)B);
   h.perb = h.dalloc<float>(4 * (size_t)B);
   h.pairv = h.dalloc<float>(4 * (size_t)C * B);
-  h.loss_sums = h.dalloc<float>(8);
+  h.loss_sums = h.dalloc<float>(16);
   h.splitsC = std::max(1, std::min(tC, (2 * h.num_sms) / (4 * C)));
   h.splitsA = std::max(1, std::min(tB, (2 * h.num_sms) / 4));
   h.smallC = h.dalloc<float>((size_t)C * tC * SMALL_STRIDE);
@@ -195,7 +202,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
     h.packed_net_bytes_bwd = f16 ? tc::HCfg::PACKED_NET_BYTES : (bf ? tc::Cfg<false>::PACKED_NET_BYTES : tc::Cfg<true>::PACKED_NET_BYTES);
     h.packed_fwd = h.dalloc<uint8_t>((size_t)(2 + 2 * C) * h.packed_net_bytes);
     const int slices = f16 ? tc::HCfg::SLICES : (bf ? tc::Cfg<false>::SLICES : tc::Cfg<true>::SLICES);
-    h.part_floats = (size_t)C * slices * ((size_t)B * (2 * n3 + 2)) * 2 + 4096;
+    h.part_floats = (size_t)C * std::max(slices, (int)tc::H2Cfg::PARTS) * ((size_t)B * (2 * n3 + 2)) * 2 + 4096;
     h.part = h.dalloc<float>(h.part_floats);
     h.tc_slices = slices;
     h.packed_bwd = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes_bwd);
@@ -203,6 +210,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
       h.packed_net_bytes2 = tc::H2Cfg::PACKED_NET_BYTES;
       h.packed_fwd2 = h.dalloc<uint8_t>((size_t)(2 + 2 * C) * h.packed_net_bytes2);
       h.packed_bwd2 = h.dalloc<uint8_t>((size_t)(1 + C) * h.packed_net_bytes2);
+      h.w2max = h.dalloc<int>((size_t)(2 + 2 * C) * 4);
       if (const char* sw = std::getenv("CQL_PAIR_SWAP")) h.pair_swap_b = std::atoi(sw);
     }
     h.slots1 = (f16 ? tc::HCfg::NEW : 4) * h.num_sms;
@@ -210,7 +218,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
     h.small1 = h.dalloc<float>((size_t)C * h.slots1 * SMALL_STRIDE);
     h.small2 = h.dalloc<float>((size_t)C * h.splits_tc * SMALL_STRIDE);
     h.pw2_tc = h.dalloc<float>((size_t)(h.num_sms + C) * H * H);
-    h.dX_part = h.dalloc<float4>((size_t)C * slices * B);
+    h.dX_part = h.dalloc<float4>((size_t)C * std::max(slices, 8) * B);
     h.b2_tickets = h.dalloc<unsigned int>((size_t)CQL_MAX_CRITICS * 64 + 64);
   }
   // scalars start at the configured initial values; networks are set by cql_set_weights
@@ -476,6 +484,22 @@ int cql_load_transitions(cql_handle* ch, const float* obs, const float* act, con
   });
 }
 
+int cql_synth_table(cql_handle* ch, int64_t n, int64_t n_users, int64_t n_items, uint64_t seed) {
+  return guarded(ch, [&] {
+    Handle& h = ch->h;
+    CQL_REQUIRE(n >= 1 && n_users >= 1 && n_items >= 1 && n_users <= n, "cql_synth_table: bad shape");
+    CQL_REQUIRE(n_users < (1ll << 24) && n_items < (1ll << 24), "cql_synth_table: ids must stay below 2^24 (exact in float32)");
+    CQL_CUDA(cudaDeviceSynchronize());
+    if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
+    CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+    k_synth_table<<<(unsigned)((n + 255) / 256), 256, 0, h.own_stream>>>(reinterpret_cast<float4*>(h.table), n, n_users, n_items, seed);
+    CQL_LAUNCH_CHECK(&h);
+    CQL_CUDA(cudaStreamSynchronize(h.own_stream));
+    h.n_trans = n;
+    destroy_graph(ch);
+  });
+}
+
 int cql_build_mdp(cql_handle* ch, const int32_t* user_idx, const int32_t* item_idx, const int64_t* timestamp,
                   const double* relevance, const double* action_noise, int64_t n, int32_t top_k, float noise_scale,
                   float* obs_out, float* act_out, float* rew_out, float* term_out, int64_t* order_out) {
@@ -589,15 +613,9 @@ int cql_mma_bench(cql_handle* ch, int mode, int iters, int64_t* out_clk2) {
     CQL_CUDA(cudaMalloc(&d, 16));
     const size_t smem = 64 * 1024 + 64;
     CQL_CUDA(cudaFuncSetAttribute(tc::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
-    const bool pair = mode & 4;
-    cfg.gridDim = dim3(pair ? 2 : 1); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = h.own_stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pair ? 1 : 0;
-    CQL_CUDA(cudaLaunchKernelEx(&cfg, tc::mma_bench_kernel, mode, iters, d));
+    CQL_CUDA(cudaFuncSetAttribute(tc::mma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (mode & 4) tc::mma_bench_pair_kernel<<<2, 128, smem, h.own_stream>>>(mode, iters, d);
+    else tc::mma_bench_kernel<<<1, 128, smem, h.own_stream>>>(mode, iters, d);
     CQL_LAUNCH_CHECK(&h);
     long long hst[2];
     CQL_CUDA(cudaStreamSynchronize(h.own_stream));

@@ -88,10 +88,12 @@ struct Handle {
   float4* dX_part = nullptr;       // [C*SLICES][B]
   unsigned int* b2_tickets = nullptr;   // [C][64] group tickets of the f16x3 bwd2 kernel
   int slots1 = 0, splits_tc = 0, tc_slices = 1;
+  int last_dx_parts = 0;           // parts (nets x column slices) of dX_part written by the last dx launch
   // CTA-pair (cta_group::2) f16x3 kernels: W2 of every slot in the pair layout (mlp_tc_h2.cuh)
   uint8_t* packed_fwd2 = nullptr;  // [(2+2C) slots][H2Cfg::PACKED_NET_BYTES]  B[n][k] = W2[n][k]
   uint8_t* packed_bwd2 = nullptr;  // [(1+C) slots]                           B[n][k] = W2[k][n]
   size_t packed_net_bytes2 = 0;
+  int* w2max = nullptr;            // [(2+2C) slots][4]: rotating max|W2| slots of the fused Adam + pack kernel (adam_pack.cuh)
   int pair_swap_b = 0;             // which cluster rank holds the first half of the operand rows (probed at create)
 
   // optional event marks for cql_timed_update

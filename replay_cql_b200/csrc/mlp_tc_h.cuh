@@ -26,10 +26,10 @@
 namespace cql {
 namespace tc {
 
-template <int NEW_>
+template <int NEW_, int NS_ = 128>
 struct HCfgT {
   static constexpr int ES = 2, EPC = 8, UK = 16;
-  static constexpr int NS = 128;                      // output columns per work item
+  static constexpr int NS = NS_;                      // output columns per work item (128; 32 for the small launches)
   static constexpr int SLICES = H / NS;               // 2
   static constexpr int NPW = 16;
   static constexpr int KC = 64;                       // K per stage
@@ -44,7 +44,7 @@ struct HCfgT {
   static constexpr uint32_t B_BYTES = 2 * B_TERM_BYTES;            // 128 KB (hi | lo)
   static constexpr size_t META_OFF = (size_t)SLICES * B_BYTES;     // float inv_s[256] | float wmax[8]
   static constexpr size_t PACKED_NET_BYTES = META_OFF + 2048;
-  static constexpr uint32_t A_COL0 = 2 * NS;          // 256
+  static constexpr uint32_t A_COL0 = 256;             // after the two accumulators (2 x NS <= 256 columns)
   static constexpr uint32_t A_STAGE_COLS = KC;        // 32 hi + 32 lo columns
   static constexpr uint32_t A_LO_COLS = KC / 2;
   static constexpr uint32_t TMEM_ALLOC = 512;
@@ -59,8 +59,28 @@ struct HCfgT {
   static constexpr uint32_t RED_WARP_BYTES = 32 * 33 * 4 + 32 * 16;
   static constexpr uint32_t SMEM_BYTES = OFF_RED + NEW_ * RED_WARP_BYTES;
 };
-using HCfg = HCfgT<8>;     // update kernels
+using HCfg = HCfgT<8>;     // update kernels; ALSO the layout of a packed net in global memory (128-row slices)
+using HCfgS = HCfgT<8, 32>;   // small launches (B rows): 32-column work items, four times as many CTAs
 using HCfg4 = HCfgT<4>;    // scorer (one epilogue group keeps the per-row state)
+
+// The resident operand of a work item: NS rows x 256 K, hi | lo, compact K-major layout in shared memory.  The packed net
+// in global memory is laid out in 128-row slices (HCfg); a 32-row sub-slice of it is 2 x 32 pieces of 512 bytes.
+template <class C>
+__device__ __forceinline__ void load_operand_slice(uint8_t* Bs, const uint8_t* packed_net, int slice, uint64_t* bar) {
+  if constexpr (C::NS == HCfg::NS) {
+    const uint8_t* src = packed_net + (size_t)slice * HCfg::B_BYTES;
+    mbar_arrive_expect_tx(bar, C::B_BYTES);
+    for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bar);
+  } else {
+    constexpr int PER = HCfg::NS / C::NS;                                  // sub-slices per 128-row slice
+    const uint8_t* src = packed_net + (size_t)(slice / PER) * HCfg::B_BYTES + (size_t)(slice % PER) * (C::NS * 16);
+    mbar_arrive_expect_tx(bar, C::B_BYTES);
+    for (int term = 0; term < 2; ++term)
+      for (int kc = 0; kc < H / 8; ++kc)
+        bulk_g2s(Bs + term * C::B_TERM_BYTES + kc * (C::NS * 16), src + (size_t)term * HCfg::B_TERM_BYTES + (size_t)kc * (HCfg::NS * 16),
+                 C::NS * 16, bar);
+  }
+}
 
 // meta block of a packed net
 struct HMeta {
@@ -162,6 +182,7 @@ __global__ void __launch_bounds__(256) k_pack_multi_h(const PackJobs jobs, int o
 constexpr int FWD_H2_COST = 13;     // relative cost of a forward item that stores H2 (plain item = 10)
 
 struct HItem { int job, net, slice, tile, pair_id; };
+template <int SLICES = HCfg::SLICES>
 __device__ __forceinline__ HItem decode_item_h(const TcFwdJobs& jobs, int item) {
   HItem it;
   it.job = 0;
@@ -170,8 +191,8 @@ __device__ __forceinline__ HItem decode_item_h(const TcFwdJobs& jobs, int item) 
   const int tiles = (jobs.j[it.job].rows + TM - 1) / TM;
   const int pair = local / tiles;
   it.tile = local % tiles;
-  it.net = pair / HCfg::SLICES;
-  it.slice = pair % HCfg::SLICES;
+  it.net = pair / SLICES;
+  it.slice = pair % SLICES;
   it.pair_id = it.job * 64 + pair;
   return it;
 }
@@ -181,9 +202,8 @@ __device__ __forceinline__ float h1_row_bound(const float4& x, const float4& wm)
   return fmaf(fabsf(x.x), wm.x, fmaf(fabsf(x.y), wm.y, fmaf(fabsf(x.z), wm.z, wm.w)));
 }
 
-template <int IN, int OUT>
+template <int IN, int OUT, class C = HCfg>
 __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJobs jobs) {
-  using C = HCfg;
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Bs = sm + C::OFF_B;
   float4* w1p = reinterpret_cast<float4*>(sm + C::OFF_W1);   // [k/2][2]: {wx_k,wx_k1,wy_k,wy_k1}, {wz_k,wz_k1,b_k,b_k1}
@@ -244,7 +264,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
     int cur_pair = -1;
     uint32_t it = 0, nb = 0, nd = 0, tcount = 0;
     for (int item = item_lo; item < item_hi; ++item) {
-      const HItem ii = decode_item_h(jobs, item);
+      const HItem ii = decode_item_h<C::SLICES>(jobs, item);
       if (ii.pair_id != cur_pair) {
         if (cur_pair >= 0) {
           if (elect_one()) umma_commit(drain);
@@ -253,11 +273,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
           ++nd;
         }
         const TcFwdJob& jb = jobs.j[ii.job];
-        const uint8_t* src = jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + (size_t)ii.slice * C::B_BYTES;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bload, C::B_BYTES);
-          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
-        }
+        if (elect_one()) load_operand_slice<C>(Bs, jb.packed + (size_t)ii.net * HCfg::PACKED_NET_BYTES, ii.slice, bload);
         __syncwarp();
         mbar_wait(bload, nb & 1);
         ++nb;
@@ -304,10 +320,10 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
       return r < nj.rows ? __ldg(nj.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     float4 x_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    HItem ii_next = item_lo < item_hi ? decode_item_h(jobs, item_lo) : HItem{};   // one decode (integer division) per item
+    HItem ii_next = item_lo < item_hi ? decode_item_h<C::SLICES>(jobs, item_lo) : HItem{};   // one decode (integer division) per item
     for (int item = item_lo; item < item_hi; ++item) {
       const HItem ii = ii_next;
-      if (item + 1 < item_hi) ii_next = decode_item_h(jobs, item + 1);
+      if (item + 1 < item_hi) ii_next = decode_item_h<C::SLICES>(jobs, item + 1);
       const TcFwdJob& jb = jobs.j[ii.job];
       const int netkey = ii.job * 64 + ii.net;
       if (netkey != cur_netkey) {
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
           w1p[2 * pr] = make_float4(wa[0], wb[0], wa[1], wb[1]);
           w1p[2 * pr + 1] = make_float4(IN == 3 ? wa[2] : 0.f, IN == 3 ? wb[2] : 0.f, net[off_b1(IN) + k], net[off_b1(IN) + k + 1]);
         }
-        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * HCfg::PACKED_NET_BYTES + HCfg::META_OFF);
         wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
         asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
       }
@@ -364,13 +380,13 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
     float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int item = item_lo + grp; item < item_hi; item += 2) {
       const uint32_t tcount = (uint32_t)(item - item_lo);
-      const HItem ii = decode_item_h(jobs, item);
+      const HItem ii = decode_item_h<C::SLICES>(jobs, item);
       const TcFwdJob& jb = jobs.j[ii.job];
       if (ii.pair_id != cur_pair) {
         cur_pair = ii.pair_id;
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
         const float* net = jb.params + (size_t)ii.net * NET_STRIDE;
-        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * HCfg::PACKED_NET_BYTES + HCfg::META_OFF);
         for (int cidx = gtid; cidx < C::NS; cidx += 128) {
           const int col = ii.slice * C::NS + cidx;
           const float inv_n = __ldg(&meta->inv_s[col]);
@@ -448,9 +464,8 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_fwd_h_kernel(const TcFwdJ
 // and (optionally) dx.  Structure of tc_bwd1_ts_kernel (mlp_tc_bwd1.cuh); differences: W2^T packed as scaled fp16
 // hi|lo in 128-column slices, the dZ2 row scaled by 2^e from the bound |dOut_0| max|W3_0| + |dOut_1| max|W3_1|,
 // two epilogue groups (one per accumulator), accumulator unscaled by 1/(s_m s_n) before the ReLU mask.
-template <int IN, int OUT, bool WGRADS, bool DX>
+template <int IN, int OUT, bool WGRADS, bool DX, class C = HCfg>
 __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1Job jb) {
-  using C = HCfg;
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Bs = sm + C::OFF_B;
   float2* w3s = reinterpret_cast<float2*>(sm + C::OFF_W1);    // [256] (W3[0][j], W3[1][j])
@@ -498,11 +513,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
       const int pair = item / tiles;
       if (pair != cur_pair) {
         if (cur_pair >= 0) { if (elect_one()) umma_commit(drain); __syncwarp(); mbar_wait(drain, nd & 1); ++nd; }
-        const uint8_t* src = jb.packedT + (size_t)(pair / C::SLICES) * C::PACKED_NET_BYTES + (size_t)(pair % C::SLICES) * C::B_BYTES;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bload, C::B_BYTES);
-          for (uint32_t o = 0; o < C::B_BYTES; o += 32768) bulk_g2s(Bs + o, src + o, 32768, bload);
-        }
+        if (elect_one()) load_operand_slice<C>(Bs, jb.packedT + (size_t)(pair / C::SLICES) * HCfg::PACKED_NET_BYTES, pair % C::SLICES, bload);
         __syncwarp();
         mbar_wait(bload, nb & 1);
         ++nb;
@@ -551,7 +562,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
         const float* net = jb.params + (size_t)net_i * NET_STRIDE;
         for (int j = ptid; j < H; j += C::PROD_THREADS)
           w3s[j] = make_float2(net[off_W3(IN) + j], OUT == 2 ? net[off_W3(IN) + H + j] : 0.f);
-        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * HCfg::PACKED_NET_BYTES + HCfg::META_OFF);
         w3m0 = __ldg(&meta->wmax[4]);
         w3m1 = OUT == 2 ? __ldg(&meta->wmax[5]) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
       asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
       float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 2 + grp) * SMALL_STRIDE;
       // warp w of the group sums chunk q = w over the four warps (order 0..3) and writes that chunk's columns
-      {
+      if (qw < NCH) {
         const int q = qw;
         float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
@@ -648,7 +659,7 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
         cur_pair = pair;
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
         const float* net = jb.params + (size_t)net_i * NET_STRIDE;
-        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
+        const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * HCfg::PACKED_NET_BYTES + HCfg::META_OFF);
         for (int cidx = gtid; cidx < C::NS; cidx += 128) {
           const int k = slice * C::NS + cidx;
           ebg[cidx] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],

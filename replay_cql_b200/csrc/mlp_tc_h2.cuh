@@ -91,6 +91,7 @@ struct H2Cfg {
   static constexpr int NP = 128;                         // output columns per pass (UMMA N)
   static constexpr int NLOC = NP / 2;                    // operand rows of a pass held by ONE CTA
   static constexpr int PASSES = H / NP;                  // 2
+  static constexpr int PARTS = 2 * PASSES;               // layer-3 partial sums per row: (pass, column half)
   static constexpr int TMP = 2 * TM;                     // rows per pair tile (UMMA M)
   static constexpr int MMA_WARP = NEW + NPW;
   static constexpr int THREADS = (NEW + NPW + 1) * 32;   // 800
@@ -188,7 +189,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
   uint64_t* full = bars;                         // [STAGES] leader: 2 x NPW producer warps
   uint64_t* empty = bars + C::STAGES;            // [STAGES] both CTAs: multicast commit
   uint64_t* tfull = bars + 2 * C::STAGES;        // [2] both CTAs: multicast commit
-  uint64_t* tempty = tfull + 2;                  // [2] leader: 2 x 4 epilogue warps
+  uint64_t* tempty = tfull + 2;                  // [2] leader: 2 x 8 epilogue warps
   uint64_t* bload = tempty + 2;                  // own W2 half landed
   uint64_t* bready = bload + 1;                  // leader: both halves landed
   uint64_t* drain = bready + 1;                  // both CTAs: every MMA issued so far has retired
@@ -227,7 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
     tmem_alloc2(slot, 512);
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 2 * C::NPW); mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * C::NEW); }
       mbar_init(bload, 1);
       mbar_init(bready, 2);
       mbar_init(drain, 1);
@@ -366,10 +367,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
     if (item_hi > item_lo)
       for (int c = 0; c < C::NCHUNK; ++c) mbar_wait_cluster(&empty[c], (tcount & 1) ^ 1);
   } else {
-    // ============ epilogue (both CTAs): group g drains pass g: unscale -> +b2 -> ReLU -> layer 3 (+ H2) ============
-    const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;
-    float4* ebg = ebs + grp * C::NP;
-    float2* efg = efs + grp * C::NP;
+    // ============ epilogue (both CTAs): unscale -> +b2 -> ReLU -> layer 3 (+ H2) ============
+    // ALL eight warps drain pass 0's accumulator (warp w: TMEM lane quarter w % 4, column half w / 4 = 64 columns),
+    // then pass 1's.  An accumulator is single-buffered (tensor memory: 256 columns of A + 2 x 128 of D), so the MMA of
+    // pass p of the NEXT tile waits for this drain; with one 4-warp group per pass the drain of a 128-column
+    // accumulator had to fit into the other pass's 3 k clocks (measured 4-5 k on the tiles that store H2: the tensor
+    // pipe idled), with eight warps on each accumulator it takes half as long against the same budget.
+    const int hh = warp >> 2, qw = warp & 3;
     int cur_key = -1;
     const int row_in_tile = (int)rank * TM + qw * 32 + lane;
     float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -379,99 +383,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
       const TcFwdJob& jb = jobs.j[ii.job];
       if (ii.netkey != cur_key) {
         cur_key = ii.netkey;
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        asm volatile("bar.sync 2, 256;");
         const float* net = jb.params + (size_t)ii.net * NET_STRIDE;
         const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packed + (size_t)ii.net * C::PACKED_NET_BYTES + C::META_OFF);
-        for (int cidx = gtid; cidx < C::NP; cidx += 128) {
-          const int col = grp * C::NP + cidx;
+        {
+          const int col = tid;                       // 256 epilogue threads = 256 output columns
           const float inv_n = __ldg(&meta->inv_s[col]);
-          ebg[cidx] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col],
-                                  OUT == 2 ? net[off_W3(IN) + H + col] : 0.f, inv_n);
+          ebs[col] = make_float4(net[off_b2(IN) + col], net[off_W3(IN) + col],
+                                 OUT == 2 ? net[off_W3(IN) + H + col] : 0.f, inv_n);
           // folded form for items that do not store H2 (exact, powers of two):
-          // relu(v/(s_m s_n) + b2) w3 = relu(v/s_m + b2 s_n) (w3/s_n)
-          if (OUT == 1) {                 // pairs of columns: (b2'_c, b2'_c+1, w3'_c, w3'_c+1) -- natural fp32x2 operands
-            float* ef = reinterpret_cast<float*>(efg) + (cidx >> 1) * 4 + (cidx & 1);
+          // relu(v/(s_m s_n) + b2) w3 = relu(v/s_m + b2 s_n) (w3/s_n); pairs of columns (b2'_c, b2'_c+1, w3'_c, w3'_c+1)
+          if (OUT == 1) {
+            float* ef = reinterpret_cast<float*>(efs) + (col >> 1) * 4 + (col & 1);
             ef[0] = net[off_b2(IN) + col] / inv_n;
             ef[2] = net[off_W3(IN) + col] * inv_n;
           }
         }
         wm = make_float4(__ldg(&meta->wmax[0]), __ldg(&meta->wmax[1]), IN == 3 ? __ldg(&meta->wmax[2]) : 0.f, __ldg(&meta->wmax[3]));
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        asm volatile("bar.sync 2, 256;");
       }
       const int row = ii.tp * C::TMP + row_in_tile;
       const float4 x = row < jb.rows ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
       float sa, inv_sa;
       pow2_scale(h1_row_bound(x, wm), sa, inv_sa);                 // the producers' scale of this row, recomputed
-      mbar_wait_cluster(&tfull[grp], tcount & 1);
-      tc_fence_after();
       const bool store_h2 = jb.h2 != nullptr;
       const int tiles64 = (jb.rows + 63) / 64;
-      float* h2row = store_h2 ? jb.h2 + (((size_t)ii.net * tiles64 + (row >> 6)) * H + grp * C::NP) * 64 + (row & 63)
-                              : nullptr;
-      const uint32_t t_acc = tmem + ((uint32_t)(qw * 32) << 16) + grp * C::NP;
-      float q0 = 0.f, q1 = 0.f;
-      // The per-column constants are warp-uniform shared-memory loads.  They are fetched in BATCHES (8 x LDS.128 issued
-      // back to back, together with the TMEM load) before the math of a step: interleaved one by one each LDS exposed
-      // its ~30-clock latency inside the dependent chain and a 128-column epilogue took ~6 k clocks (ncu r02), three
-      // times the 3 k clocks the other pass leaves it.
-      if (OUT == 1 && !store_h2) {
-        const float2 isa2 = make_float2(inv_sa, inv_sa);
-        const float4* ef4 = reinterpret_cast<const float4*>(efg);   // [64]: (b2'_c, b2'_c+1, w3'_c, w3'_c+1)
-        float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int c0 = 0; c0 < C::NP; c0 += 16) {
-          float v[16];
-          float4 e[8];
-          tmem_ld16(t_acc + c0, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = ef4[(c0 >> 1) + j];
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float2 ha = ffma2(make_float2(v[2 * j], v[2 * j + 1]), isa2, make_float2(e[j].x, e[j].y));
-            float2 hb = ffma2(make_float2(v[2 * j + 2], v[2 * j + 3]), isa2, make_float2(e[j + 1].x, e[j + 1].y));
-            ha.x = fmaxf(ha.x, 0.f); ha.y = fmaxf(ha.y, 0.f);
-            hb.x = fmaxf(hb.x, 0.f); hb.y = fmaxf(hb.y, 0.f);
-            qa = ffma2(ha, make_float2(e[j].z, e[j].w), qa);
-            qb = ffma2(hb, make_float2(e[j + 1].z, e[j + 1].w), qb);
-          }
-        }
-        q0 = (qa.x + qa.y) + (qb.x + qb.y);
-      } else {
-        float q0b = 0.f, q1b = 0.f;
+      for (int p = 0; p < C::PASSES; ++p) {
+        constexpr int NC = C::NP / 2;                              // 64 columns per warp per pass
+        const int cb = p * C::NP + hh * NC;                        // first output column of this warp in this pass
+        mbar_wait(&tfull[p], tcount & 1);
+        tc_fence_after();
+        float* h2row = store_h2 ? jb.h2 + (((size_t)ii.net * tiles64 + (row >> 6)) * H + cb) * 64 + (row & 63) : nullptr;
+        const uint32_t t_acc = tmem + ((uint32_t)(qw * 32) << 16) + cb;
+        float q0 = 0.f, q1 = 0.f;
+        // The per-column constants are warp-uniform shared-memory loads, fetched in BATCHES (issued back to back,
+        // together with the TMEM load) before the math of a step: interleaved one by one each LDS exposed its
+        // ~30-clock latency inside the dependent chain.
+        if (OUT == 1 && !store_h2) {
+          const float2 isa2 = make_float2(inv_sa, inv_sa);
+          const float4* ef4 = reinterpret_cast<const float4*>(efs) + (cb >> 1);   // (b2'_c, b2'_c+1, w3'_c, w3'_c+1)
+          float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int c0 = 0; c0 < C::NP; c0 += 8) {
-          float v[8];
-          float4 e[8];
-          tmem_ld8(t_acc + c0, v);
+          for (int c0 = 0; c0 < NC; c0 += 16) {
+            float v[16];
+            float4 e[8];
+            tmem_ld16(t_acc + c0, v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ebg[c0 + i];
-          tmem_ld_wait();
+            for (int j = 0; j < 8; ++j) e[j] = ef4[(c0 >> 1) + j];
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float ha = fmaxf(fmaf(v[i] * inv_sa, e[i].w, e[i].x), 0.f);
-            const float hb = fmaxf(fmaf(v[i + 1] * inv_sa, e[i + 1].w, e[i + 1].x), 0.f);
-            v[i] = ha;
-            v[i + 1] = hb;
-            q0 = fmaf(ha, e[i].y, q0);
-            q0b = fmaf(hb, e[i + 1].y, q0b);
-            if (OUT == 2) { q1 = fmaf(ha, e[i].z, q1); q1b = fmaf(hb, e[i + 1].z, q1b); }
+            for (int j = 0; j < 8; j += 2) {
+              float2 ha = ffma2(make_float2(v[2 * j], v[2 * j + 1]), isa2, make_float2(e[j].x, e[j].y));
+              float2 hb = ffma2(make_float2(v[2 * j + 2], v[2 * j + 3]), isa2, make_float2(e[j + 1].x, e[j + 1].y));
+              ha.x = fmaxf(ha.x, 0.f); ha.y = fmaxf(ha.y, 0.f);
+              hb.x = fmaxf(hb.x, 0.f); hb.y = fmaxf(hb.y, 0.f);
+              qa = ffma2(ha, make_float2(e[j].z, e[j].w), qa);
+              qb = ffma2(hb, make_float2(e[j + 1].z, e[j + 1].w), qb);
+            }
           }
-          if (store_h2 && (row >> 6) < tiles64) {
+          q0 = (qa.x + qa.y) + (qb.x + qb.y);
+        } else {
+          const float4* ebg = ebs + cb;
+          float q0b = 0.f, q1b = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < NC; c0 += 8) {
+            float v[8];
+            float4 e[8];
+            tmem_ld8(t_acc + c0, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) h2row[(size_t)(c0 + i) * 64] = v[i];
+            for (int i = 0; i < 8; ++i) e[i] = ebg[c0 + i];
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float ha = fmaxf(fmaf(v[i] * inv_sa, e[i].w, e[i].x), 0.f);
+              const float hb = fmaxf(fmaf(v[i + 1] * inv_sa, e[i + 1].w, e[i + 1].x), 0.f);
+              v[i] = ha;
+              v[i + 1] = hb;
+              q0 = fmaf(ha, e[i].y, q0);
+              q0b = fmaf(hb, e[i + 1].y, q0b);
+              if (OUT == 2) { q1 = fmaf(ha, e[i].z, q1); q1b = fmaf(hb, e[i + 1].z, q1b); }
+            }
+            if (store_h2 && (row >> 6) < tiles64) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h2row[(size_t)(c0 + i) * 64] = v[i];
+            }
           }
+          q0 += q0b;
+          q1 += q1b;
         }
-        q0 += q0b;
-        q1 += q1b;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty[grp], 0);
-      if (row < jb.rows) {
-        float* o = jb.out_part + (((size_t)ii.net * C::PASSES + grp) * jb.rows + row) * OUT;
-        o[0] = q0;
-        if (OUT == 2) o[1] = q1;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty[p], 0);
+        if (row < jb.rows) {
+          float* o = jb.out_part + (((size_t)ii.net * C::PARTS + p * 2 + hh) * jb.rows + row) * OUT;
+          o[0] = q0;
+          if (OUT == 2) o[1] = q1;
+        }
       }
     }
   }
@@ -530,7 +538,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
     tmem_alloc2(slot, 512);
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 2 * C::NPW); mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * C::NEW); }
       mbar_init(bload, 1);
       mbar_init(bready, 2);
       mbar_init(drain, 1);
@@ -666,42 +674,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
     if (item_hi > item_lo)
       for (int c = 0; c < C::NCHUNK; ++c) mbar_wait_cluster(&empty[c], (tcount & 1) ^ 1);
   } else {
-    // ---------------- epilogue: group g = pass g = columns [128 g, 128 g + 128): dZ1, dx, dW1/db1 ----------------
-    constexpr int NCH = C::NP / 32;
-    const int grp = warp >> 2, qw = warp & 3, gtid = tid & 127;
-    float4* ebg = ebs + grp * C::NP;
-    float* ivg = invs + grp * C::NP;
-    float a_b[NCH], a_w0[NCH], a_w1[NCH], a_w2[NCH];      // lane l <-> column chunk*32 + l of the group's pass
+    // ---------------- epilogue: dZ1 = dH1 * relu'(Z1), dx, dW1/db1 column sums ----------------
+    // All eight warps drain pass 0's accumulator, then pass 1's (warp w: lane quarter w % 4, column half w / 4 =
+    // 64 columns of each pass) -- see the forward kernel for why.
+    constexpr int NC = C::NP / 2;                          // 64 columns per warp per pass
+    constexpr int NCH = NC / 32;                           // 2 chunks of 32 columns
+    const int hh = warp >> 2, qw = warp & 3, gtid = tid & 127;
+    float a_b[C::PASSES][NCH], a_w0[C::PASSES][NCH], a_w1[C::PASSES][NCH], a_w2[C::PASSES][NCH];   // lane l <-> column
 #pragma unroll
-    for (int q = 0; q < NCH; ++q) { a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f; }
-    float* flbuf = reinterpret_cast<float*>(sm + C::OFF_FLUSH) + grp * (4 * 16 * 32);
+    for (int p = 0; p < C::PASSES; ++p)
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) { a_b[p][q] = 0.f; a_w0[p][q] = 0.f; a_w1[p][q] = 0.f; a_w2[p][q] = 0.f; }
+    float* flbuf = reinterpret_cast<float*>(sm + C::OFF_FLUSH) + hh * (4 * 16 * 32);
     float* red_t = reinterpret_cast<float*>(sm + C::OFF_RED + warp * C::RED_WARP_BYTES);       // [32][33]
     float4* red_x = reinterpret_cast<float4*>(red_t + 32 * 33);                                 // [32] this item's input rows
-    auto flush = [&](int net_i) {                    // called uniformly by the 4 warps of the group
+    auto flush = [&](int net_i) {                    // called uniformly by the 4 warps of a column half
       if (!WGRADS || net_i < 0) return;
 #pragma unroll
-      for (int q = 0; q < NCH; ++q) {
-        float* f = flbuf + (qw * 16 + q * 4) * 32 + lane;
-        f[0] = a_w0[q]; f[32] = a_w1[q]; f[64] = a_w2[q]; f[96] = a_b[q];
-        a_b[q] = 0.f; a_w0[q] = 0.f; a_w1[q] = 0.f; a_w2[q] = 0.f;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
-      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 2 + grp) * SMALL_STRIDE;
+      for (int p = 0; p < C::PASSES; ++p)
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          float* f = flbuf + (qw * 16 + (p * NCH + q) * 4) * 32 + lane;
+          f[0] = a_w0[p][q]; f[32] = a_w1[p][q]; f[64] = a_w2[p][q]; f[96] = a_b[p][q];
+          a_b[p][q] = 0.f; a_w0[p][q] = 0.f; a_w1[p][q] = 0.f; a_w2[p][q] = 0.f;
+        }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + hh));
+      float* o = jb.small1 + ((size_t)net_i * jb.slots + blockIdx.x * 2 + hh) * SMALL_STRIDE;
       {
-        const int q = qw;                            // warp w sums chunk q = w over the four warps (order 0..3)
+        const int pq = qw;                           // warp w sums chunk (p, q) = w over the four warps (order 0..3)
         float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const float* f = flbuf + (w * 16 + q * 4) * 32 + lane;
+          const float* f = flbuf + (w * 16 + pq * 4) * 32 + lane;
           t0 += f[0]; t1 += f[32]; t2 += f[64]; t3 += f[96];
         }
-        const int k = grp * C::NP + q * 32 + lane;
+        const int k = (pq / NCH) * C::NP + hh * NC + (pq % NCH) * 32 + lane;
         o[k * IN + 0] = t0;
         o[k * IN + 1] = t1;
         if (IN == 3) o[k * IN + 2] = t2;
         o[H * IN + k] = t3;
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + hh));
     };
     int cur_net = -1;
     float w3m0 = 0.f, w3m1 = 0.f;
@@ -711,18 +724,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
       if (net_i != cur_net) {
         flush(cur_net);
         cur_net = net_i;
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        asm volatile("bar.sync 4, 256;");
         const float* net = jb.params + (size_t)net_i * NET_STRIDE;
         const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
-        for (int cidx = gtid; cidx < C::NP; cidx += 128) {
-          const int k = grp * C::NP + cidx;
-          ebg[cidx] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
-                                  IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
-          ivg[cidx] = __ldg(&meta->inv_s[k]);
+        {
+          const int k = tid;                          // 256 epilogue threads = 256 hidden units
+          ebs[k] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
+                               IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+          invs[k] = __ldg(&meta->inv_s[k]);
         }
         w3m0 = __ldg(&meta->wmax[4]);
         w3m1 = OUT == 2 ? __ldg(&meta->wmax[5]) : 0.f;
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp));
+        asm volatile("bar.sync 4, 256;");
       }
       const int row = tp * C::TMP + (int)rank * TM + qw * 32 + lane;
       const bool ok = row < jb.rows;
@@ -733,71 +746,369 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
       pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);     // the producers' scale of this row
       if (WGRADS) {
         __syncwarp();
-        red_x[lane] = x;                                                      // rows beyond jb.rows are zero
+        red_x[lane] = make_float4(x.x, x.y, x.z, 1.f);                        // rows beyond jb.rows: x = 0, dZ1 = 0
       }
-      mbar_wait_cluster(&tfull[grp], tcount & 1);
-      tc_fence_after();
-      const uint32_t t_acc = tmem + ((uint32_t)(qw * 32) << 16) + grp * C::NP;
-      float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
 #pragma unroll
-      for (int q = 0; q < NCH; ++q) {                   // (unrolled: a_w*[q] must stay in registers)
-        if (WGRADS) __syncwarp();                       // the previous chunk's column sums have read red_t
-        // 8 columns per step: the TMEM load and the step's constants (warp-uniform LDS) are issued together, then the
-        // math -- one LDS per column inside the dependent chain made this epilogue latency-bound (ncu r02)
+      for (int p = 0; p < C::PASSES; ++p) {
+        const int cb = p * C::NP + hh * NC;
+        const float4* ebg = ebs + cb;
+        const float* ivg = invs + cb;
+        mbar_wait(&tfull[p], tcount & 1);
+        tc_fence_after();
+        const uint32_t t_acc = tmem + ((uint32_t)(qw * 32) << 16) + cb;
+        float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {                   // (unrolled: a_w*[p][q] must stay in registers)
+          if (WGRADS) __syncwarp();                       // the previous chunk's column sums have read red_t
+          // 8 columns per step: the TMEM load and the step's constants (warp-uniform LDS) are issued together, then the
+          // math -- one LDS per column inside the dependent chain made this epilogue latency-bound (ncu r02)
 #pragma unroll 1
-        for (int c8 = 0; c8 < 32; c8 += 8) {
-          float v[8];
-          float4 w[8];
-          float iv[8];
-          tmem_ld8(t_acc + q * 32 + c8, v);
+          for (int c8 = 0; c8 < 32; c8 += 8) {
+            float v[8];
+            float4 w[8];
+            float iv[8];
+            tmem_ld8(t_acc + q * 32 + c8, v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = ebg[q * 32 + c8 + i];
-          if (DX) {
-            const float4 i0 = *reinterpret_cast<const float4*>(ivg + q * 32 + c8);
-            const float4 i1 = *reinterpret_cast<const float4*>(ivg + q * 32 + c8 + 4);
-            iv[0] = i0.x; iv[1] = i0.y; iv[2] = i0.z; iv[3] = i0.w; iv[4] = i1.x; iv[5] = i1.y; iv[6] = i1.z; iv[7] = i1.w;
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // layer-1 pre-activation in the FORWARD's order (chain starts from the bias): same ReLU mask bit for bit
-            float z = fmaf(x.y, w[i].y, fmaf(x.x, w[i].x, w[i].w));
-            if (IN == 3) z = fmaf(x.z, w[i].z, z);
-            // without dx the column scale 1/s_n is applied once per column sum instead of once per element
-            const float d = z > 0.f ? (DX ? v[i] * inv_sa * iv[i] : v[i] * inv_sa) : 0.f;
+            for (int i = 0; i < 8; ++i) w[i] = ebg[q * 32 + c8 + i];
             if (DX) {
-              dx0 = fmaf(d, w[i].x, dx0);
-              dx1 = fmaf(d, w[i].y, dx1);
-              if (IN == 3) dx2 = fmaf(d, w[i].z, dx2);
+              const float4 i0 = *reinterpret_cast<const float4*>(ivg + q * 32 + c8);
+              const float4 i1 = *reinterpret_cast<const float4*>(ivg + q * 32 + c8 + 4);
+              iv[0] = i0.x; iv[1] = i0.y; iv[2] = i0.z; iv[3] = i0.w; iv[4] = i1.x; iv[5] = i1.y; iv[6] = i1.z; iv[7] = i1.w;
             }
-            if (WGRADS) red_t[lane * 33 + c8 + i] = d;
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              // layer-1 pre-activation in the FORWARD's order (chain starts from the bias): same ReLU mask bit for bit
+              float z = fmaf(x.y, w[i].y, fmaf(x.x, w[i].x, w[i].w));
+              if (IN == 3) z = fmaf(x.z, w[i].z, z);
+              // without dx the column scale 1/s_n is applied once per column sum instead of once per element
+              const float d = z > 0.f ? (DX ? v[i] * inv_sa * iv[i] : v[i] * inv_sa) : 0.f;
+              if (DX) {
+                dx0 = fmaf(d, w[i].x, dx0);
+                dx1 = fmaf(d, w[i].y, dx1);
+                if (IN == 3) dx2 = fmaf(d, w[i].z, dx2);
+              }
+              if (WGRADS) red_t[lane * 33 + c8 + i] = d;
+            }
           }
-        }
-        if (WGRADS) {
-          // column sums over the warp's 32 rows through the transposed shared-memory tile (fixed row order)
-          __syncwarp();
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, sb = 0.f;
+          if (WGRADS) {
+            // column sums over the warp's 32 rows through the transposed shared-memory tile (fixed row order); packed
+            // FMAs on (x0, x1) and (x2, 1)
+            __syncwarp();
+            float2 s01 = make_float2(0.f, 0.f), s2b = make_float2(0.f, 0.f);
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const float dv = red_t[r * 33 + lane];
-            const float4 xr = red_x[r];
-            s0 = fmaf(dv, xr.x, s0);
-            s1 = fmaf(dv, xr.y, s1);
-            if (IN == 3) s2 = fmaf(dv, xr.z, s2);
-            sb += dv;
+            for (int r = 0; r < 32; ++r) {
+              const float dv = red_t[r * 33 + lane];
+              const float4 xr = red_x[r];
+              const float2 dd = make_float2(dv, dv);
+              s01 = ffma2(dd, make_float2(xr.x, xr.y), s01);
+              s2b = ffma2(dd, make_float2(xr.z, xr.w), s2b);
+            }
+            const float cs = DX ? 1.f : ivg[q * 32 + lane];
+            a_w0[p][q] = fmaf(s01.x, cs, a_w0[p][q]); a_w1[p][q] = fmaf(s01.y, cs, a_w1[p][q]);
+            a_w2[p][q] = fmaf(s2b.x, cs, a_w2[p][q]); a_b[p][q] = fmaf(s2b.y, cs, a_b[p][q]);
           }
-          const float cs = DX ? 1.f : ivg[q * 32 + lane];
-          a_w0[q] = fmaf(s0, cs, a_w0[q]); a_w1[q] = fmaf(s1, cs, a_w1[q]); a_w2[q] = fmaf(s2, cs, a_w2[q]);
-          a_b[q] = fmaf(sb, cs, a_b[q]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty[p], 0);
+        if (DX && ok)
+          jb.dX_part[((size_t)net_i * C::PARTS + p * 2 + hh) * jb.rows + row] = make_float4(dx0, dx1, dx2, 0.f);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty[grp], 0);
-      if (DX && ok)
-        jb.dX_part[((size_t)net_i * C::PASSES + grp) * jb.rows + row] = make_float4(dx0, dx1, dx2, 0.f);
     }
     flush(cur_net);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == C::MMA_WARP) tmem_dealloc2(tmem, 512);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the hidden layer on CTA pairs: dW2[j][k] = sum_r dZ2[r][j] H1[r][k], contraction over batch rows.
+// The one-CTA kernel (tc_bwd2_h_kernel) reads BOTH operands from shared memory -- an SS-mode MMA of N = 256 takes
+// 171 clocks instead of 128 (cql_mma_bench, profiles/r02_mma_issue_rate.txt) and the port also carries the producers'
+// stores: tensor pipe 21 %.  Here the 256 x 256 accumulator is split over a pair: CTA c owns the output rows
+// j in [128c, 128c + 128) (its 128 TMEM lanes, all 256 columns = 256 of its 512 TMEM columns) and holds the operand rows
+// k in [128c, 128c + 128) of B = H1^T in shared memory; `tcgen05.mma.cta_group::2` (M = 256, N = 256) reads both halves.
+// That frees 256 TMEM columns for the A operand (dZ2^T: lane = j, columns = batch rows, two fp16 each), so the MMA runs
+// in TS mode at its 128-clock floor, and each CTA generates only HALF of either operand: producer thread (unit u, row
+// group g) owns hidden unit 128c + u for 8 of a stage's 32 rows and writes dZ2[.][unit] to tensor memory and
+// H1[.][unit] to shared memory, as scaled fp16 hi|lo (scales per hidden unit, as in tc_bwd2_h_kernel).
+struct B2PCfg {
+  static constexpr int RS = 32;                             // batch rows (K extent) per stage
+  static constexpr int STAGES = 4;
+  static constexpr int PROD_WARPS = 16;                     // 4 lane quarters x 4 row groups of 8 rows
+  static constexpr int PROD_THREADS = PROD_WARPS * 32;
+  static constexpr int MMA_WARP = PROD_WARPS;
+  static constexpr int THREADS = PROD_THREADS + 32;
+  static constexpr int HU = H / 2;                          // hidden units per CTA (128)
+  static constexpr uint32_t B_TERM_BYTES = HU * RS * 2;     // 8 KB
+  static constexpr uint32_t B_STAGE_BYTES = 2 * B_TERM_BYTES;   // hi | lo
+  static constexpr uint32_t A_COL0 = 256, A_STAGE_COLS = RS, A_LO_COLS = RS / 2;
+  static constexpr uint32_t OFF_X = STAGES * B_STAGE_BYTES;     // float4[STAGES][RS]
+  static constexpr uint32_t OFF_DO = OFF_X + STAGES * RS * 16;  // float[STAGES][RS][2]
+  static constexpr uint32_t OFF_INV = OFF_DO + STAGES * RS * 8; // float invA[128] (own units) | invB[256]
+  static constexpr uint32_t OFF_SMALL = OFF_INV + (HU + H) * 4; // float4[3][128]: row groups 1..3: db2 | dW3[0..1] | db3_0
+  static constexpr uint32_t OFF_MAX = OFF_SMALL + 3 * HU * 16;  // int[8] row maxima (float bits)
+  static constexpr uint32_t OFF_BAR = OFF_MAX + 32;
+  static constexpr uint32_t OFF_SLOT = OFF_BAR + (2 * STAGES + 1) * 8 + 8;
+  static constexpr uint32_t BYTES = OFF_SLOT + 16;
+};
+
+template <int IN, int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B2PCfg::THREADS, 1) tc_bwd2_h2_kernel(const Bwd2Job jb) {
+  using C = B2PCfg;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  float4* xs = reinterpret_cast<float4*>(sm + C::OFF_X);
+  float* dos = reinterpret_cast<float*>(sm + C::OFF_DO);
+  float* invA = reinterpret_cast<float*>(sm + C::OFF_INV);
+  float* invB = invA + C::HU;
+  float4* small_g = reinterpret_cast<float4*>(sm + C::OFF_SMALL);
+  int* rmax = reinterpret_cast<int*>(sm + C::OFF_MAX);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);     // leader: 2 x PROD_WARPS
+  uint64_t* empty = full + C::STAGES;                                // both CTAs: multicast commit
+  uint64_t* done = empty + C::STAGES;                                // both CTAs: multicast commit
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + C::OFF_SLOT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int split = blockIdx.x >> 1, net_i = blockIdx.y;
+  const float* net = jb.params + (size_t)net_i * NET_STRIDE;
+  const int tiles64 = (jb.rows + 63) / 64;
+  const int n_stage_total = (jb.rows + C::RS - 1) / C::RS;
+  const int st_lo = (int)((long long)n_stage_total * split / jb.splits);
+  const int st_hi = (int)((long long)n_stage_total * (split + 1) / jb.splits);
+
+  if (warp == C::MMA_WARP) {
+    tmem_alloc2(slot, 512);
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 2 * C::PROD_WARPS); mbar_init(&empty[s], 1); }
+      mbar_init(done, 1);
+      fence_mbar_init();
+    }
+  }
+  if (tid < 8) rmax[tid] = 0;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  grid_dep_wait();
+
+  if (warp == C::MMA_WARP) {
+    if (leader) {
+      const uint32_t idesc = instr_desc(FMT_F16, 256, 256);
+      const uint32_t lbo = C::HU * 16;
+      uint32_t it = 0;
+      for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
+        const uint32_t s = it % C::STAGES;
+        mbar_wait(&full[s], (it / C::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(sm + s * C::B_STAGE_BYTES);
+        const uint32_t a_stage = tmem + C::A_COL0 + s * C::A_STAGE_COLS;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < C::RS / 16; ++j) {
+            const uint64_t b_hi = smem_desc(b_base + 2 * j * lbo, lbo, 128);
+            const uint64_t b_lo = smem_desc(b_base + C::B_TERM_BYTES + 2 * j * lbo, lbo, 128);
+            const uint32_t a_hi = a_stage + j * 8, a_lo = a_hi + C::A_LO_COLS;
+            umma_ts2(tmem, a_lo, b_hi, idesc, (it == 0 && j == 0) ? 0u : 1u);
+            umma_ts2(tmem, a_hi, b_lo, idesc, 1u);
+            umma_ts2(tmem, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit2(&empty[s], 3);
+          if (sg == st_hi - 1) umma_commit2(done, 3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- producers: thread (u, g): hidden unit 128 rank + u, rows 8g .. 8g + 8 of every stage ----------------
+    const int u = (warp & 3) * 32 + lane, g = warp >> 2;
+    const int t = (int)rank * C::HU + u;                      // global hidden unit: A row j = t, B row k = t
+    float w3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) w3[o] = net[off_W3(IN) + o * H + t];
+    const float w1x = net[off_W1(IN) + t * IN], w1y = net[off_W1(IN) + t * IN + 1];
+    const float w1z = IN == 3 ? net[off_W1(IN) + t * IN + 2] : 0.f;
+    const float b1v = net[off_b1(IN) + t];
+    // pre-pass: maxima of |x| and |dOut| components over the pair's rows -> per-unit scales (identical in both CTAs)
+    {
+      float mx0 = 0.f, mx1 = 0.f, mx2 = 0.f, md0 = 0.f, md1 = 0.f;
+      const int r_lo = st_lo * C::RS, r_hi = min(jb.rows, st_hi * C::RS);
+      for (int r = r_lo + tid; r < r_hi; r += C::PROD_THREADS) {
+        const float4 x = __ldg(jb.X + r);
+        mx0 = fmaxf(mx0, fabsf(x.x)); mx1 = fmaxf(mx1, fabsf(x.y)); mx2 = fmaxf(mx2, fabsf(x.z));
+        md0 = fmaxf(md0, fabsf(__ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT)));
+        if (OUT == 2) md1 = fmaxf(md1, fabsf(__ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+        mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o)); md0 = fmaxf(md0, __shfl_xor_sync(0xffffffffu, md0, o));
+        md1 = fmaxf(md1, __shfl_xor_sync(0xffffffffu, md1, o));
+      }
+      if (lane == 0) {
+        atomicMax(&rmax[0], __float_as_int(mx0)); atomicMax(&rmax[1], __float_as_int(mx1)); atomicMax(&rmax[2], __float_as_int(mx2));
+        atomicMax(&rmax[3], __float_as_int(md0)); atomicMax(&rmax[4], __float_as_int(md1));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+    }
+    float sA, sB;
+    {
+      float ia, ib;
+      float bA = fabsf(w3[0]) * __int_as_float(rmax[3]);
+      if (OUT == 2) bA = fmaf(fabsf(w3[OUT - 1]), __int_as_float(rmax[4]), bA);
+      pow2_scale(bA, sA, ia);
+      const float bB = fmaf(fabsf(w1x), __int_as_float(rmax[0]), fmaf(fabsf(w1y), __int_as_float(rmax[1]),
+                       fmaf(fabsf(w1z), __int_as_float(rmax[2]), fabsf(b1v))));
+      pow2_scale(bB, sB, ib);
+      if (g == 0) { invA[u] = ia; invB[t] = ib; }
+      if (g == 1) {                                         // the PEER's units: their B scales unscale my columns
+        const int tp = (int)(rank ^ 1u) * C::HU + u;
+        const float px = net[off_W1(IN) + tp * IN], py = net[off_W1(IN) + tp * IN + 1];
+        const float pz = IN == 3 ? net[off_W1(IN) + tp * IN + 2] : 0.f;
+        const float pb = fmaf(fabsf(px), __int_as_float(rmax[0]), fmaf(fabsf(py), __int_as_float(rmax[1]),
+                         fmaf(fabsf(pz), __int_as_float(rmax[2]), fabsf(net[off_b1(IN) + tp]))));
+        float ps, pi;
+        pow2_scale(pb, ps, pi);
+        invB[tp] = pi;
+      }
+    }
+    float s_db2 = 0.f, s_dw3[OUT], s_db3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) { s_dw3[o] = 0.f; s_db3[o] = 0.f; }
+    const uint32_t a_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + g * 4;    // 8 rows = 4 columns
+    auto h2_ptr = [&](int sg) {
+      const int row0 = sg * C::RS + g * 8;
+      return jb.h2 + (((size_t)net_i * tiles64 + (row0 >> 6)) * H + t) * 64 + (row0 & 63);
+    };
+    float4 hn0, hn1;
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dn[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) dn[o] = 0.f;
+    auto prefetch = [&](int sg) {
+      const float* h2p = h2_ptr(sg);
+      hn0 = __ldg(reinterpret_cast<const float4*>(h2p));
+      hn1 = __ldg(reinterpret_cast<const float4*>(h2p) + 1);
+      if (tid < C::RS) {
+        const int r = sg * C::RS + tid;
+        xn = r < jb.rows ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dn[o] = r < jb.rows ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + o) : 0.f;
+      }
+    };
+    hn0 = hn1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (st_lo < st_hi) prefetch(st_lo);
+    uint32_t it = 0;
+    for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
+      const uint32_t s = it % C::STAGES;
+      const float hv[8] = {hn0.x, hn0.y, hn0.z, hn0.w, hn1.x, hn1.y, hn1.z, hn1.w};
+      const float4 xc = xn;
+      float dc[OUT];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) dc[o] = dn[o];
+      if (sg + 1 < st_hi) prefetch(sg + 1);
+      mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+      tc_fence_after();
+      float4* xst = xs + s * C::RS;
+      float* dost = dos + s * C::RS * 2;
+      if (tid < C::RS) {
+        xst[tid] = xc;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dost[tid * 2 + o] = dc[o];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+      float dz[8], h1[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int rl = g * 8 + e;
+        float gsum = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+          const float d = dost[rl * 2 + o];
+          gsum = fmaf(d, w3[o], gsum);
+          s_dw3[o] = fmaf(d, hv[e], s_dw3[o]);
+          if (t == 0) s_db3[o] += d;
+        }
+        dz[e] = hv[e] > 0.f ? gsum : 0.f;
+        s_db2 += dz[e];
+        const float4 x = xst[rl];
+        float z = fmaf(x.y, w1y, fmaf(x.x, w1x, b1v));        // the forward's order: chain starts from the bias
+        if (IN == 3) z = fmaf(x.z, w1z, z);
+        h1[e] = fmaxf(z, 0.f);
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_h2_trunc(make_float2(dz[2 * e] * sA, dz[2 * e + 1] * sA), hi[e], lo[e]);
+      tmem_st4(a_lane + s * C::A_STAGE_COLS, hi);
+      tmem_st4(a_lane + s * C::A_STAGE_COLS + C::A_LO_COLS, lo);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_h2_trunc(make_float2(h1[2 * e] * sB, h1[2 * e + 1] * sB), hi[e], lo[e]);
+      uint8_t* Bst = sm + s * C::B_STAGE_BYTES + chunk_off(C::HU, u, g);
+      *reinterpret_cast<uint4*>(Bst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(Bst + C::B_TERM_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&full[s], 0);
+    }
+    // small gradients of unit t: the four row groups are added in a fixed order (group 0 + 1 + 2 + 3)
+    if (g > 0) small_g[(g - 1) * C::HU + u] = make_float4(s_db2, s_dw3[0], OUT == 2 ? s_dw3[OUT - 1] : 0.f, s_db3[0]);
+    if (OUT == 2 && t == 0 && g > 0) rmax[4 + g] = __float_as_int(s_db3[OUT - 1]);       // (plain bit copies; slots 5..7)
+    asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
+    if (g == 0) {
+      float db3_1 = s_db3[OUT - 1];
+      float a0 = s_db2, a1 = s_dw3[0], a2 = OUT == 2 ? s_dw3[OUT - 1] : 0.f, a3 = s_db3[0];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 o2 = small_g[q * C::HU + u];
+        a0 += o2.x; a1 += o2.y; a2 += o2.z; a3 += o2.w;
+        if (OUT == 2 && t == 0) db3_1 += __int_as_float(rmax[5 + q]);
+      }
+      float* sm2 = jb.small2 + ((size_t)net_i * jb.splits + split) * SMALL_STRIDE;
+      sm2[H * IN + H + t] = a0;
+      sm2[H * IN + 2 * H + t] = a1;
+      if (OUT == 2) sm2[H * IN + 2 * H + H + t] = a2;
+      if (t == 0) {
+        sm2[H * IN + 2 * H + OUT * H] = a3;
+        if (OUT == 2) sm2[H * IN + 2 * H + OUT * H + 1] = db3_1;
+      }
+    }
+    // the leader's last multicast commits land in THIS CTA's barriers: do not exit before they have
+    if (st_hi > st_lo) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+    }
+    // ---------------- epilogue: unscale and dump this CTA's 128 x 256 half of the accumulator as the split's partial ----------------
+    // warp w reads TMEM lane quarter w % 4 and every fourth 32-column chunk
+    float* out = jb.pw2 + ((size_t)net_i * jb.splits + split) * H * H;
+    {
+      const int qw = warp & 3, part = warp >> 2;
+      const int jl = qw * 32 + lane;
+      const float ia = invA[jl];
+      float* orow = out + (size_t)((int)rank * C::HU + jl) * H;
+#pragma unroll 1
+      for (int c0 = part * 32; c0 < H; c0 += 32 * (C::PROD_WARPS / 4)) {
+        float v[32];
+        if (st_hi > st_lo) {
+          tmem_ld32(tmem + ((uint32_t)(qw * 32) << 16) + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] * ia * invB[c0 + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -11,22 +11,25 @@ namespace tc {
 
 // mode bits: 0 = A in TMEM (TS) else shared memory (SS); 1 = N 256 else 128; 2 = cta_group::2 (M = 256) else ::1 (M = 128)
 // bit 3: issue the 3-term pattern (alternating two A / two B operand addresses) instead of one address pair
-__global__ void __launch_bounds__(128, 1) mma_bench_kernel(int mode, int iters, long long* __restrict__ out) {
+template <bool PAIR>
+__device__ __forceinline__ void mma_bench_body(int mode, int iters, long long* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t sm[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 64 * 1024);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
-  const bool ts = mode & 1, n256 = mode & 2, pair = mode & 4, three = mode & 8;
+  const bool ts = mode & 1, n256 = mode & 2, three = mode & 8;
+  constexpr bool pair = PAIR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = pair ? cluster_ctarank() : 0;
+  uint32_t rank = 0;
+  if constexpr (PAIR) rank = cluster_ctarank();
   for (int i = threadIdx.x; i < 16 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;   // fp16 1.0
   fence_proxy_async_smem();
   if (warp == 0) {
-    if (pair) tmem_alloc2(slot, 512); else tmem_alloc(slot, 512);
+    if constexpr (PAIR) tmem_alloc2(slot, 512); else tmem_alloc(slot, 512);
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   }
   tc_fence_before();
   __syncthreads();
-  if (pair) cluster_sync_all();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *slot;
   if (warp == 0 && rank == 0) {
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int mode, int iters, 
       for (int i = 0; i < iters; ++i) {
         const bool alt = three && (i % 3 == 0);
         const bool altb = three && (i % 3 == 1);
-        if (pair) {
+        if constexpr (PAIR) {
           if (ts) umma_ts2(tmem, alt ? ta1 : ta0, altb ? b1 : b0, idesc, 1u);
           else {
             const uint32_t z = 0;
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int mode, int iters, 
           else umma<false>(tmem, alt ? a1 : a0, altb ? b1 : b0, idesc, 1u);
         }
       }
-      if (pair) umma_commit2(bar, 1); else umma_commit(bar);
+      if constexpr (PAIR) umma_commit2(bar, 1); else umma_commit(bar);
       t1 = clock64();
     }
     __syncwarp();
@@ -66,8 +69,14 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int mode, int iters, 
   }
   tc_fence_before();
   __syncthreads();
-  if (pair) cluster_sync_all();
-  if (warp == 0) { if (pair) tmem_dealloc2(tmem, 512); else tmem_dealloc(tmem, 512); }
+  if constexpr (PAIR) cluster_sync_all();
+  if (warp == 0) { if constexpr (PAIR) tmem_dealloc2(tmem, 512); else tmem_dealloc(tmem, 512); }
+}
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(int mode, int iters, long long* __restrict__ out) {
+  mma_bench_body<false>(mode, iters, out);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_bench_pair_kernel(int mode, int iters, long long* __restrict__ out) {
+  mma_bench_body<true>(mode, iters, out);
 }
 
 }  // namespace tc

@@ -16,6 +16,7 @@
 #include "mlp_tc_bwd2.cuh"
 #include "mlp_tc_h.cuh"
 #include "mlp_tc_h2.cuh"
+#include "adam_pack.cuh"
 
 namespace cql {
 
@@ -84,6 +85,35 @@ __global__ void k_build_transitions(const float2* __restrict__ obs, const float*
   if (tm == 0.f && i + 1 < n) nx = obs[i + 1];
   table[2 * i] = make_float4(o.x, o.y, act[i], rew[i]);
   table[2 * i + 1] = make_float4(nx.x, nx.y, tm, 0.f);
+}
+
+// Synthetic replay table of a BASELINE shape generated in place (bench / stress configuration: 1e9 rows = 32 GB would
+// not fit through the host).  Episodes are user-major with a fixed length L = ceil(n / n_users); item ~ Zipf(1)-like
+// (inverse-CDF of 1/x on [1, n_items]), action = rating in {1..5} (ML-like pmf) + N(0, 1e-3), reward = 1 on ~10 rows
+// per episode, terminal on the episode's last row.  Row i depends only on (seed, i): reproducible.
+__device__ __forceinline__ float2 synth_obs(int64_t i, int64_t L, int64_t n_users, int64_t n_items, uint64_t seed, uint32_t (&r)[4]) {
+  Philox::gen(seed ^ 0x53594E5448ull, 0x7ab1eull, (uint64_t)i, r);
+  const int64_t u = i / L < n_users ? i / L : n_users - 1;
+  const float z = expf(u01(r[0]) * logf((float)n_items));          // in [1, n_items]
+  int64_t it = (int64_t)z - 1;
+  it = it < 0 ? 0 : (it >= n_items ? n_items - 1 : it);
+  return make_float2((float)u, (float)it);
+}
+__global__ void k_synth_table(float4* __restrict__ table, int64_t n, int64_t n_users, int64_t n_items, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t L = (n + n_users - 1) / n_users;
+  uint32_t r[4], r2[4];
+  const float2 o = synth_obs(i, L, n_users, n_items, seed, r);
+  const bool last = (i == n - 1) || ((i + 1) / L != i / L && i / L < n_users - 1) ;
+  const float u = u01(r[1]);
+  const float rating = u < 0.06f ? 1.f : (u < 0.17f ? 2.f : (u < 0.43f ? 3.f : (u < 0.78f ? 4.f : 5.f)));
+  const float nz = sqrtf(-2.f * logf(u01(r[2]))) * cospif(2.f * u01(r[3])) * 1e-3f;
+  const float rew = (r[3] % (uint32_t)L) < 10u ? 1.f : 0.f;
+  float2 nx = make_float2(0.f, 0.f);
+  if (!last) nx = synth_obs(i + 1, L, n_users, n_items, seed, r2);
+  table[2 * i] = make_float4(o.x, o.y, rating + nz, rew);
+  table[2 * i + 1] = make_float4(nx.x, nx.y, last ? 1.f : 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------- noise (Philox)
@@ -170,6 +200,22 @@ __device__ __forceinline__ Sample policy_sample(float mu, float ls, float eps, i
 }
 __device__ __forceinline__ float clamp_ls(float x) { return fminf(fmaxf(x, -20.f), 2.f); }
 
+// Where the layer-3 outputs of a forward job live: final values [n_nets][rows][OUT] (n_parts == 0: FP32 path, or after
+// k_sum_partials_multi) or the tensor-core kernels' partial sums [n_nets][n_parts][rows][OUT] with the bias b3 still to
+// add.  The consumers of a forward (k_prep, k_lse, k_actor_dq) read through q_at(), which adds the parts in the order
+// k_sum_partials_multi does -- the separate summation launch (three per update) is gone, the results are bit-identical.
+struct QSrc {
+  const float* q;
+  const float* params;     // first net slot (b3), used when n_parts > 0
+  int n_parts, rows, in_dim, out_dim;
+};
+__device__ __forceinline__ float q_at(const QSrc& s, int net, int r, int o = 0) {
+  if (s.n_parts == 0) return s.q[((size_t)net * s.rows + r) * s.out_dim + o];
+  float v = 0.f;
+  for (int p = 0; p < s.n_parts; ++p) v += s.q[(((size_t)net * s.n_parts + p) * s.rows + r) * s.out_dim + o];
+  return v + s.params[(size_t)net * NET_STRIDE + off_b3(s.in_dim, s.out_dim) + o];
+}
+
 __global__ void k_actor_rows(const float4* __restrict__ batch, int B, float4* __restrict__ XA) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * B) return;
@@ -184,19 +230,26 @@ __global__ void k_actor_rows(const float4* __restrict__ batch, int B, float4* __
 
 // Builds every critic input row of the update from the shared actor outputs.
 // thread (b, l): rows j = l, l+64, ... of batch element b; j in [0, 6n+4).
-__global__ void k_prep(const float4* __restrict__ batch, const float* __restrict__ outA,
+__global__ void __launch_bounds__(256) k_prep(const float4* __restrict__ batch, const QSrc srcS, const QSrc srcN, float* __restrict__ outA,
                        const float* __restrict__ noise, int B, int n, int squash,
                        float4* __restrict__ XAl, float* __restrict__ offAl,
                        float4* __restrict__ XC, float* __restrict__ offC,
                        float4* __restrict__ XT, float4* __restrict__ XP, float4* __restrict__ perb) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
- 
+
+  __shared__ float sv[4][4];                 // per batch element of this block: mu(s), logstd(s), mu(s'), logstd(s')
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = g >> 6, l = g & 63;
+  const int b = g >> 6, l = g & 63, bl = threadIdx.x >> 6;
+  if (b < B && l < 4) {                      // actor outputs of the s rows (srcS) and the s' rows (srcN), summed ONCE per element
+    const float v = q_at(l < 2 ? srcS : srcN, 0, b, l & 1);
+    sv[bl][l] = v;
+    outA[2 * ((l < 2 ? 0 : B) + b) + (l & 1)] = v;          // k_actor_dout reads these
+  }
+  __syncthreads();
   if (b >= B) return;
   const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
-  const float mu_s = outA[2 * b], ls_s = clamp_ls(outA[2 * b + 1]);
-  const float mu_n = outA[2 * (B + b)], ls_n = clamp_ls(outA[2 * (B + b) + 1]);
+  const float mu_s = sv[bl][0], ls_s = clamp_ls(sv[bl][1]);
+  const float mu_n = sv[bl][2], ls_n = clamp_ls(sv[bl][3]);
   const int64_t Bn = (int64_t)B * n;
   const int n3 = 3 * n;
   for (int j = l; j < 2 * n3 + 4; j += 64) {
@@ -285,28 +338,42 @@ __device__ __forceinline__ float warp_lse(const float* __restrict__ q, const flo
   return m + logf(s);
 }
 
-__global__ void __launch_bounds__(256) k_lse(const float4* __restrict__ batch, const float* __restrict__ QAl,
-                                             const float* __restrict__ offAl, const float* __restrict__ QC,
-                                             const float* __restrict__ offC, const float* __restrict__ QT, LossConsts k,
+// logsumexp over the lanes' values v (lane < cnt valid); m_out = max, v_out = softmax weight of this lane's value
+__device__ __forceinline__ float warp_lse_v(float v, int cnt, int lane, float& m_out, float& v_out) {
+  v = lane < cnt ? v : -INFINITY;
+  const float m = warp_max(v);
+  const float e = lane < cnt ? expf(v - m) : 0.f;
+  const float s = warp_sum(e);
+  m_out = m;
+  v_out = e / s;
+  return m + logf(s);
+}
+
+__global__ void __launch_bounds__(256) k_lse(const float4* __restrict__ batch, const QSrc srcAl,
+                                             const float* __restrict__ offAl, const QSrc srcC,
+                                             const float* __restrict__ offC, const QSrc srcT, LossConsts k,
                                              float* __restrict__ dQ, PairVals* __restrict__ pairv) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
- 
+
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= k.C * k.B) return;
   const int c = p / k.B, b = p % k.B;
   const int n3 = 3 * k.n, rsC = n3 + 1;
   float m, w;
   PairVals pv;
-  pv.lse_a = warp_lse(QAl + ((int64_t)c * k.B + b) * n3, offAl + (int64_t)b * n3, n3, lane, m, w);
-  const float* q = QC + ((int64_t)c * k.B + b) * rsC;
-  pv.lse_c = warp_lse(q, offC + (int64_t)b * rsC, n3, lane, m, w);
+  const float va = lane < n3 ? q_at(srcAl, c, b * n3 + lane) - offAl[(int64_t)b * n3 + lane] : 0.f;
+  pv.lse_a = warp_lse_v(va, n3, lane, m, w);
+  const float qc = lane < rsC ? q_at(srcC, c, b * rsC + lane) : 0.f;       // lane n3 = the data row (s, a)
+  const float vc = lane < n3 ? qc - offC[(int64_t)b * rsC + lane] : 0.f;
+  pv.lse_c = warp_lse_v(vc, n3, lane, m, w);
   if (lane < n3) dQ[((int64_t)c * k.B + b) * rsC + lane] = w;
+  const float qd = __shfl_sync(0xffffffffu, qc, n3 & 31);
   if (lane == 0) {
-    float qt = QT[b];
-    for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, QT[(int64_t)c2 * k.B + b]);
+    float qt = q_at(srcT, 0, b);
+    for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, q_at(srcT, c2, b));
     const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
     const float y = r0.w + k.gamma * qt * (1.f - r1.z);
-    pv.qd = q[n3];
+    pv.qd = qd;
     pv.err = pv.qd - y;
     pairv[p] = pv;
   }
@@ -314,7 +381,8 @@ __global__ void __launch_bounds__(256) k_lse(const float4* __restrict__ batch, c
 
 // sums[0]=sum td err^2  [1]=sum lse_c  [2]=sum qd
 __global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict__ perb, const PairVals* __restrict__ pairv,
-                                                        const float* __restrict__ scalars, LossConsts k,
+                                                        const float* __restrict__ scalars, const float* __restrict__ sc_m,
+                                                        const float* __restrict__ sc_v, LossConsts k,
                                                         float* __restrict__ g_scalars, float* __restrict__ sums,
                                                         float* __restrict__ metrics) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
@@ -344,6 +412,9 @@ __global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict
     metrics[0] = temp_loss;
     metrics[2] = alpha_loss;
     sums[0] = se; sums[1] = sc; sums[2] = sd;
+    // snapshot for k_scalar_adam_dq (every block of which recomputes the scalar Adam steps from these)
+    sums[8] = lt; sums[9] = la;
+    sums[10] = sc_m[0]; sums[11] = sc_v[0]; sums[12] = sc_m[1]; sums[13] = sc_v[1];
   }
 }
 
@@ -355,42 +426,45 @@ __device__ __forceinline__ float adam_scalar(float p, float g, float& m, float& 
   return p - (float)((double)lr / si.bc1) * (m / denom);
 }
 
-// sums[3] <- conservative coefficient alpha*cw/(C*B) for k_dq
-__global__ void k_scalar_adam(float* __restrict__ scalars, float* __restrict__ sc_m, float* __restrict__ sc_v,
-                              const float* __restrict__ g_scalars, const StepInfo* __restrict__ si, LossConsts k,
-                              float* __restrict__ sums, float* __restrict__ metrics) {
+// Adam on log_temp / log_alpha, conservative coefficient, loss metrics -- and, in the same launch, dQ of every
+// critic-job row: coef * softmax (samples) or 2 (q - y) / B - coef (data row).  Every thread recomputes the two scalar
+// Adam steps (a few dozen flops, bit-identical everywhere) from the SNAPSHOT of (log_temp, log_alpha, their moments)
+// that k_scalar_reduce left in sums[8..13]; thread 0 of block 0 stores the results into the live locations, which no
+// other thread of this launch reads.
+__global__ void __launch_bounds__(256) k_scalar_adam_dq(float* __restrict__ scalars, float* __restrict__ sc_m, float* __restrict__ sc_v,
+                                 const float* __restrict__ g_scalars, const StepInfo* __restrict__ si, LossConsts k,
+                                 float* __restrict__ sums, float* __restrict__ metrics, const PairVals* __restrict__ pairv,
+                                 float* __restrict__ dQ) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
- 
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float lt = scalars[0], la = scalars[1];
-  if (k.temp_lr > 0.f) { float m = sc_m[0], v = sc_v[0]; lt = adam_scalar(lt, g_scalars[0], m, v, k.temp_lr, k, *si); sc_m[0] = m; sc_v[0] = v; scalars[0] = lt; }
-  if (k.alpha_lr > 0.f) { float m = sc_m[1], v = sc_v[1]; la = adam_scalar(la, g_scalars[1], m, v, k.alpha_lr, k, *si); sc_m[1] = m; sc_v[1] = v; scalars[1] = la; }
-  metrics[1] = expf(lt);
-  metrics[3] = expf(la);
+
+  float lt = sums[8], la = sums[9];
+  float mt = sums[10], vt = sums[11], ma = sums[12], va = sums[13];
+  if (k.temp_lr > 0.f) lt = adam_scalar(lt, g_scalars[0], mt, vt, k.temp_lr, k, *si);
+  if (k.alpha_lr > 0.f) la = adam_scalar(la, g_scalars[1], ma, va, k.alpha_lr, k, *si);
   const float alpha = fminf(fmaxf(expf(la), 0.f), 1e6f);
   const float inv = 1.f / ((float)k.C * (float)k.B);
-  const float td = sums[0] / (float)k.B;
-  const float cons = alpha * (k.cw * (sums[1] * inv - sums[2] * inv) - k.thr);
-  metrics[4] = td + cons;
-  metrics[6] = td;
-  sums[3] = alpha * k.cw * inv;
-}
-
-__global__ void k_dq(const PairVals* __restrict__ pairv, const float* __restrict__ sums, LossConsts k,
-                     float* __restrict__ dQ) {
-  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
- 
+  const float coef = alpha * k.cw * inv;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rsC = 3 * k.n + 1;
-  if (i >= (int64_t)k.C * k.B * rsC) return;
-  const int j = (int)(i % rsC);
-  const float coef = sums[3];
-  if (j < rsC - 1) dQ[i] = coef * dQ[i];
-  else dQ[i] = 2.f * pairv[i / rsC].err / (float)k.B - coef;
+  if (i < (int64_t)k.C * k.B * rsC) {
+    const int j = (int)(i % rsC);
+    dQ[i] = j < rsC - 1 ? coef * dQ[i] : 2.f * pairv[i / rsC].err / (float)k.B - coef;
+  }
+  if (i == 0) {
+    if (k.temp_lr > 0.f) { scalars[0] = lt; sc_m[0] = mt; sc_v[0] = vt; }
+    if (k.alpha_lr > 0.f) { scalars[1] = la; sc_m[1] = ma; sc_v[1] = va; }
+    sums[3] = coef;
+    metrics[1] = expf(lt);
+    metrics[3] = expf(la);
+    const float td = sums[0] / (float)k.B;
+    const float cons = alpha * (k.cw * (sums[1] * inv - sums[2] * inv) - k.thr);
+    metrics[4] = td + cons;
+    metrics[6] = td;
+  }
 }
 
 // actor loss + d/dQ through the min over critics (one CTA)
-__global__ void __launch_bounds__(1024) k_actor_dq(const float* __restrict__ QP, const float4* __restrict__ perb,
+__global__ void __launch_bounds__(1024) k_actor_dq(const QSrc srcP, const float4* __restrict__ perb,
                                                    const float* __restrict__ scalars, int B, int C,
                                                    float* __restrict__ dQP, float* __restrict__ metrics) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
@@ -400,9 +474,9 @@ __global__ void __launch_bounds__(1024) k_actor_dq(const float* __restrict__ QP,
   float s = 0.f;
   for (int b = threadIdx.x; b < B; b += 1024) {
     int arg = 0;
-    float qm = QP[b];
+    float qm = q_at(srcP, 0, b);
     for (int c = 1; c < C; ++c) {
-      const float q = QP[(int64_t)c * B + b];
+      const float q = q_at(srcP, c, b);
       if (q < qm) { qm = q; arg = c; }
     }
     for (int c = 0; c < C; ++c) dQP[(int64_t)c * B + b] = c == arg ? -1.f / (float)B : 0.f;
@@ -545,7 +619,7 @@ inline void launch_fwd(Handle* h, FwdJobs& jobs, cudaStream_t st) {
 
 // ---- tensor-core forward: same job list, W2 from the packed copy, partial sums folded afterwards
 template <bool TF32, int IN, int OUT, bool F16X3 = false>
-inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
+inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st, QSrc* defer = nullptr) {
   using C = std::conditional_t<F16X3, tc::HCfg, tc::Cfg<TF32>>;
   tc::TcFwdJobs tj{};
   tj.n = jobs.n;
@@ -557,6 +631,17 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
     for (int i = 0; i < jobs.n; ++i) pair_items += jobs.j[i].n_nets * ((jobs.j[i].rows + 2 * tc::TM - 1) / (2 * tc::TM));
     pair = !no_pair && pair_items >= h->num_sms / 2;
   }
+  // small launches (the B-row passes of the actor step: 16-32 work items of 128 columns) run on 32-column work items
+  // instead -- four times as many CTAs, a quarter of the operand load each; CQL_NO_SMALL=1 = A/B switch
+  bool small = false;
+  if constexpr (F16X3) {
+    static const bool no_small = std::getenv("CQL_NO_SMALL") != nullptr;
+    int items128 = 0;
+    for (int i = 0; i < jobs.n; ++i) items128 += jobs.j[i].n_nets * tc::HCfg::SLICES * ((jobs.j[i].rows + tc::TM - 1) / tc::TM);
+    small = !pair && !no_small && items128 * 2 <= h->num_sms;
+  }
+  const int n_slices = small ? tc::HCfgS::SLICES : C::SLICES;
+  const int n_parts = pair ? tc::H2Cfg::PARTS : n_slices;       // layer-3 partial sums per row
   size_t part_off = 0;
   int items = 0;
   float* part_of[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -564,9 +649,9 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
     const FwdJob& j = jobs.j[i];
     const int slot = (int)((j.params - h->params) / NET_STRIDE);
     tj.item_begin[i] = items;
-    items += j.n_nets * C::SLICES * ((j.rows + tc::TM - 1) / tc::TM);
+    items += j.n_nets * n_slices * ((j.rows + tc::TM - 1) / tc::TM);
     part_of[i] = h->part + part_off;
-    part_off += (size_t)j.n_nets * C::SLICES * j.rows * OUT;
+    part_off += (size_t)j.n_nets * n_parts * j.rows * OUT;
     tj.j[i] = tc::TcFwdJob{j.X, j.params,
                            pair ? h->packed_fwd2 + (size_t)slot * h->packed_net_bytes2 : h->packed_fwd + (size_t)slot * h->packed_net_bytes,
                            part_of[i], j.h2, j.rows, j.n_nets};
@@ -578,12 +663,19 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
   const int grid = items < h->num_sms ? items : h->num_sms;
   if constexpr (F16X3) {
     if (pair) launch_pdl_pair(tc::tc_fwd_h2_kernel<IN, OUT>, h->num_sms / 2, dim3(tc::H2Cfg::THREADS), tc::H2Cfg::SMEM_BYTES, st, tj, h->pair_swap_b);
+    else if (small) launch_pdl(tc::tc_fwd_h_kernel<IN, OUT, tc::HCfgS>, dim3(grid), dim3(tc::HCfgS::THREADS), tc::HCfgS::SMEM_BYTES, st, tj);
     else launch_pdl(tc::tc_fwd_h_kernel<IN, OUT>, dim3(grid), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, tj);
   } else if constexpr (TF32)
     tc::tc_fwd_ts_kernel<IN, OUT><<<grid, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(tj);
   else
     tc::tc_fwd_kernel<TF32, IN, OUT><<<grid, tc::Pipe<TF32, tc::FWD_NPW>::THREADS, tc::FwdSmem<TF32, tc::FWD_NPW>::BYTES, st>>>(tj);
   CQL_LAUNCH_CHECK(h);
+  if (defer != nullptr && F16X3) {       // the consumers add the partial sums themselves (q_at): no summation launch
+    for (int i = 0; i < jobs.n; ++i) defer[i] = QSrc{part_of[i], jobs.j[i].params, n_parts, jobs.j[i].rows, IN, OUT};
+    return;
+  }
+  if (defer != nullptr)
+    for (int i = 0; i < jobs.n; ++i) defer[i] = QSrc{jobs.j[i].out, jobs.j[i].params, 0, jobs.j[i].rows, IN, OUT};
   tc::SumJobs sj{};
   sj.n = jobs.n;
   int max_n = 0;
@@ -592,16 +684,21 @@ inline void launch_fwd_tc(Handle* h, const FwdJobs& jobs, cudaStream_t st) {
     sj.j[i] = {part_of[i], j.params, j.out, j.rows, j.n_nets};
     max_n = std::max(max_n, j.n_nets * j.rows * OUT);
   }
-  launch_pdl(tc::k_sum_partials_multi<IN, OUT>, dim3(dim3((max_n + 255) / 256, jobs.n)), dim3(256), 0, st, sj, C::SLICES);
+  launch_pdl(tc::k_sum_partials_multi<IN, OUT>, dim3(dim3((max_n + 255) / 256, jobs.n)), dim3(256), 0, st, sj, n_parts);
   CQL_LAUNCH_CHECK(h);
 }
 
+// defer[i] (optional, one per job) tells the consumer kernels where job i's outputs are (see QSrc)
 template <int IN, int OUT>
-inline void launch_fwd_any(Handle* h, FwdJobs& jobs, cudaStream_t st) {
-  if (h->cfg.precision == CQL_PREC_TF32X3) launch_fwd_tc<true, IN, OUT>(h, jobs, st);
-  else if (h->cfg.precision == CQL_PREC_F16X3) launch_fwd_tc<true, IN, OUT, true>(h, jobs, st);
-  else if (h->cfg.precision == CQL_PREC_BF16) launch_fwd_tc<false, IN, OUT>(h, jobs, st);
-  else launch_fwd<IN, OUT>(h, jobs, st);
+inline void launch_fwd_any(Handle* h, FwdJobs& jobs, cudaStream_t st, QSrc* defer = nullptr) {
+  if (h->cfg.precision == CQL_PREC_TF32X3) launch_fwd_tc<true, IN, OUT>(h, jobs, st, defer);
+  else if (h->cfg.precision == CQL_PREC_F16X3) launch_fwd_tc<true, IN, OUT, true>(h, jobs, st, defer);
+  else if (h->cfg.precision == CQL_PREC_BF16) launch_fwd_tc<false, IN, OUT>(h, jobs, st, defer);
+  else {
+    launch_fwd<IN, OUT>(h, jobs, st);
+    if (defer != nullptr)
+      for (int i = 0; i < jobs.n; ++i) defer[i] = QSrc{jobs.j[i].out, jobs.j[i].params, 0, jobs.j[i].rows, IN, OUT};
+  }
 }
 
 // refresh the packed (tensor-core operand layout) copies of W2 -- forward orientation for every listed slot,
@@ -664,7 +761,15 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     static const bool no_pair = std::getenv("CQL_NO_PAIR") != nullptr || std::getenv("CQL_NO_PAIR_BWD1") != nullptr;
     pair = !no_pair && IN == 3 && jb.n_nets * ((jb.rows + 2 * tc::TM - 1) / (2 * tc::TM)) >= h->num_sms / 2;
   }
-  const int grid1 = pair ? 2 * (h->num_sms / 2) : (items < h->num_sms ? items : h->num_sms);
+  bool small = false;
+  if constexpr (F16X3) {
+    static const bool no_small = std::getenv("CQL_NO_SMALL") != nullptr;
+    small = !pair && !no_small && items * 2 <= h->num_sms;
+  }
+  const int n_slices = small ? tc::HCfgS::SLICES : C::SLICES;
+  const int items_s = jb.n_nets * n_slices * tiles;
+  const int grid1 = pair ? 2 * (h->num_sms / 2) : (items_s < h->num_sms ? items_s : h->num_sms);
+  h->last_dx_parts = jb.n_nets * (pair ? (int)tc::H2Cfg::PARTS : n_slices);
   const int slots1 = (F16X3 ? 2 : 4) * grid1;      // f16x3: one slot per (CTA, epilogue group)
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
   tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params,
@@ -678,6 +783,12 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   if (splits > n_stage) splits = n_stage;      // (fewer, longer splits for the small jobs were measured: slower)
   if (splits > h->splits_tc) splits = h->splits_tc;
   if (splits < 1) splits = 1;
+  bool pair2 = false;                            // dW2 on CTA pairs (A operand in tensor memory): the big launches
+  if constexpr (F16X3) {
+    static const bool no_pair2 = std::getenv("CQL_NO_PAIR") != nullptr || std::getenv("CQL_NO_PAIR_BWD2") != nullptr;
+    pair2 = pair && !no_pair2;
+    if (pair2) splits = std::max(1, (h->num_sms / 2) / jb.n_nets);
+  }
   static const bool no_fork = std::getenv("CQL_NO_FORK") != nullptr;      // A/B switch for measurements
   const bool fork = WGRADS && !no_fork && !h->timing && h->side_stream != nullptr && grid1 + splits * jb.n_nets <= h->num_sms;
   cudaStream_t st2 = st;
@@ -688,6 +799,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   }
   if constexpr (F16X3) {
     if (pair) launch_pdl_pair(tc::tc_bwd1_h2_kernel<IN, OUT, WGRADS, DX>, h->num_sms / 2, dim3(tc::H2Cfg::THREADS), tc::H2B1Cfg::SMEM_BYTES, st, j1, h->pair_swap_b);
+    else if (small) launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX, tc::HCfgS>, dim3(grid1), dim3(tc::HCfgS::THREADS), tc::HCfgS::SMEM_BYTES, st, j1);
     else launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX>, dim3(grid1), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, j1);
   } else if constexpr (TF32)
     tc::tc_bwd1_ts_kernel<IN, OUT, WGRADS, DX><<<grid1, tc::TsCfg::THREADS, tc::TsCfg::SMEM_BYTES, st>>>(j1);
@@ -699,9 +811,21 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   tc::Bwd2Job j2{jb.X, jb.dOut, jb.h2, jb.params, h->pw2_tc, h->small2, jb.rows, jb.n_nets, splits};
   constexpr bool GROUP_SUM = false;   // in-kernel group sums of the dW2 partials: measured slower (one CTA re-reads 1 MB at the tail)
   if (F16X3 && GROUP_SUM) j2.tickets = h->b2_tickets;
-  if constexpr (F16X3)
-    launch_pdl(tc::tc_bwd2_h_kernel<IN, OUT>, dim3(splits, jb.n_nets), dim3(tc::B2HCfg::THREADS), tc::B2HCfg::BYTES, st2, j2);
-  else
+  if constexpr (F16X3) {
+    if (pair2) {
+      static const bool no_pdl_env = std::getenv("CQL_NO_PDL") != nullptr;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * splits, jb.n_nets); cfg.blockDim = dim3(tc::B2PCfg::THREADS); cfg.dynamicSmemBytes = tc::B2PCfg::BYTES; cfg.stream = st2;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = (no_pdl_env || g_timing_no_pdl) ? 0 : 1;
+      CQL_CUDA(cudaLaunchKernelEx(&cfg, tc::tc_bwd2_h2_kernel<IN, OUT>, j2));
+    } else {
+      launch_pdl(tc::tc_bwd2_h_kernel<IN, OUT>, dim3(splits, jb.n_nets), dim3(tc::B2HCfg::THREADS), tc::B2HCfg::BYTES, st2, j2);
+    }
+  } else
     tc::tc_bwd2_kernel<TF32, IN, OUT><<<dim3(splits, jb.n_nets), tc::B2_THREADS, tc::B2Cfg<TF32>::BYTES, st2>>>(j2);
   CQL_LAUNCH_CHECK(h);
   if (fork) {
@@ -715,7 +839,39 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   CQL_LAUNCH_CHECK(h);
 }
 
+// f16x3: Adam + Polyak + every operand copy of W2 (network and target, both orientations, both layouts) in one launch
+inline void adam_pack(Handle* h, int first_slot, int n_nets, int in_dim, int out_dim, float lr, cudaStream_t st, bool last = false) {
+  const cql_config& c = h->cfg;
+  tc::AdamPackJobs j{};
+  j.in_dim = in_dim; j.out_dim = out_dim;
+  j.lr = lr; j.beta1 = c.beta1; j.beta2 = c.beta2; j.eps = c.adam_eps; j.tau = c.tau;
+  j.step_inc = last ? h->step_dev : nullptr;
+  for (int i = 0; i < n_nets; ++i) {
+    const int slot = first_slot + i, tslot = slot + 1 + h->C;       // [actor | critics | targ_actor | targ_critics]
+    const bool critic = in_dim == 3;
+    tc::AdamPackNet& n = j.n[i];
+    n.p = h->net_params(slot);
+    n.m = h->adam_m + (size_t)slot * NET_STRIDE;
+    n.v = h->adam_v + (size_t)slot * NET_STRIDE;
+    n.g = h->grads + (size_t)slot * NET_STRIDE;                      // grads: [actor | critics | scalars], same slot order
+    n.targ = h->net_params(tslot);
+    n.fwd = h->packed_fwd + (size_t)slot * h->packed_net_bytes;
+    n.bwd = h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd;
+    n.tfwd = h->packed_fwd + (size_t)tslot * h->packed_net_bytes;
+    n.fwd2 = critic ? h->packed_fwd2 + (size_t)slot * h->packed_net_bytes2 : nullptr;
+    n.bwd2 = critic ? h->packed_bwd2 + (size_t)slot * h->packed_net_bytes2 : nullptr;
+    n.tfwd2 = critic ? h->packed_fwd2 + (size_t)tslot * h->packed_net_bytes2 : nullptr;
+    n.w2max = h->w2max + slot * 4;
+  }
+  launch_pdl(tc::k_adam_pack, dim3(tc::AP_W2_BLOCKS + 1, n_nets), dim3(256), 0, st, j, h->stepinfo);
+  CQL_LAUNCH_CHECK(h);
+}
+
 inline void pack_all_weights(Handle* h, cudaStream_t st) {
+  if (h->cfg.precision == CQL_PREC_F16X3) {
+    tc::k_w2max_init<<<2 + 2 * h->C, 256, 0, st>>>(h->params, 2 + 2 * h->C, h->w2max);
+    CQL_LAUNCH_CHECK(h);
+  }
   pack_weights(h, slot_actor(), 1, 2, st);
   pack_weights(h, slot_critic(0), h->C, 3, st);
   pack_weights(h, slot_targ_actor(h->C), 1, 2, st);
@@ -791,11 +947,12 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     jobs.j[0] = FwdJob{h->XA, h->net_params(slot_actor()), h->outA, h->h2A, B, 1, 0};
     jobs.j[1] = FwdJob{h->XA + B, h->net_params(slot_actor()), h->outA + 2 * (size_t)B, nullptr, B, 1, 0};
     mark(h, st, 1);
-    launch_fwd_any<2, 2>(h, jobs, st);
+    QSrc srcA[2];
+    launch_fwd_any<2, 2>(h, jobs, st, srcA);
     mark(h, st, 2);
+    launch_pdl(k_prep, dim3((B * 64 + 255) / 256), dim3(256), 0, st, batch4, srcA[0], srcA[1], h->outA, h->noise, B, h->n, c.squash, h->XAl,
+               h->offAl, h->XC, h->offC, h->XT, h->XP, reinterpret_cast<float4*>(h->perb));
   }
-  launch_pdl(k_prep, dim3((B * 64 + 255) / 256), dim3(256), 0, st, batch4, h->outA, h->noise, B, h->n, c.squash, h->XAl, h->offAl, h->XC,
-                                               h->offC, h->XT, h->XP, reinterpret_cast<float4*>(h->perb));
   CQL_LAUNCH_CHECK(h);
   {
     FwdJobs jobs{};
@@ -804,26 +961,27 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     jobs.j[1] = FwdJob{h->XC, h->net_params(slot_critic(0)), h->QC, h->h2C, B * (n3 + 1), C, 0};
     jobs.j[2] = FwdJob{h->XT, h->net_params(slot_targ_critic(C, 0)), h->QT, nullptr, B, C, 0};
     mark(h, st, 3);
-    launch_fwd_any<3, 1>(h, jobs, st);
+    QSrc srcQ[3];
+    launch_fwd_any<3, 1>(h, jobs, st, srcQ);
     mark(h, st, 4);
+    launch_pdl(k_lse, dim3((C * B * 32 + 255) / 256), dim3(256), 0, st, batch4, srcQ[0], h->offAl, srcQ[1], h->offC, srcQ[2], loss_consts(h),
+               h->dQ, reinterpret_cast<PairVals*>(h->pairv));
+    CQL_LAUNCH_CHECK(h);
   }
-  launch_pdl(k_lse, dim3((C * B * 32 + 255) / 256), dim3(256), 0, st, batch4, h->QAl, h->offAl, h->QC, h->offC, h->QT, loss_consts(h), h->dQ,
-                                                 reinterpret_cast<PairVals*>(h->pairv));
-  CQL_LAUNCH_CHECK(h);
-  launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
-                                      h->scalars(), loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics);
-  CQL_LAUNCH_CHECK(h);
+  {
+    const int64_t so = scalars_off(C);
+    launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
+               h->scalars(), h->adam_m + so, h->adam_v + so, loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics);
+    CQL_LAUNCH_CHECK(h);
+  }
 }
 
 // phase 1: temp/alpha Adam, critic backward -> critic gradients
 inline void phase1(Handle* h, cudaStream_t st) {
   const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
   const int64_t so = scalars_off(C);
-  launch_pdl(k_scalar_adam, dim3(1), dim3(32), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so, h->g_scalars(), h->stepinfo,
-                                 loss_consts(h), h->loss_sums, h->metrics);
-  CQL_LAUNCH_CHECK(h);
-  launch_pdl(k_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const PairVals*>(h->pairv), h->loss_sums,
-                                                              loss_consts(h), h->dQ);
+  launch_pdl(k_scalar_adam_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so,
+             h->g_scalars(), h->stepinfo, loss_consts(h), h->loss_sums, h->metrics, reinterpret_cast<const PairVals*>(h->pairv), h->dQ);
   CQL_LAUNCH_CHECK(h);
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);
@@ -846,12 +1004,15 @@ inline void phase1(Handle* h, cudaStream_t st) {
 inline void phase2(Handle* h, cudaStream_t st) {
   const int B = h->B, C = h->C;
   const cql_config& c = h->cfg;
-  const int64_t cnt = (int64_t)C * NET_STRIDE;
-  launch_pdl(k_adam_polyak, dim3((int)((cnt + 255) / 256)), dim3(256), 0, st, 
-      h->net_params(slot_critic(0)), h->adam_m + (size_t)NET_STRIDE, h->adam_v + (size_t)NET_STRIDE, h->g_critics(),
-      h->net_params(slot_targ_critic(C, 0)), cnt, c.critic_lr, c.beta1, c.beta2, c.adam_eps, c.tau, h->stepinfo);
-  CQL_LAUNCH_CHECK(h);
-  {
+  static const bool no_fused_adam = std::getenv("CQL_NO_FUSED_ADAM") != nullptr;      // A/B switch
+  if (h->cfg.precision == CQL_PREC_F16X3 && !no_fused_adam) {
+    adam_pack(h, slot_critic(0), C, 3, 1, c.critic_lr, st);
+  } else {
+    const int64_t cnt = (int64_t)C * NET_STRIDE;
+    launch_pdl(k_adam_polyak, dim3((int)((cnt + 255) / 256)), dim3(256), 0, st,
+        h->net_params(slot_critic(0)), h->adam_m + (size_t)NET_STRIDE, h->adam_v + (size_t)NET_STRIDE, h->g_critics(),
+        h->net_params(slot_targ_critic(C, 0)), cnt, c.critic_lr, c.beta1, c.beta2, c.adam_eps, c.tau, h->stepinfo);
+    CQL_LAUNCH_CHECK(h);
     int slots[2 * CQL_MAX_CRITICS];
     for (int i = 0; i < C; ++i) { slots[i] = slot_critic(i); slots[C + i] = slot_targ_critic(C, i); }
     pack_slots(h, slots, 2 * C, st);
@@ -861,12 +1022,13 @@ inline void phase2(Handle* h, cudaStream_t st) {
     jobs.n = 1;
     jobs.j[0] = FwdJob{h->XP, h->net_params(slot_critic(0)), h->QP, h->h2P, B, C, 0};
     mark(h, st, 8);
-    launch_fwd_any<3, 1>(h, jobs, st);
+    QSrc srcP[1];
+    launch_fwd_any<3, 1>(h, jobs, st, srcP);
     mark(h, st, 9);
+    launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, srcP[0], reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
+               h->metrics);
+    CQL_LAUNCH_CHECK(h);
   }
-  launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, h->QP, reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
-                                 h->metrics);
-  CQL_LAUNCH_CHECK(h);
   {
     BwdJob jb{h->XP, h->dQP, h->h2P, h->net_params(slot_critic(0)), nullptr, h->dXP, nullptr, B, C, 1};
     if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, false, true, true>(h, jb, nullptr, st);
@@ -877,7 +1039,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
   const bool tcm = h->cfg.precision != CQL_PREC_FP32;
   launch_pdl(k_actor_dout, dim3((B + 127) / 128), dim3(128), 0, st, h->outA, h->noise + B + 6 * (int64_t)B * h->n,
                                                 tcm ? h->dX_part : h->dXP, h->scalars(), B,
-                                                tcm ? C * h->tc_slices : C, c.squash, h->dOutA);
+                                                tcm ? h->last_dx_parts : C, c.squash, h->dOutA);
   CQL_LAUNCH_CHECK(h);
   BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
   mark(h, st, 10);
@@ -899,12 +1061,19 @@ inline void phase2(Handle* h, cudaStream_t st) {
 // phase 3: actor Adam + Polyak of the target policy, step counter
 inline void phase3(Handle* h, cudaStream_t st) {
   const cql_config& c = h->cfg;
-  launch_pdl(k_adam_polyak, dim3((NET_STRIDE + 255) / 256), dim3(256), 0, st, h->net_params(slot_actor()), h->adam_m, h->adam_v,
-                                                         h->g_actor(), h->net_params(slot_targ_actor(h->C)),
-                                                         (int64_t)NET_STRIDE, c.actor_lr, c.beta1, c.beta2, c.adam_eps,
-                                                         c.tau, h->stepinfo);
-  CQL_LAUNCH_CHECK(h);
-  pack_weights(h, slot_actor(), 1, 2, st);
+  static const bool no_fused_adam = std::getenv("CQL_NO_FUSED_ADAM") != nullptr;      // A/B switch
+  if (h->cfg.precision == CQL_PREC_F16X3 && !no_fused_adam) {
+    adam_pack(h, slot_actor(), 1, 2, 2, c.actor_lr, st, /*last=*/true);      // also counts the step
+    mark(h, st, 12);
+    return;
+  } else {
+    launch_pdl(k_adam_polyak, dim3((NET_STRIDE + 255) / 256), dim3(256), 0, st, h->net_params(slot_actor()), h->adam_m, h->adam_v,
+                                                           h->g_actor(), h->net_params(slot_targ_actor(h->C)),
+                                                           (int64_t)NET_STRIDE, c.actor_lr, c.beta1, c.beta2, c.adam_eps,
+                                                           c.tau, h->stepinfo);
+    CQL_LAUNCH_CHECK(h);
+    pack_weights(h, slot_actor(), 1, 2, st);
+  }
   launch_pdl(k_step_end, dim3(1), dim3(1), 0, st, h->step_dev);
   CQL_LAUNCH_CHECK(h);
   mark(h, st, 12);

@@ -192,6 +192,11 @@ class CqlEngine:
                                             float(action_randomization_scale), *[_ptr(o) for o in outs]), "cql_build_mdp")
         return tuple(outs) if want_outputs else None
 
+    def synth_table(self, n_rows: int, n_users: int, n_items: int, seed: int = 12345) -> None:
+        """Fill the replay table with a seeded synthetic log of the given shape, generated on the device (stress shape)."""
+        self._check(self._lib.cql_synth_table(self._h, int(n_rows), int(n_users), int(n_items), int(seed) & (2**64 - 1)),
+                    "cql_synth_table")
+
     @property
     def n_transitions(self) -> int:
         return int(self._lib.cql_num_transitions(self._h))

@@ -14,6 +14,8 @@ SHAPES = {
     "ml1m": dict(n_users=6040, n_items=3706, n_rows=1_000_209),
     "ml20m": dict(n_users=138_493, n_items=26_744, n_rows=20_000_263),
     "tiny": dict(n_users=64, n_items=300, n_rows=4_000),
+    # BASELINE.json configs[4]; too large for a host-side generator -- CqlEngine.synth_table builds it in HBM
+    "stress": dict(n_users=10_000_000, n_items=1_000_000, n_rows=1_000_000_000),
 }
 RATING_PMF = np.array([0.06, 0.11, 0.26, 0.35, 0.22])
 
