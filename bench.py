@@ -252,19 +252,25 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    from replay_cql_b200.parallel import DataParallelStepper
-    stepper = DataParallelStepper(eng) if world > 1 else None
+    from replay_cql_b200.parallel import DataParallelStepper, make_grad_exchange
+    # N > 1: gradient exchange over NVLink peer memory.  With the f16x3 kernels it is FUSED into the update (the reduce
+    # kernels publish, the Adam kernels read the peers' buffers): the library's own step graph is data-parallel as it is.
+    # Otherwise (NCCL fallback / other precisions) the four phases + exchanges are captured as one graph by the stepper.
+    reducer = make_grad_exchange(eng) if world > 1 else None
+    fused_dp = world > 1 and bool(getattr(reducer, "fused", False))
+    stepper = DataParallelStepper(eng, reducer=reducer) if (world > 1 and not fused_dp) else None
     if stepper is not None:
         stream = stepper.stream
         sh = stream.cuda_stream
-    reducer = stepper.reducer if stepper is not None else None
     stepper_e2e = None
     if stepper is not None:        # same stream and exchange; the captured step reads the uploaded minibatch
         stepper_e2e = DataParallelStepper(eng, uploaded_batch=True, reducer=reducer)
         stepper_e2e.stream = stream
+    if world > 1:
+        dist.barrier()
 
     def do_steps(k):
-        if world == 1:
+        if stepper is None:
             with torch.cuda.stream(stream):
                 eng.update(k, want_metrics=False, stream=sh)
         else:
@@ -312,24 +318,27 @@ def run_ours(args):
                      "rew": np.ascontiguousarray(rows[:, 3:4]), "next_obs": np.ascontiguousarray(rows[:, 4:6]),
                      "term": np.ascontiguousarray(rows[:, 6:7])})
     def e2e_step(i):
-        if world == 1:
+        if stepper is None:
             eng.update_batch(pool[i % 8])
         else:   # host minibatch in, the data-parallel step (gradient exchanges included) as one graph, metrics out
             with torch.cuda.stream(stream):
                 eng.upload_batch(pool[i % 8], stream=sh)
                 stepper_e2e.run(1)
                 eng.read_metrics()
-    if world == 1:
+    if stepper is None:
         # the host loop of a trainer that owns its minibatches: every step's batch goes host -> pinned ring -> device and
-        # its six metrics come back; the library pipelines copies and steps (cql_update_batches)
+        # its six metrics come back; the library pipelines copies and steps (cql_update_batches).  N > 1 (fused exchange):
+        # every rank runs the same call on its own minibatches, the kernels average the gradients across the ranks.
         stacked = {k: np.stack([pool[i % 8][k] for i in range(n_e2e)]) for k in pool[0]}
         eng.update_batches([pool[i] for i in range(3)])
         barrier()
         t0 = time.perf_counter()
         e2e_metrics = eng.update_batches(stacked)
         torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
         assert len(e2e_metrics) == n_e2e and all(np.isfinite(m["critic_loss"]) for m in e2e_metrics)
+        if reducer is not None:
+            reducer.check()
     else:
         for i in range(3):
             e2e_step(i)
@@ -373,7 +382,13 @@ def run_ours(args):
     s1.record(stream)
     barrier()
     score_clk = score_clocks.stop()
-    score_ms = max_over_ranks(s0.elapsed_time(s1)) / SCORE_REPS
+    score_ms_local = s0.elapsed_time(s1) / SCORE_REPS
+    score_ms = max_over_ranks(score_ms_local)
+    score_ms_ranks = [score_ms_local]
+    if world > 1:
+        tl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([score_ms_local], dtype=torch.float64, device=dev))
+        score_ms_ranks = [float(t.item()) for t in tl]
     score_launches = (eng.launch_count - l1) // SCORE_REPS
     users_per_s = n_score / (score_ms / 1e3)
     top_dev = oi.cpu().numpy()
@@ -452,6 +467,8 @@ def run_ours(args):
                        "rows": int(n_rows), "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "parallelism": f"dp{world}",
                        "grad_exchange": ("none" if world == 1 else
+                                         "NVLink peer memory, fused into the update kernels (reduce kernels publish + signal, Adam kernels read the "
+                                         "peers' buffers: no exchange launch; csrc/dp_peer.cuh)" if fused_dp else
                                          {"PeerGradExchange": "NVLink peer-memory one-shot all-reduce kernel (csrc/dp_peer.cuh), 3 per update",
                                           "GradAllReducer": "NCCL all-reduce, 3 per update"}.get(type(reducer).__name__, type(reducer).__name__)),
                        "hidden": 256, "n_critics": 2, "n_action_samples": 10,
@@ -459,7 +476,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2: 640 MB replay table, fresh random gather every step; "
                              "weights/activations are the step-to-step state of the algorithm"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": BATCH * 32,
-                    "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batches (host minibatches in, per-step metrics out; copies and steps pipelined by the library)" if world == 1 else
+                    "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batches (host minibatches in, per-step metrics out; copies and steps pipelined by the library)" if stepper is None else
                            "cql_upload_batch + the data-parallel step as one CUDA graph (cql_step_phase x4 with the gradient exchange between phases) + metrics D2H"},
             "gpu_launches": int(launches),
             "clocks": clk,
@@ -478,7 +495,7 @@ def run_ours(args):
             "scoring": {"metric": "users scored top-10/sec", "value": users_per_s, "unit": "users/s",
                         "users": int(n_score), "users_note": "every user of the ML-20M shape, sharded over the ranks (configs[3])",
                         "items": shape["n_items"], "k": K_TOP, "filter_seen": True,
-                        "ms": score_ms, "tflops": score_tf * world, "frac_of_peak": score_tf / peak_tf,
+                        "ms": score_ms, "ms_per_rank": score_ms_ranks, "tflops": score_tf * world, "frac_of_peak": score_tf / peak_tf,
                         "gpu_launches": int(score_launches), "clocks": score_clk,
                         "e2e": {"value": n_score / score_e2e_s, "unit": "users/s",
                                 "h2d_bytes": int(users.nbytes + items.nbytes + indptr.nbytes + seen.nbytes),
@@ -503,6 +520,8 @@ def run_ours(args):
         stepper.graph = None
         stepper_e2e.graph = None
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()             # no rank frees its staging buffers while a peer's kernel may still read them
     eng.close()
     if world > 1:
         try:

@@ -169,6 +169,12 @@ int  cql_dp_attach(cql_handle* h, int32_t world, int32_t rank, const void* const
                    const void* const* signal_ptrs, int64_t stage_floats);
 int  cql_dp_allreduce(cql_handle* h, int which, void* stream);
 int  cql_dp_error(cql_handle* h, int32_t* flag_out);
+/* *fused_out = 1 when, after cql_dp_attach, the gradient exchange happens INSIDE the update kernels (f16x3 path): the
+ *   kernel that produces a gradient group writes it to this rank's staging buffer and signals the peers, the kernel
+ *   that consumes it (scalar Adam / Adam + Polyak + pack) waits for the peers and reads the mean over NVLink -- no
+ *   exchange launch, and cql_update / cql_update_batches / cql_step_phase run data-parallel as they are
+ *   (cql_dp_allreduce is then a no-op).  0: call cql_dp_allreduce (or an NCCL all-reduce) between the phases. */
+int  cql_dp_mode(cql_handle* h, int32_t* fused_out);
 
 /* ---- scoring (K5) ------------------------------------------------------ */
 /* For each user: relevance of every candidate item, minus the user's seen

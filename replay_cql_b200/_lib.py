@@ -62,6 +62,7 @@ SIGNATURES = {
     "cql_dp_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int64]),
     "cql_dp_allreduce": (C.c_int, [_P, C.c_int, _P]),
     "cql_dp_error": (C.c_int, [_P, _P]),
+    "cql_dp_mode": (C.c_int, [_P, _P]),
     "cql_device_buffer": (C.c_int, [_P, C.c_int, C.POINTER(_P), _I64]),
     "cql_score_topk": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "cql_score_topk_dev": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),

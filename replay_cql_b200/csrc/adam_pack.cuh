@@ -37,6 +37,9 @@ struct AdamPackJobs {
   int in_dim, out_dim;
   float lr, beta1, beta2, eps, tau;
   long long* step_inc;      // the update's LAST launch: completed-steps counter to increment (else null)
+  DpPeer dp;                // data-parallel peers (world > 1: gradients = mean over the ranks' staging buffers)
+  int dp_group;             // gradient group of this launch (1 critics, 2 actor)
+  long long dp_off;         // offset of network 0 of this launch inside a staging buffer
 };
 
 __device__ __forceinline__ float adam_one(float& p, float& m, float& v, float g, float step_size, float bc2s, float beta1,
@@ -76,13 +79,20 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
   const float step_size = (float)((double)jobs.lr / si->bc1), bc2s = (float)si->bc2_sqrt;
   const int slot_rd = (int)(si->step % 3), slot_acc = (int)((si->step + 1) % 3), slot_clr = (int)((si->step + 2) % 3);
   const int tid = threadIdx.x, lane = tid & 31;
+  const bool dp = jobs.dp.world > 1;
+  long long dpb = 0;                                       // staging index of this network's element 0
+  if (dp) {
+    dp_wait_peers(jobs.dp, jobs.dp_group);
+    dpb = dp_base(jobs.dp, jobs.dp_group, jobs.dp_off) + (long long)blockIdx.y * NET_STRIDE;
+  }
   if (blockIdx.x < AP_W2_BLOCKS) {
     // ---------------- 8 rows of W2: Adam + Polyak, forward packs, then the transposed K chunk ----------------
     const int n = blockIdx.x * AP_ROWS + (tid >> 5), kc = lane;
     const size_t off = (size_t)off_W2(in_dim) + (size_t)n * H + kc * 8;
     float p[8], t[8];
     {
-      const float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
+      const float4 g0 = dp ? dp_mean4(jobs.dp, dpb + (long long)off) : *reinterpret_cast<const float4*>(nt.g + off);
+      const float4 g1 = dp ? dp_mean4(jobs.dp, dpb + (long long)off + 4) : *reinterpret_cast<const float4*>(nt.g + off + 4);
       float4 m0 = *reinterpret_cast<const float4*>(nt.m + off), m1 = *reinterpret_cast<const float4*>(nt.m + off + 4);
       float4 v0 = *reinterpret_cast<const float4*>(nt.v + off), v1 = *reinterpret_cast<const float4*>(nt.v + off + 4);
       const float4 p0 = *reinterpret_cast<const float4*>(nt.p + off), p1 = *reinterpret_cast<const float4*>(nt.p + off + 4);
@@ -147,35 +157,64 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
         if (nt.bwd2) reinterpret_cast<HMeta*>(nt.bwd2 + H2Cfg::META_OFF)->inv_s[np] = inv_sT;
       }
     }
+    if (dp) dp_consume_done(jobs.dp, jobs.dp_group, gridDim.x * gridDim.y);
     return;
   }
   // ---------------- the small tensors: W1 | b1, b2, W3 | b3 (+ layer maxima for the operand generators) ----------------
   if (tid < 16) wm[tid] = 0;
   if (tid == 0) nt.w2max[slot_clr] = 0;
   __syncthreads();
-  auto upd = [&](int idx) {
+  // data-parallel: the mean gradients of the small entries are fetched into shared memory FIRST, two 16-byte groups per
+  // thread with all ranks' loads in flight together (one after the other, each entry would cost an NVLink round trip)
+  __shared__ float gsm[2048];
+  const int w2_lo = off_W2(in_dim), w2_hi = w2_lo + H * H;
+  if (dp) {
+    for (int c = tid * 4; c < 2048; c += 256 * 4) {
+      const int idx = c < w2_lo ? c : c + H * H;             // compact index -> index inside the network slot
+      if (idx + 3 < NET_STRIDE) *reinterpret_cast<float4*>(gsm + c) = dp_mean4(jobs.dp, dpb + idx);
+    }
+    __syncthreads();
+  }
+  auto grad_of = [&](int idx) { return dp ? gsm[idx < w2_lo ? idx : idx - H * H] : nt.g[idx]; };
+  const int k = tid;                                        // 256 threads = 256 hidden units
+  int idxs[8];
+  int n_idx = 0;
+  for (int c = 0; c < in_dim; ++c) idxs[n_idx++] = off_W1(in_dim) + k * in_dim + c;
+  idxs[n_idx++] = off_b1(in_dim) + k;
+  idxs[n_idx++] = off_b2(in_dim) + k;
+  for (int o = 0; o < out_dim; ++o) idxs[n_idx++] = off_W3(in_dim) + o * H + k;
+  float gv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n_idx) gv[i] = grad_of(idxs[i]);
+  auto upd_g = [&](int idx, float g) {
     float pp = nt.p[idx], mm = nt.m[idx], vv = nt.v[idx];
-    adam_one(pp, mm, vv, nt.g[idx], step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
+    adam_one(pp, mm, vv, g, step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
     const float tt = nt.targ[idx] * (1.f - jobs.tau) + jobs.tau * pp;
     nt.p[idx] = pp; nt.m[idx] = mm; nt.v[idx] = vv; nt.targ[idx] = tt;
     return make_float2(pp, tt);
   };
-  const int k = tid;                                        // 256 threads = 256 hidden units
-  for (int c = 0; c < in_dim; ++c) {
-    const float2 r = upd(off_W1(in_dim) + k * in_dim + c);
-    atomicMax(&wm[c], __float_as_int(fabsf(r.x)));
-    atomicMax(&wm[8 + c], __float_as_int(fabsf(r.y)));
-  }
+  auto upd = [&](int idx) { return upd_g(idx, grad_of(idx)); };
   {
-    const float2 r = upd(off_b1(in_dim) + k);
-    atomicMax(&wm[3], __float_as_int(fabsf(r.x)));
-    atomicMax(&wm[8 + 3], __float_as_int(fabsf(r.y)));
-  }
-  upd(off_b2(in_dim) + k);
-  for (int o = 0; o < out_dim; ++o) {
-    const float2 r = upd(off_W3(in_dim) + o * H + k);
-    atomicMax(&wm[4 + o], __float_as_int(fabsf(r.x)));
-    atomicMax(&wm[8 + 4 + o], __float_as_int(fabsf(r.y)));
+    int i = 0;
+    for (int c = 0; c < in_dim; ++c, ++i) {
+      const float2 r = upd_g(idxs[i], gv[i]);
+      atomicMax(&wm[c], __float_as_int(fabsf(r.x)));
+      atomicMax(&wm[8 + c], __float_as_int(fabsf(r.y)));
+    }
+    {
+      const float2 r = upd_g(idxs[i], gv[i]);
+      ++i;
+      atomicMax(&wm[3], __float_as_int(fabsf(r.x)));
+      atomicMax(&wm[8 + 3], __float_as_int(fabsf(r.y)));
+    }
+    upd_g(idxs[i], gv[i]);
+    ++i;
+    for (int o = 0; o < out_dim; ++o, ++i) {
+      const float2 r = upd_g(idxs[i], gv[i]);
+      atomicMax(&wm[4 + o], __float_as_int(fabsf(r.x)));
+      atomicMax(&wm[8 + 4 + o], __float_as_int(fabsf(r.y)));
+    }
   }
   if (tid < out_dim) upd(off_b3(in_dim, out_dim) + tid);
   __syncthreads();
@@ -190,6 +229,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
   }
   // the step counter (position in the epoch permutation, Philox stream); nothing in this launch reads it
   if (jobs.step_inc != nullptr && blockIdx.y == 0 && tid == 0) *jobs.step_inc += 1;
+  if (dp) dp_consume_done(jobs.dp, jobs.dp_group, gridDim.x * gridDim.y);
 }
 
 // after the weights were set from the host: every rotating slot of every network = its true max|W2|

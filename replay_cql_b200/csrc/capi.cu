@@ -40,7 +40,6 @@ struct cql_handle {
   cudaEvent_t ring_ev[8] = {};
   float* metrics_rows = nullptr;     // pinned [metrics_rows_cap][8]
   int64_t metrics_rows_cap = 0;
-  DpPeer dp;                         // NVLink peer-memory gradient exchange (cql_dp_attach)
   void* dp_local = nullptr;          // epochs | tickets | error flag
 };
 
@@ -809,7 +808,7 @@ int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const
     CQL_REQUIRE(stage_ptrs && signal_ptrs, "cql_dp_attach: NULL pointer table");
     const int64_t need = (int64_t)grad_floats(h.C);
     CQL_REQUIRE(stage_floats >= need && stage_floats % 4 == 0, "cql_dp_attach: staging buffer too small (need the CQL_BUF_ALL_GRADS size, multiple of 4)");
-    DpPeer& p = ch->dp;
+    DpPeer& p = ch->h.dp;
     p.world = world; p.rank = rank; p.stage_floats = stage_floats;
     for (int r = 0; r < world; ++r) {
       CQL_REQUIRE(stage_ptrs[r] && signal_ptrs[r], "cql_dp_attach: NULL peer pointer");
@@ -821,6 +820,7 @@ int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const
     p.epoch = (unsigned long long*)ch->dp_local;
     p.ticket = (unsigned int*)((char*)ch->dp_local + 64);
     p.error = (int*)((char*)ch->dp_local + 128);
+    h.dp_fused = world > 1 && h.cfg.precision == CQL_PREC_F16X3 && std::getenv("CQL_NO_FUSED_DP") == nullptr;
     destroy_graph(ch);
   });
 }
@@ -828,8 +828,9 @@ int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const
 int cql_dp_allreduce(cql_handle* ch, int which, void* stream) {
   return guarded(ch, [&] {
     Handle& h = ch->h;
-    DpPeer& p = ch->dp;
+    DpPeer& p = h.dp;
     CQL_REQUIRE(p.world >= 1, "cql_dp_allreduce: call cql_dp_attach first");
+    if (h.dp_fused) return;                // the update kernels exchange the gradients themselves (dp_peer.cuh)
     float* buf = nullptr;
     int64_t n = 0, off = 0;
     int group = 0;
@@ -852,6 +853,13 @@ int cql_dp_error(cql_handle* ch, int32_t* flag_out) {
     CQL_REQUIRE(flag_out, "cql_dp_error: NULL output");
     *flag_out = 0;
     if (ch->dp_local) CQL_CUDA(cudaMemcpy(flag_out, (char*)ch->dp_local + 128, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  });
+}
+
+int cql_dp_mode(cql_handle* ch, int32_t* fused_out) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(fused_out, "cql_dp_mode: NULL output");
+    *fused_out = ch->h.dp_fused ? 1 : 0;
   });
 }
 

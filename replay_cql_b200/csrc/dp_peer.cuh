@@ -44,10 +44,100 @@ __device__ __forceinline__ float4 ld_volatile4(const float* p) {   // bypasses L
   return v;
 }
 
+// ---- fused mode (f16x3 path): no exchange launch at all.  The kernel that PRODUCES a gradient group (k_scalar_reduce,
+// k_reduce_grads_tc) also writes it into this rank's staging buffer and -- its last block -- signals the peers
+// (dp_publish_done); the kernel that CONSUMES the group (k_scalar_adam_dq, k_adam_pack) waits for every peer's signal
+// (dp_wait_peers, one thread per block) and reads the mean straight from the peers' staging buffers over NVLink
+// (dp_mean4 / dp_mean1), in rank order, so every rank applies bit-identical gradients; its last block advances the
+// epoch (dp_consume_done).  Same double-buffering argument as above: a rank rewrites staging[parity] two epochs later,
+// after it has seen every peer's next signal, which a peer sends only after its consumer kernel of this epoch ended.
+__device__ __forceinline__ long long dp_base(const DpPeer& p, int group, long long off) {
+  return (long long)(p.epoch[group] & 1ull) * p.stage_floats + off;
+}
+// call by ONE thread after all of this rank's staging writes of the group are visible device-wide
+__device__ __forceinline__ void dp_signal_peers(const DpPeer& p, int group) {
+  const unsigned long long e = p.epoch[group];
+  __threadfence_system();
+  for (int r = 0; r < p.world; ++r)
+    if (r != p.rank) st_release_sys(p.sig[r] + p.rank * DP_GROUPS + group, e + 1);
+}
+// multi-block producer: every block calls this after its staging writes; the last one signals
+__device__ __forceinline__ void dp_publish_done(const DpPeer& p, int group, unsigned int n_blocks) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&p.ticket[group], 1u);
+    if (t == n_blocks - 1) {
+      p.ticket[group] = 0;
+      dp_signal_peers(p, group);
+    }
+  }
+}
+// every block of a consumer kernel, before its first staging read (contains a __syncthreads)
+__device__ __forceinline__ void dp_wait_peers(const DpPeer& p, int group) {
+  if (threadIdx.x == 0) {
+    const unsigned long long e = p.epoch[group];
+    for (int r = 0; r < p.world; ++r) {
+      if (r == p.rank) continue;
+      const unsigned long long* f = p.sig[p.rank] + r * DP_GROUPS + group;
+      long long spins = 0;
+      while (ld_acquire_sys(f) < e + 1) {
+        if (++spins > (1ll << 24)) { *p.error = 1; break; }      // tens of seconds: give up instead of hanging the GPU
+        __nanosleep(64);
+      }
+    }
+  }
+  __syncthreads();
+}
+// (loads of up to 8 ranks are ISSUED together before the first sum: each is a round trip over NVLink)
+__device__ __forceinline__ float4 dp_mean4(const DpPeer& p, long long base_i) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r0 = 0; r0 < p.world; r0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r0 + i < p.world) v[i] = ld_volatile4(p.stage[r0 + i] + base_i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r0 + i < p.world) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+  }
+  const float w = (float)p.world;
+  return make_float4(s.x / w, s.y / w, s.z / w, s.w / w);
+}
+__device__ __forceinline__ float ld_volatile1(const float* ptr) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float dp_mean1(const DpPeer& p, long long base_i) {
+  float s = 0.f;
+  for (int r0 = 0; r0 < p.world; r0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r0 + i < p.world) v[i] = ld_volatile1(p.stage[r0 + i] + base_i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r0 + i < p.world) s += v[i];
+  }
+  return s / (float)p.world;
+}
+// multi-block consumer: every block calls this at its end; the last one advances the epoch
+__device__ __forceinline__ void dp_consume_done(const DpPeer& p, int group, unsigned int n_blocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&p.ticket[DP_GROUPS + group], 1u);
+    if (t == n_blocks - 1) {
+      p.ticket[DP_GROUPS + group] = 0;
+      p.epoch[group] = p.epoch[group] + 1;
+    }
+  }
+}
+
 // One kernel per exchange; grid <= number of SMs, so every block is resident while it waits for the peers.
 // n is a multiple of 4; buffer / staging offsets are 16-byte aligned.  A block reduces exactly the elements it
 // published itself, so there is no dependency between the blocks of one rank.
-__global__ void __launch_bounds__(256) k_dp_exchange(const DpPeer p, float* __restrict__ buf, long long off, long long n, int group) {
+static __global__ void __launch_bounds__(256) k_dp_exchange(const DpPeer p, float* __restrict__ buf, long long off, long long n, int group) {
   __shared__ int ok;
   const unsigned long long e = p.epoch[group];
   const long long base = (long long)(e & 1) * p.stage_floats + off;

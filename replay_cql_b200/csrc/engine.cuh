@@ -4,6 +4,7 @@
 #include <string>
 #include "common.cuh"
 #include "mlp_simt.cuh"
+#include "dp_peer.cuh"
 
 namespace cql {
 
@@ -93,6 +94,8 @@ struct Handle {
   uint8_t* packed_fwd2 = nullptr;  // [(2+2C) slots][H2Cfg::PACKED_NET_BYTES]  B[n][k] = W2[n][k]
   uint8_t* packed_bwd2 = nullptr;  // [(1+C) slots]                           B[n][k] = W2[k][n]
   size_t packed_net_bytes2 = 0;
+  DpPeer dp;                       // data-parallel peers (cql_dp_attach); world <= 1: single GPU
+  bool dp_fused = false;           // the gradient exchange happens INSIDE the update kernels (f16x3 path, dp_peer.cuh)
   int* w2max = nullptr;            // [(2+2C) slots][4]: rotating max|W2| slots of the fused Adam + pack kernel (adam_pack.cuh)
   int pair_swap_b = 0;             // which cluster rank holds the first half of the operand rows (probed at create)
 

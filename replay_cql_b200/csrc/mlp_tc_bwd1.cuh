@@ -550,7 +550,8 @@ __device__ __forceinline__ float4 sum_strided4(const float* __restrict__ p, int 
 __global__ void __launch_bounds__(256) k_reduce_grads_tc(const float* __restrict__ small1, int slots1,
                                                          const float* __restrict__ small2, const float* __restrict__ pw2,
                                                          int splits, int in_dim, int out_dim, float* __restrict__ grads,
-                                                         int w2_group = 1) {
+                                                         int w2_group = 1, const DpPeer dp = DpPeer{}, int dp_group = 0,
+                                                         long long dp_off = 0) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
  
   __shared__ float4 part[8][32];
@@ -580,7 +581,11 @@ __global__ void __launch_bounds__(256) k_reduce_grads_tc(const float* __restrict
 #pragma unroll
     for (int c = 1; c < 8; ++c) { const float4 v = part[c][g]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
     *reinterpret_cast<float4*>(grads + (size_t)net * NET_STRIDE + idx) = t;
+    // data-parallel (fused exchange): the local sum also goes into this rank's staging buffer for the peers to read
+    if (dp.world > 1)
+      *reinterpret_cast<float4*>(dp.stage[dp.rank] + dp_base(dp, dp_group, dp_off) + (size_t)net * NET_STRIDE + idx) = t;
   }
+  if (dp.world > 1) dp_publish_done(dp, dp_group, gridDim.x * gridDim.y);
 }
 
 }  // namespace tc

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict
                                                         const float* __restrict__ scalars, const float* __restrict__ sc_m,
                                                         const float* __restrict__ sc_v, LossConsts k,
                                                         float* __restrict__ g_scalars, float* __restrict__ sums,
-                                                        float* __restrict__ metrics) {
+                                                        float* __restrict__ metrics, const DpPeer dp, long long dp_off) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
  
   __shared__ float red[32];
@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict
     // snapshot for k_scalar_adam_dq (every block of which recomputes the scalar Adam steps from these)
     sums[8] = lt; sums[9] = la;
     sums[10] = sc_m[0]; sums[11] = sc_v[0]; sums[12] = sc_m[1]; sums[13] = sc_v[1];
+    if (dp.world > 1) {              // fused data-parallel exchange: publish the two scalar gradients (group 0)
+      float* mine = dp.stage[dp.rank] + dp_base(dp, 0, dp_off);
+      mine[0] = g_scalars[0];
+      mine[1] = g_scalars[1];
+      dp_signal_peers(dp, 0);
+    }
   }
 }
 
@@ -434,13 +440,22 @@ __device__ __forceinline__ float adam_scalar(float p, float g, float& m, float& 
 __global__ void __launch_bounds__(256) k_scalar_adam_dq(float* __restrict__ scalars, float* __restrict__ sc_m, float* __restrict__ sc_v,
                                  const float* __restrict__ g_scalars, const StepInfo* __restrict__ si, LossConsts k,
                                  float* __restrict__ sums, float* __restrict__ metrics, const PairVals* __restrict__ pairv,
-                                 float* __restrict__ dQ) {
+                                 float* __restrict__ dQ, const DpPeer dp, long long dp_off) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
 
   float lt = sums[8], la = sums[9];
   float mt = sums[10], vt = sums[11], ma = sums[12], va = sums[13];
-  if (k.temp_lr > 0.f) lt = adam_scalar(lt, g_scalars[0], mt, vt, k.temp_lr, k, *si);
-  if (k.alpha_lr > 0.f) la = adam_scalar(la, g_scalars[1], ma, va, k.alpha_lr, k, *si);
+  float g_t = g_scalars[0], g_a = g_scalars[1];
+  if (dp.world > 1) {                // fused data-parallel exchange: mean of the ranks' scalar gradients (group 0)
+    __shared__ float gsh[2];
+    dp_wait_peers(dp, 0);
+    if (threadIdx.x < 2) gsh[threadIdx.x] = dp_mean1(dp, dp_base(dp, 0, dp_off) + threadIdx.x);    // one NVLink read per block
+    __syncthreads();
+    g_t = gsh[0];
+    g_a = gsh[1];
+  }
+  if (k.temp_lr > 0.f) lt = adam_scalar(lt, g_t, mt, vt, k.temp_lr, k, *si);
+  if (k.alpha_lr > 0.f) la = adam_scalar(la, g_a, ma, va, k.alpha_lr, k, *si);
   const float alpha = fminf(fmaxf(expf(la), 0.f), 1e6f);
   const float inv = 1.f / ((float)k.C * (float)k.B);
   const float coef = alpha * k.cw * inv;
@@ -461,6 +476,7 @@ __global__ void __launch_bounds__(256) k_scalar_adam_dq(float* __restrict__ scal
     metrics[4] = td + cons;
     metrics[6] = td;
   }
+  if (dp.world > 1) dp_consume_done(dp, 0, gridDim.x);
 }
 
 // actor loss + d/dQ through the min over critics (one CTA)
@@ -835,7 +851,9 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   if (mark_end >= 0) mark(h, st, mark_end);
   launch_pdl(tc::k_reduce_grads_tc, dim3(dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets)), dim3(256), 0, st, h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out,
-                                                                                  (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1);
+                                                                                  (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1,
+                                                                                  h->dp_fused ? h->dp : DpPeer{}, IN == 3 ? 1 : 2,
+                                                                                  (long long)(IN == 3 ? NET_STRIDE : 0));
   CQL_LAUNCH_CHECK(h);
 }
 
@@ -846,6 +864,9 @@ inline void adam_pack(Handle* h, int first_slot, int n_nets, int in_dim, int out
   j.in_dim = in_dim; j.out_dim = out_dim;
   j.lr = lr; j.beta1 = c.beta1; j.beta2 = c.beta2; j.eps = c.adam_eps; j.tau = c.tau;
   j.step_inc = last ? h->step_dev : nullptr;
+  j.dp = h->dp_fused ? h->dp : DpPeer{};
+  j.dp_group = in_dim == 3 ? 1 : 2;
+  j.dp_off = (long long)first_slot * NET_STRIDE;       // staging layout = gradient buffer layout [actor | critics | scalars]
   for (int i = 0; i < n_nets; ++i) {
     const int slot = first_slot + i, tslot = slot + 1 + h->C;       // [actor | critics | targ_actor | targ_critics]
     const bool critic = in_dim == 3;
@@ -971,7 +992,8 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
   {
     const int64_t so = scalars_off(C);
     launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
-               h->scalars(), h->adam_m + so, h->adam_v + so, loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics);
+               h->scalars(), h->adam_m + so, h->adam_v + so, loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics,
+               h->dp_fused ? h->dp : DpPeer{}, (long long)(1 + C) * NET_STRIDE);
     CQL_LAUNCH_CHECK(h);
   }
 }
@@ -981,7 +1003,8 @@ inline void phase1(Handle* h, cudaStream_t st) {
   const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
   const int64_t so = scalars_off(C);
   launch_pdl(k_scalar_adam_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so,
-             h->g_scalars(), h->stepinfo, loss_consts(h), h->loss_sums, h->metrics, reinterpret_cast<const PairVals*>(h->pairv), h->dQ);
+             h->g_scalars(), h->stepinfo, loss_consts(h), h->loss_sums, h->metrics, reinterpret_cast<const PairVals*>(h->pairv), h->dQ,
+             h->dp_fused ? h->dp : DpPeer{}, (long long)(1 + C) * NET_STRIDE);
   CQL_LAUNCH_CHECK(h);
   BwdJob jb{h->XC, h->dQ, h->h2C, h->net_params(slot_critic(0)), h->smallC, nullptr, h->pw2C, rows, C, h->splitsC};
   mark(h, st, 5);

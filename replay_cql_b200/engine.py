@@ -335,6 +335,14 @@ class CqlEngine:
         """Mean over ranks of one gradient buffer through NVLink peer memory (after ``dp_attach``)."""
         self._check(self._lib.cql_dp_allreduce(self._h, int(which), self._torch_stream(stream)), "cql_dp_allreduce")
 
+    @property
+    def dp_fused(self) -> bool:
+        """True when (after ``dp_attach``) the update kernels exchange the gradients themselves: ``update`` /
+        ``update_batches`` are then data-parallel as they are and ``dp_allreduce`` is a no-op."""
+        flag = C.c_int32(0)
+        self._check(self._lib.cql_dp_mode(self._h, C.byref(flag)), "cql_dp_mode")
+        return bool(flag.value)
+
     def dp_error(self) -> bool:
         flag = C.c_int32(0)
         self._check(self._lib.cql_dp_error(self._h, C.byref(flag)), "cql_dp_error")

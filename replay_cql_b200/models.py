@@ -189,18 +189,27 @@ class CQL(Recommender):
         if per_epoch:
             every = min(every, max(1, int(per_epoch)))
         first = eng.get_optimizer()[2]
-        stepper = None
+        stepper = exchange = None
         if world > 1:
-            from .parallel import DataParallelStepper
+            from .parallel import DataParallelStepper, PeerGradExchange, make_grad_exchange
             import torch
             torch.cuda.set_device(eng.device)
-            stepper = DataParallelStepper(eng)              # whole step (kernels + gradient exchanges) as one CUDA graph
-            stepper.stream.wait_stream(torch.cuda.current_stream())
+            exchange = getattr(self, "_exchange", None)
+            if exchange is None or exchange.engine is not eng:
+                exchange = self._exchange = make_grad_exchange(eng)     # NVLink peer memory if available, else NCCL
+            fused = isinstance(exchange, PeerGradExchange) and exchange.fused
+            if not fused:                                   # the step (phases + exchanges between them) as one CUDA graph
+                stepper = DataParallelStepper(eng, reducer=exchange)
+                stepper.stream.wait_stream(torch.cuda.current_stream())
+            torch.distributed.barrier()                     # every rank's engine is attached before the first exchange
         done = 0
         while done < total:
             chunk = min(every, total - done)
             if stepper is None:
+                # single GPU -- or data parallel with the exchange INSIDE the update kernels: the library's own graph
                 self.last_metrics = eng.update(chunk)
+                if exchange is not None:
+                    exchange.check()                        # raises if a wait for a peer timed out
             else:
                 stepper.run(chunk)                          # exactly `chunk` updates (eager warm-up steps included)
                 stepper.finish()                            # raises if a gradient exchange timed out

@@ -51,11 +51,16 @@ class GradAllReducer:
         self.group = group
         self._views = {}
 
+    fused = False
+
     def __call__(self, buffer_id: int) -> None:
         view = self._views.get(buffer_id)
         if view is None:
             view = self._views[buffer_id] = self.engine.grad_tensor(buffer_id)
         allreduce_mean_(view, self.group)
+
+    def check(self) -> None:          # a collective library call cannot time out silently
+        pass
 
 
 class PeerGradExchange:
@@ -85,8 +90,20 @@ class PeerGradExchange:
         engine.dp_attach(world, rank, list(self.handle.buffer_ptrs), list(self.handle.signal_pad_ptrs), self.stage_floats)
         dist.barrier(pg)
 
+    @property
+    def fused(self) -> bool:
+        """The update kernels do the exchange themselves (f16x3): no call is needed between the phases, and
+        ``engine.update`` / ``engine.update_batches`` are data-parallel as they are."""
+        return self.engine.dp_fused
+
     def __call__(self, buffer_id: int) -> None:
-        self.engine.dp_allreduce(buffer_id)               # on torch's current stream
+        self.engine.dp_allreduce(buffer_id)               # on torch's current stream (a no-op in fused mode)
+
+    def check(self) -> None:
+        """Raise if a wait for a peer timed out: the replicas no longer hold the same averaged gradients."""
+        if self.engine.dp_error():
+            raise RuntimeError("data-parallel gradient exchange timed out (a peer rank stalled for too long); "
+                               "replicas are no longer identical -- restart from the last checkpoint")
 
 
 def make_grad_exchange(engine, group=None, prefer_peer: bool = True):

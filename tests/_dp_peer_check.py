@@ -1,5 +1,9 @@
-"""torchrun --nproc-per-node N tests/_dp_peer_check.py : peer-memory gradient exchange vs NCCL (needs N GPUs).
-N = 2: bitwise equality with the NCCL path (a + b is commutative); any N: replicas bit-identical, no time-outs."""
+"""torchrun --nproc-per-node N tests/_dp_peer_check.py : data-parallel gradient exchange over NVLink peer memory vs NCCL
+(needs N GPUs).  Three engines per rank take the same 6 updates from the same state:
+  a: NCCL all-reduce between the four phases (GradAllReducer),
+  b: fused exchange -- the update kernels publish / read the gradients themselves; plain `engine.update(6)` (library graph),
+  c: the stand-alone peer-memory exchange kernel between the phases (CQL_NO_FUSED_DP path), when requested by env.
+N = 2: b == a bitwise (a + b is commutative); any N: replicas bit-identical, no time-outs.  Then timings."""
 import os, sys, time
 sys.path.insert(0, '.')
 import numpy as np
@@ -26,32 +30,48 @@ try:
 except Exception as ex:
     print(f"rank {rank}: PeerGradExchange unavailable: {type(ex).__name__}: {ex}", flush=True)
     dist.destroy_process_group(); sys.exit(0)
+fused = red_b.fused
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
     for _ in range(6):
         a.update_data_parallel(red_a, stream=st.cuda_stream)
-        b.update_data_parallel(red_b, stream=st.cuda_stream)
 st.synchronize()
+dist.barrier()
+if fused:
+    b.update(6)                       # the library's own CUDA graph; the kernels exchange the gradients
+else:
+    with torch.cuda.stream(st):
+        for _ in range(6):
+            b.update_data_parallel(red_b, stream=st.cuda_stream)
+    st.synchronize()
 sa, sb = a.get_state(), b.get_state()
 same_as_nccl = bool(np.array_equal(sa, sb))
 t = torch.from_numpy(sb.astype(np.float64)).cuda()
 mx, mn = t.clone(), t.clone()
 dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
 replicas_identical = bool(torch.equal(mx, mn))
-print(f"rank {rank}: peer==nccl bitwise: {same_as_nccl} (expected for world=2); replicas identical: {replicas_identical}; "
+assert b.get_optimizer()[2] == a.get_optimizer()[2] == 6
+print(f"rank {rank}: fused={fused}; peer==nccl bitwise: {same_as_nccl} (expected for world=2); replicas identical: {replicas_identical}; "
       f"timeout flag: {b.dp_error()}; max|diff| {np.abs(sa - sb).max():.3e}", flush=True)
-# timing: whole DP step as one CUDA graph, NCCL vs peer
-for name, eng, red in (("nccl", a, red_a), ("peer", b, red_b)):
-    stp = DataParallelStepper.__new__(DataParallelStepper)
-    stp.engine, stp.reducer, stp.device = eng, red, torch.device("cuda", local)
-    stp.stream, stp.graph, stp._warmup, stp.launches_per_step, stp.replayed_steps = torch.cuda.Stream(), None, 3, 0, 0
+# timing: NCCL (whole DP step as one CUDA graph) vs the peer path
+stp = DataParallelStepper(a, reducer=red_a)
+stp.run(20); stp.stream.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stp.stream); stp.run(300); e1.record(stp.stream); stp.stream.synchronize()
+print(f"rank {rank}: nccl: {e0.elapsed_time(e1) / 300 * 1e3:.1f} us/step (graph={'yes' if stp.graph else 'no'})", flush=True)
+stp.graph = None
+dist.barrier()
+if fused:
+    b.update(20); dist.barrier()
+    t0 = time.perf_counter(); b.update(300); dt = time.perf_counter() - t0
+    print(f"rank {rank}: peer fused (engine.update, library graph): {dt / 300 * 1e6:.1f} us/step, timeout flag {b.dp_error()}", flush=True)
+else:
+    stp = DataParallelStepper(b, reducer=red_b)
     stp.run(20); stp.stream.synchronize(); dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stp.stream); stp.run(300); e1.record(stp.stream); stp.stream.synchronize()
-    ms = e0.elapsed_time(e1) / 300
-    print(f"rank {rank}: {name}: {ms * 1e3:.1f} us/step (graph={'yes' if stp.graph else 'no'}), timeout flag {eng.dp_error()}", flush=True)
-    dist.barrier()
+    print(f"rank {rank}: peer exchange kernel: {e0.elapsed_time(e1) / 300 * 1e3:.1f} us/step, timeout flag {b.dp_error()}", flush=True)
     stp.graph = None
+dist.barrier()
 torch.cuda.synchronize()
 a.close(); b.close()
 dist.barrier(); dist.destroy_process_group()
