@@ -225,10 +225,16 @@ def run_ours(args):
     log, shape = build_workload(args.rows)
     eng = CqlEngine(CqlHyperParams(batch_size=BATCH, seed=12345, precision=args.precision), device=local_rank,
                     rank=rank, world_size=world)
-    build_mdp_on_device(eng, log.iloc[:100_000], top_k=K_TOP)          # warm-up (CUB temp, allocator)
-    t0 = time.perf_counter()
-    build_mdp_on_device(eng, log, top_k=K_TOP, action_randomization_scale=1e-3)   # host columns in, table in HBM
-    mdp_gpu_s = time.perf_counter() - t0
+    import pyarrow as pa
+    from replay_cql_b200.mdp import ingest_log
+    log_arrow = pa.Table.from_pandas(log, preserve_index=False)        # the log as Arrow columns (what Spark's Arrow path hands over)
+    ingest_log(eng, log_arrow.slice(0, 100_000), top_k=K_TOP)          # warm-up (CUB temp, allocator, pinned ring)
+    mdp_times = []
+    for _ in range(3):                                                 # Arrow buffers -> pinned ring -> HBM, sorts, replay table
+        t0 = time.perf_counter()
+        ingest_log(eng, log_arrow, top_k=K_TOP, action_randomization_scale=1e-3)
+        mdp_times.append(time.perf_counter() - t0)
+    mdp_gpu_s = float(np.median(mdp_times))
     n_rows = eng.n_transitions
     mdp_host = None
     if rank == 0 and world == 1 and not args.no_cpu:                    # host builder on a bounded 2M-row sample
@@ -504,8 +510,9 @@ def run_ours(args):
                             "unit": "GB/s", "rows": int(TOPK_ROWS), "cols": shape["n_items"], "ms": topk_ms,
                             "bound": "hbm", "peak": pk.get("hbm_gbs", 6650.0), "frac": topk_gbs / pk.get("hbm_gbs", 6650.0),
                             "bytes_per_pair": 4},
-            "mdp_build": {"metric": "MDP builder: log columns (host) -> replay table (HBM)", "rows": int(n_rows),
-                          "gpu_seconds": mdp_gpu_s, "rows_per_s": n_rows / mdp_gpu_s, "host_numpy_sample": mdp_host},
+            "mdp_build": {"metric": "ingestion: pyarrow.Table columns (pageable host memory) -> pinned ring -> replay table (HBM)",
+                          "rows": int(n_rows), "gpu_seconds": mdp_gpu_s, "gpu_seconds_runs": mdp_times, "rows_per_s": n_rows / mdp_gpu_s,
+                          "host_bytes": int(n_rows) * 24, "host_numpy_sample": mdp_host},
             "sampler": {"metric": "replay gather", "value": gather_gbs, "unit": "GB/s", "rows": cnt,
                         "frac_of_hbm": gather_gbs / pk.get("hbm_gbs", 6650.0)},
         }

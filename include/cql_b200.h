@@ -101,6 +101,22 @@ int64_t cql_num_transitions(const cql_handle* h);
 int  cql_build_mdp(cql_handle* h, const int32_t* user_idx, const int32_t* item_idx, const int64_t* timestamp,
                    const double* relevance, const double* action_noise, int64_t n, int32_t top_k, float noise_scale,
                    float* obs_out, float* act_out, float* rew_out, float* term_out, int64_t* order_out);
+/* The same builder fed in CHUNKS (Arrow record batches / Parquet row groups / pandas columns, each in its
+ * own dtype, no intermediate frame): cql_mdp_begin announces n rows; cql_mdp_append adds the next `count` values of
+ * one column (col: 0 user_idx, 1 item_idx, 2 timestamp, 3 relevance, 4 action noise [optional]; dtype CQL_DT_*; chunks
+ * of a column arrive in row order, columns in any order -- timestamps first lets their sorts overlap the other
+ * uploads).  Every chunk goes host -> pinned ring (up to four copy threads) -> device asynchronously.
+ * cql_mdp_finish sorts, builds the replay table and ends the session (outputs as for cql_build_mdp).
+ * replaces: `log.toPandas()` (pattern replay/models/neuromf.py:332) + MdpDatasetBuilder.build [EXT] */
+enum { CQL_DT_I32 = 0, CQL_DT_I64 = 1, CQL_DT_F32 = 2, CQL_DT_F64 = 3 };
+int  cql_mdp_begin(cql_handle* h, int64_t n_rows);
+int  cql_mdp_append(cql_handle* h, int32_t col, int32_t dtype, const void* host_chunk, int64_t count);
+int  cql_mdp_finish(cql_handle* h, int32_t top_k, float noise_scale,
+                    float* obs_out, float* act_out, float* rew_out, float* term_out, int64_t* order_out);
+/* Data parallel with the replay table SHARDED by user range: this rank's table holds only its own users'
+ * episodes, so on-device sampling walks this rank's own epoch permutation (position = step * B + j) instead of the
+ * job-wide one ((step * world + rank) * B + j over a replicated table).  The Philox streams stay per rank. */
+int  cql_set_table_sharded(cql_handle* h, int32_t sharded);
 /* Synthetic replay table of a BASELINE.json shape generated IN PLACE on the device (measurement aid for the stress
  * configuration: 1e9 rows x 32 B = 32 GB): user-major episodes of fixed length ceil(n / n_users), Zipf-like items,
  * ML-like ratings + N(0, 1e-3) as actions, ~10 rewarded rows per episode, terminal on each episode's last row.

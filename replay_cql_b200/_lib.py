@@ -16,6 +16,7 @@ SQUASH_EPS, SQUASH_SOFTPLUS = 0, 1
 SCORE_Q, SCORE_POLICY = 0, 1
 BUF_SCALAR_GRADS, BUF_CRITIC_GRADS, BUF_ACTOR_GRADS, BUF_METRICS, BUF_PARAMS, BUF_ALL_GRADS = range(6)
 MAX_TOPK = 1024
+DT_I32, DT_I64, DT_F32, DT_F64 = 0, 1, 2, 3          # cql_mdp_append chunk dtypes
 
 
 class CqlConfig(C.Structure):
@@ -72,6 +73,10 @@ SIGNATURES = {
     "cql_timed_update": (C.c_int, [_P, _P, _P]),
     "cql_mma_bench": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "cql_synth_table": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_uint64]),
+    "cql_set_table_sharded": (C.c_int, [_P, C.c_int32]),
+    "cql_mdp_begin": (C.c_int, [_P, C.c_int64]),
+    "cql_mdp_append": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int64]),
+    "cql_mdp_finish": (C.c_int, [_P, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
     "cql_selftest_umma": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "cql_launch_count": (C.c_int64, [_P]),
 }

@@ -20,7 +20,7 @@ STAMP = HERE / ".libcql_b200.stamp"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-ldl",
 ]
 
 

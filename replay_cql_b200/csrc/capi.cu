@@ -483,6 +483,31 @@ int cql_load_transitions(cql_handle* ch, const float* obs, const float* act, con
   });
 }
 
+int cql_mdp_begin(cql_handle* ch, int64_t n_rows) {
+  return guarded(ch, [&] {
+    CQL_CUDA(cudaDeviceSynchronize());
+    mdp_begin(ch->h, n_rows);
+  });
+}
+int cql_mdp_append(cql_handle* ch, int32_t col, int32_t dtype, const void* host_chunk, int64_t count) {
+  return guarded(ch, [&] { mdp_append(ch->h, col, dtype, host_chunk, count); });
+}
+int cql_mdp_finish(cql_handle* ch, int32_t top_k, float noise_scale, float* obs_out, float* act_out, float* rew_out,
+                   float* term_out, int64_t* order_out) {
+  return guarded(ch, [&] {
+    CQL_REQUIRE(top_k >= 0, "cql_mdp_finish: top_k < 0");
+    ch->h.launches += mdp_finish(ch->h, top_k, noise_scale, obs_out, act_out, rew_out, term_out, order_out);
+    destroy_graph(ch);
+  });
+}
+
+int cql_set_table_sharded(cql_handle* ch, int32_t sharded) {
+  return guarded(ch, [&] {
+    ch->h.table_sharded = sharded != 0;
+    destroy_graph(ch);
+  });
+}
+
 int cql_synth_table(cql_handle* ch, int64_t n, int64_t n_users, int64_t n_items, uint64_t seed) {
   return guarded(ch, [&] {
     Handle& h = ch->h;
@@ -528,6 +553,7 @@ int cql_sample_rows(cql_handle* ch, const int64_t* idx_dev, int64_t pos, int64_t
 
 int cql_update(cql_handle* ch, int64_t n_steps, float* metrics6, void* stream) {
   return guarded(ch, [&] {
+    NvtxRange nvtx("cql_update: graph replays");
     Handle& h = ch->h;
     CQL_REQUIRE(n_steps >= 0, "cql_update: n_steps < 0");
     CQL_REQUIRE(h.n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
@@ -708,6 +734,7 @@ int cql_update_batch(cql_handle* ch, const float* obs, const float* act, const f
 int cql_update_batches(cql_handle* ch, int64_t n_batches, const float* obs, const float* act, const float* rew,
                        const float* next_obs, const float* term, float* metrics_out, void* stream) {
   return guarded(ch, [&] {
+    NvtxRange nvtx("cql_update_batches");
     Handle& h = ch->h;
     CQL_REQUIRE(n_batches >= 0, "cql_update_batches: n_batches < 0");
     if (n_batches == 0) return;
@@ -883,6 +910,7 @@ int cql_score_topk_dev(cql_handle* ch, const int32_t* users, int64_t n_users, co
                        const int64_t* seen_indptr, const int32_t* seen_items, int32_t k, int32_t mode,
                        int32_t* out_items, float* out_scores, void* stream) {
   return guarded(ch, [&] {
+    NvtxRange nvtx("cql_score_topk_dev");
     CQL_REQUIRE((n_users == 0 || users) && (n_items == 0 || items) && out_items && out_scores,
                 "cql_score_topk_dev: NULL pointer");
     score_topk_dev_impl(ch, users, n_users, items, n_items, seen_indptr, seen_items, k, mode, out_items, out_scores,
@@ -895,6 +923,7 @@ int cql_score_topk(cql_handle* ch, const int32_t* users, int64_t n_users, const 
                    const int64_t* seen_indptr, const int32_t* seen_items, int32_t k, int32_t mode, int32_t* out_items,
                    float* out_scores, void* stream) {
   return guarded(ch, [&] {
+    NvtxRange nvtx("cql_score_topk");
     CQL_REQUIRE((n_users == 0 || users) && (n_items == 0 || items) && (n_users == 0 || (out_items && out_scores)),
                 "cql_score_topk: NULL pointer");
     CQL_REQUIRE(k >= 1 && k <= CQL_MAX_TOPK, "cql_score_topk: k must be 1..1024");
@@ -955,6 +984,7 @@ int cql_rank_metrics(cql_handle* ch, const int32_t* rec_items, int64_t n_users, 
                      const int64_t* gt_indptr, const int32_t* gt_items, const int32_t* ks, int32_t n_ks,
                      double* out_means, void* stream) {
   return guarded(ch, [&] {
+    NvtxRange nvtx("cql_rank_metrics");
     Handle& h = ch->h;
     CQL_REQUIRE(n_users >= 0 && k_rec >= 1 && n_ks >= 1 && n_ks <= MET_MAX_KS && ks && out_means, "cql_rank_metrics: bad arguments");
     for (int q = 0; q < n_ks; ++q) CQL_REQUIRE(ks[q] >= 1, "cql_rank_metrics: k must be >= 1");

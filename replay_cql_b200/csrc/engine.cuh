@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "dp_peer.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 namespace cql {
 
@@ -14,6 +15,18 @@ struct StepInfo {          // written by k_step_begin, read by the Adam kernels
   double bc1, bc2_sqrt;    // 1 - beta1^t, sqrt(1 - beta2^t)
   long long step;          // t (1-based) of the update in flight
 };
+
+// NVTX range (SURVEY.md section 5 "Tracing / profiling"): the phases of an update, scoring and ingestion show up by name
+// on an Nsight Systems / ncu --nvtx timeline.  Header-only NVTX3: a no-op unless a tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
+struct MdpSession;                   // chunked ingestion session (mdp_gpu.cu)
+void mdp_session_free(MdpSession*);
 
 struct Handle {
   cql_config cfg{};
@@ -37,6 +50,7 @@ struct Handle {
   // ---- replay table ----
   float* table = nullptr;    // [n_trans][8]: obs.x obs.y act rew nobs.x nobs.y term pad
   int64_t n_trans = 0;
+  bool table_sharded = false;   // data parallel: this rank holds only its own users' episodes (cql_set_table_sharded)
   int64_t sample_pos_host = 0;  // position in the epoch stream for the stand-alone sampler
   long long* sample_pos = nullptr;   // device: next position in the permutation stream
 
@@ -103,6 +117,8 @@ struct Handle {
   bool timing = false;
   cudaEvent_t ev[16] = {};
 
+  MdpSession* mdp = nullptr;       // between cql_mdp_begin and cql_mdp_finish
+  uint8_t* mdp_ring = nullptr;     // pinned staging ring of the ingestion sessions
   std::vector<void*> allocs;
 
   template <typename T>
@@ -116,6 +132,8 @@ struct Handle {
   void free_all() {
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
+    if (mdp) { mdp_session_free(mdp); mdp = nullptr; }
+    if (mdp_ring) { cudaFreeHost(mdp_ring); mdp_ring = nullptr; }
     if (table) { cudaFree(table); table = nullptr; }
     if (metrics_host) { cudaFreeHost(metrics_host); metrics_host = nullptr; }
     if (batch_host) { cudaFreeHost(batch_host); batch_host = nullptr; }
@@ -134,6 +152,11 @@ struct Handle {
   float* g_critics() const { return grads + NET_STRIDE; }
   float* g_scalars() const { return grads + (size_t)(1 + C) * NET_STRIDE; }
 };
+
+void mdp_begin(Handle& h, int64_t n);
+void mdp_append(Handle& h, int col, int dtype, const void* host, int64_t count);
+int64_t mdp_finish(Handle& h, int top_k, float noise_scale, float* obs_out, float* act_out, float* rew_out, float* term_out,
+                   int64_t* order_out);
 
 inline void mark(Handle* h, cudaStream_t st, int i) {
   if (h->timing) CQL_CUDA(cudaEventRecord(h->ev[i], st));

@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <initializer_list>
 #include <vector>
+#include <cstring>
+#include <memory>
+#include <thread>
 #include <cub/cub.cuh>
 #include "engine.cuh"
 
@@ -75,104 +78,262 @@ T* dmalloc(size_t n, std::vector<void*>& pool) {
   return reinterpret_cast<T*>(p);
 }
 
+// raw column chunk (any accepted dtype) -> the builder's column type
+template <typename S, typename D>
+__global__ void k_convert(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (D)src[i];
+}
+
+void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  constexpr size_t MIN_PER_THREAD = 2u << 20;
+  const int n_thr = (int)std::min<size_t>(4, std::max<size_t>(1, bytes / MIN_PER_THREAD));
+  if (n_thr <= 1) { std::memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = (bytes / n_thr + 63) & ~(size_t)63;
+  for (int t = 1; t < n_thr; ++t) {
+    const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+    if (hi > lo) th.emplace_back([=] { std::memcpy(dst + lo, src + lo, hi - lo); });
+  }
+  std::memcpy(dst, src, std::min(bytes, per));
+  for (auto& x : th) x.join();
+}
+
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ingestion session: Arrow record batches / Parquet row groups / pandas columns arrive as CHUNKS of
+// host memory in their own dtype.  Each chunk is copied -- by up to four host threads -- into a slot of a pinned ring and
+// goes to the device with cudaMemcpyAsync on a copy stream (pageable memory handed to cudaMemcpy directly is staged by
+// the driver in small pieces: r01 measured 0.14 - 1.3 s for the 480 MB of an ML-20M log); a one-line kernel converts the
+// dtype where it differs from the builder's.  As soon as the TIMESTAMP column is complete the first two radix sorts (by
+// timestamp, ascending and descending) start on the compute stream while the other columns are still in flight.
+struct cql::MdpSession {
+  int64_t n = 0;
+  int32_t *user = nullptr, *item = nullptr;
+  int64_t* ts = nullptr;
+  double *rel = nullptr, *noise = nullptr;
+  int64_t filled[5] = {0, 0, 0, 0, 0};
+  uint32_t *ia = nullptr, *ib = nullptr, *perm_desc = nullptr, *order = nullptr;
+  int64_t *k64a = nullptr, *k64b = nullptr;
+  double *kda = nullptr, *kdb = nullptr;
+  int32_t *k32a = nullptr, *k32b = nullptr;
+  uint8_t* rewarded = nullptr;
+  void* temp = nullptr;
+  size_t tbytes = 0;
+  static constexpr int SLOTS = 4;
+  static constexpr size_t SLOT_BYTES = 16u << 20;
+  uint8_t* ring = nullptr;          // pinned [SLOTS][SLOT_BYTES] (owned by the handle: allocated once, 64 MB of page-locking is not free)
+  uint8_t* raw = nullptr;           // device [SLOTS][SLOT_BYTES] (chunks whose dtype needs converting)
+  cudaEvent_t slot_ev[SLOTS] = {};
+  int next_slot = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ts = nullptr, ev_all = nullptr;
+  bool stage_a = false;
+  int64_t launches = 0;
+  std::vector<void*> pool;
+
+  ~MdpSession() {
+    for (void* p : pool) cudaFree(p);
+    for (auto& e : slot_ev) if (e) cudaEventDestroy(e);
+    if (ev_ts) cudaEventDestroy(ev_ts);
+    if (ev_all) cudaEventDestroy(ev_all);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
+};
+
+namespace {
+size_t dtype_bytes(int dt) { return dt == CQL_DT_I32 || dt == CQL_DT_F32 ? 4 : 8; }
+
+template <typename D>
+void convert_chunk(int dtype, const void* raw, D* dst, int64_t cnt, cudaStream_t st) {
+  const unsigned nb = (unsigned)((cnt + 255) / 256);
+  switch (dtype) {
+    case CQL_DT_I32: k_convert<int32_t, D><<<nb, 256, 0, st>>>((const int32_t*)raw, dst, cnt); break;
+    case CQL_DT_I64: k_convert<int64_t, D><<<nb, 256, 0, st>>>((const int64_t*)raw, dst, cnt); break;
+    case CQL_DT_F32: k_convert<float, D><<<nb, 256, 0, st>>>((const float*)raw, dst, cnt); break;
+    default: k_convert<double, D><<<nb, 256, 0, st>>>((const double*)raw, dst, cnt); break;
+  }
+  CQL_CUDA(cudaGetLastError());
+}
+
+// the two timestamp sorts: need nothing but the timestamp column
+void mdp_stage_a(Handle& h, MdpSession& m) {
+  cudaStream_t st = h.own_stream;
+  const int64_t n = m.n;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  size_t tb;
+  CQL_CUDA(cudaStreamWaitEvent(st, m.ev_ts, 0));
+  k_iota<<<nb, 256, 0, st>>>(m.ia, n);
+  tb = m.tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairs(m.temp, tb, m.ts, m.k64a, m.ia, m.ib, (int)n, 0, 64, st));            // ib = by ts asc
+  tb = m.tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairsDescending(m.temp, tb, m.ts, m.k64a, m.ia, m.perm_desc, (int)n, 0, 64, st));   // by ts desc
+  m.launches += 7;
+  m.stage_a = true;
+}
+}  // namespace
+
+void cql::mdp_session_free(MdpSession* m) { delete m; }
+
+void cql::mdp_begin(Handle& h, int64_t n) {
+  CQL_REQUIRE(n >= 1 && n < (1ll << 31), "cql_mdp_begin: n must be in 1..2^31-1");
+  if (h.mdp) { delete h.mdp; h.mdp = nullptr; }
+  auto* m = new MdpSession();
+  h.mdp = m;
+  m->n = n;
+  m->user = dmalloc<int32_t>(n, m->pool);
+  m->item = dmalloc<int32_t>(n, m->pool);
+  m->ts = dmalloc<int64_t>(n, m->pool);
+  m->rel = dmalloc<double>(n, m->pool);
+  m->ia = dmalloc<uint32_t>(n, m->pool);
+  m->ib = dmalloc<uint32_t>(n, m->pool);
+  m->perm_desc = dmalloc<uint32_t>(n, m->pool);
+  m->order = dmalloc<uint32_t>(n, m->pool);
+  m->k64a = dmalloc<int64_t>(n, m->pool);
+  m->k64b = dmalloc<int64_t>(n, m->pool);
+  m->kda = dmalloc<double>(n, m->pool);
+  m->kdb = dmalloc<double>(n, m->pool);
+  m->k32a = dmalloc<int32_t>(n, m->pool);
+  m->k32b = dmalloc<int32_t>(n, m->pool);
+  m->rewarded = dmalloc<uint8_t>(n, m->pool);
+  size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+  cudaStream_t st = h.own_stream;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, m->ts, m->k64a, m->ia, m->ib, (int)n, 0, 64, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, t2, m->k32a, m->k32b, m->ia, m->ib, (int)n, 0, 32, st);
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, t3, m->ts, m->k64a, m->ia, m->ib, (int)n, 0, 64, st);
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, t4, m->kda, m->kdb, m->ia, m->ib, (int)n, 0, 64, st);
+  cub::DeviceScan::InclusiveScan(nullptr, t5, m->k64a, m->k64b, MaxOp(), (int)n, st);
+  m->tbytes = t1;
+  for (size_t t : {t2, t3, t4, t5}) m->tbytes = t > m->tbytes ? t : m->tbytes;
+  m->temp = dmalloc<uint8_t>(m->tbytes, m->pool);
+  if (h.mdp_ring == nullptr) CQL_CUDA(cudaMallocHost(&h.mdp_ring, MdpSession::SLOTS * MdpSession::SLOT_BYTES));
+  m->ring = h.mdp_ring;
+  m->raw = dmalloc<uint8_t>(MdpSession::SLOTS * MdpSession::SLOT_BYTES, m->pool);
+  for (auto& e : m->slot_ev) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CQL_CUDA(cudaEventCreateWithFlags(&m->ev_ts, cudaEventDisableTiming));
+  CQL_CUDA(cudaEventCreateWithFlags(&m->ev_all, cudaEventDisableTiming));
+  CQL_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+}
+
+void cql::mdp_append(Handle& h, int col, int dtype, const void* host, int64_t count) {
+  CQL_REQUIRE(h.mdp != nullptr, "cql_mdp_append: call cql_mdp_begin first");
+  NvtxRange nvtx("cql.mdp.append: host chunk -> pinned ring -> device");
+  MdpSession& m = *h.mdp;
+  CQL_REQUIRE(col >= 0 && col <= 4, "cql_mdp_append: column must be 0 user, 1 item, 2 timestamp, 3 relevance, 4 action noise");
+  CQL_REQUIRE(dtype >= CQL_DT_I32 && dtype <= CQL_DT_F64, "cql_mdp_append: dtype must be one of CQL_DT_*");
+  CQL_REQUIRE(count >= 0 && m.filled[col] + count <= m.n, "cql_mdp_append: more rows than cql_mdp_begin announced");
+  CQL_REQUIRE(host != nullptr || count == 0, "cql_mdp_append: NULL chunk");
+  if (col == 4 && m.noise == nullptr) m.noise = dmalloc<double>(m.n, m.pool);
+  const int native = (col <= 1) ? CQL_DT_I32 : (col == 2 ? CQL_DT_I64 : CQL_DT_F64);
+  const size_t eb = dtype_bytes(dtype);
+  const int64_t per_slot = (int64_t)(MdpSession::SLOT_BYTES / eb);
+  const uint8_t* src = (const uint8_t*)host;
+  for (int64_t done = 0; done < count;) {
+    const int64_t cnt = std::min(per_slot, count - done);
+    const int slot = m.next_slot;
+    m.next_slot = (m.next_slot + 1) % MdpSession::SLOTS;
+    CQL_CUDA(cudaEventSynchronize(m.slot_ev[slot]));                        // the slot's previous copy (and conversion) is done
+    uint8_t* pin = m.ring + (size_t)slot * MdpSession::SLOT_BYTES;
+    parallel_memcpy(pin, src + (size_t)done * eb, (size_t)cnt * eb);
+    const int64_t at = m.filled[col] + done;
+    void* dst = col == 0 ? (void*)(m.user + at) : col == 1 ? (void*)(m.item + at) : col == 2 ? (void*)(m.ts + at)
+              : col == 3 ? (void*)(m.rel + at) : (void*)(m.noise + at);
+    if (dtype == native) {
+      CQL_CUDA(cudaMemcpyAsync(dst, pin, (size_t)cnt * eb, cudaMemcpyHostToDevice, m.copy_stream));
+    } else {
+      uint8_t* rawd = m.raw + (size_t)slot * MdpSession::SLOT_BYTES;
+      CQL_CUDA(cudaMemcpyAsync(rawd, pin, (size_t)cnt * eb, cudaMemcpyHostToDevice, m.copy_stream));
+      if (col <= 1) convert_chunk<int32_t>(dtype, rawd, (int32_t*)dst, cnt, m.copy_stream);
+      else if (col == 2) convert_chunk<int64_t>(dtype, rawd, (int64_t*)dst, cnt, m.copy_stream);
+      else convert_chunk<double>(dtype, rawd, (double*)dst, cnt, m.copy_stream);
+      m.launches += 1;
+    }
+    CQL_CUDA(cudaEventRecord(m.slot_ev[slot], m.copy_stream));
+    done += cnt;
+  }
+  m.filled[col] += count;
+  if (col == 2 && m.filled[2] == m.n && !m.stage_a) {                        // timestamps complete: sort while the rest uploads
+    CQL_CUDA(cudaEventRecord(m.ev_ts, m.copy_stream));
+    mdp_stage_a(h, m);
+  }
+}
+
 // returns the number of kernels launched (for the handle's launch counter)
+int64_t cql::mdp_finish(Handle& h, int top_k, float noise_scale, float* obs_out, float* act_out, float* rew_out, float* term_out,
+                        int64_t* order_out) {
+  CQL_REQUIRE(h.mdp != nullptr, "cql_mdp_finish: call cql_mdp_begin first");
+  NvtxRange nvtx("cql.mdp.finish: radix sorts + replay table");
+  std::unique_ptr<MdpSession> guard(h.mdp);
+  h.mdp = nullptr;
+  MdpSession& m = *guard;
+  const int64_t n = m.n;
+  for (int c = 0; c < 4; ++c) CQL_REQUIRE(m.filled[c] == n, "cql_mdp_finish: a column is incomplete (user, item, timestamp, relevance need n rows each)");
+  CQL_REQUIRE(m.noise == nullptr || m.filled[4] == n, "cql_mdp_finish: the action-noise column is incomplete");
+  cudaStream_t st = h.own_stream;
+  if (!m.stage_a) { CQL_CUDA(cudaEventRecord(m.ev_ts, m.copy_stream)); mdp_stage_a(h, m); }
+  CQL_CUDA(cudaEventRecord(m.ev_all, m.copy_stream));
+  CQL_CUDA(cudaStreamWaitEvent(st, m.ev_all, 0));
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  size_t tb;
+  int64_t* head = m.k64a;            // reused after the timestamp sorts
+  int64_t* gstart = m.k64b;
+  // ---- order: (user, ts, input order): stable sort by user of the ts-ascending permutation
+  k_gather<int32_t><<<nb, 256, 0, st>>>(m.user, m.ib, n, m.k32a);
+  tb = m.tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairs(m.temp, tb, m.k32a, m.k32b, m.ib, m.order, (int)n, 0, 32, st));
+  // ---- rank order: (user, rel desc, ts desc, input order)
+  k_gather<double><<<nb, 256, 0, st>>>(m.rel, m.perm_desc, n, m.kda);
+  tb = m.tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairsDescending(m.temp, tb, m.kda, m.kdb, m.perm_desc, m.ia, (int)n, 0, 64, st));
+  k_gather<int32_t><<<nb, 256, 0, st>>>(m.user, m.ia, n, m.k32a);
+  tb = m.tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairs(m.temp, tb, m.k32a, m.k32b, m.ia, m.ib, (int)n, 0, 32, st));   // ib = rank order
+  k_heads<<<nb, 256, 0, st>>>(m.k32b, n, head);
+  tb = m.tbytes; CQL_CUDA(cub::DeviceScan::InclusiveScan(m.temp, tb, head, gstart, MaxOp(), (int)n, st));
+  k_rewarded<<<nb, 256, 0, st>>>(m.ib, gstart, n, top_k, m.rewarded);
+  m.launches += 13;
+
+  // ---- emit transition rows straight into the replay table
+  if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
+  CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+  float *d_obs = nullptr, *d_act = nullptr, *d_rew = nullptr, *d_term = nullptr;
+  if (obs_out) {
+    CQL_REQUIRE(act_out && rew_out && term_out, "cql_build_mdp: give all four output columns or none");
+    d_obs = dmalloc<float>(2 * n, m.pool); d_act = dmalloc<float>(n, m.pool);
+    d_rew = dmalloc<float>(n, m.pool); d_term = dmalloc<float>(n, m.pool);
+  }
+  k_emit<<<nb, 256, 0, st>>>(m.order, m.user, m.item, m.rel, m.noise, m.rewarded, n, noise_scale, h.cfg.seed,
+                             reinterpret_cast<float4*>(h.table), d_obs, d_act, d_rew, d_term);
+  CQL_CUDA(cudaGetLastError());
+  m.launches += 1;
+  if (obs_out) {
+    CQL_CUDA(cudaMemcpyAsync(obs_out, d_obs, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaMemcpyAsync(act_out, d_act, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaMemcpyAsync(rew_out, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaMemcpyAsync(term_out, d_term, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (order_out) {
+    std::vector<uint32_t> tmp((size_t)n);          // widen on the host: order is uint32 on the device
+    CQL_CUDA(cudaMemcpyAsync(tmp.data(), m.order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n; ++i) order_out[i] = tmp[(size_t)i];
+  }
+  CQL_CUDA(cudaStreamSynchronize(st));
+  h.n_trans = n;
+  return m.launches;
+}
+
+// one-call form (cql_build_mdp): whole columns in the builder's own dtypes
 int64_t mdp_build_on_device(Handle& h, const int32_t* user_h, const int32_t* item_h, const int64_t* ts_h, const double* rel_h,
                             const double* noise_h, int64_t n, int top_k, float noise_scale, float* obs_out, float* act_out,
                             float* rew_out, float* term_out, int64_t* order_out) {
-  CQL_REQUIRE(n >= 1 && n < (1ll << 31), "cql_build_mdp: n must be in 1..2^31-1");
   CQL_REQUIRE(user_h && item_h && ts_h && rel_h, "cql_build_mdp: NULL column");
-  cudaStream_t st = h.own_stream;
-  std::vector<void*> pool;
-  int64_t launches = 0;
+  mdp_begin(h, n);
   try {
-    int32_t* user = dmalloc<int32_t>(n, pool);
-    int32_t* item = dmalloc<int32_t>(n, pool);
-    int64_t* ts = dmalloc<int64_t>(n, pool);
-    double* rel = dmalloc<double>(n, pool);
-    double* noise = noise_h ? dmalloc<double>(n, pool) : nullptr;
-    CQL_CUDA(cudaMemcpyAsync(user, user_h, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CQL_CUDA(cudaMemcpyAsync(item, item_h, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CQL_CUDA(cudaMemcpyAsync(ts, ts_h, n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CQL_CUDA(cudaMemcpyAsync(rel, rel_h, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (noise) CQL_CUDA(cudaMemcpyAsync(noise, noise_h, n * sizeof(double), cudaMemcpyHostToDevice, st));
-
-    uint32_t* ia = dmalloc<uint32_t>(n, pool);
-    uint32_t* ib = dmalloc<uint32_t>(n, pool);
-    int64_t* k64a = dmalloc<int64_t>(n, pool);
-    int64_t* k64b = dmalloc<int64_t>(n, pool);
-    double* kda = dmalloc<double>(n, pool);
-    double* kdb = dmalloc<double>(n, pool);
-    int32_t* k32a = dmalloc<int32_t>(n, pool);
-    int32_t* k32b = dmalloc<int32_t>(n, pool);
-    uint32_t* order = dmalloc<uint32_t>(n, pool);
-    uint8_t* rewarded = dmalloc<uint8_t>(n, pool);
-    int64_t* head = k64a;            // reused after the timestamp sorts
-    int64_t* gstart = k64b;
-
-    // one temp buffer big enough for every CUB call below
-    size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, ts, k64a, ia, ib, (int)n, 0, 64, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, k32a, k32b, ia, ib, (int)n, 0, 32, st);
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, t3, ts, k64a, ia, ib, (int)n, 0, 64, st);
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, t4, kda, kdb, ia, ib, (int)n, 0, 64, st);
-    cub::DeviceScan::InclusiveScan(nullptr, t5, head, gstart, MaxOp(), (int)n, st);
-    size_t tbytes = t1;
-    for (size_t t : {t2, t3, t4, t5}) tbytes = t > tbytes ? t : tbytes;
-    void* temp = dmalloc<uint8_t>(tbytes, pool);
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    size_t tb;
-
-    // ---- order: (user, ts, input order)
-    k_iota<<<nb, 256, 0, st>>>(ia, n);
-    tb = tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ts, k64a, ia, ib, (int)n, 0, 64, st));
-    k_gather<int32_t><<<nb, 256, 0, st>>>(user, ib, n, k32a);
-    tb = tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, k32a, k32b, ib, order, (int)n, 0, 32, st));
-    // ---- rank order: (user, rel desc, ts desc, input order)
-    k_iota<<<nb, 256, 0, st>>>(ia, n);
-    tb = tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairsDescending(temp, tb, ts, k64a, ia, ib, (int)n, 0, 64, st));
-    k_gather<double><<<nb, 256, 0, st>>>(rel, ib, n, kda);
-    tb = tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairsDescending(temp, tb, kda, kdb, ib, ia, (int)n, 0, 64, st));
-    k_gather<int32_t><<<nb, 256, 0, st>>>(user, ia, n, k32a);
-    tb = tbytes; CQL_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, k32a, k32b, ia, ib, (int)n, 0, 32, st));   // ib = rank order
-    k_heads<<<nb, 256, 0, st>>>(k32b, n, head);
-    tb = tbytes; CQL_CUDA(cub::DeviceScan::InclusiveScan(temp, tb, head, gstart, MaxOp(), (int)n, st));
-    k_rewarded<<<nb, 256, 0, st>>>(ib, gstart, n, top_k, rewarded);
-    launches += 20;
-
-    // ---- emit transition rows straight into the replay table
-    if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
-    CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
-    float *d_obs = nullptr, *d_act = nullptr, *d_rew = nullptr, *d_term = nullptr;
-    if (obs_out) {
-      CQL_REQUIRE(act_out && rew_out && term_out, "cql_build_mdp: give all four output columns or none");
-      d_obs = dmalloc<float>(2 * n, pool); d_act = dmalloc<float>(n, pool);
-      d_rew = dmalloc<float>(n, pool); d_term = dmalloc<float>(n, pool);
-    }
-    k_emit<<<nb, 256, 0, st>>>(order, user, item, rel, noise, rewarded, n, noise_scale, h.cfg.seed,
-                               reinterpret_cast<float4*>(h.table), d_obs, d_act, d_rew, d_term);
-    CQL_CUDA(cudaGetLastError());
-    launches += 1;
-    if (obs_out) {
-      CQL_CUDA(cudaMemcpyAsync(obs_out, d_obs, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
-      CQL_CUDA(cudaMemcpyAsync(act_out, d_act, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-      CQL_CUDA(cudaMemcpyAsync(rew_out, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-      CQL_CUDA(cudaMemcpyAsync(term_out, d_term, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
-    if (order_out) {
-      // widen on the host: order is uint32 on the device
-      std::vector<uint32_t> tmp((size_t)n);
-      CQL_CUDA(cudaMemcpyAsync(tmp.data(), order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      CQL_CUDA(cudaStreamSynchronize(st));
-      for (int64_t i = 0; i < n; ++i) order_out[i] = tmp[(size_t)i];
-    }
-    CQL_CUDA(cudaStreamSynchronize(st));
-    h.n_trans = n;
+    mdp_append(h, 2, CQL_DT_I64, ts_h, n);          // timestamps first: their sorts overlap the other uploads
+    mdp_append(h, 0, CQL_DT_I32, user_h, n);
+    mdp_append(h, 1, CQL_DT_I32, item_h, n);
+    mdp_append(h, 3, CQL_DT_F64, rel_h, n);
+    if (noise_h) mdp_append(h, 4, CQL_DT_F64, noise_h, n);
+    return mdp_finish(h, top_k, noise_scale, obs_out, act_out, rew_out, term_out, order_out);
   } catch (...) {
-    for (void* p : pool) cudaFree(p);
+    if (h.mdp) { delete h.mdp; h.mdp = nullptr; }
     throw;
   }
-  for (void* p : pool) cudaFree(p);
-  return launches;
 }

@@ -145,7 +145,7 @@ __global__ void k_step_end(long long* step_dev) {
 __global__ void k_step_head(const float4* __restrict__ table, int64_t n_trans, const long long* __restrict__ step_dev,
                             StepInfo* __restrict__ info, float beta1, float beta2, int B, int n, int rank, int world,
                             uint64_t seed, float4* __restrict__ batch, float4* __restrict__ XA,
-                            float* __restrict__ noise, int64_t noise_total) {
+                            float* __restrict__ noise, int64_t noise_total, int prank, int pworld) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
  
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,8 +157,10 @@ __global__ void k_step_head(const float4* __restrict__ table, int64_t n_trans, c
     info->bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)t));
   }
   if (i < B) {
-    const int64_t p = ((int64_t)done * world + rank) * B + i;
-    const int64_t t = stream_index(p, n_trans, (int64_t)B * world, seed);
+    // position in the epoch permutation: (rank, world) of the data-parallel job for a replicated table, (0, 1) when this
+    // rank holds only its own user shard (prank / pworld); the Philox stream below always uses the job's rank
+    const int64_t p = ((int64_t)done * pworld + prank) * B + i;
+    const int64_t t = stream_index(p, n_trans, (int64_t)B * pworld, seed);
     const float4 a = __ldg(table + 2 * t), b = __ldg(table + 2 * t + 1);
     batch[2 * i] = a;
     batch[2 * i + 1] = b;
@@ -932,6 +934,7 @@ enum class NoiseSource { Philox, Provided };
 
 // phase 0: (sample, noise,) shared actor forward, all critic forwards, scalar gradients
 inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
+  NvtxRange nvtx("cql.update.phase0: sample, actor forward, critic forwards, temp/alpha gradients");
   const int B = h->B, C = h->C, n3 = 3 * h->n;
   const cql_config& c = h->cfg;
   mark(h, st, 0);
@@ -942,7 +945,8 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     launch_pdl(k_step_head, dim3((int)((nthr + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(h->table), h->n_trans, h->step_dev,
                                                           h->stepinfo, c.beta1, c.beta2, B, h->n, c.rank, c.world_size,
                                                           c.seed, reinterpret_cast<float4*>(h->batch), h->XA, h->noise,
-                                                          h->noise_floats);
+                                                          h->noise_floats, h->table_sharded ? 0 : c.rank,
+                                                          h->table_sharded ? 1 : c.world_size);
     CQL_LAUNCH_CHECK(h);
   } else {
     k_step_begin<<<1, 1, 0, st>>>(h->step_dev, h->stepinfo, c.beta1, c.beta2);
@@ -950,7 +954,8 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     if (bs == BatchSource::Sampled) {
       CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
       k_sample<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4*>(h->table), h->n_trans, nullptr,
-                                                h->step_dev, 0, B, (int64_t)B * c.world_size, c.rank, c.world_size,
+                                                h->step_dev, 0, B, (int64_t)B * (h->table_sharded ? 1 : c.world_size),
+                                                h->table_sharded ? 0 : c.rank, h->table_sharded ? 1 : c.world_size,
                                                 c.seed, reinterpret_cast<float4*>(h->batch));
       CQL_LAUNCH_CHECK(h);
     }
@@ -1000,6 +1005,7 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
 
 // phase 1: temp/alpha Adam, critic backward -> critic gradients
 inline void phase1(Handle* h, cudaStream_t st) {
+  NvtxRange nvtx("cql.update.phase1: temp/alpha Adam, critic backward");
   const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
   const int64_t so = scalars_off(C);
   launch_pdl(k_scalar_adam_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so,
@@ -1025,6 +1031,7 @@ inline void phase1(Handle* h, cudaStream_t st) {
 
 // phase 2: critic Adam + Polyak, actor loss through the updated critics -> actor gradients
 inline void phase2(Handle* h, cudaStream_t st) {
+  NvtxRange nvtx("cql.update.phase2: critic Adam + Polyak + pack, actor step forward/backward");
   const int B = h->B, C = h->C;
   const cql_config& c = h->cfg;
   static const bool no_fused_adam = std::getenv("CQL_NO_FUSED_ADAM") != nullptr;      // A/B switch
@@ -1083,6 +1090,7 @@ inline void phase2(Handle* h, cudaStream_t st) {
 
 // phase 3: actor Adam + Polyak of the target policy, step counter
 inline void phase3(Handle* h, cudaStream_t st) {
+  NvtxRange nvtx("cql.update.phase3: actor Adam + Polyak + pack");
   const cql_config& c = h->cfg;
   static const bool no_fused_adam = std::getenv("CQL_NO_FUSED_ADAM") != nullptr;      // A/B switch
   if (h->cfg.precision == CQL_PREC_F16X3 && !no_fused_adam) {

@@ -192,6 +192,36 @@ class CqlEngine:
                                             float(action_randomization_scale), *[_ptr(o) for o in outs]), "cql_build_mdp")
         return tuple(outs) if want_outputs else None
 
+    # ---- chunked ingestion (Arrow record batches / Parquet row groups / pandas columns; see mdp.ingest_log)
+    _COLS = {"user_idx": 0, "item_idx": 1, "timestamp": 2, "relevance": 3, "action_noise": 4}
+    _DTS = {np.dtype(np.int32): _lib.DT_I32, np.dtype(np.int64): _lib.DT_I64,
+            np.dtype(np.float32): _lib.DT_F32, np.dtype(np.float64): _lib.DT_F64}
+
+    def mdp_begin(self, n_rows: int) -> None:
+        self._check(self._lib.cql_mdp_begin(self._h, int(n_rows)), "cql_mdp_begin")
+
+    def mdp_append(self, column: str, address: int, dtype, count: int) -> None:
+        """Next ``count`` values of ``column`` from host memory at ``address`` (any of int32/int64/float32/float64)."""
+        dt = self._DTS.get(np.dtype(dtype))
+        if dt is None:
+            raise ValueError(f"unsupported chunk dtype {dtype} for {column}")
+        self._check(self._lib.cql_mdp_append(self._h, self._COLS[column], dt, C.c_void_p(int(address)), int(count)),
+                    "cql_mdp_append")
+
+    def mdp_finish(self, top_k: int = 10, action_randomization_scale: float = 1e-3, want_outputs: bool = False, n_rows: int = 0):
+        outs = [None] * 5
+        if want_outputs:
+            n = int(n_rows)
+            outs = [np.empty((n, 2), np.float32), np.empty(n, np.float32), np.empty(n, np.float32),
+                    np.empty(n, np.float32), np.empty(n, np.int64)]
+        self._check(self._lib.cql_mdp_finish(self._h, int(top_k), float(action_randomization_scale), *[_ptr(o) for o in outs]),
+                    "cql_mdp_finish")
+        return tuple(outs) if want_outputs else None
+
+    def set_table_sharded(self, sharded: bool) -> None:
+        """Data parallel: the table holds only this rank's user range -> sample this rank's own epoch permutation."""
+        self._check(self._lib.cql_set_table_sharded(self._h, 1 if sharded else 0), "cql_set_table_sharded")
+
     def synth_table(self, n_rows: int, n_users: int, n_items: int, seed: int = 12345) -> None:
         """Fill the replay table with a seeded synthetic log of the given shape, generated on the device (stress shape)."""
         self._check(self._lib.cql_synth_table(self._h, int(n_rows), int(n_users), int(n_items), int(seed) & (2**64 - 1)),

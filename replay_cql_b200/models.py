@@ -28,10 +28,12 @@ class CQL(Recommender):
     d3rlpy ``predict_value(x, predict(x))``) or the greedy action itself (``score="policy"``).
     """
 
+    SHARD_ROWS = 200_000_000      # data-parallel fits shard the replay table by user range from this log size on
     _observation_shape = (2,)
     _action_size = 1
     can_predict_cold_users = False
     can_predict_cold_items = False
+    accepts_arrow = True          # `_fit` ingests a pyarrow.Table chunk by chunk (mdp.ingest_log): no frame conversion
 
     _search_space = {
         "actor_learning_rate": {"type": "loguniform", "args": [1e-5, 1e-3]},
@@ -70,6 +72,7 @@ class CQL(Recommender):
         n_steps_per_epoch: Optional[int] = None,
         save_replay_table: bool = False,
         log_every: int = 1000,
+        shard_table: Optional[bool] = None,
     ):
         if soft_q_backup:
             raise ValueError("soft_q_backup=True is not supported (d3rlpy default False is restated)")
@@ -104,6 +107,7 @@ class CQL(Recommender):
         self.n_steps_per_epoch = n_steps_per_epoch
         self.save_replay_table = save_replay_table
         self.log_every = log_every
+        self.shard_table = shard_table
         self.engine: Optional[CqlEngine] = None
         self.last_metrics: Optional[Dict[str, float]] = None
 
@@ -135,6 +139,7 @@ class CQL(Recommender):
             "n_steps_per_epoch": self.n_steps_per_epoch,
             "save_replay_table": self.save_replay_table,
             "log_every": self.log_every,
+            "shard_table": self.shard_table,
         }
 
     # ------------------------------------------------------------------ engine
@@ -162,15 +167,24 @@ class CQL(Recommender):
     def _fit(self, log: pd.DataFrame, user_features=None, item_features=None) -> None:
         """MDP build -> HBM replay table -> ``n_epochs`` x (N // (B*world)) fused updates."""
         eng = self._make_engine()
-        if len(log) == 0:
+        n_log = int(log.num_rows) if hasattr(log, "num_rows") else len(log)
+        if n_log == 0:
             self.logger.warning("CQL.fit: empty log")
             return
-        build_mdp_on_device(eng, log, top_k=self.top_k, action_randomization_scale=self.action_randomization_scale)
-        n_rows = eng.n_transitions
         rank, world, _ = dist_info()
+        # Data parallel: every rank holds the whole replay table, or -- for shapes that would not be worth replicating
+        # (`shard_table=True`, default above SHARD_ROWS rows) -- only the episodes of ITS contiguous user range, balanced
+        # by row count (SURVEY.md 8e "MDP build: by user"); it then walks its own epoch permutation.
+        sharded = world > 1 and (self.shard_table if self.shard_table is not None else n_log >= self.SHARD_ROWS)
+        if sharded:
+            from .mdp import shard_log_by_user
+            log = shard_log_by_user(log, rank, world)
+        build_mdp_on_device(eng, log, top_k=self.top_k, action_randomization_scale=self.action_randomization_scale)
+        eng.set_table_sharded(sharded)
+        n_rows = eng.n_transitions
         per_epoch = self.n_steps_per_epoch
         if per_epoch is None:
-            per_epoch = n_rows // (self.batch_size * world)   # d3rlpy drops the last partial minibatch
+            per_epoch = n_log // (self.batch_size * world)    # d3rlpy drops the last partial minibatch
         total = int(self.n_epochs) * int(per_epoch)
         if total == 0:
             self.logger.warning("CQL.fit: 0 update steps (log has %d rows, batch_size*world = %d)",

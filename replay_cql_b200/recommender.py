@@ -323,9 +323,19 @@ class Recommender(ABC):
 
     def _fit_wrap(self, log: Any, user_features=None, item_features=None) -> None:
         self.logger.debug("Starting fit %s", type(self).__name__)
-        pdf = to_pandas(log)
-        self.fit_users = pd.DataFrame({"user_idx": np.sort(pd.unique(pdf["user_idx"]))})
-        self.fit_items = pd.DataFrame({"item_idx": np.sort(pd.unique(pdf["item_idx"]))})
+        from . import frames
+        if frames.pa is not None and isinstance(log, frames.pa.Table) and getattr(self, "accepts_arrow", False):
+            # Arrow in: distinct ids with pyarrow.compute, the table itself goes to `_fit` -- no `toPandas()` at all
+            # (the step being replaced: replay/models/neuromf.py:332)
+            import pyarrow.compute as pc
+            uniq = lambda c: np.sort(pc.unique(log.column(c)).to_numpy(zero_copy_only=False))
+            self.fit_users = pd.DataFrame({"user_idx": uniq("user_idx")})
+            self.fit_items = pd.DataFrame({"item_idx": uniq("item_idx")})
+            pdf = log
+        else:
+            pdf = to_pandas(log)
+            self.fit_users = pd.DataFrame({"user_idx": np.sort(pd.unique(pdf["user_idx"]))})
+            self.fit_items = pd.DataFrame({"item_idx": np.sort(pd.unique(pdf["item_idx"]))})
         self._num_users = len(self.fit_users)
         self._num_items = len(self.fit_items)
         self._user_dim_size = int(self.fit_users["user_idx"].max()) + 1
