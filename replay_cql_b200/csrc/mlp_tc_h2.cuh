@@ -502,7 +502,8 @@ struct H2B1Cfg : H2Cfg {
   static constexpr uint32_t OFF_SLOT = OFF_BAR + 128;                // (N_BARS * 8 = 120, rounded up: what follows holds float4)
   static constexpr uint32_t OFF_FLUSH = OFF_SLOT + 16;               // float[2 groups][4 warps][16][32]
   static constexpr uint32_t OFF_RED = OFF_FLUSH + 2 * 4 * 16 * 32 * 4;
-  static constexpr uint32_t RED_WARP_BYTES = 32 * 33 * 4 + 32 * 16;
+  static constexpr int RED_LD = 34;                                  // row stride of the transposed tile: 8-byte aligned pair stores, conflict-free
+  static constexpr uint32_t RED_WARP_BYTES = 32 * RED_LD * 4 + 32 * 16;
   static constexpr uint32_t SMEM_BYTES = OFF_RED + NEW * RED_WARP_BYTES;
 };
 
@@ -687,7 +688,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
       for (int q = 0; q < NCH; ++q) { a_b[p][q] = 0.f; a_w0[p][q] = 0.f; a_w1[p][q] = 0.f; a_w2[p][q] = 0.f; }
     float* flbuf = reinterpret_cast<float*>(sm + C::OFF_FLUSH) + hh * (4 * 16 * 32);
     float* red_t = reinterpret_cast<float*>(sm + C::OFF_RED + warp * C::RED_WARP_BYTES);       // [32][33]
-    float4* red_x = reinterpret_cast<float4*>(red_t + 32 * 33);                                 // [32] this item's input rows
+    float4* red_x = reinterpret_cast<float4*>(red_t + 32 * C::RED_LD);                          // [32] this item's input rows
     auto flush = [&](int net_i) {                    // called uniformly by the 4 warps of a column half
       if (!WGRADS || net_i < 0) return;
 #pragma unroll
@@ -729,8 +730,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
         const HMeta* meta = reinterpret_cast<const HMeta*>(jb.packedT + (size_t)net_i * C::PACKED_NET_BYTES + C::META_OFF);
         {
           const int k = tid;                          // 256 epilogue threads = 256 hidden units
-          ebs[k] = make_float4(net[off_W1(IN) + k * IN], net[off_W1(IN) + k * IN + 1],
-                               IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f, net[off_b1(IN) + k]);
+          // column PAIRS (k even, k + 1): ebs[k] = (wx_k, wx_k1, wy_k, wy_k1), ebs[k + 1] = (wz_k, wz_k1, b_k, b_k1)
+          float* e = reinterpret_cast<float*>(ebs) + (k >> 1) * 8 + (k & 1);
+          e[0] = net[off_W1(IN) + k * IN];
+          e[2] = net[off_W1(IN) + k * IN + 1];
+          e[4] = IN == 3 ? net[off_W1(IN) + k * IN + 2] : 0.f;
+          e[6] = net[off_b1(IN) + k];
           invs[k] = __ldg(&meta->inv_s[k]);
         }
         w3m0 = __ldg(&meta->wmax[4]);
@@ -765,7 +770,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
 #pragma unroll 1
           for (int c8 = 0; c8 < 32; c8 += 8) {
             float v[8];
-            float4 w[8];
+            float4 w[8];                                  // 4 column pairs x {(wx, wx', wy, wy'), (wz, wz', b, b')}
             float iv[8];
             tmem_ld8(t_acc + q * 32 + c8, v);
 #pragma unroll
@@ -776,19 +781,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
               iv[0] = i0.x; iv[1] = i0.y; iv[2] = i0.z; iv[3] = i0.w; iv[4] = i1.x; iv[5] = i1.y; iv[6] = i1.z; iv[7] = i1.w;
             }
             tmem_ld_wait();
+            const float2 xx2 = make_float2(x.x, x.x), xy2 = make_float2(x.y, x.y), xz2 = make_float2(x.z, x.z);
+            const float2 isa2 = make_float2(inv_sa, inv_sa);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 8; i += 2) {              // columns c8 + i, c8 + i + 1: packed fp32x2 arithmetic
+              const float4 wa = w[i], wb = w[i + 1];
               // layer-1 pre-activation in the FORWARD's order (chain starts from the bias): same ReLU mask bit for bit
-              float z = fmaf(x.y, w[i].y, fmaf(x.x, w[i].x, w[i].w));
-              if (IN == 3) z = fmaf(x.z, w[i].z, z);
+              float2 z = ffma2(xy2, make_float2(wa.z, wa.w), ffma2(xx2, make_float2(wa.x, wa.y), make_float2(wb.z, wb.w)));
+              if (IN == 3) z = ffma2(xz2, make_float2(wb.x, wb.y), z);
               // without dx the column scale 1/s_n is applied once per column sum instead of once per element
-              const float d = z > 0.f ? (DX ? v[i] * inv_sa * iv[i] : v[i] * inv_sa) : 0.f;
+              float2 vs = fmul2(make_float2(v[i], v[i + 1]), isa2);
+              if (DX) vs = fmul2(vs, make_float2(iv[i], iv[i + 1]));
+              const float2 d = make_float2(z.x > 0.f ? vs.x : 0.f, z.y > 0.f ? vs.y : 0.f);
               if (DX) {
-                dx0 = fmaf(d, w[i].x, dx0);
-                dx1 = fmaf(d, w[i].y, dx1);
-                if (IN == 3) dx2 = fmaf(d, w[i].z, dx2);
+                dx0 = fmaf(d.x, wa.x, dx0); dx0 = fmaf(d.y, wa.y, dx0);
+                dx1 = fmaf(d.x, wa.z, dx1); dx1 = fmaf(d.y, wa.w, dx1);
+                if (IN == 3) { dx2 = fmaf(d.x, wb.x, dx2); dx2 = fmaf(d.y, wb.y, dx2); }
               }
-              if (WGRADS) red_t[lane * 33 + c8 + i] = d;
+              if (WGRADS) *reinterpret_cast<float2*>(red_t + lane * C::RED_LD + c8 + i) = d;
             }
           }
           if (WGRADS) {
@@ -798,7 +808,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2Cfg::THREADS, 1) t
             float2 s01 = make_float2(0.f, 0.f), s2b = make_float2(0.f, 0.f);
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              const float dv = red_t[r * 33 + lane];
+              const float dv = red_t[r * C::RED_LD + lane];
               const float4 xr = red_x[r];
               const float2 dd = make_float2(dv, dv);
               s01 = ffma2(dd, make_float2(xr.x, xr.y), s01);
@@ -847,9 +857,10 @@ struct B2PCfg {
   static constexpr uint32_t B_TERM_BYTES = HU * RS * 2;     // 8 KB
   static constexpr uint32_t B_STAGE_BYTES = 2 * B_TERM_BYTES;   // hi | lo
   static constexpr uint32_t A_COL0 = 256, A_STAGE_COLS = RS, A_LO_COLS = RS / 2;
-  static constexpr uint32_t OFF_X = STAGES * B_STAGE_BYTES;     // float4[STAGES][RS]
-  static constexpr uint32_t OFF_DO = OFF_X + STAGES * RS * 16;  // float[STAGES][RS][2]
-  static constexpr uint32_t OFF_INV = OFF_DO + STAGES * RS * 8; // float invA[128] (own units) | invB[256]
+  static constexpr int SS_ROWS = 4 * RS;                         // rows of a super-stage (x / dOut staged 4 stages at a time)
+  static constexpr uint32_t OFF_X = STAGES * B_STAGE_BYTES;     // float[3][2][SS_ROWS]: x.x | x.y | x.z, double-buffered
+  static constexpr uint32_t OFF_SS = OFF_X + 3 * 2 * SS_ROWS * 4;   // float[2][2][SS_ROWS]: dOut[.][0] | dOut[.][1]
+  static constexpr uint32_t OFF_INV = OFF_SS + 2 * 2 * SS_ROWS * 4; // float invA[128] (own units) | invB[256]
   static constexpr uint32_t OFF_SMALL = OFF_INV + (HU + H) * 4; // float4[3][128]: row groups 1..3: db2 | dW3[0..1] | db3_0
   static constexpr uint32_t OFF_MAX = OFF_SMALL + 3 * HU * 16;  // int[8] row maxima (float bits)
   static constexpr uint32_t OFF_BAR = OFF_MAX + 32;
@@ -862,7 +873,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B2PCfg::THREADS, 1) 
   using C = B2PCfg;
   extern __shared__ __align__(1024) uint8_t sm[];
   float4* xs = reinterpret_cast<float4*>(sm + C::OFF_X);
-  float* dos = reinterpret_cast<float*>(sm + C::OFF_DO);
   float* invA = reinterpret_cast<float*>(sm + C::OFF_INV);
   float* invB = invA + C::HU;
   float4* small_g = reinterpret_cast<float4*>(sm + C::OFF_SMALL);
@@ -977,93 +987,124 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B2PCfg::THREADS, 1) 
         invB[tp] = pi;
       }
     }
-    float s_db2 = 0.f, s_dw3[OUT], s_db3[OUT];
+    // Row PAIRS are processed with packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: the FMA pipe issues one warp
+    // instruction per two clocks either way), the layer-1 ReLU is folded into the fp16 conversion, the x / dOut rows of
+    // FOUR stages are staged in shared memory at once (structure of arrays, so that a row pair is one 8-byte load; one
+    // block barrier per 128 rows instead of one per 32) and the H2 values are fetched two stages ahead -- the
+    // operand generators, not the tensor pipe, bound this kernel (ncu r02: tensor pipe 25 %, top stalls = the per-stage
+    // barrier and the H2 loads).
+    float2 s_db2 = make_float2(0.f, 0.f), s_dw3[OUT];
+    float s_db3[OUT];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) { s_dw3[o] = 0.f; s_db3[o] = 0.f; }
+    for (int o = 0; o < OUT; ++o) { s_dw3[o] = make_float2(0.f, 0.f); s_db3[o] = 0.f; }
     const uint32_t a_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0 + g * 4;    // 8 rows = 4 columns
+    float* sxx = reinterpret_cast<float*>(xs);                // [2][128] x.x | [2][128] x.y | [2][128] x.z  (OFF_X region: 3 KB of 2 KB + OFF_DO 1 KB)
+    float* sxy = sxx + 2 * C::SS_ROWS;
+    float* sxz = sxy + 2 * C::SS_ROWS;
+    float* sd0 = reinterpret_cast<float*>(sm + C::OFF_SS);    // [2][128] dOut[.][0] | [2][128] dOut[.][1]
+    float* sd1 = sd0 + 2 * C::SS_ROWS;
     auto h2_ptr = [&](int sg) {
       const int row0 = sg * C::RS + g * 8;
       return jb.h2 + (((size_t)net_i * tiles64 + (row0 >> 6)) * H + t) * 64 + (row0 & 63);
     };
-    float4 hn0, hn1;
-    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
-    float dn[OUT];
+    const float2 w1x2 = make_float2(w1x, w1x), w1y2 = make_float2(w1y, w1y), w1z2 = make_float2(w1z, w1z), b12 = make_float2(b1v, b1v);
+    const float2 sA2 = make_float2(sA, sA), sB2 = make_float2(sB, sB);
+    // x / dOut rows of a super-stage (4 stages = 128 rows): thread tid < 128 fetches one row, one super-stage ahead
+    float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dr[OUT];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) dn[o] = 0.f;
-    auto prefetch = [&](int sg) {
-      const float* h2p = h2_ptr(sg);
-      hn0 = __ldg(reinterpret_cast<const float4*>(h2p));
-      hn1 = __ldg(reinterpret_cast<const float4*>(h2p) + 1);
-      if (tid < C::RS) {
-        const int r = sg * C::RS + tid;
-        xn = r < jb.rows ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int o = 0; o < OUT; ++o) dr[o] = 0.f;
+    const int r_end = min(jb.rows, st_hi * C::RS);
+    auto fetch_rows = [&](int k) {
+      if (tid < C::SS_ROWS) {
+        const int r = (st_lo + 4 * k) * C::RS + tid;
+        const bool ok = r < r_end;
+        xr = ok ? __ldg(jb.X + r) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) dn[o] = r < jb.rows ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + o) : 0.f;
+        for (int o = 0; o < OUT; ++o) dr[o] = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + o) : 0.f;
       }
     };
-    hn0 = hn1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (st_lo < st_hi) prefetch(st_lo);
+    const int n_st = st_hi - st_lo, n_ss = (n_st + 3) / 4;
+    // H2 values of this thread's 8 rows, two stages ahead
+    // (two register sets used alternately -- slot = stage parity inside the super-stage, static after unrolling -- so
+    // that a set is refilled right after its values were copied out, never moved while a load is in flight)
+    float4 hs[2][2];
+    hs[0][0] = hs[0][1] = hs[1][0] = hs[1][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_h2 = [&](int sg, float4& a, float4& b) {
+      const float* h2p = h2_ptr(sg);
+      a = __ldg(reinterpret_cast<const float4*>(h2p));
+      b = __ldg(reinterpret_cast<const float4*>(h2p) + 1);
+    };
+    if (n_st > 0) { fetch_h2(st_lo, hs[0][0], hs[0][1]); fetch_rows(0); }
+    if (n_st > 1) fetch_h2(st_lo + 1, hs[1][0], hs[1][1]);
     uint32_t it = 0;
-    for (int sg = st_lo; sg < st_hi; ++sg, ++it) {
-      const uint32_t s = it % C::STAGES;
-      const float hv[8] = {hn0.x, hn0.y, hn0.z, hn0.w, hn1.x, hn1.y, hn1.z, hn1.w};
-      const float4 xc = xn;
-      float dc[OUT];
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) dc[o] = dn[o];
-      if (sg + 1 < st_hi) prefetch(sg + 1);
-      mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
-      tc_fence_after();
-      float4* xst = xs + s * C::RS;
-      float* dost = dos + s * C::RS * 2;
-      if (tid < C::RS) {
-        xst[tid] = xc;
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) dost[tid * 2 + o] = dc[o];
+    for (int k = 0; k < n_ss; ++k) {
+      const int buf = (k & 1) * C::SS_ROWS;
+      if (tid < C::SS_ROWS) {
+        sxx[buf + tid] = xr.x; sxy[buf + tid] = xr.y; sxz[buf + tid] = xr.z;
+        sd0[buf + tid] = dr[0];
+        if (OUT == 2) sd1[buf + tid] = dr[OUT - 1];
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
-      float dz[8], h1[8];
+      if (k + 1 < n_ss) fetch_rows(k + 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));      // (the buffer was last read two super-stages ago)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int rl = g * 8 + e;
-        float gsum = 0.f;
+      for (int q = 0; q < 4; ++q, ++it) {
+        const int sg = st_lo + 4 * k + q;
+        if (sg >= st_hi) break;
+        const uint32_t s = it % C::STAGES;
+        float4& h0 = hs[q & 1][0];
+        float4& h1r = hs[q & 1][1];
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1r.x, h1r.y, h1r.z, h1r.w};
+        if (sg + 2 < st_hi) fetch_h2(sg + 2, h0, h1r);
+        uint32_t ahi[4], alo[4], bhi[4], blo[4];
+        const int rl0 = buf + q * C::RS + g * 8;
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) {
-          const float d = dost[rl * 2 + o];
-          gsum = fmaf(d, w3[o], gsum);
-          s_dw3[o] = fmaf(d, hv[e], s_dw3[o]);
-          if (t == 0) s_db3[o] += d;
+        for (int e = 0; e < 4; ++e) {                               // rows rl0 + 2e, rl0 + 2e + 1
+          const float2 d0 = *reinterpret_cast<const float2*>(sd0 + rl0 + 2 * e);
+          const float2 hp = make_float2(hv[2 * e], hv[2 * e + 1]);
+          float2 gs = fmul2(d0, make_float2(w3[0], w3[0]));
+          s_dw3[0] = ffma2(d0, hp, s_dw3[0]);
+          if (t == 0) s_db3[0] += d0.x + d0.y;
+          if (OUT == 2) {
+            const float2 d1 = *reinterpret_cast<const float2*>(sd1 + rl0 + 2 * e);
+            gs = ffma2(d1, make_float2(w3[OUT - 1], w3[OUT - 1]), gs);
+            s_dw3[OUT - 1] = ffma2(d1, hp, s_dw3[OUT - 1]);
+            if (t == 0) s_db3[OUT - 1] += d1.x + d1.y;
+          }
+          const float2 dz = make_float2(hp.x > 0.f ? gs.x : 0.f, hp.y > 0.f ? gs.y : 0.f);
+          s_db2.x += dz.x; s_db2.y += dz.y;
+          const float2 xxp = *reinterpret_cast<const float2*>(sxx + rl0 + 2 * e);
+          const float2 xyp = *reinterpret_cast<const float2*>(sxy + rl0 + 2 * e);
+          float2 z = ffma2(xyp, w1y2, ffma2(xxp, w1x2, b12));       // the forward's order: chain starts from the bias
+          if (IN == 3) z = ffma2(*reinterpret_cast<const float2*>(sxz + rl0 + 2 * e), w1z2, z);
+          split_h2_trunc(fmul2(dz, sA2), ahi[e], alo[e]);
+          split_h2_trunc_relu(fmul2(z, sB2), bhi[e], blo[e]);      // H1 = relu(z): folded into the conversions
         }
-        dz[e] = hv[e] > 0.f ? gsum : 0.f;
-        s_db2 += dz[e];
-        const float4 x = xst[rl];
-        float z = fmaf(x.y, w1y, fmaf(x.x, w1x, b1v));        // the forward's order: chain starts from the bias
-        if (IN == 3) z = fmaf(x.z, w1z, z);
-        h1[e] = fmaxf(z, 0.f);
+        mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);          // values are ready before the stage is: wait late
+        tc_fence_after();
+        tmem_st4(a_lane + s * C::A_STAGE_COLS, ahi);
+        tmem_st4(a_lane + s * C::A_STAGE_COLS + C::A_LO_COLS, alo);
+        uint8_t* Bst = sm + s * C::B_STAGE_BYTES + chunk_off(C::HU, u, g);
+        *reinterpret_cast<uint4*>(Bst) = make_uint4(bhi[0], bhi[1], bhi[2], bhi[3]);
+        *reinterpret_cast<uint4*>(Bst + C::B_TERM_BYTES) = make_uint4(blo[0], blo[1], blo[2], blo[3]);
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&full[s], 0);
       }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split_h2_trunc(make_float2(dz[2 * e] * sA, dz[2 * e + 1] * sA), hi[e], lo[e]);
-      tmem_st4(a_lane + s * C::A_STAGE_COLS, hi);
-      tmem_st4(a_lane + s * C::A_STAGE_COLS + C::A_LO_COLS, lo);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split_h2_trunc(make_float2(h1[2 * e] * sB, h1[2 * e + 1] * sB), hi[e], lo[e]);
-      uint8_t* Bst = sm + s * C::B_STAGE_BYTES + chunk_off(C::HU, u, g);
-      *reinterpret_cast<uint4*>(Bst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(Bst + C::B_TERM_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      tmem_st_wait();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&full[s], 0);
     }
+    const float s_db2s = s_db2.x + s_db2.y;
+    float s_dw3s[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) s_dw3s[o] = s_dw3[o].x + s_dw3[o].y;
     // small gradients of unit t: the four row groups are added in a fixed order (group 0 + 1 + 2 + 3)
-    if (g > 0) small_g[(g - 1) * C::HU + u] = make_float4(s_db2, s_dw3[0], OUT == 2 ? s_dw3[OUT - 1] : 0.f, s_db3[0]);
+    if (g > 0) small_g[(g - 1) * C::HU + u] = make_float4(s_db2s, s_dw3s[0], OUT == 2 ? s_dw3s[OUT - 1] : 0.f, s_db3[0]);
     if (OUT == 2 && t == 0 && g > 0) rmax[4 + g] = __float_as_int(s_db3[OUT - 1]);       // (plain bit copies; slots 5..7)
     asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS));
     if (g == 0) {
       float db3_1 = s_db3[OUT - 1];
-      float a0 = s_db2, a1 = s_dw3[0], a2 = OUT == 2 ? s_dw3[OUT - 1] : 0.f, a3 = s_db3[0];
+      float a0 = s_db2s, a1 = s_dw3s[0], a2 = OUT == 2 ? s_dw3s[OUT - 1] : 0.f, a3 = s_db3[0];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const float4 o2 = small_g[q * C::HU + u];

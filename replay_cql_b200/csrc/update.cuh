@@ -804,11 +804,13 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   bool pair2 = false;                            // dW2 on CTA pairs (A operand in tensor memory): the big launches
   if constexpr (F16X3) {
     static const bool no_pair2 = std::getenv("CQL_NO_PAIR") != nullptr || std::getenv("CQL_NO_PAIR_BWD2") != nullptr;
-    pair2 = pair && !no_pair2;
-    if (pair2) splits = std::max(1, (h->num_sms / 2) / jb.n_nets);
+    static const bool no_pair2_small = std::getenv("CQL_NO_PAIR_BWD2_SMALL") != nullptr;
+    pair2 = !no_pair2 && (pair || !no_pair2_small);     // also the small (actor) launch: a pair CTA dumps half an accumulator
+    if (pair2) splits = std::max(1, std::min(n_stage, (h->num_sms / 2) / jb.n_nets));
   }
   static const bool no_fork = std::getenv("CQL_NO_FORK") != nullptr;      // A/B switch for measurements
-  const bool fork = WGRADS && !no_fork && !h->timing && h->side_stream != nullptr && grid1 + splits * jb.n_nets <= h->num_sms;
+  const bool fork = WGRADS && !no_fork && !h->timing && h->side_stream != nullptr &&
+                    grid1 + (pair2 ? 2 : 1) * splits * jb.n_nets <= h->num_sms;
   cudaStream_t st2 = st;
   if (fork) {
     CQL_CUDA(cudaEventRecord(h->ev_fork, st));
