@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libcql_b200.so"
+import os
+
+# CQL_LIB: load another build of the same library (A/B measurements of compile-time variants); never a fallback
+LIB_PATH = Path(os.environ["CQL_LIB"]) if os.environ.get("CQL_LIB") else Path(__file__).resolve().parent / "libcql_b200.so"
 
 PREC_FP32, PREC_TF32X3, PREC_BF16, PREC_F16X3 = 0, 1, 2, 3
 SQUASH_EPS, SQUASH_SOFTPLUS = 0, 1

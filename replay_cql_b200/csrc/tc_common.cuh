@@ -57,7 +57,21 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- programmatic dependent launch: wait for the predecessor grids (no-op when launched without the attribute)
-__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Every kernel of the update chain waits for its predecessors to complete and flush, THEN lets its own dependents launch
+// (griddepcontrol.launch_dependents: the next kernel's CTAs become resident as soon as all of this kernel's CTAs have
+// passed this point and SM resources allow, run their prologue -- barrier init, tensor-memory allocation -- and park at
+// their own griddepcontrol.wait).  Without the trigger the dependent grid is only launched when this grid has drained:
+// ~19 launch gaps per update.  Trigger AFTER the wait, never before: a kernel that triggers first lets a chain of grids
+// pile up, each parked on its predecessor only; measured on B200, eager launches of such a chain (the phase-split path)
+// read stale data (whole state differs after 5 updates) while graph replays of the same chain do not.  With the trigger
+// after the wait at most one dependent is parked, and its predecessor's predecessors have completed before it launches.
+// -DCQL_NO_EARLY_TRIGGER removes the trigger (A/B builds).
+__device__ __forceinline__ void grid_dep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef CQL_NO_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // ---- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
