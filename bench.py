@@ -551,7 +551,9 @@ def run_ml1m(args):
     shape = SHAPES["ml1m"]
     log = make_log("ml1m", seed=12345)
     dev = torch.device("cuda", 0)
-    CQL(n_epochs=1, n_steps_per_epoch=3, batch_size=BATCH).fit(log.iloc[:50_000]).engine.close()     # context / allocator warm-up
+    warm = CQL(n_epochs=1, n_steps_per_epoch=3, batch_size=BATCH)      # context / allocator warm-up (fit returns None, as the reference's)
+    warm.fit(log.iloc[:50_000])
+    warm.engine.close()
     model = CQL(n_epochs=1, batch_size=BATCH, seed=12345)
     clocks = ClockSampler(0); clocks.start(); clocks.wait_first()
     t0 = time.perf_counter()

@@ -236,7 +236,14 @@ void destroy_graph(cql_handle* ch) {
 template <typename F>
 int guarded(cql_handle* ch, F&& f) {
   if (!ch) { g_create_error = "NULL handle"; return 1; }
+  // the caller's current device is restored on every exit path (the handle's device is only current inside the call)
+  struct DeviceScope {
+    int prev = -1;
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+  } scope;
   try {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != ch->h.cfg.device) scope.prev = cur;
     CQL_CUDA(cudaSetDevice(ch->h.cfg.device));
     f();
     return 0;

@@ -1028,15 +1028,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B2PCfg::THREADS, 1) 
     // H2 values of this thread's 8 rows, two stages ahead
     // (two register sets used alternately -- slot = stage parity inside the super-stage, static after unrolling -- so
     // that a set is refilled right after its values were copied out, never moved while a load is in flight)
-    float4 hs[2][2];
-    hs[0][0] = hs[0][1] = hs[1][0] = hs[1][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int AH = 2;                                   // (4 stages ahead measured: no gain, registers spill)
+    float4 hs[AH][2];
+#pragma unroll
+    for (int i = 0; i < AH; ++i) hs[i][0] = hs[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch_h2 = [&](int sg, float4& a, float4& b) {
       const float* h2p = h2_ptr(sg);
       a = __ldg(reinterpret_cast<const float4*>(h2p));
       b = __ldg(reinterpret_cast<const float4*>(h2p) + 1);
     };
-    if (n_st > 0) { fetch_h2(st_lo, hs[0][0], hs[0][1]); fetch_rows(0); }
-    if (n_st > 1) fetch_h2(st_lo + 1, hs[1][0], hs[1][1]);
+    if (n_st > 0) fetch_rows(0);
+#pragma unroll
+    for (int i = 0; i < AH; ++i)
+      if (n_st > i) fetch_h2(st_lo + i, hs[i][0], hs[i][1]);
     uint32_t it = 0;
     for (int k = 0; k < n_ss; ++k) {
       const int buf = (k & 1) * C::SS_ROWS;
@@ -1052,10 +1056,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B2PCfg::THREADS, 1) 
         const int sg = st_lo + 4 * k + q;
         if (sg >= st_hi) break;
         const uint32_t s = it % C::STAGES;
-        float4& h0 = hs[q & 1][0];
-        float4& h1r = hs[q & 1][1];
+        float4& h0 = hs[q % AH][0];
+        float4& h1r = hs[q % AH][1];
         const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1r.x, h1r.y, h1r.z, h1r.w};
-        if (sg + 2 < st_hi) fetch_h2(sg + 2, h0, h1r);
+        if (sg + AH < st_hi) fetch_h2(sg + AH, h0, h1r);
         uint32_t ahi[4], alo[4], bhi[4], blo[4];
         const int rl0 = buf + q * C::RS + g * 8;
 #pragma unroll

@@ -626,11 +626,6 @@ inline void launch_fwd(Handle* h, FwdJobs& jobs, cudaStream_t st) {
   }
   jobs.total_tiles = t;
   if (t == 0) return;
-  static bool attr = false;
-  if (!attr) {
-    CQL_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<IN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    attr = true;
-  }
   mlp_fwd_kernel<IN, OUT><<<t, NT, FWD_SMEM, st>>>(jobs);
   CQL_LAUNCH_CHECK(h);
 }
@@ -786,7 +781,17 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   }
   const int n_slices = small ? tc::HCfgS::SLICES : C::SLICES;
   const int items_s = jb.n_nets * n_slices * tiles;
-  const int grid1 = pair ? 2 * (h->num_sms / 2) : (items_s < h->num_sms ? items_s : h->num_sms);
+  // The big launch's bwd1 and bwd2 are independent too and run SIDE BY SIDE: bwd1 on 30 of the 74 CTA pairs, bwd2 on the
+  // other 44 (22 splits per critic).  Back to back on all SMs each, the fixed cost of either kernel -- prologue,
+  // accumulator dump (half as many dW2 partials now), tail -- was serial: with the main loop skipped bwd2 still took
+  // 16 of its 44 us.  Measured sweep of the bwd1 share (pairs -> us per update): 74 (serial) 222.4, 46 238, 42 229,
+  // 38 222.5, 34 216.5, 32 213.1, 30 212.7, 28 212.9, 26 219, 22 230.  CQL_BIG_FORK=<pairs> overrides (0 = serial).
+  static const bool no_fork = std::getenv("CQL_NO_FORK") != nullptr;      // A/B switch for measurements
+  static const int big_fork = std::getenv("CQL_BIG_FORK") ? std::atoi(std::getenv("CQL_BIG_FORK")) : -1;
+  const int fork_pairs = big_fork >= 0 ? big_fork : (h->num_sms / 2) * 30 / 74;
+  const int clusters1 = (pair && WGRADS && fork_pairs > 0 && fork_pairs < h->num_sms / 2 && !no_fork && !h->timing && h->side_stream != nullptr)
+                            ? fork_pairs : h->num_sms / 2;
+  const int grid1 = pair ? 2 * clusters1 : (items_s < h->num_sms ? items_s : h->num_sms);
   h->last_dx_parts = jb.n_nets * (pair ? (int)tc::H2Cfg::PARTS : n_slices);
   const int slots1 = (F16X3 ? 2 : 4) * grid1;      // f16x3: one slot per (CTA, epilogue group)
   if (WGRADS) CQL_CUDA(cudaMemsetAsync(h->small1, 0, (size_t)jb.n_nets * slots1 * SMALL_STRIDE * sizeof(float), st));
@@ -807,8 +812,8 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     static const bool no_pair2_small = std::getenv("CQL_NO_PAIR_BWD2_SMALL") != nullptr;
     pair2 = !no_pair2 && (pair || !no_pair2_small);     // also the small (actor) launch: a pair CTA dumps half an accumulator
     if (pair2) splits = std::max(1, std::min(n_stage, (h->num_sms / 2) / jb.n_nets));
+    if (pair2 && pair && clusters1 < h->num_sms / 2) splits = std::max(1, (h->num_sms / 2 - clusters1) / jb.n_nets);
   }
-  static const bool no_fork = std::getenv("CQL_NO_FORK") != nullptr;      // A/B switch for measurements
   const bool fork = WGRADS && !no_fork && !h->timing && h->side_stream != nullptr &&
                     grid1 + (pair2 ? 2 : 1) * splits * jb.n_nets <= h->num_sms;
   cudaStream_t st2 = st;
@@ -818,7 +823,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     st2 = h->side_stream;
   }
   if constexpr (F16X3) {
-    if (pair) launch_pdl_pair(tc::tc_bwd1_h2_kernel<IN, OUT, WGRADS, DX>, h->num_sms / 2, dim3(tc::H2Cfg::THREADS), tc::H2B1Cfg::SMEM_BYTES, st, j1, h->pair_swap_b);
+    if (pair) launch_pdl_pair(tc::tc_bwd1_h2_kernel<IN, OUT, WGRADS, DX>, clusters1, dim3(tc::H2Cfg::THREADS), tc::H2B1Cfg::SMEM_BYTES, st, j1, h->pair_swap_b);
     else if (small) launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX, tc::HCfgS>, dim3(grid1), dim3(tc::HCfgS::THREADS), tc::HCfgS::SMEM_BYTES, st, j1);
     else launch_pdl(tc::tc_bwd1_h_kernel<IN, OUT, WGRADS, DX>, dim3(grid1), dim3(tc::HCfg::THREADS), tc::HCfg::SMEM_BYTES, st, j1);
   } else if constexpr (TF32)
@@ -905,22 +910,12 @@ inline void pack_all_weights(Handle* h, cudaStream_t st) {
 
 template <int IN, int OUT, bool WGRADS, bool DX>
 inline void launch_bwd1(Handle* h, const BwdJob& jb, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    CQL_CUDA(cudaFuncSetAttribute(mlp_bwd1_kernel<IN, OUT, WGRADS, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD1_SMEM));
-    attr = true;
-  }
   mlp_bwd1_kernel<IN, OUT, WGRADS, DX><<<tiles_of(jb.rows) * jb.n_nets, NT, BWD1_SMEM, st>>>(jb);
   CQL_LAUNCH_CHECK(h);
 }
 
 template <int IN, int OUT>
 inline void launch_bwd2(Handle* h, const BwdJob& jb, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    CQL_CUDA(cudaFuncSetAttribute(mlp_bwd2_kernel<IN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM));
-    attr = true;
-  }
   mlp_bwd2_kernel<IN, OUT><<<dim3(4, jb.splits, jb.n_nets), NT, BWD2_SMEM, st>>>(jb);
   CQL_LAUNCH_CHECK(h);
 }

@@ -276,7 +276,7 @@ class CQL(Recommender):
             sub = log[log["user_idx"].isin(u_local)] if u_local.size else log.iloc[:0]
             indptr, seen = seen_csr(sub, int(u.max()) + 1)
         kk = min(int(k), int(it.size))
-        top_i, top_s = self.engine.score_topk(u_local, it, kk, indptr, seen, mode=self.score)
+        top_i, top_s = self._score_topk_any_k(u_local, it, kk, indptr, seen, int(u.max()) + 1)
         rows_u = np.repeat(u_local, kk).reshape(-1, 1)
         packed = np.concatenate([rows_u.astype(np.float64), top_i.reshape(-1, 1).astype(np.float64),
                                  top_s.reshape(-1, 1).astype(np.float64)], axis=1)
@@ -284,6 +284,34 @@ class CQL(Recommender):
             packed = gather_rows(packed)
         keep = packed[:, 1] >= 0
         return _rec_frame(packed[keep, 0], packed[keep, 1], packed[keep, 2])
+
+    def _score_topk_any_k(self, u_local, items, k: int, indptr, seen, n_users_dim: int):
+        """``engine.score_topk`` for any ``k`` (the reference's ``predict`` accepts any k, ``base_rec.py:466-539``): the
+        kernel selects at most ``MAX_TOPK`` per pass, so a larger ``k`` runs in passes of ``MAX_TOPK``, each pass
+        treating the items already selected as seen -- the concatenation is the descending top-``k`` (no CPU scoring)."""
+        from . import _lib
+        if k <= _lib.MAX_TOPK:
+            return self.engine.score_topk(u_local, items, k, indptr, seen, mode=self.score)
+        parts_i, parts_s = [], []
+        if indptr is None:
+            indptr, seen = np.zeros(n_users_dim + 1, dtype=np.int64), np.zeros(0, dtype=np.int32)
+        left = k
+        while left > 0:
+            kk = min(left, _lib.MAX_TOPK)
+            ti, ts = self.engine.score_topk(u_local, items, kk, indptr, seen, mode=self.score)
+            parts_i.append(ti)
+            parts_s.append(ts)
+            left -= kk
+            if left > 0:        # picked items join the seen lists of their users (sorted, de-duplicated CSR over user id)
+                pu = np.repeat(u_local.astype(np.int64), kk)[(ti >= 0).reshape(-1)]
+                pi = ti.reshape(-1)[(ti >= 0).reshape(-1)].astype(np.int64)
+                su = np.repeat(np.arange(indptr.size - 1, dtype=np.int64), np.diff(indptr))
+                key = np.unique(np.concatenate([su * (2 ** 32) + seen.astype(np.int64), pu * (2 ** 32) + pi]))
+                counts = np.bincount(key >> 32, minlength=indptr.size - 1)
+                indptr = np.zeros(indptr.size, dtype=np.int64)
+                np.cumsum(counts, out=indptr[1:])
+                seen = (key & 0xFFFFFFFF).astype(np.int32)
+        return np.concatenate(parts_i, axis=1), np.concatenate(parts_s, axis=1)
 
     def _predict_pairs(self, pairs: pd.DataFrame, log: Optional[pd.DataFrame] = None) -> pd.DataFrame:
         """Native pair scoring instead of the generic fallback (``base_rec.py:784-823``)."""

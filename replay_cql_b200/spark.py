@@ -31,6 +31,21 @@ class CQL(_SparkRecommender):  # pragma: no cover
     def _init_args(self):
         return self._impl._init_args
 
+    def __getattr__(self, name):
+        # hyper-parameters live on the pandas model (only called when normal lookup fails)
+        impl = self.__dict__.get("_impl")
+        if impl is not None and name in impl._init_args:
+            return getattr(impl, name)
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        # `set_params` (base_rec.py:151-163) does setattr on the wrapper: optimize() trials must reach the engine's model
+        impl = self.__dict__.get("_impl")
+        if impl is not None and name in impl._init_args:
+            setattr(impl, name, value)
+        else:
+            object.__setattr__(self, name, value)
+
     def _fit(self, log, user_features=None, item_features=None) -> None:
         self._impl._fit(log.select("user_idx", "item_idx", "timestamp", "relevance").toPandas())
 

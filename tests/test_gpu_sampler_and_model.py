@@ -90,6 +90,28 @@ def test_predict_and_predict_pairs_agree(fitted):   # tests/models/test_all_mode
     assert model.predict_pairs(recs[["user_idx", "item_idx"]], log, k=2).groupby("user_idx").size().max() <= 2
 
 
+def test_predict_k_above_kernel_limit(fitted):
+    """The reference's predict takes any k (base_rec.py:466-539); above the kernel's per-pass limit (1024) the model
+    selects in passes, each treating the items already picked as seen: same list as ranking every pair score."""
+    from replay_cql_b200 import _lib
+    model, log = fitted
+    users = np.array([0, 5, 9], dtype=np.int32)
+    items = np.arange(2500, dtype=np.int32)
+    k = _lib.MAX_TOPK + 76
+    from replay_cql_b200.mdp import seen_csr
+    indptr, seen = seen_csr(log[log["user_idx"].isin(users)], 64)
+    ti, ts = model._score_topk_any_k(users, items, k, indptr, seen, 64)
+    assert ti.shape == (3, k)
+    for r, u in enumerate(users):
+        sc = model.engine.score_pairs(np.full(items.size, u, dtype=np.int32), items, mode="q")
+        sc[seen[indptr[u]:indptr[u + 1]]] = -np.inf
+        order = np.argsort(-sc, kind="stable")[:k]
+        assert len(set(ti[r].tolist())) == k and not np.isin(ti[r], seen[indptr[u]:indptr[u + 1]]).any()
+        assert np.all(np.diff(ts[r]) <= 0)
+        np.testing.assert_allclose(ts[r], sc[order], rtol=1e-5, atol=1e-5 * np.abs(sc[order]).max())
+        assert len(set(ti[r].tolist()) ^ set(order.tolist())) <= 4        # swaps among (near-)ties at the cut only
+
+
 def test_save_load_roundtrip(fitted, tmp_path):     # tests/models/test_save_load_models.py:48-70
     model, log = fitted
     base = model.predict(log, k=5)
