@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CQL_ABI_VERSION 1
+#define CQL_ABI_VERSION 2
 #define CQL_HIDDEN 256          /* d3rlpy default encoder: [256, 256] */
 #define CQL_OBS_DIM 2           /* (user_idx, item_idx) */
 #define CQL_ACT_DIM 1           /* relevance */
@@ -174,22 +174,26 @@ enum { CQL_BUF_SCALAR_GRADS = 0,   /* 64 floats: [0]=d log_temp [1]=d log_alpha 
 int  cql_device_buffer(cql_handle* h, int which, void** dev_ptr, int64_t* n_floats);
 
 /* Data-parallel gradient exchange over NVLink peer memory instead of a collective library call.
- * cql_dp_attach: stage_ptrs[world] / signal_ptrs[world] are every rank's symmetric staging buffer (>= 2 x
- *   stage_floats floats, stage_floats >= the CQL_BUF_ALL_GRADS size) and zero-initialised signal pad (>= world x 4
- *   64-bit words), mapped into this process (e.g. torch.distributed._symmetric_memory handles); all ranks must attach
- *   before the first exchange and call the exchanges in the same order.
+ * cql_dp_attach: stage_ptrs[world] / signal_ptrs[world] are every rank's symmetric, zero-initialised staging buffer
+ *   (buffer_floats floats: >= 2 x stage_floats, stage_floats >= the CQL_BUF_ALL_GRADS size; with another
+ *   4 x world x stage_floats behind them the exchange is fused into the update kernels, see cql_dp_mode) and
+ *   zero-initialised signal pad (>= world x 4 64-bit words), mapped into this process (e.g.
+ *   torch.distributed._symmetric_memory handles); all ranks must attach before the first exchange and call the
+ *   exchanges in the same order.
  * cql_dp_allreduce: mean over ranks of one gradient buffer (CQL_BUF_SCALAR_GRADS / _CRITIC_GRADS / _ACTOR_GRADS), in
  *   place, one kernel on `stream` (publish + one-shot reduce in rank order: bit-identical on every rank).  Replaces the
  *   torch.distributed.all_reduce between cql_step_phase calls.  cql_dp_error returns 1 after a wait timed out. */
 int  cql_dp_attach(cql_handle* h, int32_t world, int32_t rank, const void* const* stage_ptrs,
-                   const void* const* signal_ptrs, int64_t stage_floats);
+                   const void* const* signal_ptrs, int64_t stage_floats, int64_t buffer_floats);
 int  cql_dp_allreduce(cql_handle* h, int which, void* stream);
 int  cql_dp_error(cql_handle* h, int32_t* flag_out);
-/* *fused_out = 1 when, after cql_dp_attach, the gradient exchange happens INSIDE the update kernels (f16x3 path): the
- *   kernel that produces a gradient group writes it to this rank's staging buffer and signals the peers, the kernel
- *   that consumes it (scalar Adam / Adam + Polyak + pack) waits for the peers and reads the mean over NVLink -- no
- *   exchange launch, and cql_update / cql_update_batches / cql_step_phase run data-parallel as they are
- *   (cql_dp_allreduce is then a no-op).  0: call cql_dp_allreduce (or an NCCL all-reduce) between the phases. */
+/* *fused_out = 1 when, after cql_dp_attach, the gradient exchange happens INSIDE the update kernels (f16x3 path, staging
+ *   buffers with room for the pushed packets): the kernel that produces a gradient group stores its sums straight into
+ *   every peer's staging buffer over NVLink as {value, epoch tag} pairs, the kernel that consumes it (Adam + Polyak +
+ *   pack) polls its own buffer for the tags and sums in rank order; the two scalar gradients travel inside the signal
+ *   words -- no exchange launch, no fence, one NVLink one-way latency per group, and cql_update / cql_update_batches /
+ *   cql_step_phase run data-parallel as they are (cql_dp_allreduce is then a no-op).
+ *   0: call cql_dp_allreduce (or an NCCL all-reduce) between the phases. */
 int  cql_dp_mode(cql_handle* h, int32_t* fused_out);
 
 /* ---- scoring (K5) ------------------------------------------------------ */
@@ -241,7 +245,10 @@ int  cql_rank_metrics(cql_handle* h, const int32_t* rec_items, int64_t n_users, 
  * returns their durations in milliseconds (synchronises).  out_ms[0] = critic forward (alpha +
  * critic + target rows), [1] = critic backward-1, [2] = critic backward-2 (dW2), [3] = whole
  * update, [4] = actor-step critic forward, [5] = actor backward (1+2), [6] = shared actor
- * forward, [7] = everything else.  The update is a real one (weights advance). */
+ * forward, [7] = everything else.  The update is a real one (weights advance).  Programmatic dependent launch is
+ * off for this step (events between overlapping kernels would not separate them), and the critic forward is launched
+ * four times back to back between its two events (same inputs, same outputs): [0] is that span / 4, the kernel's
+ * steady-state duration without the launch latency of a lone launch; [3] counts it once. */
 int  cql_timed_update(cql_handle* h, float* out_ms8, void* stream);
 
 /* Self-test of the tensor-core building blocks (tcgen05.mma + TMEM + operand layout):

@@ -63,7 +63,7 @@ SIGNATURES = {
     "cql_update_batches": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "cql_step_phase": (C.c_int, [_P, C.c_int, _P]),
     "cql_upload_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
-    "cql_dp_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int64]),
+    "cql_dp_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int64]),
     "cql_dp_allreduce": (C.c_int, [_P, C.c_int, _P]),
     "cql_dp_error": (C.c_int, [_P, _P]),
     "cql_dp_mode": (C.c_int, [_P, _P]),
@@ -112,7 +112,7 @@ def load() -> C.CDLL:
             raise CqlLibraryError(f"{LIB_PATH} does not export {name}") from exc
         fn.restype = res
         fn.argtypes = args
-    if lib.cql_abi_version() != 1:
+    if lib.cql_abi_version() != 2:
         raise CqlLibraryError("libcql_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -80,19 +80,15 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
   const int slot_rd = (int)(si->step % 3), slot_acc = (int)((si->step + 1) % 3), slot_clr = (int)((si->step + 2) % 3);
   const int tid = threadIdx.x, lane = tid & 31;
   const bool dp = jobs.dp.world > 1;
-  long long dpb = 0;                                       // staging index of this network's element 0
-  if (dp) {
-    dp_wait_peers(jobs.dp, jobs.dp_group);
-    dpb = dp_base(jobs.dp, jobs.dp_group, jobs.dp_off) + (long long)blockIdx.y * NET_STRIDE;
-  }
+  const long long dpb = jobs.dp_off + (long long)blockIdx.y * NET_STRIDE;      // this network's element 0 in the gradient layout
   if (blockIdx.x < AP_W2_BLOCKS) {
     // ---------------- 8 rows of W2: Adam + Polyak, forward packs, then the transposed K chunk ----------------
     const int n = blockIdx.x * AP_ROWS + (tid >> 5), kc = lane;
     const size_t off = (size_t)off_W2(in_dim) + (size_t)n * H + kc * 8;
     float p[8], t[8];
     {
-      const float4 g0 = dp ? dp_mean4(jobs.dp, dpb + (long long)off) : *reinterpret_cast<const float4*>(nt.g + off);
-      const float4 g1 = dp ? dp_mean4(jobs.dp, dpb + (long long)off + 4) : *reinterpret_cast<const float4*>(nt.g + off + 4);
+      float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
+      if (dp) dp_ll_mean8(jobs.dp, jobs.dp_group, dpb + (long long)off, g0, g1, g0, g1);      // mean over ranks, rank order
       float4 m0 = *reinterpret_cast<const float4*>(nt.m + off), m1 = *reinterpret_cast<const float4*>(nt.m + off + 4);
       float4 v0 = *reinterpret_cast<const float4*>(nt.v + off), v1 = *reinterpret_cast<const float4*>(nt.v + off + 4);
       const float4 p0 = *reinterpret_cast<const float4*>(nt.p + off), p1 = *reinterpret_cast<const float4*>(nt.p + off + 4);
@@ -169,9 +165,15 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
   __shared__ float gsm[2048];
   const int w2_lo = off_W2(in_dim), w2_hi = w2_lo + H * H;
   if (dp) {
-    for (int c = tid * 4; c < 2048; c += 256 * 4) {
-      const int idx = c < w2_lo ? c : c + H * H;             // compact index -> index inside the network slot
-      if (idx + 3 < NET_STRIDE) *reinterpret_cast<float4*>(gsm + c) = dp_mean4(jobs.dp, dpb + idx);
+    {                                                        // 2048 compact entries = 256 threads x two 16-byte groups
+      const int c = tid * 8;
+      const int idx = c < w2_lo ? c : c + H * H;             // compact index -> index inside the network slot (w2_lo % 8 == 0)
+      if (idx + 7 < NET_STRIDE) {
+        float4 a = *reinterpret_cast<const float4*>(nt.g + idx), b = *reinterpret_cast<const float4*>(nt.g + idx + 4);
+        dp_ll_mean8(jobs.dp, jobs.dp_group, dpb + idx, a, b, a, b);
+        *reinterpret_cast<float4*>(gsm + c) = a;
+        *reinterpret_cast<float4*>(gsm + c + 4) = b;
+      }
     }
     __syncthreads();
   }

@@ -678,7 +678,9 @@ int cql_timed_update(cql_handle* ch, float* out_ms8, void* stream) {
     g_timing_no_pdl = false;
     CQL_CUDA(cudaStreamSynchronize(st));
     auto ms = [&](int a, int b) { float t = 0.f; CQL_CUDA(cudaEventElapsedTime(&t, h.ev[a], h.ev[b])); return t; };
-    out_ms8[0] = ms(3, 4); out_ms8[1] = ms(5, 6); out_ms8[2] = ms(6, 7); out_ms8[3] = ms(0, 12);
+    const float fwd_all = ms(3, 4);           // TIMED_FWD_REPS launches of the critic forward, back to back
+    out_ms8[0] = fwd_all / TIMED_FWD_REPS; out_ms8[1] = ms(5, 6); out_ms8[2] = ms(6, 7);
+    out_ms8[3] = ms(0, 12) - (fwd_all - out_ms8[0]);
     out_ms8[4] = ms(8, 9); out_ms8[5] = ms(10, 11); out_ms8[6] = ms(1, 2);
     out_ms8[7] = out_ms8[3] - (out_ms8[0] + out_ms8[1] + out_ms8[2] + out_ms8[4] + out_ms8[5] + out_ms8[6]);
   });
@@ -835,13 +837,16 @@ int cql_step_phase(cql_handle* ch, int phase, void* stream) {
 }
 
 int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const* stage_ptrs,
-                  const void* const* signal_ptrs, int64_t stage_floats) {
+                  const void* const* signal_ptrs, int64_t stage_floats, int64_t buffer_floats) {
   return guarded(ch, [&] {
     Handle& h = ch->h;
     CQL_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "cql_dp_attach: bad world / rank");
     CQL_REQUIRE(stage_ptrs && signal_ptrs, "cql_dp_attach: NULL pointer table");
     const int64_t need = (int64_t)grad_floats(h.C);
     CQL_REQUIRE(stage_floats >= need && stage_floats % 4 == 0, "cql_dp_attach: staging buffer too small (need the CQL_BUF_ALL_GRADS size, multiple of 4)");
+    CQL_REQUIRE(buffer_floats >= 2 * stage_floats, "cql_dp_attach: buffer_floats must cover the two staging halves (2 x stage_floats)");
+    // fused exchange: behind the two halves, [2][world][stage_floats] {value, tag} pairs pushed by the peers
+    const bool ll_room = buffer_floats >= 2 * stage_floats + 4 * (int64_t)world * stage_floats;
     DpPeer& p = ch->h.dp;
     p.world = world; p.rank = rank; p.stage_floats = stage_floats;
     for (int r = 0; r < world; ++r) {
@@ -854,7 +859,8 @@ int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const
     p.epoch = (unsigned long long*)ch->dp_local;
     p.ticket = (unsigned int*)((char*)ch->dp_local + 64);
     p.error = (int*)((char*)ch->dp_local + 128);
-    h.dp_fused = world > 1 && h.cfg.precision == CQL_PREC_F16X3 && std::getenv("CQL_NO_FUSED_DP") == nullptr;
+    p.debug = std::getenv("CQL_DP_DEBUG") ? std::atoi(std::getenv("CQL_DP_DEBUG")) : 0;
+    h.dp_fused = world > 1 && ll_room && h.cfg.precision == CQL_PREC_F16X3 && std::getenv("CQL_NO_FUSED_DP") == nullptr;
     destroy_graph(ch);
   });
 }

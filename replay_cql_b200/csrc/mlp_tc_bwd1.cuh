@@ -581,11 +581,9 @@ __global__ void __launch_bounds__(256) k_reduce_grads_tc(const float* __restrict
 #pragma unroll
     for (int c = 1; c < 8; ++c) { const float4 v = part[c][g]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
     *reinterpret_cast<float4*>(grads + (size_t)net * NET_STRIDE + idx) = t;
-    // data-parallel (fused exchange): the local sum also goes into this rank's staging buffer for the peers to read
-    if (dp.world > 1)
-      *reinterpret_cast<float4*>(dp.stage[dp.rank] + dp_base(dp, dp_group, dp_off) + (size_t)net * NET_STRIDE + idx) = t;
+    // data-parallel (fused exchange): the local sum is pushed into every peer's staging buffer, tagged with the epoch
+    if (dp.world > 1) dp_ll_push4(dp, dp_group, dp_off + (long long)net * NET_STRIDE + idx, t);
   }
-  if (dp.world > 1) dp_publish_done(dp, dp_group, gridDim.x * gridDim.y);
 }
 
 }  // namespace tc

@@ -355,11 +355,14 @@ class CqlEngine:
         self._check(self._lib.cql_upload_batch(self._h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(nobs), _ptr(term), stream),
                     "cql_upload_batch")
 
-    def dp_attach(self, world: int, rank: int, stage_ptrs, signal_ptrs, stage_floats: int) -> None:
-        """Hand the library every rank's symmetric staging buffer / signal pad (raw device pointers)."""
+    def dp_attach(self, world: int, rank: int, stage_ptrs, signal_ptrs, stage_floats: int,
+                  buffer_floats: int | None = None) -> None:
+        """Hand the library every rank's symmetric staging buffer / signal pad (raw device pointers).
+        ``buffer_floats`` = floats in each staging buffer (default: the two staging halves only, no fused exchange)."""
         PtrArr = C.c_void_p * len(stage_ptrs)
+        total = int(buffer_floats) if buffer_floats is not None else 2 * int(stage_floats)
         self._check(self._lib.cql_dp_attach(self._h, int(world), int(rank), PtrArr(*[int(p) for p in stage_ptrs]),
-                                            PtrArr(*[int(p) for p in signal_ptrs]), int(stage_floats)), "cql_dp_attach")
+                                            PtrArr(*[int(p) for p in signal_ptrs]), int(stage_floats), total), "cql_dp_attach")
 
     def dp_allreduce(self, which: int, stream: int | None = None) -> None:
         """Mean over ranks of one gradient buffer through NVLink peer memory (after ``dp_attach``)."""

@@ -80,14 +80,18 @@ class PeerGradExchange:
         _, n = engine.device_buffer(_lib.BUF_ALL_GRADS)
         self.stage_floats = (n + 3) // 4 * 4
         dev = torch.device("cuda", engine.device)
-        self.buf = symm_mem.empty(2 * self.stage_floats, dtype=torch.float32, device=dev)
+        # [2][stage] halves of the stand-alone exchange kernel, then [2][world][stage] {value, tag} pairs that the peers'
+        # update kernels push into (fused exchange, csrc/dp_peer.cuh)
+        self.buffer_floats = 2 * self.stage_floats + 4 * world * self.stage_floats
+        self.buf = symm_mem.empty(self.buffer_floats, dtype=torch.float32, device=dev)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, pg)
         if self.handle.signal_pad_size < world * 4 * 8:
             raise RuntimeError("symmetric-memory signal pad too small")
         torch.cuda.synchronize(dev)
         dist.barrier(pg)                                  # every staging buffer is zeroed before anyone publishes
-        engine.dp_attach(world, rank, list(self.handle.buffer_ptrs), list(self.handle.signal_pad_ptrs), self.stage_floats)
+        engine.dp_attach(world, rank, list(self.handle.buffer_ptrs), list(self.handle.signal_pad_ptrs), self.stage_floats,
+                         self.buffer_floats)
         dist.barrier(pg)
 
     @property

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert sorted(_lib.SIGNATURES) == declared_functions()   # the ctypes binding covers the whole header
     lib = _lib.load()
-    assert lib.cql_abi_version() == 1
+    assert lib.cql_abi_version() == 2
 
 
 def test_config_struct_matches_header_size():
