@@ -81,6 +81,14 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
   const int tid = threadIdx.x, lane = tid & 31;
   const bool dp = jobs.dp.world > 1;
   const long long dpb = jobs.dp_off + (long long)blockIdx.y * NET_STRIDE;      // this network's element 0 in the gradient layout
+  DpSlices sl{};
+  if (dp) {
+    // phase B of the exchange: this rank owns one slice of the group -- sum the ranks' contributions (rank order),
+    // push the mean to everybody; then every block goes on to consume (phase C) whatever owner holds its values
+    sl = dp_slices(jobs.dp, jobs.dp_off, (long long)gridDim.y * NET_STRIDE);
+    dp_ll_owner_reduce(jobs.dp, jobs.dp_group, sl, jobs.n[0].g, ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + tid,
+                       (long long)gridDim.x * gridDim.y * 256);
+  }
   if (blockIdx.x < AP_W2_BLOCKS) {
     // ---------------- 8 rows of W2: Adam + Polyak, forward packs, then the transposed K chunk ----------------
     const int n = blockIdx.x * AP_ROWS + (tid >> 5), kc = lane;
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
     float p[8], t[8];
     {
       float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
-      if (dp) dp_ll_mean8(jobs.dp, jobs.dp_group, dpb + (long long)off, g0, g1, g0, g1);      // mean over ranks, rank order
+      if (dp) dp_ll_mean8(jobs.dp, jobs.dp_group, sl, dpb + (long long)off, g0, g1);      // mean over ranks, from the slice's owner
       float4 m0 = *reinterpret_cast<const float4*>(nt.m + off), m1 = *reinterpret_cast<const float4*>(nt.m + off + 4);
       float4 v0 = *reinterpret_cast<const float4*>(nt.v + off), v1 = *reinterpret_cast<const float4*>(nt.v + off + 4);
       const float4 p0 = *reinterpret_cast<const float4*>(nt.p + off), p1 = *reinterpret_cast<const float4*>(nt.p + off + 4);
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
       const int idx = c < w2_lo ? c : c + H * H;             // compact index -> index inside the network slot (w2_lo % 8 == 0)
       if (idx + 7 < NET_STRIDE) {
         float4 a = *reinterpret_cast<const float4*>(nt.g + idx), b = *reinterpret_cast<const float4*>(nt.g + idx + 4);
-        dp_ll_mean8(jobs.dp, jobs.dp_group, dpb + idx, a, b, a, b);
+        dp_ll_mean8(jobs.dp, jobs.dp_group, sl, dpb + idx, a, b);
         *reinterpret_cast<float4*>(gsm + c) = a;
         *reinterpret_cast<float4*>(gsm + c + 4) = b;
       }

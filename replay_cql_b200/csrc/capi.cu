@@ -846,7 +846,8 @@ int cql_dp_attach(cql_handle* ch, int32_t world, int32_t rank, const void* const
     CQL_REQUIRE(stage_floats >= need && stage_floats % 4 == 0, "cql_dp_attach: staging buffer too small (need the CQL_BUF_ALL_GRADS size, multiple of 4)");
     CQL_REQUIRE(buffer_floats >= 2 * stage_floats, "cql_dp_attach: buffer_floats must cover the two staging halves (2 x stage_floats)");
     // fused exchange: behind the two halves, [2][world][stage_floats] {value, tag} pairs pushed by the peers
-    const bool ll_room = buffer_floats >= 2 * stage_floats + 4 * (int64_t)world * stage_floats;
+    // (packets are tiled by 32 value groups = 128 floats: a slot must be a whole number of tiles)
+    const bool ll_room = stage_floats % 128 == 0 && buffer_floats >= 2 * stage_floats + 4 * (int64_t)world * stage_floats;
     DpPeer& p = ch->h.dp;
     p.world = world; p.rank = rank; p.stage_floats = stage_floats;
     for (int r = 0; r < world; ++r) {

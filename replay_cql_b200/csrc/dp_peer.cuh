@@ -64,65 +64,108 @@ __device__ __forceinline__ uint2* dp_ll_slot(const DpPeer& p, int dst_rank, int 
          ((long long)(p.epoch[group] & 1ull) * p.world + src_rank) * p.stage_floats;
 }
 __device__ __forceinline__ unsigned int dp_ll_tag(const DpPeer& p, int group) { return (unsigned int)(p.epoch[group] + 1); }
-// producer: four consecutive values -> every peer (index i counts floats inside the gradient layout)
-__device__ __forceinline__ void dp_ll_push4(const DpPeer& p, int group, long long i, float4 v) {
+// Position (in 16-byte packets) of the two packets of the 16-byte value group q (= float index / 4) inside a source
+// rank's slot: groups are tiled by 32 -- [tile][half][lane] -- so that a warp of the producer, whose lanes hold 32
+// consecutive groups, writes 512 contiguous bytes with each of its two stores: full 128-byte lines on NVLink instead
+// of 16 bytes out of every 32.
+__device__ __forceinline__ long long dp_ll_pkt(long long q, int half) { return (q >> 5) * 64 + half * 32 + (q & 31); }
+// ---- two-shot schedule of a big group (critics: 134 k floats, actor: 67 k).  One-shot (every rank pushes everything to
+// every peer) moves 7 x 2 x 0.8 MB per rank and update at 8 GPUs: measured +28 us for the sends and +24 us for the
+// consumers' polls (profiles/r02_dp_decomposition.txt).  Here the group's 16-byte value groups are cut into `world`
+// contiguous slices; slice o is OWNED by rank o:
+//   A  (k_reduce_grads_tc)  a rank pushes its sums of slice o to rank o only            (slot [source = me] at rank o)
+//   B  (k_adam_pack, first) the owner polls the world - 1 contributions of its slice, adds its own IN RANK ORDER, divides
+//                           and pushes the mean to every peer and to itself             (slot [source = owner] everywhere)
+//   C  (k_adam_pack)        every consumer polls the owner's packets of the values it needs.
+// 2 x (world - 1) / world of the group crosses NVLink per rank instead of world - 1 times the group, every rank applies
+// the owner's bits (replicas bit-identical; at world 2 the mean is still (g0 + g1) / 2 = the NCCL result), and phase B
+// depends on phase A packets only -- sent by the previous kernel of every rank -- so no rank's B waits for another
+// rank's B or C.  Contributions to owner o and results from owner o use the same slot space: disjoint value ranges.
+struct DpSlices {
+  long long q_lo;      // first 16-byte value group of the gradient group (absolute index in the gradient layout / 4)
+  long long n_q;       // value groups in the gradient group
+  long long per;       // value groups per slice (even: an 8-float chunk never straddles two owners)
+};
+__device__ __forceinline__ DpSlices dp_slices(const DpPeer& p, long long off_floats, long long n_floats) {
+  DpSlices sl;
+  sl.q_lo = off_floats >> 2;
+  sl.n_q = n_floats >> 2;
+  sl.per = ((sl.n_q + p.world - 1) / p.world + 1) & ~1ll;
+  return sl;
+}
+__device__ __forceinline__ int dp_owner(const DpSlices& sl, long long q_abs) { return (int)((q_abs - sl.q_lo) / sl.per); }
+__device__ __forceinline__ void dp_ll_store(uint4* slot, long long q_abs, float4 v, unsigned int tag) {
+  asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(slot + dp_ll_pkt(q_abs, 0)), "r"(__float_as_uint(v.x)), "r"(tag),
+               "r"(__float_as_uint(v.y)), "r"(tag) : "memory");
+  asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(slot + dp_ll_pkt(q_abs, 1)), "r"(__float_as_uint(v.z)), "r"(tag),
+               "r"(__float_as_uint(v.w)), "r"(tag) : "memory");
+}
+// both packets of value group q_abs; polls until they carry `tag` (timeout -> error flag); `first` = already requested
+__device__ __forceinline__ float4 dp_ll_wait(const DpPeer& p, const uint4* slot, long long q_abs, unsigned int tag) {
+  uint4 a, b;
+  long long spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(slot + dp_ll_pkt(q_abs, 0)) : "memory");
+    asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(slot + dp_ll_pkt(q_abs, 1)) : "memory");
+    if (a.y == tag && a.w == tag && b.y == tag && b.w == tag) break;
+    if (++spins > (1ll << 22)) { *p.error = 1; break; }         // seconds: give up instead of hanging the GPU
+    __nanosleep(20);
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+// phase A -- producer: the sums of value group q (absolute float index i = 4 q) go to the slice's owner
+__device__ __forceinline__ void dp_ll_push4(const DpPeer& p, int group, const DpSlices& sl, long long i, float4 v) {
   if (p.debug & 8) return;
+  const int o = dp_owner(sl, i >> 2);
+  if (o == p.rank) return;                                   // the owner takes its own sums from its gradient buffer
+  dp_ll_store(reinterpret_cast<uint4*>(dp_ll_slot(p, o, p.rank, group)), i >> 2, v, dp_ll_tag(p, group));
+}
+// phase B -- owner: thread `gid` of `n_threads` reduces value groups gid, gid + n_threads, ... of this rank's slice.
+// `own` = this rank's gradient buffer at the group's first float.
+__device__ __forceinline__ void dp_ll_owner_reduce(const DpPeer& p, int group, const DpSlices& sl, const float* own,
+                                                   long long gid, long long n_threads) {
   const unsigned int tag = dp_ll_tag(p, group);
-  for (int r = 0; r < p.world; ++r) {
-    if (r == p.rank) continue;
-    uint2* dst = dp_ll_slot(p, r, p.rank, group) + i;
-    asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(__float_as_uint(v.x)), "r"(tag),
-                 "r"(__float_as_uint(v.y)), "r"(tag) : "memory");
-    asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2), "r"(__float_as_uint(v.z)), "r"(tag),
-                 "r"(__float_as_uint(v.w)), "r"(tag) : "memory");
+  const long long lo = sl.q_lo + (long long)p.rank * sl.per;
+  const long long hi = min(sl.q_lo + sl.n_q, lo + sl.per);
+  for (long long q = lo + gid; q < hi; q += n_threads) {
+    const float4 mine = *reinterpret_cast<const float4*>(own + ((q - sl.q_lo) << 2));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < p.world; r0 += 8) {                // (all packets of up to 8 ranks requested before the first check)
+      uint4 a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + j < p.world && r0 + j != p.rank && !(p.debug & 4)) {
+          const uint4* slot = reinterpret_cast<const uint4*>(dp_ll_slot(p, p.rank, r0 + j, group));
+          asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[j].x), "=r"(a[j].y), "=r"(a[j].z), "=r"(a[j].w) : "l"(slot + dp_ll_pkt(q, 0)));
+          asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b[j].x), "=r"(b[j].y), "=r"(b[j].z), "=r"(b[j].w) : "l"(slot + dp_ll_pkt(q, 1)));
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                          // rank order
+        if (r0 + j >= p.world) continue;
+        float4 v = mine;
+        if (r0 + j != p.rank && !(p.debug & 4)) {
+          if (a[j].y == tag && a[j].w == tag && b[j].y == tag && b[j].w == tag)
+            v = make_float4(__uint_as_float(a[j].x), __uint_as_float(a[j].z), __uint_as_float(b[j].x), __uint_as_float(b[j].z));
+          else
+            v = dp_ll_wait(p, reinterpret_cast<const uint4*>(dp_ll_slot(p, p.rank, r0 + j, group)), q, tag);
+        }
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    const float n = (float)p.world;
+    const float4 m = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
+    for (int r = 0; r < p.world; ++r)
+      if (r == p.rank || !(p.debug & 8)) dp_ll_store(reinterpret_cast<uint4*>(dp_ll_slot(p, r, p.rank, group)), q, m, tag);
   }
 }
-// consumer: mean over ranks of EIGHT consecutive values (i .. i + 7); `own` = this rank's values.  All packets of all
-// peers are requested before the first tag is checked; stale ones are polled again (timeout -> error flag).
-__device__ __forceinline__ void dp_ll_mean8(const DpPeer& p, int group, long long i, const float4& own0, const float4& own1,
-                                            float4& m0, float4& m1) {
+// phase C -- consumer: means of EIGHT consecutive values (float index i .. i + 7) from their owner's packets
+__device__ __forceinline__ void dp_ll_mean8(const DpPeer& p, int group, const DpSlices& sl, long long i, float4& m0, float4& m1) {
   const unsigned int tag = dp_ll_tag(p, group);
-  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-  for (int r0 = 0; r0 < p.world; r0 += 8) {
-    uint4 q[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = r0 + j;
-      if (r < p.world && r != p.rank && !(p.debug & 4)) {
-        const uint4* src = reinterpret_cast<const uint4*>(dp_ll_slot(p, p.rank, r, group) + i);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[j][c].x), "=r"(q[j][c].y), "=r"(q[j][c].z), "=r"(q[j][c].w) : "l"(src + c));
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = r0 + j;
-      if (r >= p.world) continue;
-      if (r == p.rank || (p.debug & 4)) {
-        s0.x += own0.x; s0.y += own0.y; s0.z += own0.z; s0.w += own0.w;
-        s1.x += own1.x; s1.y += own1.y; s1.z += own1.z; s1.w += own1.w;
-        continue;
-      }
-      const uint4* src = reinterpret_cast<const uint4*>(dp_ll_slot(p, p.rank, r, group) + i);
-      long long spins = 0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        while (q[j][c].y != tag || q[j][c].w != tag) {
-          if (++spins > (1ll << 22)) { *p.error = 1; break; }     // seconds: give up instead of hanging the GPU
-          __nanosleep(20);
-          asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[j][c].x), "=r"(q[j][c].y), "=r"(q[j][c].z), "=r"(q[j][c].w) : "l"(src + c) : "memory");
-        }
-      }
-      s0.x += __uint_as_float(q[j][0].x); s0.y += __uint_as_float(q[j][0].z);
-      s0.z += __uint_as_float(q[j][1].x); s0.w += __uint_as_float(q[j][1].z);
-      s1.x += __uint_as_float(q[j][2].x); s1.y += __uint_as_float(q[j][2].z);
-      s1.z += __uint_as_float(q[j][3].x); s1.w += __uint_as_float(q[j][3].z);
-    }
-  }
-  const float n = (float)p.world;
-  m0 = make_float4(s0.x / n, s0.y / n, s0.z / n, s0.w / n);
-  m1 = make_float4(s1.x / n, s1.y / n, s1.z / n, s1.w / n);
+  const int o = dp_owner(sl, i >> 2);
+  if ((p.debug & 8) && o != p.rank) return;                  // (timing experiments: nothing was sent; keep the own values)
+  const uint4* slot = reinterpret_cast<const uint4*>(dp_ll_slot(p, p.rank, o, group));
+  m0 = dp_ll_wait(p, slot, i >> 2, tag);
+  m1 = dp_ll_wait(p, slot, (i >> 2) + 1, tag);
 }
 
 // ---- the scalar group (two floats: d loss / d log_temp, d loss / d log_alpha) travels INSIDE the signal words: word of

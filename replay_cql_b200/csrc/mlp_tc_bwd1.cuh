@@ -582,7 +582,8 @@ __global__ void __launch_bounds__(256) k_reduce_grads_tc(const float* __restrict
     for (int c = 1; c < 8; ++c) { const float4 v = part[c][g]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
     *reinterpret_cast<float4*>(grads + (size_t)net * NET_STRIDE + idx) = t;
     // data-parallel (fused exchange): the local sum is pushed into every peer's staging buffer, tagged with the epoch
-    if (dp.world > 1) dp_ll_push4(dp, dp_group, dp_off + (long long)net * NET_STRIDE + idx, t);
+    if (dp.world > 1)
+      dp_ll_push4(dp, dp_group, dp_slices(dp, dp_off, (long long)gridDim.y * NET_STRIDE), dp_off + (long long)net * NET_STRIDE + idx, t);
   }
 }
 

@@ -78,7 +78,7 @@ class PeerGradExchange:
         pg = group if group is not None else dist.group.WORLD
         world, rank = dist.get_world_size(pg), dist.get_rank(pg)
         _, n = engine.device_buffer(_lib.BUF_ALL_GRADS)
-        self.stage_floats = (n + 3) // 4 * 4
+        self.stage_floats = (n + 127) // 128 * 128        # whole tiles of 32 16-byte value groups (fused exchange)
         dev = torch.device("cuda", engine.device)
         # [2][stage] halves of the stand-alone exchange kernel, then [2][world][stage] {value, tag} pairs that the peers'
         # update kernels push into (fused exchange, csrc/dp_peer.cuh)
