@@ -188,11 +188,12 @@ int  cql_dp_attach(cql_handle* h, int32_t world, int32_t rank, const void* const
 int  cql_dp_allreduce(cql_handle* h, int which, void* stream);
 int  cql_dp_error(cql_handle* h, int32_t* flag_out);
 /* *fused_out = 1 when, after cql_dp_attach, the gradient exchange happens INSIDE the update kernels (f16x3 path, staging
- *   buffers with room for the pushed packets): the kernel that produces a gradient group stores its sums straight into
- *   every peer's staging buffer over NVLink as {value, epoch tag} pairs, the kernel that consumes it (Adam + Polyak +
- *   pack) polls its own buffer for the tags and sums in rank order; the two scalar gradients travel inside the signal
- *   words -- no exchange launch, no fence, one NVLink one-way latency per group, and cql_update / cql_update_batches /
- *   cql_step_phase run data-parallel as they are (cql_dp_allreduce is then a no-op).
+ *   buffers with room for the pushed packets): the kernel that produces a gradient group stores its sums of slice o
+ *   straight into rank o's staging buffer over NVLink as {value, epoch tag} pairs; in the kernel that consumes the group
+ *   (Adam + Polyak + pack) the owner of a slice polls its own buffer for the tags, sums in rank order and pushes the mean
+ *   to every rank, and every thread polls the means it needs; the two scalar gradients travel inside the signal words --
+ *   no exchange launch, no fence, and cql_update / cql_update_batches / cql_step_phase run data-parallel as they are
+ *   (cql_dp_allreduce is then a no-op).
  *   0: call cql_dp_allreduce (or an NCCL all-reduce) between the phases. */
 int  cql_dp_mode(cql_handle* h, int32_t* fused_out);
 

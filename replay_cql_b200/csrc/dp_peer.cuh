@@ -38,18 +38,19 @@ __device__ __forceinline__ float4 ld_volatile4(const float* p) {   // bypasses L
   return v;
 }
 
-// ---- fused mode (f16x3 path): no exchange launch at all, and no signal either for the two big groups.
-// PUSH with the flag inside the data ("LL" packets): the kernel that PRODUCES a gradient group (k_reduce_grads_tc)
-// stores every value it has summed straight into EVERY peer's staging buffer as 8-byte {value, epoch tag} pairs (two
-// pairs per 16-byte store; NVLink keeps an aligned 8-byte store whole); the kernel that CONSUMES the group (k_adam_pack)
-// polls its OWN staging buffer -- local memory -- until the tags of the pairs it needs carry this epoch, takes its own
-// contribution from its gradient buffer, and sums in RANK ORDER, so every rank applies bit-identical gradients.  One
-// NVLink one-way latency per exchange.  History (2 GPUs, us per update; 1 GPU = 213): publish + fence + signal, then the
-// consumer reads the peers' buffers over NVLink: 251 (of which the peer reads 15, signal + fences + store
-// acknowledgement ~20; waiting itself 0: the ranks run in lock step); one fence per signal round and relaxed polling,
-// peer loads batched: 248; LL push: see profiles/.  Staging[parity][source rank] is rewritten two epochs later; a rank
-// gets there only after consuming the next epoch, whose packets a peer sends only after its own consumer of THIS epoch
-// has ended -- no second barrier.  The consumer's last block advances the epoch (dp_consume_done).
+// ---- fused mode (f16x3 path): no exchange launch at all, and no signal or fence either for the two big groups.
+// PUSH with the flag inside the data ("LL" packets): values travel as 8-byte {value, epoch tag} pairs (two pairs per
+// 16-byte store; NVLink keeps an aligned 8-byte store whole) written straight into a peer's staging buffer; whoever
+// needs a value polls its OWN staging buffer -- local memory -- until the pair carries this epoch's tag.  The schedule
+// is two-shot (see DpSlices below): k_reduce_grads_tc pushes slices to their owners, k_adam_pack's owner phase sums in
+// RANK ORDER and pushes the mean, every consumer thread polls the means it needs -- every rank applies the owner's bits.
+// History (us per update; independent replicas 217.5): publish + fence + signal, consumers read the peers' buffers over
+// NVLink: 251 at 2 GPUs (peer reads 11-15, signal + fences + store acknowledgement ~20; waiting itself 0: the ranks run
+// in lock step); one fence per signal round, relaxed polls, batched peer loads: 248; one-shot push: 230.5 at 2 GPUs but
+// 270 at 8 (sends +28, polls +24); two-shot push: 231 / 240 (profiles/r02_dp_decomposition.txt).
+// Slot [parity][source rank] is rewritten two epochs later; a rank gets there only after consuming the next epoch,
+// whose packets a peer sends only after its own consumer of THIS epoch has ended -- no second barrier.  The consumer's
+// last block advances the epoch (dp_consume_done).
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
