@@ -40,6 +40,14 @@ struct cql_handle {
   cudaEvent_t ring_ev[8] = {};
   float* metrics_rows = nullptr;     // pinned [metrics_rows_cap][8]
   int64_t metrics_rows_cap = 0;
+  // ... and its copy pipeline: a second stream moves minibatch i + 1 host -> device ring and the metrics of step i - 1
+  // device -> host while step i computes
+  cudaStream_t copy_stream = nullptr, copy_stream_out = nullptr;      // one per direction: neither queues behind the other
+  float* dev_ring = nullptr;         // device [8][B*8]
+  float* dev_metrics = nullptr;      // device [8][8]
+  cudaEvent_t ev_used[8] = {};       // compute stream: slot's minibatch has been copied into h.batch
+  cudaEvent_t ev_met[8] = {};        // compute stream: slot's metrics are in dev_metrics
+  cudaEvent_t ev_met_out[8] = {};    // copy stream: slot's metrics have left dev_metrics
   void* dp_local = nullptr;          // epochs | tickets | error flag
 };
 
@@ -409,6 +417,13 @@ void cql_destroy(cql_handle* ch) {
   if (ch->ring) cudaFreeHost(ch->ring);
   if (ch->metrics_rows) cudaFreeHost(ch->metrics_rows);
   for (auto& e : ch->ring_ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ch->ev_used) if (e) cudaEventDestroy(e);
+  for (auto& e : ch->ev_met) if (e) cudaEventDestroy(e);
+  for (auto& e : ch->ev_met_out) if (e) cudaEventDestroy(e);
+  if (ch->dev_ring) cudaFree(ch->dev_ring);
+  if (ch->dev_metrics) cudaFree(ch->dev_metrics);
+  if (ch->copy_stream) cudaStreamDestroy(ch->copy_stream);
+  if (ch->copy_stream_out) cudaStreamDestroy(ch->copy_stream_out);
   ch->h.free_all();
   delete ch;
 }
@@ -754,8 +769,16 @@ int cql_update_batches(cql_handle* ch, int64_t n_batches, const float* obs, cons
     const size_t row_floats = (size_t)B * 8;
     if (!ch->ring) {
       CQL_CUDA(cudaMallocHost(&ch->ring, RING * row_floats * sizeof(float)));
+      CQL_CUDA(cudaMalloc(&ch->dev_ring, RING * row_floats * sizeof(float)));
+      CQL_CUDA(cudaMalloc(&ch->dev_metrics, RING * 8 * sizeof(float)));
+      CQL_CUDA(cudaStreamCreateWithFlags(&ch->copy_stream, cudaStreamNonBlocking));
+      CQL_CUDA(cudaStreamCreateWithFlags(&ch->copy_stream_out, cudaStreamNonBlocking));
       for (auto& e : ch->ring_ev) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : ch->ev_used) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : ch->ev_met) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : ch->ev_met_out) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    cudaStream_t cs = ch->copy_stream, cso = ch->copy_stream_out;
     if (ch->metrics_rows_cap < n_batches) {
       if (ch->metrics_rows) CQL_CUDA(cudaFreeHost(ch->metrics_rows));
       ch->metrics_rows = nullptr; ch->metrics_rows_cap = 0;
@@ -781,6 +804,12 @@ int cql_update_batches(cql_handle* ch, int64_t n_batches, const float* obs, cons
       CQL_CUDA(cudaGraphDestroy(g));
       ch->step_graph_stream = st;
     }
+    // Copies ride on their own stream: minibatch i goes pinned ring -> device ring there (every step, 32 B x B), the
+    // compute stream only waits for its event, moves it into h.batch (device to device), replays the step and drops the
+    // step's metrics into a device slot, which the copy stream takes to the host (every step).  On one stream each
+    // step paid both PCIe copies' start-up latency in series (e2e 0.885 of the HBM-resident rate).
+    CQL_CUDA(cudaEventRecord(ch->ev_used[0], st));                        // orders the copy stream behind earlier work on st
+    CQL_CUDA(cudaStreamWaitEvent(cs, ch->ev_used[0], 0));
     for (int64_t i = 0; i < n_batches; ++i) {
       const int slot = (int)(i % RING);
       if (i >= RING) CQL_CUDA(cudaEventSynchronize(ch->ring_ev[slot]));     // that slot's host->device copy has run
@@ -792,13 +821,25 @@ int cql_update_batches(cql_handle* ch, int64_t n_batches, const float* obs, cons
         w[0] = o[2 * b]; w[1] = o[2 * b + 1]; w[2] = a[b]; w[3] = r[b];
         w[4] = no[2 * b]; w[5] = no[2 * b + 1]; w[6] = t[b]; w[7] = 0.f;
       }
-      CQL_CUDA(cudaMemcpyAsync(h.batch, stage, row_floats * sizeof(float), cudaMemcpyHostToDevice, st));
-      CQL_CUDA(cudaEventRecord(ch->ring_ev[slot], st));
+      float* dslot = ch->dev_ring + (size_t)slot * row_floats;
+      if (i >= RING) CQL_CUDA(cudaStreamWaitEvent(cs, ch->ev_used[slot], 0));   // the device slot has been consumed
+      CQL_CUDA(cudaMemcpyAsync(dslot, stage, row_floats * sizeof(float), cudaMemcpyHostToDevice, cs));
+      CQL_CUDA(cudaEventRecord(ch->ring_ev[slot], cs));
+      CQL_CUDA(cudaStreamWaitEvent(st, ch->ring_ev[slot], 0));
+      CQL_CUDA(cudaMemcpyAsync(h.batch, dslot, row_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CQL_CUDA(cudaEventRecord(ch->ev_used[slot], st));
       CQL_CUDA(cudaGraphLaunch(ch->step_graph, st));
       h.launches += ch->step_graph_launches;
-      CQL_CUDA(cudaMemcpyAsync(ch->metrics_rows + (size_t)i * 8, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (i >= RING) CQL_CUDA(cudaStreamWaitEvent(st, ch->ev_met_out[slot], 0));   // the metrics slot has left the device
+      CQL_CUDA(cudaMemcpyAsync(ch->dev_metrics + (size_t)slot * 8, h.metrics, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CQL_CUDA(cudaEventRecord(ch->ev_met[slot], st));
+      CQL_CUDA(cudaStreamWaitEvent(cso, ch->ev_met[slot], 0));
+      CQL_CUDA(cudaMemcpyAsync(ch->metrics_rows + (size_t)i * 8, ch->dev_metrics + (size_t)slot * 8, 8 * sizeof(float),
+                               cudaMemcpyDeviceToHost, cso));
+      CQL_CUDA(cudaEventRecord(ch->ev_met_out[slot], cso));
     }
     CQL_CUDA(cudaStreamSynchronize(st));
+    CQL_CUDA(cudaStreamSynchronize(cso));
     if (metrics_out)
       for (int64_t i = 0; i < n_batches; ++i) std::memcpy(metrics_out + i * 6, ch->metrics_rows + i * 8, 6 * sizeof(float));
   });
