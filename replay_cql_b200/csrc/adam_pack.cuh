@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
     // ---------------- 8 rows of W2: Adam + Polyak, forward packs, then the transposed K chunk ----------------
     const int n = blockIdx.x * AP_ROWS + (tid >> 5), kc = lane;
     const size_t off = (size_t)off_W2(in_dim) + (size_t)n * H + kc * 8;
+    const float w2max_prev = __int_as_float(nt.w2max[slot_rd]);      // (read with the first loads, not after the barrier)
     float p[8], t[8];
     {
       float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
     // transposed orientation: operand row n' = W2 column n', K index = W2 row: these 8 rows are K chunk blockIdx.x of
     // EVERY operand row.  One power-of-two scale per network (see the header of this file).
     {
-      const float bound = 2.f * (__int_as_float(nt.w2max[slot_rd]) + 4.f * jobs.lr);
+      const float bound = 2.f * (w2max_prev + 4.f * jobs.lr);
       float sT, inv_sT;
       pow2_scale(bound, sT, inv_sT);
       const int np = tid;
@@ -193,40 +194,42 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
   idxs[n_idx++] = off_b1(in_dim) + k;
   idxs[n_idx++] = off_b2(in_dim) + k;
   for (int o = 0; o < out_dim; ++o) idxs[n_idx++] = off_W3(in_dim) + o * H + k;
-  float gv[8];
+  // Every load of this thread (gradient, parameter, both moments, target: 5 x n_idx, plus b3 in the first out_dim
+  // threads) is issued BEFORE the first store: with load / compute / store per entry the compiler cannot move a load
+  // above the previous entry's stores (the pointers may alias), and this one CTA then walked through 7 dependent L2 round
+  // trips -- with the launch skipped the update was 12 us shorter per k_adam_pack, most of it this chain (r02 skip test).
+  const bool has_b3 = tid < out_dim;
+  const int ib3 = off_b3(in_dim, out_dim) + tid;
+  float gv[9], pv[9], mv[9], vv[9], tv[9];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    if (i < n_idx) gv[i] = grad_of(idxs[i]);
-  auto upd_g = [&](int idx, float g) {
-    float pp = nt.p[idx], mm = nt.m[idx], vv = nt.v[idx];
-    adam_one(pp, mm, vv, g, step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
-    const float tt = nt.targ[idx] * (1.f - jobs.tau) + jobs.tau * pp;
-    nt.p[idx] = pp; nt.m[idx] = mm; nt.v[idx] = vv; nt.targ[idx] = tt;
-    return make_float2(pp, tt);
-  };
-  auto upd = [&](int idx) { return upd_g(idx, grad_of(idx)); };
+    if (i < n_idx) { gv[i] = grad_of(idxs[i]); pv[i] = nt.p[idxs[i]]; mv[i] = nt.m[idxs[i]]; vv[i] = nt.v[idxs[i]]; tv[i] = nt.targ[idxs[i]]; }
+  if (has_b3) { gv[8] = grad_of(ib3); pv[8] = nt.p[ib3]; mv[8] = nt.m[ib3]; vv[8] = nt.v[ib3]; tv[8] = nt.targ[ib3]; }
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    if (i < n_idx || (i == 8 && has_b3)) {
+      adam_one(pv[i], mv[i], vv[i], gv[i], step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
+      tv[i] = tv[i] * (1.f - jobs.tau) + jobs.tau * pv[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n_idx) { nt.p[idxs[i]] = pv[i]; nt.m[idxs[i]] = mv[i]; nt.v[idxs[i]] = vv[i]; nt.targ[idxs[i]] = tv[i]; }
+  if (has_b3) { nt.p[ib3] = pv[8]; nt.m[ib3] = mv[8]; nt.v[ib3] = vv[8]; nt.targ[ib3] = tv[8]; }
   {
+    // layer maxima for the operand generators: W1 columns -> wm[c], b1 -> wm[3], W3 rows -> wm[4 + o] (targets at + 8)
     int i = 0;
     for (int c = 0; c < in_dim; ++c, ++i) {
-      const float2 r = upd_g(idxs[i], gv[i]);
-      atomicMax(&wm[c], __float_as_int(fabsf(r.x)));
-      atomicMax(&wm[8 + c], __float_as_int(fabsf(r.y)));
+      atomicMax(&wm[c], __float_as_int(fabsf(pv[i])));
+      atomicMax(&wm[8 + c], __float_as_int(fabsf(tv[i])));
     }
-    {
-      const float2 r = upd_g(idxs[i], gv[i]);
-      ++i;
-      atomicMax(&wm[3], __float_as_int(fabsf(r.x)));
-      atomicMax(&wm[8 + 3], __float_as_int(fabsf(r.y)));
-    }
-    upd_g(idxs[i], gv[i]);
-    ++i;
+    atomicMax(&wm[3], __float_as_int(fabsf(pv[i])));
+    atomicMax(&wm[8 + 3], __float_as_int(fabsf(tv[i])));
+    i += 2;                                                   // (b2 has no maximum)
     for (int o = 0; o < out_dim; ++o, ++i) {
-      const float2 r = upd_g(idxs[i], gv[i]);
-      atomicMax(&wm[4 + o], __float_as_int(fabsf(r.x)));
-      atomicMax(&wm[8 + 4 + o], __float_as_int(fabsf(r.y)));
+      atomicMax(&wm[4 + o], __float_as_int(fabsf(pv[i])));
+      atomicMax(&wm[8 + 4 + o], __float_as_int(fabsf(tv[i])));
     }
   }
-  if (tid < out_dim) upd(off_b3(in_dim, out_dim) + tid);
   __syncthreads();
   if (tid < 8) {
     const float w = __int_as_float(wm[tid]), wt = __int_as_float(wm[8 + tid]);

@@ -583,6 +583,11 @@ __global__ void k_adam_polyak(float* __restrict__ p, float* __restrict__ m, floa
 // cql_timed_update switches PDL off for its one timed step: with PDL a kernel's prologue starts under its predecessor,
 // so a CUDA event recorded between two kernels no longer separates their durations (r01: bwd1 0.118 ms / bwd2 0.003 ms)
 inline bool g_timing_no_pdl = false;
+// CQL_SKIP=<mask>: timing experiments only (results wrong) -- leaves launches out to read their cost on the critical path
+inline bool skip_launch(int bit) {
+  static const int mask = std::getenv("CQL_SKIP") ? std::atoi(std::getenv("CQL_SKIP")) : 0;
+  return (mask & bit) != 0;
+}
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   static const bool no_pdl_env = std::getenv("CQL_NO_PDL") != nullptr;
@@ -853,7 +858,8 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
     CQL_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   if (mark_end >= 0) mark(h, st, mark_end);
-  launch_pdl(tc::k_reduce_grads_tc, dim3(dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets)), dim3(256), 0, st, h->small1, slots1, h->small2, h->pw2_tc,
+  if (!skip_launch(64))
+    launch_pdl(tc::k_reduce_grads_tc, dim3(dim3((NET_STRIDE / 4 + 31) / 32, jb.n_nets)), dim3(256), 0, st, h->small1, slots1, h->small2, h->pw2_tc,
                                                                                   splits, IN, OUT, grads_out,
                                                                                   (F16X3 && GROUP_SUM) ? tc::B2H_GROUP : 1,
                                                                                   h->dp_fused ? h->dp : DpPeer{}, IN == 3 ? 1 : 2,
@@ -888,7 +894,8 @@ inline void adam_pack(Handle* h, int first_slot, int n_nets, int in_dim, int out
     n.tfwd2 = critic ? h->packed_fwd2 + (size_t)tslot * h->packed_net_bytes2 : nullptr;
     n.w2max = h->w2max + slot * 4;
   }
-  launch_pdl(tc::k_adam_pack, dim3(tc::AP_W2_BLOCKS + 1, n_nets), dim3(256), 0, st, j, h->stepinfo);
+  if (!skip_launch(128))
+    launch_pdl(tc::k_adam_pack, dim3(tc::AP_W2_BLOCKS + 1, n_nets), dim3(256), 0, st, j, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
 }
 
@@ -935,7 +942,8 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
   if (bs == BatchSource::Sampled && ns == NoiseSource::Philox) {
     CQL_REQUIRE(h->n_trans > 0, "cql_update: no transitions loaded (call cql_load_transitions first)");
     const int64_t nthr = h->noise_floats > B ? h->noise_floats : B;
-    launch_pdl(k_step_head, dim3((int)((nthr + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(h->table), h->n_trans, h->step_dev,
+    if (!skip_launch(256))
+      launch_pdl(k_step_head, dim3((int)((nthr + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(h->table), h->n_trans, h->step_dev,
                                                           h->stepinfo, c.beta1, c.beta2, B, h->n, c.rank, c.world_size,
                                                           c.seed, reinterpret_cast<float4*>(h->batch), h->XA, h->noise,
                                                           h->noise_floats, h->table_sharded ? 0 : c.rank,
@@ -969,7 +977,8 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     QSrc srcA[2];
     launch_fwd_any<2, 2>(h, jobs, st, srcA);
     mark(h, st, 2);
-    launch_pdl(k_prep, dim3((B * 64 + 255) / 256), dim3(256), 0, st, batch4, srcA[0], srcA[1], h->outA, h->noise, B, h->n, c.squash, h->XAl,
+    if (!skip_launch(1))
+      launch_pdl(k_prep, dim3((B * 64 + 255) / 256), dim3(256), 0, st, batch4, srcA[0], srcA[1], h->outA, h->noise, B, h->n, c.squash, h->XAl,
                h->offAl, h->XC, h->offC, h->XT, h->XP, reinterpret_cast<float4*>(h->perb));
   }
   CQL_LAUNCH_CHECK(h);
@@ -985,13 +994,15 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     // the reported duration is the kernel's steady-state launch-to-launch time, not one launch plus its launch latency
     for (int rep = 0; rep < (h->timing ? TIMED_FWD_REPS : 1); ++rep) launch_fwd_any<3, 1>(h, jobs, st, srcQ);
     mark(h, st, 4);
-    launch_pdl(k_lse, dim3((C * B * 32 + 255) / 256), dim3(256), 0, st, batch4, srcQ[0], h->offAl, srcQ[1], h->offC, srcQ[2], loss_consts(h),
+    if (!skip_launch(2))
+      launch_pdl(k_lse, dim3((C * B * 32 + 255) / 256), dim3(256), 0, st, batch4, srcQ[0], h->offAl, srcQ[1], h->offC, srcQ[2], loss_consts(h),
                h->dQ, reinterpret_cast<PairVals*>(h->pairv));
     CQL_LAUNCH_CHECK(h);
   }
   {
     const int64_t so = scalars_off(C);
-    launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
+    if (!skip_launch(4))
+      launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
                h->scalars(), h->adam_m + so, h->adam_v + so, loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics,
                h->dp_fused ? h->dp : DpPeer{}, (long long)(1 + C) * NET_STRIDE);
     CQL_LAUNCH_CHECK(h);
@@ -1003,7 +1014,8 @@ inline void phase1(Handle* h, cudaStream_t st) {
   NvtxRange nvtx("cql.update.phase1: temp/alpha Adam, critic backward");
   const int B = h->B, C = h->C, n3 = 3 * h->n, rows = B * (n3 + 1);
   const int64_t so = scalars_off(C);
-  launch_pdl(k_scalar_adam_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so,
+  if (!skip_launch(8))
+    launch_pdl(k_scalar_adam_dq, dim3((int)(((int64_t)C * rows + 255) / 256)), dim3(256), 0, st, h->scalars(), h->adam_m + so, h->adam_v + so,
              h->g_scalars(), h->stepinfo, loss_consts(h), h->loss_sums, h->metrics, reinterpret_cast<const PairVals*>(h->pairv), h->dQ,
              h->dp_fused ? h->dp : DpPeer{}, (long long)(1 + C) * NET_STRIDE);
   CQL_LAUNCH_CHECK(h);
@@ -1050,7 +1062,8 @@ inline void phase2(Handle* h, cudaStream_t st) {
     QSrc srcP[1];
     launch_fwd_any<3, 1>(h, jobs, st, srcP);
     mark(h, st, 9);
-    launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, srcP[0], reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
+    if (!skip_launch(16))
+      launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, srcP[0], reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
                h->metrics);
     CQL_LAUNCH_CHECK(h);
   }
@@ -1062,7 +1075,8 @@ inline void phase2(Handle* h, cudaStream_t st) {
     else launch_bwd1<3, 1, false, true>(h, jb, st);
   }
   const bool tcm = h->cfg.precision != CQL_PREC_FP32;
-  launch_pdl(k_actor_dout, dim3((B + 127) / 128), dim3(128), 0, st, h->outA, h->noise + B + 6 * (int64_t)B * h->n,
+  if (!skip_launch(32))
+    launch_pdl(k_actor_dout, dim3((B + 127) / 128), dim3(128), 0, st, h->outA, h->noise + B + 6 * (int64_t)B * h->n,
                                                 tcm ? h->dX_part : h->dXP, h->scalars(), B,
                                                 tcm ? h->last_dx_parts : C, c.squash, h->dOutA);
   CQL_LAUNCH_CHECK(h);
