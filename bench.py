@@ -605,7 +605,7 @@ def run_stress(args):
         dist.init_process_group("nccl", device_id=dev)
     shape = dict(SHAPES["stress"]); shape["n_rows"] = args.stress_rows
     B = 8192
-    prec = "bf16" if args.precision == "f16x3" else args.precision
+    prec = args.stress_precision
     eng = CqlEngine(CqlHyperParams(batch_size=B, seed=12345, precision=prec), device=local_rank, rank=rank, world_size=world)
     t0 = time.perf_counter()
     eng.synth_table(shape["n_rows"], shape["n_users"], shape["n_items"], seed=12345)
@@ -686,6 +686,8 @@ def main():
                     help="ml20m = the headline line (BASELINE configs[2,3]); ml1m = fit+predict wall clock beside the CPU "
                          "per-user path (configs[0,1]); stress = 1e9-row table, batch 8192, bf16 (configs[4], scaled scoring)")
     ap.add_argument("--stress-rows", type=int, default=1_000_000_000)
+    ap.add_argument("--stress-precision", choices=["fp32", "tf32x3", "f16x3", "bf16"], default="bf16",
+                    help="stress workload: bf16 = the variant BASELINE configs[4] names; f16x3 = the FP32-grade product path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -70,7 +70,7 @@ __device__ __forceinline__ void store_chunk(const float (&x)[8], float s, uint8_
 constexpr int AP_ROWS = 8;                    // W2 rows per CTA
 constexpr int AP_W2_BLOCKS = H / AP_ROWS;     // 32
 
-__global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, const StepInfo* __restrict__ si) {
+__global__ void __launch_bounds__(1024, 1) k_adam_pack(const AdamPackJobs jobs, const StepInfo* __restrict__ si) {
   grid_dep_wait();
   __shared__ float tile[AP_ROWS][H + 4];
   __shared__ int wm[16];
@@ -86,69 +86,87 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
     // phase B of the exchange: this rank owns one slice of the group -- sum the ranks' contributions (rank order),
     // push the mean to everybody; then every block goes on to consume (phase C) whatever owner holds its values
     sl = dp_slices(jobs.dp, jobs.dp_off, (long long)gridDim.y * NET_STRIDE);
-    dp_ll_owner_reduce(jobs.dp, jobs.dp_group, sl, jobs.n[0].g, ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + tid,
-                       (long long)gridDim.x * gridDim.y * 256);
+    dp_ll_owner_reduce(jobs.dp, jobs.dp_group, sl, jobs.n[0].g, ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + tid,
+                       (long long)gridDim.x * gridDim.y * blockDim.x);
   }
   if (blockIdx.x < AP_W2_BLOCKS) {
     // ---------------- 8 rows of W2: Adam + Polyak, forward packs, then the transposed K chunk ----------------
-    const int n = blockIdx.x * AP_ROWS + (tid >> 5), kc = lane;
-    const size_t off = (size_t)off_W2(in_dim) + (size_t)n * H + kc * 8;
+    // 1024 threads, TWO consecutive entries each (128 threads per row).  With 256 threads x 8 entries the kernel was bound
+    // by the latency of each thread's 24 IEEE sqrt / divide sequences at 8 warps per SM (ncu r02: 11.4 us warm, issue
+    // slots 20 %, 1390 warp instructions per warp).
+    __shared__ float gw2[AP_ROWS][H];                 // data-parallel: the rows' mean gradients
+    __shared__ float rmax[AP_ROWS][4], rmaxt[AP_ROWS][4];
+    const int r8 = tid >> 7, c2 = tid & 127;
+    const int n = blockIdx.x * AP_ROWS + r8;
+    const size_t off = (size_t)off_W2(in_dim) + (size_t)n * H + c2 * 2;
     const float w2max_prev = __int_as_float(nt.w2max[slot_rd]);      // (read with the first loads, not after the barrier)
-    float p[8], t[8];
-    {
-      float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
-      if (dp) dp_ll_mean8(jobs.dp, jobs.dp_group, sl, dpb + (long long)off, g0, g1);      // mean over ranks, from the slice's owner
-      float4 m0 = *reinterpret_cast<const float4*>(nt.m + off), m1 = *reinterpret_cast<const float4*>(nt.m + off + 4);
-      float4 v0 = *reinterpret_cast<const float4*>(nt.v + off), v1 = *reinterpret_cast<const float4*>(nt.v + off + 4);
-      const float4 p0 = *reinterpret_cast<const float4*>(nt.p + off), p1 = *reinterpret_cast<const float4*>(nt.p + off + 4);
-      const float4 t0 = *reinterpret_cast<const float4*>(nt.targ + off), t1 = *reinterpret_cast<const float4*>(nt.targ + off + 4);
-      p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
-      t[0] = t0.x; t[1] = t0.y; t[2] = t0.z; t[3] = t0.w; t[4] = t1.x; t[5] = t1.y; t[6] = t1.z; t[7] = t1.w;
-      float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        adam_one(p[i], mm[i], vv[i], gg[i], step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
-        t[i] = t[i] * (1.f - jobs.tau) + jobs.tau * p[i];
+    float2 g = *reinterpret_cast<const float2*>(nt.g + off);
+    float2 m = *reinterpret_cast<const float2*>(nt.m + off), v = *reinterpret_cast<const float2*>(nt.v + off);
+    float2 p = *reinterpret_cast<const float2*>(nt.p + off), t = *reinterpret_cast<const float2*>(nt.targ + off);
+    if (dp) {                                          // every fourth thread fetches the chunk's 8 means (from the slice's owner)
+      if ((c2 & 3) == 0) {
+        float4 g0 = *reinterpret_cast<const float4*>(nt.g + off), g1 = *reinterpret_cast<const float4*>(nt.g + off + 4);
+        dp_ll_mean8(jobs.dp, jobs.dp_group, sl, dpb + (long long)off, g0, g1);
+        *reinterpret_cast<float4*>(&gw2[r8][c2 * 2]) = g0;
+        *reinterpret_cast<float4*>(&gw2[r8][c2 * 2 + 4]) = g1;
       }
-      *reinterpret_cast<float4*>(nt.m + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-      *reinterpret_cast<float4*>(nt.m + off + 4) = make_float4(mm[4], mm[5], mm[6], mm[7]);
-      *reinterpret_cast<float4*>(nt.v + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-      *reinterpret_cast<float4*>(nt.v + off + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-      *reinterpret_cast<float4*>(nt.p + off) = make_float4(p[0], p[1], p[2], p[3]);
-      *reinterpret_cast<float4*>(nt.p + off + 4) = make_float4(p[4], p[5], p[6], p[7]);
-      *reinterpret_cast<float4*>(nt.targ + off) = make_float4(t[0], t[1], t[2], t[3]);
-      *reinterpret_cast<float4*>(nt.targ + off + 4) = make_float4(t[4], t[5], t[6], t[7]);
+      __syncthreads();
+      g = *reinterpret_cast<const float2*>(&gw2[r8][c2 * 2]);
     }
-    float* trow = &tile[tid >> 5][kc * 8];
-    *reinterpret_cast<float4*>(trow) = make_float4(p[0], p[1], p[2], p[3]);
-    *reinterpret_cast<float4*>(trow + 4) = make_float4(p[4], p[5], p[6], p[7]);
-    // forward orientation: operand row n = W2 row n, scale from the row maximum (this warp = this row)
-    float mx = 0.f, mt = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { mx = fmaxf(mx, fabsf(p[i])); mt = fmaxf(mt, fabsf(t[i])); }
+    adam_one(p.x, m.x, v.x, g.x, step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
+    adam_one(p.y, m.y, v.y, g.y, step_size, bc2s, jobs.beta1, jobs.beta2, jobs.eps);
+    t.x = t.x * (1.f - jobs.tau) + jobs.tau * p.x;
+    t.y = t.y * (1.f - jobs.tau) + jobs.tau * p.y;
+    *reinterpret_cast<float2*>(nt.m + off) = m;
+    *reinterpret_cast<float2*>(nt.v + off) = v;
+    *reinterpret_cast<float2*>(nt.p + off) = p;
+    *reinterpret_cast<float2*>(nt.targ + off) = t;
+    *reinterpret_cast<float2*>(&tile[r8][c2 * 2]) = p;
+    // forward orientation: operand row n = W2 row n, scale from the row maximum (4 warps per row)
+    float mx = fmaxf(fabsf(p.x), fabsf(p.y)), mt = fmaxf(fabsf(t.x), fabsf(t.y));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
     }
+    if (lane == 0) { rmax[r8][(tid >> 5) & 3] = mx; rmaxt[r8][(tid >> 5) & 3] = mt; }
+    __syncthreads();
+    mx = fmaxf(fmaxf(rmax[r8][0], rmax[r8][1]), fmaxf(rmax[r8][2], rmax[r8][3]));
+    mt = fmaxf(fmaxf(rmaxt[r8][0], rmaxt[r8][1]), fmaxf(rmaxt[r8][2], rmaxt[r8][3]));
     float s, inv_s, st, inv_st;
     pow2_scale(mx, s, inv_s);
     pow2_scale(mt, st, inv_st);
-    store_chunk(p, s, nt.fwd, nt.fwd2, n, kc);
-    store_chunk(t, st, nt.tfwd, nt.tfwd2, n, kc);
-    if (lane == 0) {
+    {
+      // this thread's quarter (4 bytes of hi, 4 bytes of lo) of the 16-byte chunk kc of operand row n
+      const int kc = c2 >> 2, piece = (c2 & 3) * 4;
+      uint32_t hi, lo, thi, tlo;
+      split_h2(p.x * s, p.y * s, hi, lo);
+      split_h2(t.x * st, t.y * st, thi, tlo);
+      const size_t one_off = (size_t)(n / HCfg::NS) * HCfg::B_BYTES + chunk_off(HCfg::NS, n % HCfg::NS, kc) + piece;
+      *reinterpret_cast<uint32_t*>(nt.fwd + one_off) = hi;
+      *reinterpret_cast<uint32_t*>(nt.fwd + one_off + HCfg::B_TERM_BYTES) = lo;
+      *reinterpret_cast<uint32_t*>(nt.tfwd + one_off) = thi;
+      *reinterpret_cast<uint32_t*>(nt.tfwd + one_off + HCfg::B_TERM_BYTES) = tlo;
+      if (nt.fwd2 != nullptr) {
+        *reinterpret_cast<uint32_t*>(nt.fwd2 + pair_chunk_off(n, kc, 0) + piece) = hi;
+        *reinterpret_cast<uint32_t*>(nt.fwd2 + pair_chunk_off(n, kc, 1) + piece) = lo;
+      }
+      if (nt.tfwd2 != nullptr) {
+        *reinterpret_cast<uint32_t*>(nt.tfwd2 + pair_chunk_off(n, kc, 0) + piece) = thi;
+        *reinterpret_cast<uint32_t*>(nt.tfwd2 + pair_chunk_off(n, kc, 1) + piece) = tlo;
+      }
+    }
+    if (c2 == 0) {
       reinterpret_cast<HMeta*>(nt.fwd + HCfg::META_OFF)->inv_s[n] = inv_s;
       reinterpret_cast<HMeta*>(nt.tfwd + HCfg::META_OFF)->inv_s[n] = inv_st;
       if (nt.fwd2) reinterpret_cast<HMeta*>(nt.fwd2 + H2Cfg::META_OFF)->inv_s[n] = inv_s;
       if (nt.tfwd2) reinterpret_cast<HMeta*>(nt.tfwd2 + H2Cfg::META_OFF)->inv_s[n] = inv_st;
       atomicMax(&nt.w2max[slot_acc], __float_as_int(mx));
     }
-    __syncthreads();
+    // (the barrier above already ordered the tile[] writes before the reads below)
     // transposed orientation: operand row n' = W2 column n', K index = W2 row: these 8 rows are K chunk blockIdx.x of
     // EVERY operand row.  One power-of-two scale per network (see the header of this file).
-    {
+    if (tid < H) {
       const float bound = 2.f * (w2max_prev + 4.f * jobs.lr);
       float sT, inv_sT;
       pow2_scale(bound, sT, inv_sT);
@@ -165,6 +183,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(const AdamPackJobs jobs, cons
     if (dp) dp_consume_done(jobs.dp, jobs.dp_group, gridDim.x * gridDim.y);
     return;
   }
+  if (tid >= 256) return;     // the small tensors are 256 threads' work (exited threads do not count at the barriers below)
   // ---------------- the small tensors: W1 | b1, b2, W3 | b3 (+ layer maxima for the operand generators) ----------------
   if (tid < 16) wm[tid] = 0;
   if (tid == 0) nt.w2max[slot_clr] = 0;

@@ -197,6 +197,7 @@ void create_impl(const cql_config* cfg, cql_handle* ch) {
   h.perb = h.dalloc<float>(4 * (size_t)B);
   h.pairv = h.dalloc<float>(4 * (size_t)C * B);
   h.loss_sums = h.dalloc<float>(16);
+  h.actor_part = h.dalloc<float>((size_t)((B + 127) / 128) * 4 + 4);
   h.splitsC = std::max(1, std::min(tC, (2 * h.num_sms) / (4 * C)));
   h.splitsA = std::max(1, std::min(tB, (2 * h.num_sms) / 4));
   h.smallC = h.dalloc<float>((size_t)C * tC * SMALL_STRIDE);

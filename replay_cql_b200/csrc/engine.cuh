@@ -83,7 +83,8 @@ struct Handle {
   float* dOutA = nullptr;    // [B][2]
   float* perb = nullptr;     // [B][4]: temp term, logp_pi, a_pi raw, -
   float* pairv = nullptr;    // [C][B] PairVals {lse_alpha, lse_critic, q_data, td_err}
-  float* loss_sums = nullptr;  // [8] reduced sums / conservative coefficient
+  float* loss_sums = nullptr;  // [16] reduced sums / conservative coefficient; [14], [15] = block tickets (k_actor_dout, k_lse)
+  float* actor_part = nullptr; // [ceil(B / 128) * 4] warp sums of the actor-loss metric (k_actor_dout)
   float* smallC = nullptr;   // [C][tilesC][SMALL_STRIDE]
   float* smallA = nullptr;   // [tilesB][SMALL_STRIDE]
   float* pw2C = nullptr;     // [C][splitsC][H*H]

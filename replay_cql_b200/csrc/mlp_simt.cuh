@@ -214,6 +214,10 @@ struct BwdJob {
   float4* dX;           // [n_nets][rows] or nullptr
   float* pw2;           // [n_nets][splits][H*H] partial dW2 (bwd2)
   int rows, n_nets, splits;
+  // f16x3 dx-only launch of the actor step: dOut is taken from the forward's partial sums (tc::Bwd1Job::q_part)
+  const float* q_part = nullptr;
+  int q_parts = 0;
+  float dq_scale = 0.f;
 };
 
 // dZ2^T tile into As[jl*stride + r] for j in [j_begin, j_begin+j_count); optional small grads.

@@ -20,7 +20,35 @@ struct Bwd1Job {
   float* small1;          // [n_nets][slots][SMALL_STRIDE]: only W1 | b1 entries written; slots = 4*gridDim.x, zeroed by caller
   float4* dX_part;        // [n_nets][SLICES][rows] or nullptr
   int rows, n_nets, slots;
+  // dx-only launch of the actor step (f16x3): dOut = d(actor loss)/dQ through the min over the critics, taken by the
+  // producers themselves from the forward's layer-3 partial sums -- the former one-CTA k_actor_dq launch (4 us on the
+  // critical path).  q_parts > 0 switches it on (OUT == 1); the sums are added in q_at()'s order.
+  const float* q_part = nullptr;   // [n_nets][q_parts][rows]
+  int q_parts = 0;
+  float dq_scale = 0.f;            // -1 / B
 };
+// d(actor loss)/dQ of row r for network net_i: dq_scale on the critic with the smallest Q (first one on ties), else 0
+template <int IN, int OUT>
+__device__ __forceinline__ float actor_dq_of(const Bwd1Job& jb, int net_i, int r) {
+  // (a critic's parts and bias are requested before the first addition: one L2 round trip per critic, not per part)
+  constexpr int MAXP = 8;
+  int arg = 0;
+  float qm = 0.f;
+  for (int c = 0; c < jb.n_nets; ++c) {
+    float part[MAXP];
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p)
+      if (p < jb.q_parts) part[p] = __ldg(jb.q_part + ((size_t)c * jb.q_parts + p) * jb.rows + r);
+    const float bias = __ldg(jb.params + (size_t)c * NET_STRIDE + off_b3(IN, OUT));
+    float v = 0.f;
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p)
+      if (p < jb.q_parts) v += part[p];
+    const float q = v + bias;
+    if (c == 0 || q < qm) { qm = q; arg = c; }
+  }
+  return net_i == arg ? jb.dq_scale : 0.f;
+}
 
 // after the call lane l holds sum over the warp's 32 lanes of v[l]
 __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32]) {

@@ -569,7 +569,9 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
       }
       const int r = tile * TM + (warp & 3) * 32 + lane;
       const bool ok = r < jb.rows;
-      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT) : 0.f;
+      float d0 = 0.f;
+      if (OUT == 1 && DX && !WGRADS && jb.q_parts > 0) { if (ok) d0 = actor_dq_of<IN, OUT>(jb, net_i, r); }
+      else if (ok) d0 = __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT);
       const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + r) * OUT + 1) : 0.f;
       float sa, inv_sa;
       pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);
@@ -674,7 +676,9 @@ __global__ void __launch_bounds__(HCfg::THREADS, 1) tc_bwd1_h_kernel(const Bwd1J
       const int row = tile * TM + qw * 32 + lane;
       const bool ok = row < jb.rows;
       const float4 x = ok ? __ldg(jb.X + row) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float d0 = ok ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT) : 0.f;
+      float d0 = 0.f;
+      if (OUT == 1 && DX && !WGRADS && jb.q_parts > 0) { if (ok) d0 = actor_dq_of<IN, OUT>(jb, net_i, row); }
+      else if (ok) d0 = __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT);
       const float d1 = (ok && OUT == 2) ? __ldg(jb.dOut + ((size_t)net_i * jb.rows + row) * OUT + 1) : 0.f;
       float sa, inv_sa;
       pow2_scale(fmaf(fabsf(d0), w3m0, fabsf(d1) * w3m1), sa, inv_sa);     // the producers' scale of this row

@@ -211,11 +211,22 @@ struct QSrc {
   const float* params;     // first net slot (b3), used when n_parts > 0
   int n_parts, rows, in_dim, out_dim;
 };
+// (all parts and the bias are REQUESTED before the first addition: a `v += q[p]` loop with a run-time trip count walks
+// through n_parts dependent L2 round trips -- the top stall sites of k_lse and k_prep in the r02 ncu capture; the order
+// of the additions is unchanged)
+constexpr int Q_MAX_PARTS = 8;
 __device__ __forceinline__ float q_at(const QSrc& s, int net, int r, int o = 0) {
   if (s.n_parts == 0) return s.q[((size_t)net * s.rows + r) * s.out_dim + o];
+  float part[Q_MAX_PARTS];
+#pragma unroll
+  for (int p = 0; p < Q_MAX_PARTS; ++p)
+    if (p < s.n_parts) part[p] = s.q[(((size_t)net * s.n_parts + p) * s.rows + r) * s.out_dim + o];
+  const float bias = s.params[(size_t)net * NET_STRIDE + off_b3(s.in_dim, s.out_dim) + o];
   float v = 0.f;
-  for (int p = 0; p < s.n_parts; ++p) v += s.q[(((size_t)net * s.n_parts + p) * s.rows + r) * s.out_dim + o];
-  return v + s.params[(size_t)net * NET_STRIDE + off_b3(s.in_dim, s.out_dim) + o];
+#pragma unroll
+  for (int p = 0; p < Q_MAX_PARTS; ++p)
+    if (p < s.n_parts) v += part[p];
+  return v + bias;
 }
 
 __global__ void k_actor_rows(const float4* __restrict__ batch, int B, float4* __restrict__ XA) {
@@ -351,74 +362,113 @@ __device__ __forceinline__ float warp_lse_v(float v, int cnt, int lane, float& m
   return m + logf(s);
 }
 
+struct ScalarReduceArgs {
+  const float4* perb; const float* scalars; const float* sc_m; const float* sc_v;
+  float* g_scalars; float* sums; float* metrics; unsigned int* ticket;
+  DpPeer dp;
+};
+__device__ void scalar_reduce_tail(const PairVals* __restrict__ pairv, const LossConsts& k, const ScalarReduceArgs& a);
+
 __global__ void __launch_bounds__(256) k_lse(const float4* __restrict__ batch, const QSrc srcAl,
                                              const float* __restrict__ offAl, const QSrc srcC,
                                              const float* __restrict__ offC, const QSrc srcT, LossConsts k,
-                                             float* __restrict__ dQ, PairVals* __restrict__ pairv) {
+                                             float* __restrict__ dQ, PairVals* __restrict__ pairv, const ScalarReduceArgs ra) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
 
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (p >= k.C * k.B) return;
-  const int c = p / k.B, b = p % k.B;
-  const int n3 = 3 * k.n, rsC = n3 + 1;
-  float m, w;
-  PairVals pv;
-  const float va = lane < n3 ? q_at(srcAl, c, b * n3 + lane) - offAl[(int64_t)b * n3 + lane] : 0.f;
-  pv.lse_a = warp_lse_v(va, n3, lane, m, w);
-  const float qc = lane < rsC ? q_at(srcC, c, b * rsC + lane) : 0.f;       // lane n3 = the data row (s, a)
-  const float vc = lane < n3 ? qc - offC[(int64_t)b * rsC + lane] : 0.f;
-  pv.lse_c = warp_lse_v(vc, n3, lane, m, w);
-  if (lane < n3) dQ[((int64_t)c * k.B + b) * rsC + lane] = w;
-  const float qd = __shfl_sync(0xffffffffu, qc, n3 & 31);
-  if (lane == 0) {
-    float qt = q_at(srcT, 0, b);
-    for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, q_at(srcT, c2, b));
-    const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
-    const float y = r0.w + k.gamma * qt * (1.f - r1.z);
-    pv.qd = qd;
-    pv.err = pv.qd - y;
-    pairv[p] = pv;
+  if (p < k.C * k.B) {
+    const int c = p / k.B, b = p % k.B;
+    const int n3 = 3 * k.n, rsC = n3 + 1;
+    float m, w;
+    PairVals pv;
+    const float va = lane < n3 ? q_at(srcAl, c, b * n3 + lane) - offAl[(int64_t)b * n3 + lane] : 0.f;
+    pv.lse_a = warp_lse_v(va, n3, lane, m, w);
+    const float qc = lane < rsC ? q_at(srcC, c, b * rsC + lane) : 0.f;       // lane n3 = the data row (s, a)
+    const float vc = lane < n3 ? qc - offC[(int64_t)b * rsC + lane] : 0.f;
+    pv.lse_c = warp_lse_v(vc, n3, lane, m, w);
+    if (lane < n3) dQ[((int64_t)c * k.B + b) * rsC + lane] = w;
+    const float qd = __shfl_sync(0xffffffffu, qc, n3 & 31);
+    if (lane == 0) {
+      float qt = q_at(srcT, 0, b);
+      for (int c2 = 1; c2 < k.C; ++c2) qt = fminf(qt, q_at(srcT, c2, b));
+      const float4 r0 = batch[2 * b], r1 = batch[2 * b + 1];
+      const float y = r0.w + k.gamma * qt * (1.f - r1.z);
+      pv.qd = qd;
+      pv.err = pv.qd - y;
+      pairv[p] = pv;
+    }
   }
+  // The block that finishes LAST sums the pair values (what the one-CTA k_scalar_reduce launch did: one launch boundary
+  // less on the critical path, 3.4 us per update by the r02 skip test) -- in exactly that kernel's order.
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ra.ticket, 1u);
+    last = t == gridDim.x - 1;
+    if (last) *ra.ticket = 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  scalar_reduce_tail(pairv, k, ra);
 }
 
-// sums[0]=sum td err^2  [1]=sum lse_c  [2]=sum qd
-__global__ void __launch_bounds__(1024) k_scalar_reduce(const float4* __restrict__ perb, const PairVals* __restrict__ pairv,
-                                                        const float* __restrict__ scalars, const float* __restrict__ sc_m,
-                                                        const float* __restrict__ sc_v, LossConsts k,
-                                                        float* __restrict__ g_scalars, float* __restrict__ sums,
-                                                        float* __restrict__ metrics, const DpPeer dp, long long dp_off) {
-  tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
- 
-  __shared__ float red[32];
-  float st = 0.f;
-  for (int b = threadIdx.x; b < k.B; b += 1024) st += perb[b].x;
-  st = block_sum<1024>(st, red);
-  float sa = 0.f, sc = 0.f, sd = 0.f, se = 0.f;
-  for (int p = threadIdx.x; p < k.C * k.B; p += 1024) {
-    const PairVals pv = pairv[p];
-    sa += pv.lse_a; sc += pv.lse_c; sd += pv.qd; se += pv.err * pv.err;
+// sums[0]=sum td err^2  [1]=sum lse_c  [2]=sum qd.  Runs in ONE block of 256 threads; every thread stands for four
+// threads t, t + 256, t + 512, t + 768 of the former 1024-thread launch and the partial sums are combined in that launch's
+// order (lanes, then the 32 warp sums), so the results are bit-identical to it.
+__device__ __forceinline__ float block_sum_as_1024(const float (&v)[4], float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float w = warp_sum(v[j]);
+    if (lane == 0) red[warp + 8 * j] = w;
   }
-  sa = block_sum<1024>(sa, red);
-  sc = block_sum<1024>(sc, red);
-  sd = block_sum<1024>(sd, red);
-  se = block_sum<1024>(se, red);
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0) {
+    t = warp_sum(red[lane]);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ void scalar_reduce_tail(const PairVals* __restrict__ pairv, const LossConsts& k, const ScalarReduceArgs& a) {
+  __shared__ float red[33];
+  float st[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    for (int b = threadIdx.x + 256 * j; b < k.B; b += 1024) st[j] += a.perb[b].x;
+  const float s_t = block_sum_as_1024(st, red);
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f}, se[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    for (int p = threadIdx.x + 256 * j; p < k.C * k.B; p += 1024) {
+      const PairVals pv = pairv[p];
+      sa[j] += pv.lse_a; sc[j] += pv.lse_c; sd[j] += pv.qd; se[j] += pv.err * pv.err;
+    }
+  const float s_a = block_sum_as_1024(sa, red);
+  const float s_c = block_sum_as_1024(sc, red);
+  const float s_d = block_sum_as_1024(sd, red);
+  const float s_e = block_sum_as_1024(se, red);
   if (threadIdx.x == 0) {
-    const float lt = scalars[0], la = scalars[1];
-    const float temp_loss = -expf(lt) * (st / (float)k.B);
+    const float lt = a.scalars[0], la = a.scalars[1];
+    const float temp_loss = -expf(lt) * (s_t / (float)k.B);
     const float inv = 1.f / ((float)k.C * (float)k.B);
-    const float raw = sa * inv - sd * inv;
+    const float raw = s_a * inv - s_d * inv;
     const float e = expf(la), clipped = fminf(fmaxf(e, 0.f), 1e6f);
     const float alpha_loss = -clipped * (k.cw * raw - k.thr);
-    g_scalars[0] = temp_loss;                 // d/d log_temp of -exp(lt)*mean = the loss itself
-    g_scalars[1] = e <= 1e6f ? alpha_loss : 0.f;
-    metrics[0] = temp_loss;
-    metrics[2] = alpha_loss;
-    sums[0] = se; sums[1] = sc; sums[2] = sd;
+    a.g_scalars[0] = temp_loss;                 // d/d log_temp of -exp(lt)*mean = the loss itself
+    a.g_scalars[1] = e <= 1e6f ? alpha_loss : 0.f;
+    a.metrics[0] = temp_loss;
+    a.metrics[2] = alpha_loss;
+    a.sums[0] = s_e; a.sums[1] = s_c; a.sums[2] = s_d;
     // snapshot for k_scalar_adam_dq (every block of which recomputes the scalar Adam steps from these)
-    sums[8] = lt; sums[9] = la;
-    sums[10] = sc_m[0]; sums[11] = sc_v[0]; sums[12] = sc_m[1]; sums[13] = sc_v[1];
+    a.sums[8] = lt; a.sums[9] = la;
+    a.sums[10] = a.sc_m[0]; a.sums[11] = a.sc_v[0]; a.sums[12] = a.sc_m[1]; a.sums[13] = a.sc_v[1];
     // fused data-parallel exchange: the two scalar gradients travel inside the signal words (group 0)
-    if (dp.world > 1) dp_signal_scalars(dp, temp_loss, e <= 1e6f ? alpha_loss : 0.f);
+    if (a.dp.world > 1) dp_signal_scalars(a.dp, temp_loss, e <= 1e6f ? alpha_loss : 0.f);
   }
 }
 
@@ -500,12 +550,42 @@ __global__ void __launch_bounds__(1024) k_actor_dq(const QSrc srcP, const float4
 }
 
 // d actor_loss / d (mu, raw logstd): mirrors autograd through rsample, tanh, log-prob, clamp.
+// With srcP.q set (f16x3 path, where the dx-only bwd1 takes dQ itself) it also produces the actor-loss metric that the
+// one-CTA k_actor_dq launch used to: warp sums into part[], the block that finishes last adds them in that launch's order.
 __global__ void k_actor_dout(const float* __restrict__ outA, const float* __restrict__ noise_actor,
                              const float4* __restrict__ dXP, const float* __restrict__ scalars, int B, int n_parts,
-                             int squash, float* __restrict__ dOutA) {
+                             int squash, float* __restrict__ dOutA, const QSrc srcP, const float4* __restrict__ perb,
+                             int C, float* __restrict__ part, unsigned int* __restrict__ ticket, float* __restrict__ metrics) {
   tc::grid_dep_wait();   /* programmatic dependent launch: the predecessor's results are needed from here on */
  
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (srcP.q != nullptr) {
+    float v = 0.f;
+    if (b < B) {
+      float qm = q_at(srcP, 0, b);
+      for (int c = 1; c < C; ++c) qm = fminf(qm, q_at(srcP, c, b));
+      v = expf(scalars[0]) * perb[b].y - qm;
+    }
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) part[b >> 5] = v;
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(ticket, 1u);
+      last = t == gridDim.x - 1;
+      if (last) *ticket = 0;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+      __threadfence();
+      const int n_w = (gridDim.x * blockDim.x) >> 5;
+      float s = 0.f;
+      for (int i = threadIdx.x; i < n_w; i += 32) s += part[i];
+      s = warp_sum(s);
+      if (threadIdx.x == 0) metrics[5] = s / (float)B;
+    }
+  }
   if (b >= B) return;
   float da = 0.f;
   for (int c = 0; c < n_parts; ++c) da += dXP[(int64_t)c * B + b].z;   // parts = critics (x column slices)
@@ -798,6 +878,7 @@ inline void launch_bwd_tc(Handle* h, const BwdJob& jb, float* grads_out, cudaStr
   tc::Bwd1Job j1{jb.X, jb.dOut, jb.h2, jb.params,
                  pair ? h->packed_bwd2 + (size_t)slot * h->packed_net_bytes2 : h->packed_bwd + (size_t)slot * h->packed_net_bytes_bwd,
                  h->small1, DX ? h->dX_part : nullptr, jb.rows, jb.n_nets, slots1};
+  j1.q_part = jb.q_part; j1.q_parts = jb.q_parts; j1.dq_scale = jb.dq_scale;
   // bwd1 and bwd2 of one job are independent (both only read X, dOut, H2).  For the small jobs (the actor's B rows:
   // a few dozen CTAs each) they run side by side on a forked branch -- the fork/join is captured into the step graph.
   constexpr int RS2 = F16X3 ? tc::B2HCfg::RS : tc::B2Cfg<TF32>::RS;
@@ -895,7 +976,7 @@ inline void adam_pack(Handle* h, int first_slot, int n_nets, int in_dim, int out
     n.w2max = h->w2max + slot * 4;
   }
   if (!skip_launch(128))
-    launch_pdl(tc::k_adam_pack, dim3(tc::AP_W2_BLOCKS + 1, n_nets), dim3(256), 0, st, j, h->stepinfo);
+    launch_pdl(tc::k_adam_pack, dim3(tc::AP_W2_BLOCKS + 1, n_nets), dim3(1024), 0, st, j, h->stepinfo);
   CQL_LAUNCH_CHECK(h);
 }
 
@@ -994,17 +1075,13 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     // the reported duration is the kernel's steady-state launch-to-launch time, not one launch plus its launch latency
     for (int rep = 0; rep < (h->timing ? TIMED_FWD_REPS : 1); ++rep) launch_fwd_any<3, 1>(h, jobs, st, srcQ);
     mark(h, st, 4);
+    // (the last block of k_lse also sums the pair values and publishes the two scalar gradients: the former k_scalar_reduce)
+    const int64_t so = scalars_off(C);
+    ScalarReduceArgs ra{reinterpret_cast<const float4*>(h->perb), h->scalars(), h->adam_m + so, h->adam_v + so, h->g_scalars(),
+                        h->loss_sums, h->metrics, reinterpret_cast<unsigned int*>(h->loss_sums + 15), h->dp_fused ? h->dp : DpPeer{}};
     if (!skip_launch(2))
       launch_pdl(k_lse, dim3((C * B * 32 + 255) / 256), dim3(256), 0, st, batch4, srcQ[0], h->offAl, srcQ[1], h->offC, srcQ[2], loss_consts(h),
-               h->dQ, reinterpret_cast<PairVals*>(h->pairv));
-    CQL_LAUNCH_CHECK(h);
-  }
-  {
-    const int64_t so = scalars_off(C);
-    if (!skip_launch(4))
-      launch_pdl(k_scalar_reduce, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(h->perb), reinterpret_cast<const PairVals*>(h->pairv),
-               h->scalars(), h->adam_m + so, h->adam_v + so, loss_consts(h), h->g_scalars(), h->loss_sums, h->metrics,
-               h->dp_fused ? h->dp : DpPeer{}, (long long)(1 + C) * NET_STRIDE);
+               h->dQ, reinterpret_cast<PairVals*>(h->pairv), ra);
     CQL_LAUNCH_CHECK(h);
   }
 }
@@ -1054,6 +1131,8 @@ inline void phase2(Handle* h, cudaStream_t st) {
     for (int i = 0; i < C; ++i) { slots[i] = slot_critic(i); slots[C + i] = slot_targ_critic(C, i); }
     pack_slots(h, slots, 2 * C, st);
   }
+  bool fold_dq = false;
+  QSrc srcP_keep{};
   {
     FwdJobs jobs{};
     jobs.n = 1;
@@ -1062,13 +1141,18 @@ inline void phase2(Handle* h, cudaStream_t st) {
     QSrc srcP[1];
     launch_fwd_any<3, 1>(h, jobs, st, srcP);
     mark(h, st, 9);
-    if (!skip_launch(16))
-      launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, srcP[0], reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
-               h->metrics);
-    CQL_LAUNCH_CHECK(h);
+    fold_dq = h->cfg.precision == CQL_PREC_F16X3 && srcP[0].n_parts > 0;
+    srcP_keep = srcP[0];
+    if (!fold_dq) {        // (f16x3: the dx-only bwd1 below takes dQ from the partial sums itself, k_actor_dout the metric)
+      if (!skip_launch(16))
+        launch_pdl(k_actor_dq, dim3(1), dim3(1024), 0, st, srcP[0], reinterpret_cast<const float4*>(h->perb), h->scalars(), B, C, h->dQP,
+                 h->metrics);
+      CQL_LAUNCH_CHECK(h);
+    }
   }
   {
     BwdJob jb{h->XP, h->dQP, h->h2P, h->net_params(slot_critic(0)), nullptr, h->dXP, nullptr, B, C, 1};
+    if (fold_dq) { jb.q_part = srcP_keep.q; jb.q_parts = srcP_keep.n_parts; jb.dq_scale = -1.f / (float)B; }
     if (h->cfg.precision == CQL_PREC_F16X3) launch_bwd_tc<true, 3, 1, false, true, true>(h, jb, nullptr, st);
     else if (h->cfg.precision == CQL_PREC_TF32X3) launch_bwd_tc<true, 3, 1, false, true>(h, jb, nullptr, st);
     else if (h->cfg.precision == CQL_PREC_BF16) launch_bwd_tc<false, 3, 1, false, true>(h, jb, nullptr, st);
@@ -1078,7 +1162,9 @@ inline void phase2(Handle* h, cudaStream_t st) {
   if (!skip_launch(32))
     launch_pdl(k_actor_dout, dim3((B + 127) / 128), dim3(128), 0, st, h->outA, h->noise + B + 6 * (int64_t)B * h->n,
                                                 tcm ? h->dX_part : h->dXP, h->scalars(), B,
-                                                tcm ? h->last_dx_parts : C, c.squash, h->dOutA);
+                                                tcm ? h->last_dx_parts : C, c.squash, h->dOutA,
+                                                fold_dq ? srcP_keep : QSrc{}, reinterpret_cast<const float4*>(h->perb), C,
+                                                h->actor_part, reinterpret_cast<unsigned int*>(h->loss_sums + 14), h->metrics);
   CQL_LAUNCH_CHECK(h);
   BwdJob ja{h->XA, h->dOutA, h->h2A, h->net_params(slot_actor()), h->smallA, nullptr, h->pw2A, B, 1, h->splitsA};
   mark(h, st, 10);
