@@ -40,10 +40,11 @@ DTYPES = {"fp32": "f32", "tf32x3": "f32 (tf32x3: tensor-core 3-term split, fp32 
           "f16x3": "f32 (f16x3: tensor-core fp16 hi/lo 3-term split with exact power-of-two row scales, fp32 accumulate, 1e-4 parity-gated)",
           "bf16": "bf16 (fp32 accumulate; non-parity variant)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from one `ncu --set full` capture
-# (profiles/r01_tc_fwd_ts_ncu_summary.txt, profiles/r01_f16x3_fwd_h_ncu_summary.txt); null where no capture exists for that variant
-KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": 2.136832e6 + 15.324416e6, "bf16": None}
+# (profiles/r01_tc_fwd_ts_ncu_summary.txt, profiles/r02_big3_ncu_summary.txt); null where no capture exists for that variant
+KERNEL_TRAFFIC = {"fp32": None, "tf32x3": 3.226112e6 + 11.174144e6, "f16x3": 2.134784e6 + 16.243456e6, "bf16": None}
 TRAFFIC_SOURCE = {"fp32": None, "tf32x3": "ncu --set full capture profiles/r01_tc_fwd_ts_ncu_summary.txt (not measured in this run)",
-                  "f16x3": "ncu --set full capture profiles/r02_pair_fwd_ncu_summary.txt (not measured in this run)", "bf16": None}
+                  "f16x3": "ncu --set full capture profiles/r02_big3_ncu_summary.txt: tc_fwd_h2_kernel<3,1> dram read 2.13 MB + write 16.24 MB "
+                           "(not measured in this run; algorithmic: 2.0 MB of input rows + 65 MB of stored H2, most of which stays in L2)", "bf16": None}
 KERNEL_NAMES = {"fp32": "mlp_fwd_kernel<3,1> (critic forward, FP32 CUDA-core path)",
                 "tf32x3": "tc_fwd_ts_kernel<3,1> (critic forward: tcgen05 kind::tf32 3-term split, A operand in TMEM)",
                 "f16x3": "tc_fwd_h2_kernel<3,1> (critic forward on CTA pairs: tcgen05 cta_group::2 kind::f16, fp16 hi/lo 3-term split, A operand in TMEM)",
@@ -482,7 +483,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2: 640 MB replay table, fresh random gather every step; "
                              "weights/activations are the step-to-step state of the algorithm"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": BATCH * 32,
-                    "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batches (host minibatches in, per-step metrics out; copies and steps pipelined by the library)" if stepper is None else
+                    "d2h_bytes_per_step": 32, "steps": n_e2e, "api": "cql_update_batches (host minibatches in, per-step metrics out; every step's H2D and D2H copies ride on the library's own copy streams while the previous step computes)" if stepper is None else
                            "cql_upload_batch + the data-parallel step as one CUDA graph (cql_step_phase x4 with the gradient exchange between phases) + metrics D2H"},
             "gpu_launches": int(launches),
             "clocks": clk,

@@ -38,7 +38,11 @@ def table(seg):
 def main(path):
     launches = load(path)
     heads = [i for i, (n, _) in enumerate(launches) if "k_step_head" in n]
-    seg = launches[heads[-2]:heads[-1]]
+    # a regular (graph-replayed) update: exactly one big critic forward -- cql_timed_update's steps launch it four times
+    # and run bwd1 / bwd2 back to back on full grids, so they are not the product schedule
+    segs = [launches[a:b] for a, b in zip(heads[:-1], heads[1:])]
+    regular = [g for g in segs if sum("tc_fwd_h2_kernel<3, 1>" in n for n, _ in g) == 1]
+    seg = (regular or segs)[-1]
     tot, rows = table(seg)
     print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 1 --no-cpu  (precision f16x3, default)")
     print(f"# raw list: {path}.  Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.")

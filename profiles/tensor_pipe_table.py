@@ -33,7 +33,11 @@ def load(path):
 def main(path):
     L = load(path)
     heads = [i for i, d in enumerate(L) if "k_step_head" in d["name"]]
-    seg = L[heads[-2]:heads[-1]]
+    # a regular (graph-replayed) update: exactly one big critic forward -- cql_timed_update's steps launch it four times
+    # and run bwd1 / bwd2 back to back on full grids, so they are not the product schedule
+    segs = [L[a:b] for a, b in zip(heads[:-1], heads[1:])]
+    regular = [g for g in segs if sum("tc_fwd_h2_kernel<3, 1>" in d["name"] for d in g) == 1]
+    seg = (regular or segs)[-1]
     tot = sum(d[T] for d in seg)
     tc = [d for d in seg if d.get(P, 0) > 0.5]
     t_tc = sum(d[T] for d in tc)
@@ -49,6 +53,8 @@ def main(path):
     print()
     print(f"{len(seg)} launches, {tot:.1f} us under ncu; {len(tc)} tcgen05 launches, {t_tc:.1f} us")
     print(f"tensor pipe, time-weighted over the tcgen05 launches: {w:.1f} % of active cycles")
+    print("note: in the product schedule the critic's bwd1 (60 CTAs) and bwd2 (88 CTAs) run SIDE BY SIDE on disjoint SMs, and so do")
+    print("      the actor's bwd1 / bwd2; ncu serialises them.  'tensor pipe' is % of the ACTIVE cycles of the SMs a launch occupies.")
     print(f"tensor pipe, time-weighted over the three big launches ({', '.join(d['name'].split('::')[-1][:16] for d in big)}): {wb:.1f} %")
 
 
