@@ -173,6 +173,16 @@ enum { CQL_BUF_SCALAR_GRADS = 0,   /* 64 floats: [0]=d log_temp [1]=d log_alpha 
        CQL_BUF_ALL_GRADS = 5 };    /* (1+C)*NET+64 floats: [actor | critics | scalars] */
 int  cql_device_buffer(cql_handle* h, int which, void** dev_ptr, int64_t* n_floats);
 
+/* Seen-items CSR of an interaction log, built on the device -- the structure the scorer's lazy seen filter searches
+ * (replaces the host-side joins of `_filter_seen`, replay/models/base_rec.py:417-464, for the GPU path).
+ * users_host / items_host [n] int32: the log's id columns in any order, duplicates allowed (host memory);
+ * wanted_host [n_users_dim] uint8 or NULL: keep only rows of users whose flag is non-zero;
+ * indptr_dev [n_users_dim + 1] int64 and seen_dev [>= n] int32: device buffers of the caller; on return user u's
+ * de-duplicated items, ascending, are seen_dev[indptr_dev[u] .. indptr_dev[u + 1]); *n_seen_out = entries written.
+ * Two column uploads, one radix sort over the significant key bits, one unique pass, one emit pass; synchronises. */
+int  cql_seen_csr(cql_handle* h, const int32_t* users_host, const int32_t* items_host, int64_t n, int64_t n_users_dim,
+                  const uint8_t* wanted_host, int64_t* indptr_dev, int32_t* seen_dev, int64_t* n_seen_out, void* stream);
+
 /* Data-parallel gradient exchange over NVLink peer memory instead of a collective library call.
  * cql_dp_attach: stage_ptrs[world] / signal_ptrs[world] are every rank's symmetric, zero-initialised staging buffer
  *   (buffer_floats floats: >= 2 x stage_floats, stage_floats >= the CQL_BUF_ALL_GRADS size; with another

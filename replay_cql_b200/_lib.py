@@ -63,6 +63,7 @@ SIGNATURES = {
     "cql_update_batches": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "cql_step_phase": (C.c_int, [_P, C.c_int, _P]),
     "cql_upload_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "cql_seen_csr": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "cql_dp_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int64]),
     "cql_dp_allreduce": (C.c_int, [_P, C.c_int, _P]),
     "cql_dp_error": (C.c_int, [_P, _P]),

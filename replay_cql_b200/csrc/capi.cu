@@ -559,6 +559,17 @@ int cql_build_mdp(cql_handle* ch, const int32_t* user_idx, const int32_t* item_i
   });
 }
 
+int cql_seen_csr(cql_handle* ch, const int32_t* users_host, const int32_t* items_host, int64_t n, int64_t n_users_dim,
+                 const uint8_t* wanted_host, int64_t* indptr_dev, int32_t* seen_dev, int64_t* n_seen_out, void* stream) {
+  return guarded(ch, [&] {
+    NvtxRange nvtx("cql_seen_csr");
+    CQL_REQUIRE(n_seen_out != nullptr, "cql_seen_csr: n_seen_out is NULL");
+    cudaStream_t st = pick_stream(&ch->h, stream);
+    *n_seen_out = seen_csr_on_device(ch->h, users_host, items_host, n, n_users_dim, wanted_host, indptr_dev, seen_dev, st);
+    ch->h.launches += 4;
+  });
+}
+
 int cql_sample_rows(cql_handle* ch, const int64_t* idx_dev, int64_t pos, int64_t count, float* out_dev, void* stream) {
   return guarded(ch, [&] {
     Handle& h = ch->h;

@@ -26,6 +26,9 @@ struct NvtxRange {
 };
 
 struct MdpSession;                   // chunked ingestion session (mdp_gpu.cu)
+// seen-items CSR of a log on the device (mdp_gpu.cu); returns the number of (user, item) entries written
+int64_t seen_csr_on_device(struct Handle& h, const int32_t* users_h, const int32_t* items_h, int64_t n, int64_t n_users,
+                           const uint8_t* wanted_h, int64_t* indptr_d, int32_t* seen_d, cudaStream_t st);
 void mdp_session_free(MdpSession*);
 
 struct Handle {

@@ -337,3 +337,86 @@ int64_t mdp_build_on_device(Handle& h, const int32_t* user_h, const int32_t* ite
     throw;
   }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Seen-items CSR of an interaction log, built on the device (the data the lazy seen filter of the scorer searches;
+// reference: the joins inside `_filter_seen`, replay/models/base_rec.py:417-464).  Host: one 64-bit key per log row +
+// an introsort of 2e7 keys + masks = 1.1 s for the ML-20M shape; here: two column uploads, one LSD radix sort over the
+// significant bits, one unique pass, one emit pass.
+namespace {
+__global__ void k_seen_keys(const int32_t* __restrict__ user, const int32_t* __restrict__ item, const uint8_t* __restrict__ wanted,
+                            int64_t n, int64_t n_users, unsigned long long* __restrict__ key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t u = user[i];
+  const bool keep = u >= 0 && u < n_users && (wanted == nullptr || wanted[u] != 0);
+  key[i] = keep ? ((unsigned long long)u << 32) | (unsigned int)item[i] : (unsigned long long)n_users << 32;   // dropped rows sort last
+}
+// unique, sorted keys -> seen items + CSR row pointers (a thread fills the pointers of the users between its
+// predecessor's user and its own: users without rows get empty ranges)
+__global__ void k_seen_emit(const unsigned long long* __restrict__ key, int64_t num, int64_t n_users,
+                            int32_t* __restrict__ seen, int64_t* __restrict__ indptr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  const int64_t u = (int64_t)(key[i] >> 32), prev = i == 0 ? -1 : (int64_t)(key[i - 1] >> 32);
+  if (u < n_users) seen[i] = (int32_t)(key[i] & 0xffffffffull);
+  for (int64_t x = prev + 1; x <= (u < n_users ? u : n_users); ++x) indptr[x] = i;
+  if (i == num - 1 && u < n_users)
+    for (int64_t x = u + 1; x <= n_users; ++x) indptr[x] = num;
+}
+struct DevTmp {               // device scratch freed on every exit path
+  std::vector<void*> p;
+  ~DevTmp() { for (void* x : p) cudaFree(x); }
+  template <typename T>
+  T* get(size_t count) {
+    void* q = nullptr;
+    CQL_CUDA(cudaMalloc(&q, count * sizeof(T)));
+    p.push_back(q);
+    return (T*)q;
+  }
+};
+}  // namespace
+
+int64_t cql::seen_csr_on_device(Handle& h, const int32_t* users_h, const int32_t* items_h, int64_t n, int64_t n_users,
+                                const uint8_t* wanted_h, int64_t* indptr_d, int32_t* seen_d, cudaStream_t st) {
+  CQL_REQUIRE(n >= 0 && n_users >= 1 && n_users < (1ll << 31), "cql_seen_csr: bad sizes");
+  CQL_REQUIRE(indptr_d != nullptr && (n == 0 || (users_h && items_h && seen_d)), "cql_seen_csr: NULL pointer");
+  if (n == 0) {
+    CQL_CUDA(cudaMemsetAsync(indptr_d, 0, (size_t)(n_users + 1) * sizeof(int64_t), st));
+    CQL_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  DevTmp tmp;
+  int32_t* u_d = tmp.get<int32_t>(n);
+  int32_t* i_d = tmp.get<int32_t>(n);
+  unsigned long long* k0 = tmp.get<unsigned long long>(n);
+  unsigned long long* k1 = tmp.get<unsigned long long>(n);
+  int64_t* num_d = tmp.get<int64_t>(1);
+  uint8_t* w_d = nullptr;
+  CQL_CUDA(cudaMemcpyAsync(u_d, users_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CQL_CUDA(cudaMemcpyAsync(i_d, items_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  if (wanted_h) {
+    w_d = tmp.get<uint8_t>(n_users);
+    CQL_CUDA(cudaMemcpyAsync(w_d, wanted_h, (size_t)n_users, cudaMemcpyHostToDevice, st));
+  }
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  k_seen_keys<<<blocks, 256, 0, st>>>(u_d, i_d, w_d, n, n_users, k0);
+  int ubits = 1;
+  while ((1ll << ubits) <= n_users) ++ubits;                    // user ids 0 .. n_users (n_users = the dropped rows)
+  size_t sort_bytes = 0, uniq_bytes = 0;
+  CQL_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, k0, k1, n, 0, 32 + ubits, st));
+  CQL_CUDA(cub::DeviceSelect::Unique(nullptr, uniq_bytes, k1, k0, num_d, n, st));
+  uint8_t* cub_tmp = tmp.get<uint8_t>(std::max(sort_bytes, uniq_bytes) + 16);
+  CQL_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, sort_bytes, k0, k1, n, 0, 32 + ubits, st));
+  CQL_CUDA(cub::DeviceSelect::Unique(cub_tmp, uniq_bytes, k1, k0, num_d, n, st));
+  int64_t num = 0;
+  CQL_CUDA(cudaMemcpyAsync(&num, num_d, sizeof(num), cudaMemcpyDeviceToHost, st));
+  CQL_CUDA(cudaStreamSynchronize(st));
+  k_seen_emit<<<(unsigned)((num + 255) / 256), 256, 0, st>>>(k0, num, n_users, seen_d, indptr_d);
+  int64_t n_seen = 0;
+  CQL_CUDA(cudaMemcpyAsync(&n_seen, indptr_d + n_users, sizeof(n_seen), cudaMemcpyDeviceToHost, st));
+  CQL_CUDA(cudaStreamSynchronize(st));
+  CQL_CUDA(cudaGetLastError());
+  return n_seen;
+}

@@ -479,6 +479,31 @@ class CqlEngine:
                                                  p(out_items), p(out_scores), stream), "cql_score_topk_dev")
         return out_items, out_scores
 
+    def seen_csr_device(self, log_users, log_items, n_users_dim: int, wanted=None, stream: int | None = None):
+        """Seen-items CSR of a log built on the device (``cql_seen_csr``): int32 id columns (host, any order, duplicates
+        allowed) -> (indptr int64 [n_users_dim + 1], seen int32 [n_seen]) as cuda tensors, per user ascending and
+        de-duplicated.  ``wanted``: bool / uint8 mask over user ids -- only those users' rows are kept."""
+        import torch
+        lu = np.ascontiguousarray(log_users, dtype=np.int32).reshape(-1)
+        li = np.ascontiguousarray(log_items, dtype=np.int32).reshape(-1)
+        if lu.size != li.size:
+            raise ValueError("log_users and log_items must have the same length")
+        dev = torch.device("cuda", self.device)
+        indptr = torch.empty(int(n_users_dim) + 1, dtype=torch.int64, device=dev)
+        seen = torch.empty(max(1, lu.size), dtype=torch.int32, device=dev)
+        w = None
+        if wanted is not None:
+            w = np.ascontiguousarray(wanted, dtype=np.uint8).reshape(-1)
+            if w.size < int(n_users_dim):
+                w = np.concatenate([w, np.zeros(int(n_users_dim) - w.size, dtype=np.uint8)])
+        n_seen = C.c_int64(0)
+        stream = self._torch_stream(stream)
+        self._check(self._lib.cql_seen_csr(self._h, _ptr(lu) if lu.size else None, _ptr(li) if li.size else None, lu.size,
+                                           int(n_users_dim), _ptr(w) if w is not None else None,
+                                           C.c_void_p(indptr.data_ptr()), C.c_void_p(seen.data_ptr()), C.byref(n_seen), stream),
+                    "cql_seen_csr")
+        return indptr, seen[: n_seen.value]
+
     def topk_filter_device(self, scores_t, k: int, users_t=None, items_t=None, seen_indptr_t=None,
                            seen_items_t=None, stream: int | None = None):
         """Stand-alone top-k + lazy seen filter over a materialised cuda score matrix [U, I]."""

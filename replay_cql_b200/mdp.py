@@ -109,7 +109,10 @@ def seen_csr(log: Any, n_users_dim: int):
     item = pdf["item_idx"].to_numpy().astype(np.int64)
     if user.size:
         n_users_dim = max(n_users_dim, int(user.max()) + 1)
-    key = np.unique(user * (2 ** 32) + item)
+    key = user * (2 ** 32) + item
+    key.sort()                                  # (sort + neighbour mask: numpy's hash-based unique is ~4x slower on 1e6..2e7 keys)
+    if key.size:
+        key = key[np.concatenate(([True], key[1:] != key[:-1]))]
     u, i = key >> 32, (key & 0xFFFFFFFF).astype(np.int32)
     counts = np.bincount(u, minlength=n_users_dim)
     indptr = np.zeros(n_users_dim + 1, dtype=np.int64)

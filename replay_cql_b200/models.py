@@ -34,6 +34,7 @@ class CQL(Recommender):
     can_predict_cold_users = False
     can_predict_cold_items = False
     accepts_arrow = True          # `_fit` ingests a pyarrow.Table chunk by chunk (mdp.ingest_log): no frame conversion
+    _predict_filters_seen = True  # `_predict` returns at most k UNSEEN items per user: the template's generic pass is skipped
 
     _search_space = {
         "actor_learning_rate": {"type": "loguniform", "args": [1e-5, 1e-3]},
@@ -272,11 +273,28 @@ class CQL(Recommender):
         lo, hi = shard_range(u.size, rank, world)
         u_local = u[lo:hi]
         indptr = seen = None
-        if filter_seen_items and log is not None and len(log):
-            sub = log[log["user_idx"].isin(u_local)] if u_local.size else log.iloc[:0]
-            indptr, seen = seen_csr(sub, int(u.max()) + 1)
         kk = min(int(k), int(it.size))
-        top_i, top_s = self._score_topk_any_k(u_local, it, kk, indptr, seen, int(u.max()) + 1)
+        from . import _lib
+        on_device = kk <= _lib.MAX_TOPK and u_local.size > 0 and hasattr(self.engine, "seen_csr_device")
+        n_dim = int(u.max()) + 1
+        if filter_seen_items and log is not None and len(log):
+            wanted = np.zeros(n_dim, dtype=np.uint8)     # rows of the requested users: a table lookup, not isin()'s sort
+            wanted[u_local] = 1
+            if on_device:
+                # the seen CSR is built on the GPU from the log's id columns (cql_seen_csr) and never exists on the host
+                indptr, seen = self.engine.seen_csr_device(log["user_idx"].to_numpy(), log["item_idx"].to_numpy(), n_dim, wanted)
+            else:
+                lu = log["user_idx"].to_numpy()
+                keep = (lu < n_dim) & (wanted[np.minimum(lu, n_dim - 1)] != 0)
+                indptr, seen = seen_csr(log if keep.all() else log[keep], n_dim)
+        if on_device:
+            import torch
+            dev = torch.device("cuda", self.engine.device)
+            ti, ts = self.engine.score_topk_device(torch.from_numpy(u_local).to(dev), torch.from_numpy(it).to(dev), kk,
+                                                   indptr, seen, mode=self.score)
+            top_i, top_s = ti.cpu().numpy(), ts.cpu().numpy()
+        else:
+            top_i, top_s = self._score_topk_any_k(u_local, it, kk, indptr, seen, n_dim)
         rows_u = np.repeat(u_local, kk).reshape(-1, 1)
         packed = np.concatenate([rows_u.astype(np.float64), top_i.reshape(-1, 1).astype(np.float64),
                                  top_s.reshape(-1, 1).astype(np.float64)], axis=1)

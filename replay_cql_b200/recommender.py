@@ -399,13 +399,35 @@ class Recommender(ABC):
         if len(items_df) < k:
             self.logger.debug("k = %d > number of items = %d", k, len(items_df))
         recs = self._predict(log_pdf, k, users_df, items_df, user_features, item_features, filter_seen_items)
-        if filter_seen_items and log_pdf is not None:
+        # (a model whose `_predict` already returns at most k UNSEEN items per user -- CQL's fused scorer -- declares it:
+        #  the generic pass would sort the whole log again to drop nothing)
+        if filter_seen_items and log_pdf is not None and not getattr(self, "_predict_filters_seen", False):
             recs = self._filter_seen(recs=recs, log=log_pdf, users=users_df, k=k)
-        recs = get_top_k_recs(recs, k)[REC_COLUMNS].reset_index(drop=True)
+        if getattr(self, "_predict_filters_seen", False) and self._is_top_k(recs, k):
+            recs = recs[REC_COLUMNS].reset_index(drop=True)       # already the k best per user, best first: nothing to rank
+        else:
+            recs = get_top_k_recs(recs, k)[REC_COLUMNS].reset_index(drop=True)
         if recs_file_path is not None:
             recs.to_parquet(recs_file_path, index=False)
             return None
         return like_input(recs, template)
+
+    @staticmethod
+    def _is_top_k(recs: pd.DataFrame, k: int) -> bool:
+        """True when ``recs`` is grouped by ascending user, at most ``k`` rows per user, relevance descending inside a
+        user with ties by ascending item -- i.e. ``get_top_k_recs`` would return it unchanged (checked in O(n), no sort)."""
+        if len(recs) < 2:
+            return True
+        u = recs["user_idx"].to_numpy()
+        r = recs["relevance"].to_numpy()
+        i = recs["item_idx"].to_numpy()
+        same = u[1:] == u[:-1]
+        if not np.all((u[1:] > u[:-1]) | same):
+            return False
+        if not np.all(~same | (r[1:] < r[:-1]) | ((r[1:] == r[:-1]) & (i[1:] > i[:-1]))):
+            return False
+        starts = np.flatnonzero(np.concatenate(([True], ~same)))
+        return int(np.diff(np.concatenate((starts, [len(u)]))).max()) <= k
 
     def fit_predict(self, log: Any, k: int, users=None, items=None, filter_seen_items: bool = True,
                     recs_file_path: Optional[str] = None):

@@ -208,3 +208,32 @@ def test_staged_topk_filter_cases(engine_factory, case):
     ti2, ts2 = eng.topk_filter_device(torch.from_numpy(scores).to(dev), k)
     torch.cuda.synchronize()
     assert np.array_equal(ti2.cpu().numpy(), ri2) and np.array_equal(ts2.cpu().numpy(), rs2)
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_seen_csr_on_device_equals_host_builder(engine_factory, with_mask):
+    """cql_seen_csr (device radix sort + unique + emit) == mdp.seen_csr (host) bit for bit: unsorted log with duplicate
+    (user, item) pairs, users without rows, an optional mask of requested users, ids up to the dimension."""
+    import pandas as pd
+    from replay_cql_b200.mdp import seen_csr
+    rng = np.random.default_rng(11 + with_mask)
+    n_users, n_items, n = 700, 5000, 60_000
+    users = rng.integers(0, n_users, n).astype(np.int32)
+    users[users % 7 == 3] = 5                      # heavy user + many users without rows
+    items = rng.integers(0, n_items, n).astype(np.int32)
+    items[:2000] = items[2000:4000]                 # duplicates (same pair twice where the users agree too)
+    users[:2000] = users[2000:4000]
+    eng = engine_factory(batch_size=64)
+    wanted = None
+    log = pd.DataFrame({"user_idx": users, "item_idx": items})
+    if with_mask:
+        wanted = (rng.random(n_users) < 0.5)
+        log = log[wanted[log["user_idx"].to_numpy()]]
+    ref_ptr, ref_seen = seen_csr(log, n_users)
+    d_ptr, d_seen = eng.seen_csr_device(users, items, n_users, wanted)
+    assert d_ptr.dtype == torch.int64 and d_seen.dtype == torch.int32
+    assert np.array_equal(d_ptr.cpu().numpy(), ref_ptr)
+    assert np.array_equal(d_seen.cpu().numpy(), ref_seen)
+    # empty log -> all-empty rows
+    e_ptr, e_seen = eng.seen_csr_device(np.zeros(0, np.int32), np.zeros(0, np.int32), 9)
+    assert e_seen.numel() == 0 and not e_ptr.cpu().numpy().any()
