@@ -110,6 +110,16 @@ class PeerGradExchange:
                                "replicas are no longer identical -- restart from the last checkpoint")
 
 
+def exchange_slices(world: int, off_floats: int, n_floats: int):
+    """Host-side mirror of ``dp_slices`` / ``dp_owner`` (csrc/dp_peer.cuh): the fused exchange cuts a gradient group (its
+    16-byte value groups ``q``) into ``world`` contiguous slices, slice ``o`` owned by rank ``o``.  Returns
+    ``(q_lo, n_q, per, owner)`` with ``owner(q_abs) -> rank``.  ``per`` is even, so the 8 consecutive floats an Adam
+    thread updates never straddle two owners (tests/test_parallel_gloo.py checks the invariants the kernels rely on)."""
+    q_lo, n_q = off_floats >> 2, n_floats >> 2
+    per = ((n_q + world - 1) // world + 1) & ~1
+    return q_lo, n_q, per, (lambda q_abs: (q_abs - q_lo) // per)
+
+
 def make_grad_exchange(engine, group=None, prefer_peer: bool = True):
     """PeerGradExchange when every rank can set it up, else the NCCL/gloo reducer (decided collectively)."""
     import torch

@@ -94,3 +94,21 @@ def test_world2_gloo(tmp_path):
     dp = np.load(tmp_path / "dp.npy")
     # Adam's first step is lr*sign(g): compare where the full-batch gradient is not ~0
     np.testing.assert_allclose(dp, ref, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8, 16])
+def test_fused_exchange_slice_invariants(world):
+    """What csrc/dp_peer.cuh relies on (mirrored by parallel.exchange_slices): every value group of a gradient group has
+    exactly one owner in [0, world); owners are contiguous and ascending; the two value groups (8 floats) an Adam thread
+    updates share an owner; the critic and the actor group (gradient layout [actor | critics | scalars]) both fit."""
+    from replay_cql_b200 import layout
+    from replay_cql_b200.parallel import exchange_slices
+    net = layout.NET_STRIDE
+    for off, n in ((0, net), (net, 2 * net), (net, 4 * net)):          # actor; 2 critics; 4 critics
+        q_lo, n_q, per, owner = exchange_slices(world, off, n)
+        assert per % 2 == 0 and per * world >= n_q
+        owners = np.array([owner(q) for q in range(q_lo, q_lo + n_q)])
+        assert owners.min() == 0 and owners.max() <= world - 1
+        assert np.all(np.diff(owners) >= 0) and np.all(np.diff(owners) <= 1)
+        assert np.array_equal(owners[0::2], owners[1::2])               # an 8-float chunk never straddles two owners
+        assert (n // 4) % 2 == 0 and (off // 4) % 2 == 0                   # chunks start on even value groups
