@@ -555,20 +555,27 @@ def run_ml1m(args):
     warm = CQL(n_epochs=1, n_steps_per_epoch=3, batch_size=BATCH)      # context / allocator warm-up (fit returns None, as the reference's)
     warm.fit(log.iloc[:50_000])
     warm.engine.close()
-    model = CQL(n_epochs=1, batch_size=BATCH, seed=12345)
+    # The whole measurement is ~0.4 s of wall clock on a shared host: it is repeated (a fresh model each time) and the
+    # MEDIAN run is reported, all runs listed -- single runs on one box ranged 0.44 .. 1.9 s with the GPU time unchanged.
     clocks = ClockSampler(0); clocks.start(); clocks.wait_first()
-    t0 = time.perf_counter()
-    model.fit(log)
-    torch.cuda.synchronize(dev)
-    fit_s = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    recs = model.predict(log, K_TOP, filter_seen_items=True)
-    pred_s = time.perf_counter() - t1
+    runs = []
+    for rep in range(5):
+        model = CQL(n_epochs=1, batch_size=BATCH, seed=12345)
+        t0 = time.perf_counter()
+        model.fit(log)
+        torch.cuda.synchronize(dev)
+        fit_s = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        recs = model.predict(log, K_TOP, filter_seen_items=True)
+        pred_s = time.perf_counter() - t1
+        n_updates = model.engine.get_optimizer()[2]
+        launches = model.engine.launch_count
+        assert recs.groupby("user_idx").size().max() <= K_TOP and recs["user_idx"].nunique() == shape["n_users"]
+        model.engine.close()
+        runs.append((fit_s + pred_s, fit_s, pred_s))
     clk = clocks.stop()
-    n_updates = model.engine.get_optimizer()[2]
-    launches = model.engine.launch_count
-    assert recs.groupby("user_idx").size().max() <= K_TOP and recs["user_idx"].nunique() == shape["n_users"]
-    model.engine.close()
+    runs_sorted = sorted(runs)
+    _, fit_s, pred_s = runs_sorted[len(runs) // 2]
     cpu = None
     if not args.no_cpu:
         rate, dt, threads = cpu_update_rate(40, 3)
@@ -582,7 +589,8 @@ def run_ml1m(args):
             "config": {"workload": "ml1m-fit-predict", "users": shape["n_users"], "items": shape["n_items"], "rows": shape["n_rows"],
                        "batch_per_gpu": BATCH, "n_epochs": 1, "k": K_TOP, "filter_seen_items": True, "precision": model.precision,
                        "api": "replay_cql_b200.models.CQL().fit(log); .predict(log, 10)"},
-            "fit_seconds": fit_s, "predict_seconds": pred_s, "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu,
+            "fit_seconds": fit_s, "predict_seconds": pred_s, "runs_fit_predict_seconds": [[round(f, 4), round(p_, 4)] for _, f, p_ in runs],
+            "runs_note": "5 runs, a fresh model each; value = the median run", "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu,
             "e2e": {"value": fit_s + pred_s, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "the whole measurement IS end to end: pandas frames in, pandas frame out"}}
     print(json.dumps(line), flush=True)
