@@ -483,8 +483,7 @@ int cql_load_transitions(cql_handle* ch, const float* obs, const float* act, con
     Handle& h = ch->h;
     CQL_REQUIRE(obs && act && rew && term && n >= 1, "cql_load_transitions: bad arguments");
     CQL_CUDA(cudaDeviceSynchronize());
-    if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
-    CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+    ensure_table(h, n);
     // stage the 20 B/step columns on the device, expand to 32 B rows there
     float *d_obs, *d_act, *d_rew, *d_term;
     CQL_CUDA(cudaMalloc(&d_obs, (size_t)n * 2 * sizeof(float)));
@@ -537,8 +536,7 @@ int cql_synth_table(cql_handle* ch, int64_t n, int64_t n_users, int64_t n_items,
     CQL_REQUIRE(n >= 1 && n_users >= 1 && n_items >= 1 && n_users <= n, "cql_synth_table: bad shape");
     CQL_REQUIRE(n_users < (1ll << 24) && n_items < (1ll << 24), "cql_synth_table: ids must stay below 2^24 (exact in float32)");
     CQL_CUDA(cudaDeviceSynchronize());
-    if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
-    CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+    ensure_table(h, n);
     k_synth_table<<<(unsigned)((n + 255) / 256), 256, 0, h.own_stream>>>(reinterpret_cast<float4*>(h.table), n, n_users, n_items, seed);
     CQL_LAUNCH_CHECK(&h);
     CQL_CUDA(cudaStreamSynchronize(h.own_stream));

@@ -53,6 +53,7 @@ struct Handle {
   // ---- replay table ----
   float* table = nullptr;    // [n_trans][8]: obs.x obs.y act rew nobs.x nobs.y term pad
   int64_t n_trans = 0;
+  int64_t table_cap = 0;     // rows the table allocation can hold (re-ingesting a log of the same size re-uses it)
   bool table_sharded = false;   // data parallel: this rank holds only its own users' episodes (cql_set_table_sharded)
   int64_t sample_pos_host = 0;  // position in the epoch stream for the stand-alone sampler
   long long* sample_pos = nullptr;   // device: next position in the permutation stream
@@ -138,7 +139,7 @@ struct Handle {
     allocs.clear();
     if (mdp) { mdp_session_free(mdp); mdp = nullptr; }
     if (mdp_ring) { cudaFreeHost(mdp_ring); mdp_ring = nullptr; }
-    if (table) { cudaFree(table); table = nullptr; }
+    if (table) { cudaFree(table); table = nullptr; table_cap = 0; }
     if (metrics_host) { cudaFreeHost(metrics_host); metrics_host = nullptr; }
     if (batch_host) { cudaFreeHost(batch_host); batch_host = nullptr; }
     if (noise_host) { cudaFreeHost(noise_host); noise_host = nullptr; }
@@ -161,6 +162,16 @@ void mdp_begin(Handle& h, int64_t n);
 void mdp_append(Handle& h, int col, int dtype, const void* host, int64_t count);
 int64_t mdp_finish(Handle& h, int top_k, float noise_scale, float* obs_out, float* act_out, float* rew_out, float* term_out,
                    int64_t* order_out);
+
+// replay table for n rows: the existing allocation is kept when it is large enough (a 640 MB cudaFree + cudaMalloc per
+// ingestion synchronises the device and costs milliseconds to tens of milliseconds)
+inline void ensure_table(Handle& h, int64_t n) {
+  h.n_trans = 0;
+  if (h.table != nullptr && h.table_cap >= n) return;
+  if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.table_cap = 0; }
+  CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+  h.table_cap = n;
+}
 
 inline void mark(Handle* h, cudaStream_t st, int i) {
   if (h->timing) CQL_CUDA(cudaEventRecord(h->ev[i], st));

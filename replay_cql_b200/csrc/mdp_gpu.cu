@@ -70,10 +70,25 @@ __global__ void k_emit(const uint32_t* __restrict__ order, const int32_t* __rest
   if (obs_o) { obs_o[2 * i] = uf; obs_o[2 * i + 1] = itf; act_o[i] = act; rew_o[i] = rw; term_o[i] = last ? 1.f : 0.f; }
 }
 
+// Session scratch comes from the stream-ordered pool (cudaMallocAsync), which keeps up to 4 GB cached between calls:
+// the ~1.9 GB of cudaMalloc / cudaFree pairs per 20 M-row session synchronise the device and made ingestion (and `fit`)
+// wall clocks erratic on shared hosts -- 0.05 .. 1.2 s for the same call (r02 bench lines).  The caller synchronises
+// `st` before the pointers are used on another stream.
+inline void keep_pool_cached() {
+  static bool once = false;
+  if (once) return;
+  once = true;
+  int dev = 0;
+  cudaMemPool_t mp = nullptr;
+  unsigned long long keep = 4ull << 30;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
+    cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+}
 template <typename T>
-T* dmalloc(size_t n, std::vector<void*>& pool) {
+T* dmalloc(size_t n, std::vector<void*>& pool, cudaStream_t st) {
+  keep_pool_cached();
   void* p = nullptr;
-  CQL_CUDA(cudaMalloc(&p, std::max<size_t>(1, n) * sizeof(T)));
+  CQL_CUDA(cudaMallocAsync(&p, std::max<size_t>(1, n) * sizeof(T), st));
   pool.push_back(p);
   return reinterpret_cast<T*>(p);
 }
@@ -133,8 +148,12 @@ struct cql::MdpSession {
   int64_t launches = 0;
   std::vector<void*> pool;
 
+  cudaStream_t alloc_stream = nullptr;      // the handle's stream: every session buffer is allocated and released on it
+
   ~MdpSession() {
-    for (void* p : pool) cudaFree(p);
+    if (alloc_stream) cudaStreamSynchronize(alloc_stream);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    for (void* p : pool) cudaFreeAsync(p, alloc_stream);
     for (auto& e : slot_ev) if (e) cudaEventDestroy(e);
     if (ev_ts) cudaEventDestroy(ev_ts);
     if (ev_all) cudaEventDestroy(ev_all);
@@ -180,21 +199,22 @@ void cql::mdp_begin(Handle& h, int64_t n) {
   auto* m = new MdpSession();
   h.mdp = m;
   m->n = n;
-  m->user = dmalloc<int32_t>(n, m->pool);
-  m->item = dmalloc<int32_t>(n, m->pool);
-  m->ts = dmalloc<int64_t>(n, m->pool);
-  m->rel = dmalloc<double>(n, m->pool);
-  m->ia = dmalloc<uint32_t>(n, m->pool);
-  m->ib = dmalloc<uint32_t>(n, m->pool);
-  m->perm_desc = dmalloc<uint32_t>(n, m->pool);
-  m->order = dmalloc<uint32_t>(n, m->pool);
-  m->k64a = dmalloc<int64_t>(n, m->pool);
-  m->k64b = dmalloc<int64_t>(n, m->pool);
-  m->kda = dmalloc<double>(n, m->pool);
-  m->kdb = dmalloc<double>(n, m->pool);
-  m->k32a = dmalloc<int32_t>(n, m->pool);
-  m->k32b = dmalloc<int32_t>(n, m->pool);
-  m->rewarded = dmalloc<uint8_t>(n, m->pool);
+  m->alloc_stream = h.own_stream;
+  m->user = dmalloc<int32_t>(n, m->pool, m->alloc_stream);
+  m->item = dmalloc<int32_t>(n, m->pool, m->alloc_stream);
+  m->ts = dmalloc<int64_t>(n, m->pool, m->alloc_stream);
+  m->rel = dmalloc<double>(n, m->pool, m->alloc_stream);
+  m->ia = dmalloc<uint32_t>(n, m->pool, m->alloc_stream);
+  m->ib = dmalloc<uint32_t>(n, m->pool, m->alloc_stream);
+  m->perm_desc = dmalloc<uint32_t>(n, m->pool, m->alloc_stream);
+  m->order = dmalloc<uint32_t>(n, m->pool, m->alloc_stream);
+  m->k64a = dmalloc<int64_t>(n, m->pool, m->alloc_stream);
+  m->k64b = dmalloc<int64_t>(n, m->pool, m->alloc_stream);
+  m->kda = dmalloc<double>(n, m->pool, m->alloc_stream);
+  m->kdb = dmalloc<double>(n, m->pool, m->alloc_stream);
+  m->k32a = dmalloc<int32_t>(n, m->pool, m->alloc_stream);
+  m->k32b = dmalloc<int32_t>(n, m->pool, m->alloc_stream);
+  m->rewarded = dmalloc<uint8_t>(n, m->pool, m->alloc_stream);
   size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
   cudaStream_t st = h.own_stream;
   cub::DeviceRadixSort::SortPairs(nullptr, t1, m->ts, m->k64a, m->ia, m->ib, (int)n, 0, 64, st);
@@ -204,10 +224,11 @@ void cql::mdp_begin(Handle& h, int64_t n) {
   cub::DeviceScan::InclusiveScan(nullptr, t5, m->k64a, m->k64b, MaxOp(), (int)n, st);
   m->tbytes = t1;
   for (size_t t : {t2, t3, t4, t5}) m->tbytes = t > m->tbytes ? t : m->tbytes;
-  m->temp = dmalloc<uint8_t>(m->tbytes, m->pool);
+  m->temp = dmalloc<uint8_t>(m->tbytes, m->pool, m->alloc_stream);
   if (h.mdp_ring == nullptr) CQL_CUDA(cudaMallocHost(&h.mdp_ring, MdpSession::SLOTS * MdpSession::SLOT_BYTES));
   m->ring = h.mdp_ring;
-  m->raw = dmalloc<uint8_t>(MdpSession::SLOTS * MdpSession::SLOT_BYTES, m->pool);
+  m->raw = dmalloc<uint8_t>(MdpSession::SLOTS * MdpSession::SLOT_BYTES, m->pool, m->alloc_stream);
+  CQL_CUDA(cudaStreamSynchronize(m->alloc_stream));          // the buffers are used on the copy stream as well
   for (auto& e : m->slot_ev) CQL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CQL_CUDA(cudaEventCreateWithFlags(&m->ev_ts, cudaEventDisableTiming));
   CQL_CUDA(cudaEventCreateWithFlags(&m->ev_all, cudaEventDisableTiming));
@@ -222,7 +243,10 @@ void cql::mdp_append(Handle& h, int col, int dtype, const void* host, int64_t co
   CQL_REQUIRE(dtype >= CQL_DT_I32 && dtype <= CQL_DT_F64, "cql_mdp_append: dtype must be one of CQL_DT_*");
   CQL_REQUIRE(count >= 0 && m.filled[col] + count <= m.n, "cql_mdp_append: more rows than cql_mdp_begin announced");
   CQL_REQUIRE(host != nullptr || count == 0, "cql_mdp_append: NULL chunk");
-  if (col == 4 && m.noise == nullptr) m.noise = dmalloc<double>(m.n, m.pool);
+  if (col == 4 && m.noise == nullptr) {
+    m.noise = dmalloc<double>(m.n, m.pool, m.alloc_stream);
+    CQL_CUDA(cudaStreamSynchronize(m.alloc_stream));
+  }
   const int native = (col <= 1) ? CQL_DT_I32 : (col == 2 ? CQL_DT_I64 : CQL_DT_F64);
   const size_t eb = dtype_bytes(dtype);
   const int64_t per_slot = (int64_t)(MdpSession::SLOT_BYTES / eb);
@@ -290,13 +314,12 @@ int64_t cql::mdp_finish(Handle& h, int top_k, float noise_scale, float* obs_out,
   m.launches += 13;
 
   // ---- emit transition rows straight into the replay table
-  if (h.table) { CQL_CUDA(cudaFree(h.table)); h.table = nullptr; h.n_trans = 0; }
-  CQL_CUDA(cudaMalloc(&h.table, (size_t)n * 8 * sizeof(float)));
+  ensure_table(h, n);
   float *d_obs = nullptr, *d_act = nullptr, *d_rew = nullptr, *d_term = nullptr;
   if (obs_out) {
     CQL_REQUIRE(act_out && rew_out && term_out, "cql_build_mdp: give all four output columns or none");
-    d_obs = dmalloc<float>(2 * n, m.pool); d_act = dmalloc<float>(n, m.pool);
-    d_rew = dmalloc<float>(n, m.pool); d_term = dmalloc<float>(n, m.pool);
+    d_obs = dmalloc<float>(2 * n, m.pool, m.alloc_stream); d_act = dmalloc<float>(n, m.pool, m.alloc_stream);
+    d_rew = dmalloc<float>(n, m.pool, m.alloc_stream); d_term = dmalloc<float>(n, m.pool, m.alloc_stream);
   }
   k_emit<<<nb, 256, 0, st>>>(m.order, m.user, m.item, m.rel, m.noise, m.rewarded, n, noise_scale, h.cfg.seed,
                              reinterpret_cast<float4*>(h.table), d_obs, d_act, d_rew, d_term);
@@ -367,21 +390,11 @@ __global__ void k_seen_emit(const unsigned long long* __restrict__ key, int64_t 
 }
 // device scratch from the stream-ordered pool, released on every exit path: cudaMalloc / cudaFree pairs per call
 // synchronise the device and made `predict` wall clocks erratic (0.05 .. 1.4 s for the same ML-1M call); the pool keeps
-// up to 1 GB cached between calls
+// its memory cached between calls (keep_pool_cached)
 struct DevTmp {
   cudaStream_t st;
   std::vector<void*> p;
-  explicit DevTmp(cudaStream_t s) : st(s) {
-    static bool once = false;
-    if (!once) {
-      int dev = 0;
-      cudaMemPool_t pool = nullptr;
-      unsigned long long keep = 1ull << 30;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      once = true;
-    }
-  }
+  explicit DevTmp(cudaStream_t s) : st(s) { keep_pool_cached(); }
   ~DevTmp() { for (void* x : p) cudaFreeAsync(x, st); }
   template <typename T>
   T* get(size_t count) {
