@@ -75,13 +75,13 @@ __global__ void k_emit(const uint32_t* __restrict__ order, const int32_t* __rest
 // wall clocks erratic on shared hosts -- 0.05 .. 1.2 s for the same call (r02 bench lines).  The caller synchronises
 // `st` before the pointers are used on another stream.
 inline void keep_pool_cached() {
-  static bool once = false;
-  if (once) return;
-  once = true;
+  static unsigned long long done_mask = 0;          // per device (engines on several GPUs may live in one process)
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || (done_mask >> dev) & 1ull) return;
+  done_mask |= 1ull << dev;
   cudaMemPool_t mp = nullptr;
   unsigned long long keep = 4ull << 30;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
+  if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
     cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
 }
 template <typename T>
