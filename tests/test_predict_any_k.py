@@ -63,3 +63,37 @@ def test_any_k_equals_direct_topk(monkeypatch, k, with_seen):
         assert got.tolist() == order.tolist()                 # same items, same (descending) order
         np.testing.assert_array_equal(ts[r][: len(order)], sc[order])
         assert np.all(ti[r][len(order):] == -1)               # fewer unseen items than k: padded, never repeated
+
+
+def test_is_top_k_detects_ranked_output():
+    """`Recommender._is_top_k`: the O(n) check that lets `_predict_wrap` skip `get_top_k_recs` for a model whose
+    `_predict` already returns the k best per user, best first (ties by ascending item): it must agree with actually
+    running `get_top_k_recs` -- True iff that call would return the frame unchanged."""
+    import pandas as pd
+    from replay_cql_b200.recommender import Recommender, get_top_k_recs, REC_COLUMNS
+    rng = np.random.default_rng(0)
+
+    def frame(u, i, r):
+        return pd.DataFrame({"user_idx": np.asarray(u, np.int32), "item_idx": np.asarray(i, np.int32),
+                             "relevance": np.asarray(r, np.float64)})
+
+    good = frame([0, 0, 0, 2, 2, 5], [7, 3, 9, 1, 4, 2], [0.9, 0.5, 0.5, 2.0, 1.0, 0.1])
+    cases = {
+        "ranked": (good, 3, True),
+        "too many rows for k": (good, 2, False),
+        "relevance ascending inside a user": (frame([0, 0], [1, 2], [0.1, 0.2]), 5, False),
+        "tie with descending item": (frame([0, 0], [5, 2], [0.3, 0.3]), 5, False),
+        "users not grouped": (frame([0, 1, 0], [1, 2, 3], [0.9, 0.8, 0.7]), 5, False),
+        "users descending": (frame([3, 1], [1, 2], [0.9, 0.8]), 5, False),
+        "empty": (frame([], [], []), 3, True),
+    }
+    for name, (df, k, want) in cases.items():
+        assert Recommender._is_top_k(df, k) is want, name
+        same = get_top_k_recs(df, k)[REC_COLUMNS].reset_index(drop=True).equals(df[REC_COLUMNS].reset_index(drop=True)) if len(df) else True
+        assert same is want, name
+    for _ in range(50):                                        # random frames: the check never claims more than the sort shows
+        n = int(rng.integers(1, 12))
+        df = frame(np.sort(rng.integers(0, 4, n)), rng.integers(0, 6, n), rng.integers(0, 3, n) / 2.0)
+        k = int(rng.integers(1, 5))
+        if Recommender._is_top_k(df, k):
+            assert get_top_k_recs(df, k)[REC_COLUMNS].reset_index(drop=True).equals(df[REC_COLUMNS].reset_index(drop=True))
