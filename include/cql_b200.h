@@ -258,8 +258,9 @@ int  cql_rank_metrics(cql_handle* h, const int32_t* rec_items, int64_t n_users, 
  * update, [4] = actor-step critic forward, [5] = actor backward (1+2), [6] = shared actor
  * forward, [7] = everything else.  The update is a real one (weights advance).  Programmatic dependent launch is
  * off for this step (events between overlapping kernels would not separate them), and the critic forward is launched
- * four times back to back between its two events (same inputs, same outputs): [0] is that span / 4, the kernel's
- * steady-state duration without the launch latency of a lone launch; [3] counts it once. */
+ * four times back to back between its two events (same inputs, same outputs; the repeats with programmatic dependent
+ * launch, as in the step graph): [0] is that span / 4, the kernel's steady-state duration without the launch latency of
+ * a lone launch; [3] counts it once. */
 int  cql_timed_update(cql_handle* h, float* out_ms8, void* stream);
 
 /* Self-test of the tensor-core building blocks (tcgen05.mma + TMEM + operand layout):

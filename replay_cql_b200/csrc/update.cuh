@@ -1073,7 +1073,15 @@ inline void phase0(Handle* h, cudaStream_t st, BatchSource bs, NoiseSource ns) {
     QSrc srcQ[3];
     // cql_timed_update: the launch is repeated back to back between the two events (same inputs, same outputs), so that
     // the reported duration is the kernel's steady-state launch-to-launch time, not one launch plus its launch latency
-    for (int rep = 0; rep < (h->timing ? TIMED_FWD_REPS : 1); ++rep) launch_fwd_any<3, 1>(h, jobs, st, srcQ);
+    // (the repeats are launched the way the step graph launches this kernel -- with programmatic dependent launch -- so a
+    //  repeat's prologue overlaps its predecessor's drain exactly as it overlaps k_prep's in the product schedule; the
+    //  events on either side still separate the four launches from their neighbours)
+    for (int rep = 0; rep < (h->timing ? TIMED_FWD_REPS : 1); ++rep) {
+      const bool saved = g_timing_no_pdl;
+      if (rep > 0) g_timing_no_pdl = false;
+      launch_fwd_any<3, 1>(h, jobs, st, srcQ);
+      g_timing_no_pdl = saved;
+    }
     mark(h, st, 4);
     // (the last block of k_lse also sums the pair values and publishes the two scalar gradients: the former k_scalar_reduce)
     const int64_t so = scalars_off(C);
