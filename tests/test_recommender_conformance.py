@@ -86,7 +86,7 @@ def test_predict_pairs_k_and_columns():   # test_all_models.py:128-144
     pairs = LOG[["user_idx", "item_idx"]]
     assert model.predict_pairs(pairs, log=LOG, k=2).groupby("user_idx").size().max() <= 2
     assert model.predict_pairs(pairs, log=LOG).groupby("user_idx").size().max() > 2
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match="pairs must be a dataframe with .*"):     # test_all_models.py:170-174
         model.predict_pairs(LOG[["user_idx", "item_idx", "relevance"]])
 
 
@@ -256,3 +256,30 @@ def test_predict_and_predict_pairs_to_file(tmp_path):   # test_all_models.py:393
     path2 = str(tmp_path / "pairs.parquet")
     assert model.predict_pairs(pairs=pairs, log=LONG_LOG, recs_file_path=path2) is None
     pd.testing.assert_frame_equal(model.predict_pairs(pairs=pairs, log=LONG_LOG).reset_index(drop=True), pd.read_parquet(path2))
+
+
+class FilteredTopK(PopLike):
+    """A model whose `_predict` itself returns at most k unseen items per user, best first (what CQL's fused scorer
+    does) and says so: the template must return the same frame as the generic path computes from ALL pairs."""
+    _predict_filters_seen = True
+
+    def _predict(self, log, k, users, items, user_features=None, item_features=None, filter_seen_items=True):
+        full = super()._predict(log, k, users, items)
+        if filter_seen_items and log is not None:
+            seen = set(zip(log["user_idx"], log["item_idx"]))
+            full = full[[(u, i) not in seen for u, i in zip(full["user_idx"], full["item_idx"])]]
+        return get_top_k_recs(full, k).reset_index(drop=True)
+
+
+@pytest.mark.parametrize("filter_seen", [True, False])
+@pytest.mark.parametrize("k", [1, 2, 5])
+def test_model_that_filters_itself_equals_generic_path(k, filter_seen):
+    a, b = PopLike(), FilteredTopK()
+    a.fit(LOG)
+    b.fit(LOG)
+    ra = a.predict(LOG, k=k, filter_seen_items=filter_seen)
+    calls = []
+    b._filter_seen = lambda **kw: calls.append(1) or kw["recs"]          # must not be needed
+    rb = b.predict(LOG, k=k, filter_seen_items=filter_seen)
+    pd.testing.assert_frame_equal(ra, rb)
+    assert not calls
