@@ -274,6 +274,8 @@ class CQL(Recommender):
         u_local = u[lo:hi]
         indptr = seen = None
         kk = min(int(k), int(it.size))
+        if kk <= 0:                                     # k = 0: nothing to recommend (the reference returns an empty frame)
+            return _rec_frame([], [], [])
         from . import _lib
         on_device = kk <= _lib.MAX_TOPK and u_local.size > 0 and hasattr(self.engine, "seen_csr_device")
         n_dim = int(u.max()) + 1
